@@ -1,0 +1,135 @@
+/*
+ * prt_b200.h -- C ABI of the B200-native PRT precomputation library (libprt_b200.so).
+ *
+ * Drop-in boundary for the precomputation hot path of lvjiahui/PRT.  The reference has no FFI of its
+ * own: its boundary is a handful of C++ entry points called from App.  Every
+ * function below names the reference interface it replaces (file:line under the reference tree); the
+ * header-only C++ shim include/prt_b200_shim.hpp re-creates those C++ signatures on top of this ABI.
+ *
+ * Conventions: plain pointers and sizes only; opaque handles; int status (0 = ok, <0 = error, message
+ * via prt_last_error(), thread-local); no exceptions cross the boundary; blocking unless a stream is
+ * passed to a *_device entry point.  One handle must not be used from two threads concurrently;
+ * different handles are independent.  There is NO CPU fallback: every entry point fails with
+ * PRT_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Host-pointer entry points copy inputs host->device and results device->host themselves (this is the
+ * "e2e" path of bench.py).  *_device entry points take device pointers and a cudaStream_t (as void*).
+ */
+#ifndef PRT_B200_H
+#define PRT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRT_B200_ABI_VERSION 1
+
+enum {
+    PRT_OK = 0,
+    PRT_ERR_INVALID = -1,   /* bad argument */
+    PRT_ERR_CUDA = -2,      /* CUDA runtime / no device */
+    PRT_ERR_NOMEM = -3,
+    PRT_ERR_BUILD = -4,     /* BVH build failed (bad indices, depth limit) */
+    PRT_ERR_UNSUPPORTED = -5
+};
+
+typedef struct prt_ctx prt_ctx;
+typedef struct prt_scene prt_scene;
+
+const char *prt_last_error(void);
+int prt_abi_version(void);
+
+/* Process-global "RTCDevice device = initializeDevice()" (raytracing.cpp:42-52, light_probe.cpp:28-38):
+ * one context per GPU.  device_id < 0 -> current device. */
+int prt_ctx_create(int device_id, prt_ctx **out);
+void prt_ctx_destroy(prt_ctx *);
+int prt_ctx_device(const prt_ctx *);
+/* name/value tuning knobs for experiments (block size, occupancy, refill threshold); unknown names fail */
+int prt_ctx_set_tuning(prt_ctx *, const char *name, int value);
+
+/* RTScene::RTScene(Mesh&) / RTScene(Model&) (raytracing.cpp:58-94, light_probe.cpp:44-87): copies
+ * positions (pos_stride_bytes apart; 60 for Mesh::Vert, gl.h:76-80) and uint32 index triples, builds the
+ * 8-wide compressed BVH on the host and uploads it to the context's GPU.  ~RTScene -> prt_scene_destroy. */
+int prt_scene_create(prt_ctx *, const float *pos_xyz, size_t pos_stride_bytes, uint32_t n_verts,
+                     const uint32_t *tri_idx, uint32_t n_tris, prt_scene **out);
+void prt_scene_destroy(prt_scene *);
+
+typedef struct {
+    uint32_t n_tris, n_nodes;      /* 80-byte wide nodes, 48-byte triangles */
+    uint32_t max_depth;
+    uint32_t reserved;
+    uint64_t node_bytes, tri_bytes;
+    double build_seconds, upload_seconds;
+    double sah_cost;
+} prt_scene_info;
+int prt_scene_get_info(const prt_scene *, prt_scene_info *out);
+
+/* ---- ray queries: struct Ray::{any_hit, first_hit, hit_normal} (light_probe.cpp:95-133) -------------
+ * rays: n x 8 floats (org.xyz, tnear, dir.xyz, tfar); dir is NOT normalised by the library (segment
+ * tests pass probe-voxel with tfar = 1, light_probe.cpp:250).  A hit needs tnear < t <= tfar.
+ * any-hit : out_hit[i] = 1/0                         (rtcOccluded1, light_probe.cpp:128)
+ * closest : out_t[i] (inf on miss), out_prim[i] (0xFFFFFFFF on miss), out_ng[i][3] = unnormalised
+ *           geometric normal (v1-v0)x(v2-v0)           (rtcIntersect1, light_probe.cpp:119; Ng :124)      */
+int prt_trace_any_hit(prt_scene *, const float *rays, uint32_t n, uint8_t *out_hit);
+int prt_trace_closest_hit(prt_scene *, const float *rays, uint32_t n, float *out_t, uint32_t *out_prim, float *out_ng);
+
+/* ---- per-vertex diffuse SH transfer: bake_SH(Mesh&) (raytracing.cpp:320-360) ----------------------- */
+enum { PRT_UNSHADOWED = 0, PRT_SHADOWED = 1, PRT_INTERREFLECT = 2, PRT_UNSHADOWED_ANALYTIC = 3 };
+
+typedef struct {
+    int32_t order;        /* bands; coefficients = order^2; reference: file-scope "order"+1 = 3 (raytracing.cpp:320) */
+    int32_t samples_u;    /* radial strata;  reference App::sh_resolution = 32 (app.h:71) */
+    int32_t samples_v;    /* angular strata; reference App::sh_resolution = 32 */
+    uint32_t seed;        /* strata-jitter / bounce RNG seed (Philox4x32-10) */
+    int32_t bounces;      /* B; path depth = B+1 = App::max_path_length-1 (raytracing.cpp:345, app.h:70) */
+    float albedo[3];      /* App::albedo (app.h:55) */
+    float origin_eps;     /* 1e-4 (raytracing.cpp:343) */
+    float bounce_eps;     /* 1e-5 (raytracing.cpp:235) */
+    int32_t mode;         /* PRT_SHADOWED etc. */
+    int32_t cs_phase;     /* 0: SH_function.h convention; 1: google/spherical-harmonics sign */
+    int32_t jitter;       /* 1: jittered strata (raytracing.cpp:338-339); 0: stratum centres */
+} prt_bake_params;
+
+void prt_bake_params_default(prt_bake_params *);
+
+/* Host buffers in, host buffers out.  pos/nrm point at the first vertex's position / normal, consecutive
+ * vertices stride_bytes apart (60 for Mesh::Vert).  out_coeffs [n_verts][order^2] floats, row-major,
+ * k = l(l+1)+m.  out_vis optional: [n_verts][ceil(S/32)] uint32, bit s set <=> primary ray s (s = i*samples_v+j)
+ * is unoccluded.  vertex_id_base: id of vertex 0 for the bounce RNG key (sharded bakes).  scene may be NULL for the
+ * unshadowed modes. */
+int prt_bake_transfer(prt_ctx *, prt_scene *, const float *pos, const float *nrm, size_t stride_bytes,
+                      uint32_t n_verts, uint32_t vertex_id_base, const prt_bake_params *,
+                      float *out_coeffs, uint32_t *out_vis);
+
+/* Same with device-resident inputs/outputs, asynchronous on `stream` (a cudaStream_t). */
+int prt_bake_transfer_device(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes,
+                             uint32_t n_verts, uint32_t vertex_id_base, const prt_bake_params *,
+                             float *d_out_coeffs, uint32_t *d_out_vis, void *stream);
+
+/* Mesh::Vert scatter for the viewer (gl.h:76-80, gl.cpp:255-268): writes order-3 rows into sh_coeff[9] of an
+ * interleaved 60-byte vertex array on the host. */
+int prt_scatter_sh9(const float *coeffs, int32_t order, uint32_t n_verts, void *mesh_verts, size_t vert_stride_bytes,
+                    size_t sh_offset_bytes);
+
+/* Sample table used by the bake: uv[S][2], local_dirs[S][3] in reference order s = i*samples_v + j (host). */
+int prt_bake_sample_table(const prt_bake_params *, float *uv, float *local_dirs);
+
+/* Per-call statistics of the most recent bake on this context */
+typedef struct {
+    double kernel_ms;        /* traversal+projection kernel, CUDA events on the launching stream */
+    double h2d_ms, d2h_ms;   /* host-pointer entry point only */
+    uint64_t rays;           /* primary rays issued */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t launches;       /* kernels launched by the call */
+    uint32_t grid, block;
+    uint64_t node_visits;    /* only with tuning knob count_work=1: 80-byte node fetches ... */
+    uint64_t tri_tests;      /* ... and 48-byte triangle fetches of the launch (algorithmic traversal work) */
+} prt_bake_stats;
+int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

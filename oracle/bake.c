@@ -1,0 +1,178 @@
+/*
+ * oracle/bake.c -- CPU ORACLE, TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates the reference's per-vertex diffuse SH transfer bake:
+ *   bake_SH        src/raytracing/raytracing.cpp:320-360  (estimator, origin offset, 1/S normalisation)
+ *   renderSH       src/raytracing/raytracing.cpp:228-278  (path logic, cut-offs, bounce offsets)
+ *   sampling       src/raytracing/raytracing.cpp:101-107,130-160
+ *   lightSH        src/raytracing/raytracing.cpp:224-227  (sh-space permutation (z,x,y))
+ * Documented departures: one stratified (u,v) table per run shared by every vertex and
+ * coefficient (Philox stream 0) instead of a fresh mt19937 jitter per (vertex, coefficient, sample);
+ * counter-based bounce randoms keyed (vertex, sample, bounce); one trace per sample shared by all
+ * coefficients (faithful=1 re-traces per coefficient, identical results); accumulation in double
+ * (the reference accumulates in float, raytracing.cpp:348).
+ */
+#include "prt_oracle.h"
+#include "arith.h"
+#include "philox.h"
+#include "sh.h"
+#include <pthread.h>
+#include <stdlib.h>
+#include <unistd.h>
+
+void prt_o_sh_eval(int order, int cs_phase, const float d[3], float *out) { prt_sh_eval(order, cs_phase, d[0], d[1], d[2], out); }
+void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { prt_philox4x32_10(ctr, key, out); }
+void prt_o_sincos2pi(float v, float *s, float *c) { prt_sincos2pi(v, s, c); }
+int prt_o_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+
+void prt_o_sample_table(const prt_o_bake_params *p, float *uv, float *dirs) {
+    int Ru = p->samples_u, Rv = p->samples_v;
+    for (int i = 0; i < Ru; i++)
+        for (int j = 0; j < Rv; j++) {
+            int s = i * Rv + j;
+            float x1 = 0.5f, x2 = 0.5f;
+            if (p->jitter) prt_rand2(p->seed, (uint32_t)s, 0u, 0u, 0u, &x1, &x2);
+            /* raytracing.cpp:338-339: x = (i+random())/res -> radius^2, y = (j+random())/res -> angle */
+            float u = ((float)i + x1) / (float)Ru;
+            float v = ((float)j + x2) / (float)Rv;
+            v3 l = prt_cosine_local(u, v);
+            if (uv) { uv[2 * s] = u; uv[2 * s + 1] = v; }
+            if (dirs) { dirs[3 * s] = l.x; dirs[3 * s + 1] = l.y; dirs[3 * s + 2] = l.z; }
+        }
+}
+
+typedef struct {
+    const prt_o_scene *sc;
+    const char *pos, *nrm;
+    size_t stride;
+    uint32_t n, base;
+    const prt_o_bake_params *p;
+    const float *dirs;
+    float *out;
+    uint32_t *vis;
+    int faithful;
+    volatile uint32_t *next;
+    uint64_t rays, segs;
+} job_t;
+
+/* One path (renderSH).  Returns the weight Lw.x carried to the environment and the final
+ * direction (0 weight when the path is absorbed). *primary_visible = 1 iff the first segment escaped. */
+static float trace_path(const job_t *J, v3 pos, v3 dir, int depth, uint32_t vid, uint32_t s,
+                        v3 *final_dir, int *primary_visible, uint64_t *segs) {
+    const prt_o_bake_params *p = J->p;
+    float Lw[3] = { 1.f, 1.f, 1.f };
+    float tnear = 0.0f;
+    *primary_visible = 0;
+    for (int i = 0; i < depth; i++) {
+        if (fmaxf(Lw[0], fmaxf(Lw[1], Lw[2])) < 0.01f) break;          /* :249 */
+        float o[3] = { pos.x, pos.y, pos.z }, d[3] = { dir.x, dir.y, dir.z };
+        (*segs)++;
+        if (i == depth - 1) {
+            /* last segment: only hit/miss is observable (a hit can never reach the environment) */
+            if (!prt_o_any_hit(J->sc, o, d, tnear, INFINITY, 1)) { if (i == 0) *primary_visible = 1; *final_dir = dir; return Lw[0]; }
+            return 0.0f;
+        }
+        float t; uint32_t prim; float ng[3];
+        if (!prt_o_closest_hit(J->sc, o, d, tnear, INFINITY, 1, &t, &prim, ng)) {   /* :257-261 */
+            if (i == 0) *primary_visible = 1;
+            *final_dir = dir; return Lw[0];
+        }
+        v3 n = v3_normalize(v3_make(ng[0], ng[1], ng[2]));                  /* :263-264 */
+        if (v3_dot(dir, n) >= -1e-4f) return 0.0f;                          /* :265 */
+        pos = v3_madd(pos, t, dir);                                         /* :266 */
+        float u, v;
+        prt_rand2(p->seed, vid, s, (uint32_t)i, 1u, &u, &v);                /* :267 random(), random() */
+        v3 l = prt_cosine_local(u, v);
+        float pdf = l.z / PRT_PI_F;
+        frame3 f = prt_frame(n);
+        dir = prt_to_world(&f, l);
+        if (pdf <= 1e-4f) return 0.0f;                                      /* :269 */
+        Lw[0] *= p->albedo[0]; Lw[1] *= p->albedo[1]; Lw[2] *= p->albedo[2]; /* :271 */
+        float sign = v3_dot(dir, n) < 0.0f ? -1.0f : 1.0f;                  /* :273 */
+        pos = v3_madd(pos, sign * p->bounce_eps, dir);                      /* :274 */
+        tnear = p->bounce_eps;                                              /* :275 */
+    }
+    return 0.0f;
+}
+
+static void bake_vertex(job_t *J, uint32_t i) {
+    const prt_o_bake_params *p = J->p;
+    const float *P = (const float *)(J->pos + (size_t)i * J->stride);
+    const float *Nn = (const float *)(J->nrm + (size_t)i * J->stride);
+    int n2 = p->order * p->order;
+    int S = p->samples_u * p->samples_v;
+    int words = (S + 31) / 32;
+    float *out = J->out + (size_t)i * n2;
+    uint32_t vid = J->base + i;
+    v3 N = v3_make(Nn[0], Nn[1], Nn[2]);
+    if (p->mode == PRT_O_UNSHADOWED_ANALYTIC) {
+        /* scene/model.cpp:29-31 hint: rotate_cos_lobe(norm) * INV_PI */
+        float y[25];
+        prt_sh_eval(p->order, p->cs_phase, N.z, N.x, N.y, y);
+        for (int l = 0, k = 0; l < p->order; l++)
+            for (int m = -l; m <= l; m++, k++) out[k] = PRT_COS_LOBE[l] * y[k];
+        return;
+    }
+    frame3 f = prt_frame(N);
+    v3 org = v3_madd(v3_make(P[0], P[1], P[2]), p->origin_eps, N);          /* :343 */
+    int depth = p->mode == PRT_O_INTERREFLECT ? p->bounces + 1 : 1;          /* :345 */
+    double acc[25] = { 0 };
+    uint32_t *vis = J->vis ? J->vis + (size_t)i * words : NULL;
+    if (vis) for (int w = 0; w < words; w++) vis[w] = 0;
+    int passes = J->faithful ? n2 : 1;
+    for (int pass = 0; pass < passes; pass++) {
+        for (int s = 0; s < S; s++) {
+            v3 l = v3_make(J->dirs[3 * s], J->dirs[3 * s + 1], J->dirs[3 * s + 2]);
+            v3 wi = prt_to_world(&f, l);                                    /* :340 */
+            float w; v3 fd = wi; int pv = 0;
+            if (p->mode == PRT_O_UNSHADOWED) { w = 1.0f; pv = 1; }
+            else { J->rays++; w = trace_path(J, org, wi, depth, vid, (uint32_t)s, &fd, &pv, &J->segs); }
+            if (vis && pass == 0 && pv) vis[s >> 5] |= 1u << (s & 31);
+            if (w != 0.0f) {
+                float y[25];
+                prt_sh_eval(p->order, p->cs_phase, fd.z, fd.x, fd.y, y);    /* :226 */
+                if (J->faithful) acc[pass] += (double)(w * y[pass]);
+                else for (int k = 0; k < n2; k++) acc[k] += (double)(w * y[k]);
+            }
+        }
+    }
+    for (int k = 0; k < n2; k++) out[k] = (float)(acc[k] / (double)S);      /* :350 */
+}
+
+static void *worker(void *arg) {
+    job_t *J = (job_t *)arg;
+    for (;;) {
+        uint32_t b = __sync_fetch_and_add(J->next, 16u);
+        if (b >= J->n) break;
+        uint32_t e = b + 16u < J->n ? b + 16u : J->n;
+        for (uint32_t i = b; i < e; i++) bake_vertex(J, i);
+    }
+    return NULL;
+}
+
+int prt_o_bake_transfer(const prt_o_scene *sc, const float *pos, const float *nrm, size_t stride, uint32_t n,
+                        uint32_t vertex_id_base, const prt_o_bake_params *p, float *out, uint32_t *vis,
+                        int n_threads, int faithful, uint64_t *counters) {
+    if (!p || !pos || !nrm || !out) return -1;
+    if (p->order < 1 || p->order > 5 || p->samples_u < 1 || p->samples_v < 1) return -2;
+    if (!sc && (p->mode == PRT_O_SHADOWED || p->mode == PRT_O_INTERREFLECT)) return -3;
+    if (stride == 0) stride = 12;
+    int S = p->samples_u * p->samples_v;
+    float *dirs = (float *)malloc(sizeof(float) * 3 * (size_t)S);
+    prt_o_sample_table(p, NULL, dirs);
+    if (n_threads <= 0) n_threads = prt_o_hw_threads();
+    if ((uint32_t)n_threads > n) n_threads = n ? (int)n : 1;
+    volatile uint32_t next = 0;
+    job_t *jobs = (job_t *)calloc((size_t)n_threads, sizeof(job_t));
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t] = (job_t){ sc, (const char *)pos, (const char *)nrm, stride, n, vertex_id_base, p, dirs, out, vis, faithful, &next, 0, 0 };
+        if (t > 0) pthread_create(&th[t], NULL, worker, &jobs[t]);
+    }
+    worker(&jobs[0]);
+    uint64_t rays = jobs[0].rays, segs = jobs[0].segs;
+    for (int t = 1; t < n_threads; t++) { pthread_join(th[t], NULL); rays += jobs[t].rays; segs += jobs[t].segs; }
+    if (counters) { counters[0] = rays; counters[1] = segs; }
+    free(th); free(jobs); free(dirs);
+    return 0;
+}

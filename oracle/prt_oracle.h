@@ -1,0 +1,76 @@
+/*
+ * oracle/prt_oracle.h -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's algorithm for the PRT precomputation hot path
+ * (lvjiahui/PRT).  It exists to CHECK the sm_100a kernels in
+ * prt_b200/csrc; nothing in the product library links, includes or calls it.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY STATUS: the spherical-harmonic basis and cubeCoordToWorld are pinned against the
+ * reference's own header (src/sh/SH_function.h compiled in place, oracle/_ref, see
+ * oracle/ref_shfun.cpp).  Everything that the reference delegates to components that are NOT in
+ * /root/reference -- Intel Embree 3 (CMakeLists.txt:6; BVH + ray/triangle arithmetic),
+ * google/spherical-harmonics + Eigen (raytracing.cpp:10; sh::EvalSH) and the OpenGL 4.5 driver
+ * (raster rules, texture filtering) -- is "PARITY UNPINNED": the reference ships no tests, golden
+ * vectors or fixtures, so those parts are anchored on the analytic
+ * known-answer tests of SURVEY section 8c (tests/test_oracle_kat.py).
+ */
+#ifndef PRT_ORACLE_H
+#define PRT_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct prt_o_scene prt_o_scene;
+
+/* RTScene(Mesh&) (raytracing.cpp:58-94): copy positions + index triples, build a BVH. */
+prt_o_scene *prt_o_scene_create(const float *pos, size_t pos_stride_bytes, uint32_t n_verts,
+                                const uint32_t *tri_idx, uint32_t n_tris);
+void prt_o_scene_destroy(prt_o_scene *);
+uint32_t prt_o_scene_ntris(const prt_o_scene *);
+
+/* struct Ray::any_hit / first_hit (light_probe.cpp:95-133). use_bvh = 0 -> brute force over all
+ * triangles (validates that the BVH never culls a triangle the pinned test accepts). */
+int prt_o_any_hit(const prt_o_scene *, const float org[3], const float dir[3], float tnear, float tfar, int use_bvh);
+/* returns 1 on hit; t, primitive index, unnormalised Ng = (v1-v0)x(v2-v0) */
+int prt_o_closest_hit(const prt_o_scene *, const float org[3], const float dir[3], float tnear, float tfar,
+                      int use_bvh, float *t, uint32_t *prim, float ng[3]);
+
+enum { PRT_O_UNSHADOWED = 0, PRT_O_SHADOWED = 1, PRT_O_INTERREFLECT = 2, PRT_O_UNSHADOWED_ANALYTIC = 3 };
+
+typedef struct {
+    int32_t order;       /* bands: coefficients = order^2, 1..5 */
+    int32_t samples_u;   /* radial strata  (reference: sh_resolution, app.h:71) */
+    int32_t samples_v;   /* angular strata */
+    uint32_t seed;
+    int32_t bounces;     /* B: path depth = B+1 = max_path_length-1 (raytracing.cpp:345) */
+    float albedo[3];     /* app.h:55 */
+    float origin_eps;    /* 1e-4, raytracing.cpp:343 */
+    float bounce_eps;    /* 1e-5, raytracing.cpp:235 */
+    int32_t mode;
+    int32_t cs_phase;
+    int32_t jitter;      /* 1: (i+xi)/R jittered strata (raytracing.cpp:338-339); 0: stratum centres */
+} prt_o_bake_params;
+
+/* Sample table shared by every vertex and coefficient: uv[2*s..], local dirs[3*s..], s = i*samples_v + j */
+void prt_o_sample_table(const prt_o_bake_params *, float *uv, float *local_dirs);
+
+/* bake_SH (raytracing.cpp:320-360) with one trace per sample shared by all coefficients.
+ * faithful != 0 re-traces once per coefficient (the reference's cost model; same results).
+ * out_coeffs[n][order^2]; out_vis (optional) [n][ceil(S/32)] uint32 words, bit s = 1 <=> primary ray s is
+ * UNOCCLUDED; n_threads <= 0 -> all cores.  counters (optional) [2] = {rays traced, path segments}. */
+int prt_o_bake_transfer(const prt_o_scene *, const float *pos, const float *nrm, size_t stride_bytes,
+                        uint32_t n_verts, uint32_t vertex_id_base, const prt_o_bake_params *,
+                        float *out_coeffs, uint32_t *out_vis, int n_threads, int faithful, uint64_t *counters);
+
+void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
+void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void prt_o_sincos2pi(float v, float *s, float *c);
+int prt_o_hw_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

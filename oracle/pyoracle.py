@@ -1,0 +1,159 @@
+"""ctypes binding of the CPU oracle (oracle/libprt_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product package prt_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+UNSHADOWED, SHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC = 0, 1, 2, 3
+
+
+class BakeParams(C.Structure):
+    _fields_ = [("order", C.c_int32), ("samples_u", C.c_int32), ("samples_v", C.c_int32), ("seed", C.c_uint32),
+                ("bounces", C.c_int32), ("albedo", C.c_float * 3), ("origin_eps", C.c_float),
+                ("bounce_eps", C.c_float), ("mode", C.c_int32), ("cs_phase", C.c_int32), ("jitter", C.c_int32)]
+
+
+def make_params(order=3, samples_u=32, samples_v=32, seed=0x50525400, bounces=0, albedo=(1.0, 1.0, 1.0),
+                origin_eps=1e-4, bounce_eps=1e-5, mode=SHADOWED, cs_phase=0, jitter=1) -> BakeParams:
+    p = BakeParams()
+    p.order, p.samples_u, p.samples_v, p.seed, p.bounces = order, samples_u, samples_v, seed, bounces
+    p.albedo[:] = albedo
+    p.origin_eps, p.bounce_eps, p.mode, p.cs_phase, p.jitter = origin_eps, bounce_eps, mode, cs_phase, jitter
+    return p
+
+
+def build(force: bool = False) -> str:
+    path = os.path.join(_HERE, "libprt_oracle.so")
+    if force or not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libprt_oracle.so"])
+    return path
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, f32p, u32p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        L.prt_o_scene_create.restype = vp
+        L.prt_o_scene_create.argtypes = [vp, C.c_size_t, C.c_uint32, vp, C.c_uint32]
+        L.prt_o_scene_destroy.argtypes = [vp]
+        L.prt_o_any_hit.restype = C.c_int
+        L.prt_o_any_hit.argtypes = [vp, f32p, f32p, C.c_float, C.c_float, C.c_int]
+        L.prt_o_closest_hit.restype = C.c_int
+        L.prt_o_closest_hit.argtypes = [vp, f32p, f32p, C.c_float, C.c_float, C.c_int, f32p, u32p, f32p]
+        L.prt_o_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]
+        L.prt_o_bake_transfer.restype = C.c_int
+        L.prt_o_bake_transfer.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(BakeParams),
+                                          vp, vp, C.c_int, C.c_int, vp]
+        L.prt_o_sh_eval.argtypes = [C.c_int, C.c_int, f32p, f32p]
+        L.prt_o_philox.argtypes = [u32p, u32p, u32p]
+        L.prt_o_sincos2pi.argtypes = [C.c_float, f32p, f32p]
+        L.prt_o_hw_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Scene:
+    """RTScene (reference raytracing.cpp:58-99) on the CPU oracle."""
+
+    def __init__(self, pos: np.ndarray, tri: np.ndarray):
+        self.pos = np.ascontiguousarray(pos, dtype=np.float32)
+        self.tri = np.ascontiguousarray(tri, dtype=np.uint32)
+        self.h = lib().prt_o_scene_create(_ptr(self.pos), 12, len(self.pos), _ptr(self.tri), len(self.tri))
+        if not self.h:
+            raise RuntimeError("oracle scene_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().prt_o_scene_destroy(self.h)
+            self.h = None
+
+    def any_hit(self, org, dirs, tnear=0.0, tfar=np.inf, use_bvh=True) -> np.ndarray:
+        org = np.ascontiguousarray(np.broadcast_to(np.asarray(org, np.float32), np.asarray(dirs).shape), np.float32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        out = np.zeros(len(dirs), np.int32)
+        f32p = C.POINTER(C.c_float)
+        L = lib()
+        for i in range(len(dirs)):
+            out[i] = L.prt_o_any_hit(self.h, org[i].ctypes.data_as(f32p), dirs[i].ctypes.data_as(f32p),
+                                     C.c_float(tnear), C.c_float(tfar), int(use_bvh))
+        return out
+
+    def closest_hit(self, org, dirs, tnear=0.0, tfar=np.inf, use_bvh=True):
+        org = np.ascontiguousarray(np.broadcast_to(np.asarray(org, np.float32), np.asarray(dirs).shape), np.float32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        n = len(dirs)
+        hit, t, prim, ng = np.zeros(n, np.int32), np.full(n, np.inf, np.float32), np.full(n, 0xFFFFFFFF, np.uint32), np.zeros((n, 3), np.float32)
+        f32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        L = lib()
+        for i in range(n):
+            tt, pp = C.c_float(), C.c_uint32()
+            hit[i] = L.prt_o_closest_hit(self.h, org[i].ctypes.data_as(f32p), dirs[i].ctypes.data_as(f32p), C.c_float(tnear),
+                                         C.c_float(tfar), int(use_bvh), C.byref(tt), C.byref(pp), ng[i].ctypes.data_as(f32p))
+            if hit[i]:
+                t[i], prim[i] = tt.value, pp.value
+        return hit, t, prim, ng
+
+
+def sample_table(params: BakeParams):
+    S = params.samples_u * params.samples_v
+    uv, dirs = np.zeros((S, 2), np.float32), np.zeros((S, 3), np.float32)
+    lib().prt_o_sample_table(C.byref(params), _ptr(uv), _ptr(dirs))
+    return uv, dirs
+
+
+def bake_transfer(scene: Scene | None, pos, nrm, params: BakeParams, want_vis=False, vertex_id_base=0,
+                  n_threads=0, faithful=False):
+    """bake_SH (reference raytracing.cpp:320-360). Returns (coeffs[n, order^2], vis_words or None, counters)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    nrm = np.ascontiguousarray(nrm, np.float32)
+    n = len(pos)
+    n2 = params.order ** 2
+    S = params.samples_u * params.samples_v
+    out = np.zeros((n, n2), np.float32)
+    vis = np.zeros((n, (S + 31) // 32), np.uint32) if want_vis else None
+    counters = np.zeros(2, np.uint64)
+    rc = lib().prt_o_bake_transfer(scene.h if scene is not None else None, _ptr(pos), _ptr(nrm), 12, n, vertex_id_base,
+                                   C.byref(params), _ptr(out), _ptr(vis), n_threads, int(faithful), _ptr(counters))
+    if rc != 0:
+        raise RuntimeError(f"oracle bake_transfer failed rc={rc}")
+    return out, vis, counters
+
+
+def sh_eval(order: int, d_sh, cs_phase=0) -> np.ndarray:
+    d = np.asarray(d_sh, np.float32)
+    out = np.zeros(order * order, np.float32)
+    f32p = C.POINTER(C.c_float)
+    lib().prt_o_sh_eval(order, cs_phase, d.ctypes.data_as(f32p), out.ctypes.data_as(f32p))
+    return out
+
+
+def philox(ctr, key) -> np.ndarray:
+    c, k, o = np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), np.zeros(4, np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    lib().prt_o_philox(c.ctypes.data_as(u32p), k.ctypes.data_as(u32p), o.ctypes.data_as(u32p))
+    return o
+
+
+def sincos2pi(v: float):
+    s, c = C.c_float(), C.c_float()
+    lib().prt_o_sincos2pi(C.c_float(v), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def hw_threads() -> int:
+    return lib().prt_o_hw_threads()

@@ -1,0 +1,244 @@
+"""ctypes binding of libprt_b200.so (include/prt_b200.h) and the reference-shaped host interface."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+UNSHADOWED, SHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC = 0, 1, 2, 3
+
+# every symbol include/prt_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "prt_last_error", "prt_abi_version", "prt_ctx_create", "prt_ctx_destroy", "prt_ctx_device", "prt_ctx_set_tuning",
+    "prt_scene_create", "prt_scene_destroy", "prt_scene_get_info", "prt_trace_any_hit", "prt_trace_closest_hit",
+    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_scatter_sh9",
+    "prt_bake_sample_table", "prt_ctx_last_bake_stats",
+]
+
+
+class PRTError(RuntimeError):
+    pass
+
+
+class BakeParams(C.Structure):
+    """prt_bake_params: the App singleton fields bake_SH reads (reference app.h:55,70-71; raytracing.cpp:320,343)."""
+    _fields_ = [("order", C.c_int32), ("samples_u", C.c_int32), ("samples_v", C.c_int32), ("seed", C.c_uint32),
+                ("bounces", C.c_int32), ("albedo", C.c_float * 3), ("origin_eps", C.c_float),
+                ("bounce_eps", C.c_float), ("mode", C.c_int32), ("cs_phase", C.c_int32), ("jitter", C.c_int32)]
+
+    @classmethod
+    def make(cls, order=3, samples_u=32, samples_v=32, seed=0x50525400, bounces=0, albedo=(1.0, 1.0, 1.0),
+             origin_eps=1e-4, bounce_eps=1e-5, mode=SHADOWED, cs_phase=0, jitter=1) -> "BakeParams":
+        p = cls()
+        p.order, p.samples_u, p.samples_v, p.seed, p.bounces = order, samples_u, samples_v, seed, bounces
+        p.albedo[:] = albedo
+        p.origin_eps, p.bounce_eps, p.mode, p.cs_phase, p.jitter = origin_eps, bounce_eps, mode, cs_phase, jitter
+        return p
+
+    @property
+    def n_samples(self) -> int:
+        return self.samples_u * self.samples_v
+
+    @property
+    def n_coeffs(self) -> int:
+        return self.order * self.order
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("max_depth", C.c_uint32), ("reserved", C.c_uint32),
+                ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64), ("build_seconds", C.c_double),
+                ("upload_seconds", C.c_double), ("sah_cost", C.c_double)]
+
+
+class BakeStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("rays", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("grid", C.c_uint32),
+                ("block", C.c_uint32), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "csrc", "libprt_b200.so")
+
+
+def load_library():
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PRTError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, sz, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
+    L.prt_last_error.restype = C.c_char_p
+    L.prt_abi_version.restype = i32
+    L.prt_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.prt_ctx_destroy.argtypes = [vp]
+    L.prt_ctx_destroy.restype = None
+    L.prt_ctx_device.argtypes = [vp]
+    L.prt_ctx_set_tuning.argtypes = [vp, C.c_char_p, i32]
+    L.prt_scene_create.argtypes = [vp, vp, sz, u32, vp, u32, C.POINTER(vp)]
+    L.prt_scene_destroy.argtypes = [vp]
+    L.prt_scene_destroy.restype = None
+    L.prt_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    L.prt_trace_any_hit.argtypes = [vp, vp, u32, vp]
+    L.prt_trace_closest_hit.argtypes = [vp, vp, u32, vp, vp, vp]
+    L.prt_bake_params_default.argtypes = [C.POINTER(BakeParams)]
+    L.prt_bake_params_default.restype = None
+    L.prt_bake_transfer.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp]
+    L.prt_bake_transfer_device.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
+    L.prt_scatter_sh9.argtypes = [vp, C.c_int32, u32, vp, sz, sz]
+    L.prt_bake_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]
+    L.prt_ctx_last_bake_stats.argtypes = [vp, C.POINTER(BakeStats)]
+    _LIB = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise PRTError(f"{what} failed (rc={rc}): {load_library().prt_last_error().decode(errors='replace')}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One GPU = one context (the reference's process-global RTCDevice, raytracing.cpp:42-52)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        h = C.c_void_p()
+        _check(self.L.prt_ctx_create(device, C.byref(h)), "prt_ctx_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.prt_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def device(self) -> int:
+        return self.L.prt_ctx_device(self.h)
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            _check(self.L.prt_ctx_set_tuning(self.h, k.encode(), int(v)), f"prt_ctx_set_tuning({k})")
+
+    def last_bake_stats(self) -> BakeStats:
+        s = BakeStats()
+        _check(self.L.prt_ctx_last_bake_stats(self.h, C.byref(s)), "prt_ctx_last_bake_stats")
+        return s
+
+
+_DEFAULT_CTX = {}
+
+
+def default_context(device: int = -1) -> Context:
+    if device not in _DEFAULT_CTX:
+        _DEFAULT_CTX[device] = Context(device)
+    return _DEFAULT_CTX[device]
+
+
+class RTScene:
+    """reference RTScene(Mesh&) (raytracing.cpp:58-99): positions + index triples -> GPU-resident BVH."""
+
+    def __init__(self, pos: np.ndarray, tri: np.ndarray, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.L = self.ctx.L
+        pos = np.ascontiguousarray(pos, np.float32)
+        tri = np.ascontiguousarray(tri, np.uint32)
+        if pos.ndim != 2 or pos.shape[1] != 3 or tri.ndim != 2 or tri.shape[1] != 3:
+            raise PRTError("RTScene: pos must be [V,3] float32 and tri [F,3] uint32")
+        h = C.c_void_p()
+        _check(self.L.prt_scene_create(self.ctx.h, _ptr(pos), 12, len(pos), _ptr(tri), len(tri), C.byref(h)), "prt_scene_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.L.prt_scene_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def info(self) -> SceneInfo:
+        s = SceneInfo()
+        _check(self.L.prt_scene_get_info(self.h, C.byref(s)), "prt_scene_get_info")
+        return s
+
+    @staticmethod
+    def pack_rays(org, dirs, tnear=0.0, tfar=np.inf) -> np.ndarray:
+        dirs = np.asarray(dirs, np.float32)
+        rays = np.empty((len(dirs), 8), np.float32)
+        rays[:, 0:3] = np.asarray(org, np.float32)
+        rays[:, 3] = tnear
+        rays[:, 4:7] = dirs
+        rays[:, 7] = tfar
+        return rays
+
+    def any_hit(self, rays: np.ndarray) -> np.ndarray:
+        """struct Ray::any_hit (light_probe.cpp:125-130) for a batch: rays [n,8] = org, tnear, dir, tfar."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros(len(rays), np.uint8)
+        _check(self.L.prt_trace_any_hit(self.h, _ptr(rays), len(rays), _ptr(out)), "prt_trace_any_hit")
+        return out
+
+    def first_hit(self, rays: np.ndarray):
+        """struct Ray::first_hit + hit_normal (light_probe.cpp:115-124): returns (t, prim, Ng)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = len(rays)
+        t, prim, ng = np.zeros(n, np.float32), np.zeros(n, np.uint32), np.zeros((n, 3), np.float32)
+        _check(self.L.prt_trace_closest_hit(self.h, _ptr(rays), n, _ptr(t), _ptr(prim), _ptr(ng)), "prt_trace_closest_hit")
+        return t, prim, ng
+
+
+def bake_transfer(scene: RTScene | None, pos, nrm, params: BakeParams, want_vis=False, vertex_id_base=0,
+                  ctx: Context | None = None):
+    """prt_bake_transfer with host buffers (the e2e path). Returns (coeffs [n, order^2], vis words or None)."""
+    ctx = ctx or (scene.ctx if scene is not None else default_context())
+    pos = np.ascontiguousarray(pos, np.float32)
+    nrm = np.ascontiguousarray(nrm, np.float32)
+    n = len(pos)
+    out = np.zeros((n, params.n_coeffs), np.float32)
+    vis = np.zeros((n, (params.n_samples + 31) // 32), np.uint32) if want_vis else None
+    _check(ctx.L.prt_bake_transfer(ctx.h, scene.h if scene is not None else None, _ptr(pos), _ptr(nrm), 12, n,
+                                   vertex_id_base, C.byref(params), _ptr(out), _ptr(vis)), "prt_bake_transfer")
+    return out, vis
+
+
+def bake_SH(verts: np.ndarray, indices: np.ndarray, params: BakeParams | None = None, ctx: Context | None = None):
+    """reference ``void bake_SH(Mesh& gl_mesh)`` (raytracing.cpp:320-360).
+
+    ``verts`` is the reference's interleaved Mesh::Vert array, shape [V, 15] float32 = pos(3) norm(3) sh_coeff(9)
+    (gl.h:76-80); it is updated in place (sh_coeff columns) exactly like ``edit_verts()`` and also returned.
+    """
+    params = params or BakeParams.make()
+    verts = np.asarray(verts)
+    if verts.dtype != np.float32 or verts.ndim != 2 or verts.shape[1] != 15 or not verts.flags.c_contiguous:
+        raise PRTError("bake_SH: verts must be a C-contiguous [V,15] float32 Mesh::Vert array")
+    ctx = ctx or default_context()
+    scene = RTScene(verts[:, 0:3], np.asarray(indices, np.uint32).reshape(-1, 3), ctx)
+    n = len(verts)
+    out = np.zeros((n, params.n_coeffs), np.float32)
+    L = ctx.L
+    base = verts.ctypes.data
+    _check(L.prt_bake_transfer(ctx.h, scene.h, C.c_void_p(base), C.c_void_p(base + 12), 60, n, 0, C.byref(params),
+                               _ptr(out), None), "prt_bake_transfer")
+    if params.order >= 3:
+        _check(L.prt_scatter_sh9(_ptr(out), params.order, n, C.c_void_p(base), 60, 24), "prt_scatter_sh9")
+    scene.close()
+    return out
+
+
+def sample_table(params: BakeParams):
+    S = params.n_samples
+    uv, dirs = np.zeros((S, 2), np.float32), np.zeros((S, 3), np.float32)
+    _check(load_library().prt_bake_sample_table(C.byref(params), _ptr(uv), _ptr(dirs)), "prt_bake_sample_table")
+    return uv, dirs

@@ -1,0 +1,233 @@
+// bake.cu -- sm_100a kernels for per-vertex diffuse SH transfer and batched ray queries.
+//
+// bake_kernel replaces the body of bake_SH (reference src/raytracing/raytracing.cpp:320-360) together with
+// renderSH (:228-278): one persistent warp per vertex pulls vertices from an atomic counter, its 32 lanes
+// trace the vertex's S stratified cosine-weighted rays (any-hit for the last path segment, closest-hit for
+// interreflection segments), evaluate the SH basis of every escaping direction in registers and reduce
+// across the warp with shuffles.  Lanes whose ray has terminated are refilled with the next samples of the
+// same vertex (warp-level ray compaction), so accumulators never mix vertices.
+//
+// One trace per sample is shared by all order^2 coefficients (the reference re-traces per coefficient,
+// raytracing.cpp:332-349; see DESIGN.md section 2 for why results are unchanged).
+#include "kernels.h"
+#include "traverse.cuh"
+
+#include <cuda_runtime.h>
+
+namespace prt {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// MODE 0: shadowed (depth 1, any-hit only)   MODE 1: interreflection   MODE 2: unshadowed Monte-Carlo (V == 1)
+template <int ORDER, int MODE>
+__global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
+    constexpr int N2 = ORDER * ORDER;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float sgn = A.cs_phase ? -1.0f : 1.0f;
+    const int depth = MODE == 1 ? A.depth : 1;
+
+    for (;;) {
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(A.counter, 1u);
+        v = __shfl_sync(kFull, v, 0);
+        if (v >= A.n_verts) break;
+
+        const float *pp = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.pos) + (size_t)v * A.stride);
+        const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
+        const f3 N = mk3(__ldg(np), __ldg(np + 1), __ldg(np + 2));
+        const f3 P = mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2));
+        const Frame fr = make_frame(N);
+        const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
+
+        float acc[N2];
+#pragma unroll
+        for (int k = 0; k < N2; k++) acc[k] = 0.f;
+
+        int next = 0;
+        bool active = false;
+        Trav tr;
+        tr.reset_counters();
+        uint32_t sidx = 0;      // reference sample index s = i*samples_v + j of the lane's current path
+        int seg = 0;            // path segment
+        f3 pos = org;
+        float Lw0 = 1.f, Lw1 = 1.f, Lw2 = 1.f;
+
+        for (;;) {
+            const unsigned idle = __ballot_sync(kFull, !active);
+            if (idle && next < A.S) {
+                const int k = next + __popc(idle & lt_mask);
+                if (!active && k < A.S) {
+                    const float4 smp = __ldg(&A.samples[k]);
+                    sidx = __float_as_uint(smp.w);
+                    const f3 dir = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
+                    pos = org; seg = 0; Lw0 = Lw1 = Lw2 = 1.f;
+                    tr.init(pos, dir, 0.0f, INFINITY);
+                    active = true;
+                }
+                next += __popc(idle);
+            }
+            if (!__any_sync(kFull, active)) break;
+            if (!active) continue;
+
+            const bool more = next < A.S;
+            int rc;
+            if (MODE == 2) rc = TRAV_MISS;
+            else if (MODE == 1 && seg < depth - 1) rc = tr.template run<false>(A.nodes, A.tris, A.refill_thresh, more);
+            else rc = tr.template run<true>(A.nodes, A.tris, A.refill_thresh, more);
+            if (rc == TRAV_RUNNING) continue;
+
+            if (rc == TRAV_MISS) {
+                // environment reached: L = Lw * Y_lm(dir), sh-space (z,x,y)  (raytracing.cpp:226,257-261)
+                float y[N2];
+                sh_eval<ORDER>(tr.d.z, tr.d.x, tr.d.y, sgn, y);
+#pragma unroll
+                for (int k = 0; k < N2; k++) acc[k] = fmaf(Lw0, y[k], acc[k]);
+                if (A.vis && seg == 0) atomicOr(&A.vis[(size_t)v * A.vis_words + (sidx >> 5)], 1u << (sidx & 31u));
+                active = false;
+                continue;
+            }
+            // hit
+            if (MODE != 1 || seg >= depth - 1) { active = false; continue; }      // absorbed on the last segment
+            {
+                const f3 n = normalize3(tr.hit_ng(A.tris));                         // :263-264
+                if (dot3(tr.d, n) >= -1e-4f) { active = false; continue; }          // :265
+                pos = madd3(pos, tr.best_t, tr.d);                                  // :266
+                float u, w;
+                rand2(A.seed, A.vid_base + v, sidx, (uint32_t)seg, 1u, u, w);        // :267
+                const f3 l = cosine_local(u, w);
+                const float pdf = PRT_DIV(l.z, kPiF);
+                const Frame fb = make_frame(n);
+                const f3 nd = to_world(fb, l);
+                if (pdf <= 1e-4f) { active = false; continue; }                     // :269
+                Lw0 = PRT_MUL(Lw0, A.albedo[0]); Lw1 = PRT_MUL(Lw1, A.albedo[1]); Lw2 = PRT_MUL(Lw2, A.albedo[2]);  // :271
+                const float sg = dot3(nd, n) < 0.0f ? -1.0f : 1.0f;                 // :273
+                pos = madd3(pos, PRT_MUL(sg, A.bounce_eps), nd);                    // :274
+                seg++;
+                if (fmaxf(Lw0, fmaxf(Lw1, Lw2)) < 0.01f) { active = false; continue; }   // :249 (checked at loop top)
+                tr.init(pos, nd, A.bounce_eps, INFINITY);                           // :275
+            }
+        }
+
+        // reduce the lane partial sums and store row v (raytracing.cpp:350: /= S)
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < N2; k++) {
+            const float s = warp_sum(acc[k]);
+            if (lane == k) mine = s;
+        }
+        if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
+        if (A.work) {
+            const unsigned nv = __reduce_add_sync(kFull, tr.n_node_visits), nt = __reduce_add_sync(kFull, tr.n_tri_tests);
+            if (lane == 0) { atomicAdd(&A.work[0], (unsigned long long)nv); atomicAdd(&A.work[1], (unsigned long long)nt); }
+        }
+    }
+}
+
+// rotate_cos_lobe(norm) * INV_PI (reference src/scene/model.cpp:29-31): analytic unshadowed transfer
+template <int ORDER>
+__global__ void unshadowed_analytic_kernel(const BakeArgs A) {
+    constexpr int N2 = ORDER * ORDER;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.n_verts) return;
+    const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
+    const float nx = np[0], ny = np[1], nz = np[2];
+    float y[N2];
+    sh_eval<ORDER>(nz, nx, ny, A.cs_phase ? -1.0f : 1.0f, y);
+    const float lobe[5] = { 1.0f, 2.0f / 3.0f, 0.25f, 0.0f, -1.0f / 24.0f };
+    int k = 0;
+#pragma unroll
+    for (int l = 0; l < ORDER; l++)
+        for (int m = -l; m <= l; m++, k++) A.out[(size_t)v * N2 + k] = lobe[l] * y[k];
+}
+
+__global__ void __launch_bounds__(128) trace_any_kernel(const Node8 *nodes, const Tri48 *tris, const float4 *rays, uint32_t n, uint8_t *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+    Trav t;
+    t.reset_counters();
+    t.init(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
+    out[i] = t.run<true>(nodes, tris, 0, false) == TRAV_HIT ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(128) trace_closest_kernel(const Node8 *nodes, const Tri48 *tris, const float4 *rays, uint32_t n,
+                                                            float *out_t, uint32_t *out_prim, float *out_ng) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+    Trav t;
+    t.reset_counters();
+    t.init(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
+    const bool hit = t.run<false>(nodes, tris, 0, false) == TRAV_HIT;
+    f3 g = mk3(0.f, 0.f, 0.f);
+    if (hit) g = t.hit_ng(tris);
+    out_t[i] = hit ? t.best_t : INFINITY;
+    out_prim[i] = hit ? t.best_prim : 0xFFFFFFFFu;
+    if (out_ng) { out_ng[3 * (size_t)i] = g.x; out_ng[3 * (size_t)i + 1] = g.y; out_ng[3 * (size_t)i + 2] = g.z; }
+}
+
+template <int ORDER, int MODE>
+cudaError_t launch_persistent(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
+    if (*grid <= 0) {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_kernel<ORDER, MODE>, block, 0);
+        if (e != cudaSuccess) return e;
+        *grid = n_sms * (per_sm > 0 ? per_sm : 1);
+    }
+    // never launch more warps than vertices
+    const int warps_per_block = block / 32;
+    const long long need = ((long long)A.n_verts + warps_per_block - 1) / warps_per_block;
+    if (need < *grid) *grid = (int)(need > 0 ? need : 1);
+    bake_kernel<ORDER, MODE><<<*grid, block, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+template <int ORDER>
+cudaError_t launch_order(const BakeArgs &A, int mode, int *grid, int block, int n_sms, cudaStream_t st) {
+    switch (mode) {
+    case 0: return launch_persistent<ORDER, 0>(A, grid, block, n_sms, st);
+    case 1: return launch_persistent<ORDER, 1>(A, grid, block, n_sms, st);
+    case 2: return launch_persistent<ORDER, 2>(A, grid, block, n_sms, st);
+    default:
+        *grid = (int)((A.n_verts + 127) / 128);
+        unshadowed_analytic_kernel<ORDER><<<*grid, 128, 0, st>>>(A);
+        return cudaGetLastError();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_bake(const BakeArgs &A, int order, int mode, int *grid, int block, int n_sms, cudaStream_t st) {
+    switch (order) {
+    case 1: return launch_order<1>(A, mode, grid, block, n_sms, st);
+    case 2: return launch_order<2>(A, mode, grid, block, n_sms, st);
+    case 3: return launch_order<3>(A, mode, grid, block, n_sms, st);
+    case 4: return launch_order<4>(A, mode, grid, block, n_sms, st);
+    case 5: return launch_order<5>(A, mode, grid, block, n_sms, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_trace_any(const Node8 *nodes, const Tri48 *tris, const float *rays, uint32_t n, uint8_t *out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    trace_any_kernel<<<(n + 127) / 128, 128, 0, st>>>(nodes, tris, reinterpret_cast<const float4 *>(rays), n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_closest(const Node8 *nodes, const Tri48 *tris, const float *rays, uint32_t n, float *out_t,
+                                 uint32_t *out_prim, float *out_ng, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    trace_closest_kernel<<<(n + 127) / 128, 128, 0, st>>>(nodes, tris, reinterpret_cast<const float4 *>(rays), n, out_t, out_prim, out_ng);
+    return cudaGetLastError();
+}
+
+}  // namespace prt

@@ -1,0 +1,50 @@
+// bvh8.h -- flattened 8-wide compressed BVH layout shared by the host builder and the sm_100a kernels.
+//
+// Replaces the acceleration structure the reference obtains from Intel Embree 3 behind RTScene
+// (reference src/raytracing/raytracing.cpp:58-99, light_probe.cpp:44-93).  Layout follows the compressed
+// wide BVH of Ylitie, Karras & Laine (HPG 2017): one 80-byte node = five 16-byte vector loads, child
+// boxes quantised to 8 bits per plane relative to the node origin, children stored in an octant-sorted
+// slot order so traversal needs no per-ray distance sort.  Triangles are 48 bytes = three 16-byte loads.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace prt {
+
+struct alignas(16) Node8 {
+    float px, py, pz;       // node origin (min corner)
+    uint8_t ex, ey, ez;     // per-axis power-of-two scale, biased exponent byte: scale = as_float(e << 23)
+    uint8_t imask;          // bit s set: slot s holds an internal child
+    uint32_t child_base;    // index of first internal child node (children contiguous in slot order)
+    uint32_t tri_base;      // index of first triangle referenced by this node's leaf slots
+    uint8_t meta[8];        // internal: 0x20 | (24+slot); leaf: (unary tri count << 5) | tri offset; empty: 0
+    uint8_t qlox[8], qloy[8], qloz[8];
+    uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+// v0 + edges for the pinned Moeller-Trumbore test; w of the first vector carries the
+// caller's primitive index.
+struct alignas(16) Tri48 {
+    float v0x, v0y, v0z; uint32_t prim;
+    float e1x, e1y, e1z; uint32_t pad1;
+    float e2x, e2y, e2z; uint32_t pad2;
+};
+static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
+
+constexpr int kStackEntries = 48;   // traversal stack capacity (node groups); builder enforces max depth
+
+struct HostBVH8 {
+    Node8 *nodes = nullptr;
+    Tri48 *tris = nullptr;
+    uint32_t n_nodes = 0, n_tris = 0, max_depth = 0;
+    double sah_cost = 0.0, build_seconds = 0.0;
+    float pad = 0.f;
+};
+
+// Builds on the host with all hardware threads. Returns 0 on success, <0 on error (message in err).
+int build_bvh8(const float *pos, size_t stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris,
+               HostBVH8 *out, char *err, size_t err_len);
+void free_bvh8(HostBVH8 *);
+
+}  // namespace prt

@@ -1,0 +1,318 @@
+// bvh_build.cpp -- host builder for the 8-wide compressed BVH (layout in bvh8.h).
+//
+// Takes the place of rtcCommitScene() inside the reference's RTScene constructors
+// (reference src/raytracing/raytracing.cpp:58-94, light_probe.cpp:44-87).  Three stages:
+//   1. multi-threaded binned-SAH binary build over padded triangle boxes (leaves <= 3 triangles),
+//   2. greedy surface-area collapse of the binary tree into 8-wide nodes,
+//   3. octant-ordered slot assignment, conservative 8-bit quantisation and depth-first emission so that
+//      the internal children of a node and the triangles of its leaf slots are contiguous.
+#include "bvh8.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace prt {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct BNode {
+    Box box;
+    uint32_t left;   // internal: left child (right = left + 1); leaf: first index into ids
+    uint32_t count;  // 0 = internal
+};
+
+constexpr int kBins = 16;
+constexpr uint32_t kLeafMax = 3;
+constexpr int kMedianDepth = 36;   // beyond this binary depth fall back to median splits (bounds the stack)
+
+struct Builder {
+    const Box *tb = nullptr;        // padded triangle boxes
+    const float *cent = nullptr;    // centroids, 3 per triangle
+    uint32_t *ids = nullptr;
+    BNode *nodes = nullptr;
+    std::atomic<uint32_t> n_nodes{0};
+
+    struct Job { uint32_t node, first, count; int depth; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Job> queue;
+    int busy = 0;
+    bool done = false;
+
+    // splits [first, first+count); returns mid or 0 when it must become a leaf
+    uint32_t split(uint32_t first, uint32_t count, int depth, Box &nb) {
+        Box cb; cb.reset(); nb.reset();
+        for (uint32_t i = first; i < first + count; i++) {
+            uint32_t t = ids[i];
+            nb.grow(tb[t]);
+            for (int a = 0; a < 3; a++) { float c = cent[3 * (size_t)t + a]; cb.lo[a] = std::min(cb.lo[a], c); cb.hi[a] = std::max(cb.hi[a], c); }
+        }
+        if (count <= kLeafMax) return 0;
+        int best_axis = -1, best_bin = -1;
+        float best_cost = 3.0e38f;
+        if (depth < kMedianDepth) {
+            for (int a = 0; a < 3; a++) {
+                float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                float scale = (float)kBins / ext;
+                uint32_t cnt[kBins] = {0};
+                Box bb[kBins];
+                for (int b = 0; b < kBins; b++) bb[b].reset();
+                for (uint32_t i = first; i < first + count; i++) {
+                    uint32_t t = ids[i];
+                    int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * (size_t)t + a] - cb.lo[a]) * scale)));
+                    cnt[b]++; bb[b].grow(tb[t]);
+                }
+                float ra[kBins]; uint32_t rc[kBins];
+                Box acc; acc.reset(); uint32_t c = 0;
+                for (int b = kBins - 1; b >= 0; b--) { acc.grow(bb[b]); c += cnt[b]; rc[b] = c; ra[b] = c ? acc.area() : 0.f; }
+                acc.reset(); c = 0;
+                for (int b = 0; b < kBins - 1; b++) {
+                    acc.grow(bb[b]); c += cnt[b];
+                    if (!c || !rc[b + 1]) continue;
+                    float cost = acc.area() * (float)c + ra[b + 1] * (float)rc[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+                }
+            }
+        }
+        uint32_t mid;
+        if (best_axis >= 0) {
+            int a = best_axis;
+            float scale = (float)kBins / (cb.hi[a] - cb.lo[a]);
+            uint32_t i = first, k = first + count;
+            while (i < k) {
+                int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * (size_t)ids[i] + a] - cb.lo[a]) * scale)));
+                if (b <= best_bin) i++; else std::swap(ids[i], ids[--k]);
+            }
+            mid = i;
+            if (mid != first && mid != first + count) return mid;
+        }
+        // median split along the widest centroid axis (also the deep-tree fallback)
+        int a = 0; float e = -1.f;
+        for (int k = 0; k < 3; k++) { float d = cb.hi[k] - cb.lo[k]; if (d > e) { e = d; a = k; } }
+        mid = first + count / 2;
+        std::nth_element(ids + first, ids + mid, ids + first + count,
+                         [&](uint32_t x, uint32_t y) { return cent[3 * (size_t)x + a] < cent[3 * (size_t)y + a]; });
+        return mid;
+    }
+
+    void subtree(Job j, std::vector<Job> &local, bool share) {
+        local.clear(); local.push_back(j);
+        while (!local.empty()) {
+            Job w = local.back(); local.pop_back();
+            BNode &nd = nodes[w.node];
+            uint32_t mid = split(w.first, w.count, w.depth, nd.box);
+            if (!mid) { nd.left = w.first; nd.count = w.count; continue; }
+            uint32_t l = n_nodes.fetch_add(2);
+            nd.left = l; nd.count = 0;
+            Job jl{l, w.first, mid - w.first, w.depth + 1}, jr{l + 1, mid, w.first + w.count - mid, w.depth + 1};
+            if (share && w.count > 32768) {
+                std::lock_guard<std::mutex> g(mu);
+                queue.push_back(jl); queue.push_back(jr);
+                cv.notify_all();
+            } else { local.push_back(jr); local.push_back(jl); }
+        }
+    }
+
+    void worker() {
+        std::vector<Job> local;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !queue.empty() || (busy == 0) || done; });
+                if (queue.empty()) { if (busy == 0 || done) { done = true; cv.notify_all(); return; } continue; }
+                j = queue.back(); queue.pop_back(); busy++;
+            }
+            subtree(j, local, true);
+            {
+                std::lock_guard<std::mutex> g(mu);
+                busy--;
+                if (busy == 0 && queue.empty()) done = true;
+                cv.notify_all();
+            }
+        }
+    }
+};
+
+inline uint8_t exp_byte(float ext) {
+    // smallest e with 255 * 2^e >= ext
+    if (!(ext > 0.f)) return 1;
+    int e = (int)std::ceil(std::log2((double)ext / 255.0));
+    while (std::ldexp(255.0, e) < (double)ext) e++;
+    while (e > -126 && std::ldexp(255.0, e - 1) >= (double)ext) e--;
+    int b = e + 127;
+    return (uint8_t)std::min(254, std::max(1, b));
+}
+
+}  // namespace
+
+int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx, uint32_t nt, HostBVH8 *out,
+               char *err, size_t err_len) {
+    auto fail = [&](const char *m) { if (err && err_len) snprintf(err, err_len, "%s", m); return -1; };
+    if (!pos || !idx || !out || nt == 0 || nv == 0) return fail("build_bvh8: empty mesh");
+    if (nt > 0x7FFFFFF0u / 3) return fail("build_bvh8: too many triangles");
+    if (stride == 0) stride = 12;
+    auto t0 = std::chrono::steady_clock::now();
+    auto P = [&](uint32_t i) { return (const float *)((const char *)pos + (size_t)i * stride); };
+
+    float amax = 0.f;
+    for (uint32_t i = 0; i < nv; i++) { const float *p = P(i); for (int a = 0; a < 3; a++) { if (!std::isfinite(p[a])) return fail("build_bvh8: non-finite vertex"); amax = std::max(amax, std::fabs(p[a])); } }
+    // Boxes are padded so that box culling (float slab test on quantised planes) can never reject a
+    // triangle the pinned Moeller-Trumbore test accepts (error analysis).
+    const float pad = amax * 1.6e-5f + 1e-30f;
+
+    std::vector<Box> tb(nt);
+    std::vector<float> cent(3 * (size_t)nt);
+    std::vector<uint32_t> ids(nt);
+    for (uint32_t t = 0; t < nt; t++) {
+        uint32_t i0 = idx[3 * (size_t)t], i1 = idx[3 * (size_t)t + 1], i2 = idx[3 * (size_t)t + 2];
+        if (i0 >= nv || i1 >= nv || i2 >= nv) return fail("build_bvh8: triangle index out of range");
+        const float *a = P(i0), *b = P(i1), *c = P(i2);
+        for (int k = 0; k < 3; k++) {
+            float lo = std::min(a[k], std::min(b[k], c[k])), hi = std::max(a[k], std::max(b[k], c[k]));
+            tb[t].lo[k] = lo - pad; tb[t].hi[k] = hi + pad; cent[3 * (size_t)t + k] = 0.5f * (lo + hi);
+        }
+        ids[t] = t;
+    }
+
+    // ---- stage 1: binary build ---------------------------------------------------------------------
+    std::vector<BNode> bn(2 * (size_t)nt + 2);
+    Builder B;
+    B.tb = tb.data(); B.cent = cent.data(); B.ids = ids.data(); B.nodes = bn.data(); B.n_nodes = 1;
+    B.queue.push_back({0, 0, nt, 0});
+    unsigned nth = std::max(1u, std::thread::hardware_concurrency());
+    if (nt < 65536) nth = 1;
+    if (nth == 1) { std::vector<Builder::Job> local; Builder::Job j = B.queue.back(); B.queue.clear(); B.subtree(j, local, false); }
+    else {
+        std::vector<std::thread> th;
+        for (unsigned i = 0; i < nth; i++) th.emplace_back([&] { B.worker(); });
+        for (auto &t : th) t.join();
+    }
+
+    // ---- stage 2+3: collapse to 8-wide, order slots, quantise, emit depth-first ----------------------
+    const uint32_t n_bin = B.n_nodes.load();
+    std::vector<Node8> wn; wn.reserve(n_bin / 4 + 16);
+    Tri48 *tris = (Tri48 *)std::malloc(sizeof(Tri48) * (size_t)nt);
+    if (!tris) return fail("build_bvh8: out of memory");
+    uint32_t n_tri_out = 0, max_depth = 0;
+    double sah = 0.0;
+    const double root_area = std::max(1e-30f, bn[0].box.area());
+
+    struct WJob { uint32_t bnode, wnode, depth; };
+    std::vector<WJob> stack;
+    wn.emplace_back(); std::memset(&wn[0], 0, sizeof(Node8));
+    stack.push_back({0, 0, 1});
+    while (!stack.empty()) {
+        WJob j = stack.back(); stack.pop_back();
+        max_depth = std::max(max_depth, j.depth);
+        const BNode &root = bn[j.bnode];
+        uint32_t ch[8]; int nch = 0;
+        if (root.count) ch[nch++] = j.bnode;
+        else { ch[nch++] = root.left; ch[nch++] = root.left + 1; }
+        while (nch < 8) {
+            int best = -1; float ba = -1.f;
+            for (int i = 0; i < nch; i++) if (!bn[ch[i]].count) { float a = bn[ch[i]].box.area(); if (a > ba) { ba = a; best = i; } }
+            if (best < 0) break;
+            uint32_t c = ch[best];
+            ch[best] = bn[c].left; ch[nch++] = bn[c].left + 1;
+        }
+        // slot assignment: slot s should hold the child lying farthest along d_s = (s&4?+:-, s&2?+:-, s&1?+:-),
+        // because a ray with sign octant o visits slots in decreasing (s ^ (7-o)) order.
+        float cx = 0.5f * (root.box.lo[0] + root.box.hi[0]), cy = 0.5f * (root.box.lo[1] + root.box.hi[1]), cz = 0.5f * (root.box.lo[2] + root.box.hi[2]);
+        float cost[8][8];
+        for (int i = 0; i < nch; i++) {
+            const Box &b = bn[ch[i]].box;
+            float ox = 0.5f * (b.lo[0] + b.hi[0]) - cx, oy = 0.5f * (b.lo[1] + b.hi[1]) - cy, oz = 0.5f * (b.lo[2] + b.hi[2]) - cz;
+            for (int s = 0; s < 8; s++) cost[i][s] = ((s & 4) ? ox : -ox) + ((s & 2) ? oy : -oy) + ((s & 1) ? oz : -oz);
+        }
+        int slot_child[8]; for (int s = 0; s < 8; s++) slot_child[s] = -1;
+        bool used_c[8] = {false};
+        for (int it = 0; it < nch; it++) {
+            int bi = -1, bs = -1; float bc = -3.0e38f;
+            for (int i = 0; i < nch; i++) if (!used_c[i])
+                for (int s = 0; s < 8; s++) if (slot_child[s] < 0 && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+            used_c[bi] = true; slot_child[bs] = bi;
+        }
+        Node8 nd; std::memset(&nd, 0, sizeof(nd));
+        nd.px = root.box.lo[0]; nd.py = root.box.lo[1]; nd.pz = root.box.lo[2];
+        nd.ex = exp_byte(root.box.hi[0] - root.box.lo[0]);
+        nd.ey = exp_byte(root.box.hi[1] - root.box.lo[1]);
+        nd.ez = exp_byte(root.box.hi[2] - root.box.lo[2]);
+        const double sc[3] = { std::ldexp(1.0, (int)nd.ex - 127), std::ldexp(1.0, (int)nd.ey - 127), std::ldexp(1.0, (int)nd.ez - 127) };
+        int n_internal = 0;
+        for (int s = 0; s < 8; s++) if (slot_child[s] >= 0 && !bn[ch[slot_child[s]]].count) n_internal++;
+        nd.child_base = (uint32_t)wn.size();
+        nd.tri_base = n_tri_out;
+        if (n_internal) wn.resize(wn.size() + n_internal);
+        uint32_t rank = 0, toff = 0;
+        uint8_t *qlo[3] = { nd.qlox, nd.qloy, nd.qloz }, *qhi[3] = { nd.qhix, nd.qhiy, nd.qhiz };
+        for (int s = 0; s < 8; s++) {
+            if (slot_child[s] < 0) { for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; } nd.meta[s] = 0; continue; }
+            const BNode &c = bn[ch[slot_child[s]]];
+            const float plo[3] = { nd.px, nd.py, nd.pz };
+            for (int a = 0; a < 3; a++) {
+                double l = std::floor(((double)c.box.lo[a] - (double)plo[a]) / sc[a]);
+                double h = std::ceil(((double)c.box.hi[a] - (double)plo[a]) / sc[a]);
+                qlo[a][s] = (uint8_t)std::min(255.0, std::max(0.0, l));
+                qhi[a][s] = (uint8_t)std::min(255.0, std::max(0.0, h));
+            }
+            sah += (double)c.box.area() / root_area * (c.count ? (double)c.count : 1.0);
+            if (!c.count) {
+                nd.imask |= (uint8_t)(1u << s);
+                nd.meta[s] = (uint8_t)(0x20 | (24 + s));
+                stack.push_back({ch[slot_child[s]], nd.child_base + rank, j.depth + 1});
+                rank++;
+            } else {
+                uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
+                nd.meta[s] = (uint8_t)((unary << 5) | toff);
+                for (uint32_t k = 0; k < c.count; k++) {
+                    uint32_t t = ids[c.left + k];
+                    const float *a = P(idx[3 * (size_t)t]), *b = P(idx[3 * (size_t)t + 1]), *cc = P(idx[3 * (size_t)t + 2]);
+                    Tri48 &o = tris[n_tri_out++];
+                    o.v0x = a[0]; o.v0y = a[1]; o.v0z = a[2]; o.prim = t;
+                    o.e1x = b[0] - a[0]; o.e1y = b[1] - a[1]; o.e1z = b[2] - a[2]; o.pad1 = 0;
+                    o.e2x = cc[0] - a[0]; o.e2y = cc[1] - a[1]; o.e2z = cc[2] - a[2]; o.pad2 = 0;
+                }
+                toff += c.count;
+            }
+        }
+        wn[j.wnode] = nd;
+    }
+    if (n_tri_out != nt) { std::free(tris); return fail("build_bvh8: internal error (triangle count)"); }
+    if (max_depth + 2 > (uint32_t)kStackEntries) { std::free(tris); return fail("build_bvh8: tree too deep for the traversal stack"); }
+
+    out->n_nodes = (uint32_t)wn.size();
+    out->nodes = (Node8 *)std::malloc(sizeof(Node8) * wn.size());
+    if (!out->nodes) { std::free(tris); return fail("build_bvh8: out of memory"); }
+    std::memcpy(out->nodes, wn.data(), sizeof(Node8) * wn.size());
+    out->tris = tris; out->n_tris = nt; out->max_depth = max_depth; out->sah_cost = sah; out->pad = pad;
+    out->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+void free_bvh8(HostBVH8 *b) {
+    if (!b) return;
+    std::free(b->nodes); std::free(b->tris);
+    b->nodes = nullptr; b->tris = nullptr;
+}
+
+}  // namespace prt

@@ -1,0 +1,38 @@
+// kernels.h -- launch interface between the C-ABI layer (abi.cu) and the kernel translation units.
+#pragma once
+#include "bvh8.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace prt {
+
+struct BakeArgs {
+    const Node8 *nodes;
+    const Tri48 *tris;
+    const float *pos, *nrm;     // device; consecutive vertices `stride` bytes apart
+    size_t stride;
+    uint32_t n_verts, vid_base;
+    const float4 *samples;      // [S] (local dir xyz, bits of reference sample index s), processing order
+    int S;
+    float inv_S;
+    float *out;                 // [n_verts][order^2]
+    uint32_t *vis;              // optional [n_verts][vis_words], pre-zeroed
+    int vis_words;
+    uint32_t *counter;          // persistent-warp work counter, pre-zeroed
+    unsigned long long *work;   // optional [2]: total node visits, triangle tests (pre-zeroed)
+    uint32_t seed;
+    int depth;                  // path segments = bounces + 1
+    float albedo[3];
+    float origin_eps, bounce_eps;
+    int cs_phase;
+    int refill_thresh;          // refill idle lanes when fewer than this many lanes are traversing (0: static rounds)
+};
+
+// mode: 0 shadowed, 1 interreflect, 2 unshadowed Monte-Carlo, 3 unshadowed analytic
+// *grid <= 0: one persistent wave, grid = n_sms x occupancy(kernel, block); the grid used is written back
+cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int block, int n_sms, cudaStream_t);
+cudaError_t launch_trace_any(const Node8 *, const Tri48 *, const float *rays, uint32_t n, uint8_t *out, cudaStream_t);
+cudaError_t launch_trace_closest(const Node8 *, const Tri48 *, const float *rays, uint32_t n, float *out_t,
+                                 uint32_t *out_prim, float *out_ng, cudaStream_t);
+
+}  // namespace prt

@@ -1,0 +1,181 @@
+// traverse.cuh -- per-ray traversal of the 8-wide compressed BVH (bvh8.h) with the pinned triangle test.
+//
+// Stands in for rtcOccluded1 / rtcIntersect1 (reference src/raytracing/light_probe.cpp:119,128;
+// raytracing.cpp:167,200,254).  One ray per thread; the traversal state is resumable so a persistent warp
+// can break out, refill idle lanes with fresh rays and continue (bake.cu).  Node fetch = 5 x 16-byte loads,
+// triangle fetch = 3 x 16-byte loads through the read-only path.
+//
+// Hit rule: Moeller-Trumbore on (v0,e1,e2), sign-folded, tnear < t <= tfar, both faces,
+// det == 0 never hits; closest hit = min (t, prim) over all candidates valid in the *initial* interval, so the
+// answer does not depend on traversal order or on the tree.
+#pragma once
+#include "bvh8.h"
+#include "prt_math.cuh"
+
+namespace prt {
+
+struct u4 { uint32_t x, y, z, w; };
+struct u2 { uint32_t x, y; };
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ u4 ld16(const void *p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    u4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+#define PRT_CLZ(x) __clz((int)(x))
+#define PRT_POPC(x) __popc(x)
+#define PRT_FFS(x) __ffs((int)(x))
+#define PRT_ACTIVE_LANES() __popc(__activemask())
+#else
+inline u4 ld16(const void *p) { u4 r; memcpy(&r, p, 16); return r; }
+#define PRT_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#define PRT_POPC(x) __builtin_popcount(x)
+#define PRT_FFS(x) __builtin_ffs((int)(x))
+#define PRT_ACTIVE_LANES() 32
+#endif
+
+PRT_HD float safe_rcp(float d) {
+    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+    return 1.0f / d;
+}
+
+enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_MISS = 2 };
+
+struct Trav {
+    // ray for the pinned triangle test
+    f3 o, d;
+    float tnear, tfar0;
+    // box-test constants
+    float idx, idy, idz;
+    float tbox;          // current far limit for box culling (shrinks in closest-hit mode)
+    uint32_t octinv4;
+    u2 ng, tg;           // current node group (child base, hits|imask) and triangle group (tri base, bits)
+    int sp;
+    // closest-hit result
+    float best_t;
+    uint32_t best_prim, best_tri;
+    uint32_t n_node_visits, n_tri_tests;   // algorithmic work counters (bench roofline)
+    u2 stack[kStackEntries];
+
+    PRT_HD void init(f3 org, f3 dir, float tn, float tf) {
+        o = org; d = dir; tnear = tn; tfar0 = tf; tbox = tf;
+        idx = safe_rcp(dir.x); idy = safe_rcp(dir.y); idz = safe_rcp(dir.z);
+        // signs are taken from the clamped reciprocals so that +-0 components stay consistent with the slab order
+        uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
+        octinv4 = (7u - oct) * 0x01010101u;
+        ng.x = 0u; ng.y = 0x80000000u;
+        tg.x = 0u; tg.y = 0u;
+        sp = 0;
+        best_t = INFINITY; best_prim = 0xFFFFFFFFu; best_tri = 0xFFFFFFFFu;
+    }
+    PRT_HD void reset_counters() { n_node_visits = 0u; n_tri_tests = 0u; }
+
+    // Intersects the 8 quantised child boxes of `node`; fills ng/tg.
+    PRT_HD void visit_node(const Node8 *nodes, uint32_t node) {
+        const char *np = reinterpret_cast<const char *>(nodes + node);
+        const u4 n0 = ld16(np), n1 = ld16(np + 16), n2 = ld16(np + 32), n3 = ld16(np + 48), n4 = ld16(np + 64);
+        const float sx = PRT_U2F((n0.w & 0xFFu) << 23) * idx;
+        const float sy = PRT_U2F(((n0.w >> 8) & 0xFFu) << 23) * idy;
+        const float sz = PRT_U2F(((n0.w >> 16) & 0xFFu) << 23) * idz;
+        const float ax = (PRT_U2F(n0.x) - o.x) * idx;
+        const float ay = (PRT_U2F(n0.y) - o.y) * idy;
+        const float az = (PRT_U2F(n0.z) - o.z) * idz;
+        const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
+        uint32_t hitmask = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t meta4 = h ? n1.w : n1.z;
+            const uint32_t inner = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = (inner >> 4) * 0xFFu;
+            const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+            const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+            const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
+            const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
+            const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sh = 8 * j;
+                const float t0x = (float)((nearx >> sh) & 0xFFu) * sx + ax;
+                const float t0y = (float)((neary >> sh) & 0xFFu) * sy + ay;
+                const float t0z = (float)((nearz >> sh) & 0xFFu) * sz + az;
+                const float t1x = (float)((farx >> sh) & 0xFFu) * sx + ax;
+                const float t1y = (float)((fary >> sh) & 0xFFu) * sy + ay;
+                const float t1z = (float)((farz >> sh) & 0xFFu) * sz + az;
+                const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear));
+                const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tbox));
+                if (tmin <= tmax) hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+            }
+        }
+        ng.x = n1.x; ng.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+        tg.x = n1.y; tg.y = hitmask & 0x00FFFFFFu;
+    }
+
+    // Pinned triangle test. Returns true on a valid hit; t only computed when want_t.
+    PRT_HD bool tri_test(const Tri48 *tris, uint32_t ti, bool want_t, float &t, uint32_t &prim) const {
+        const char *tp = reinterpret_cast<const char *>(tris + ti);
+        const u4 a = ld16(tp), b = ld16(tp + 16), c = ld16(tp + 32);
+        const f3 v0 = mk3(PRT_U2F(a.x), PRT_U2F(a.y), PRT_U2F(a.z));
+        const f3 e1 = mk3(PRT_U2F(b.x), PRT_U2F(b.y), PRT_U2F(b.z));
+        const f3 e2 = mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z));
+        const f3 tv = sub3(o, v0);
+        const f3 pv = cross3(d, e2);
+        const float det = dot3(e1, pv);
+        const float U = dot3(tv, pv);
+        const f3 qv = cross3(tv, e1);
+        const float V = dot3(d, qv);
+        const float T = dot3(e2, qv);
+        const uint32_t sgn = PRT_F2U(det) & 0x80000000u;
+        const float ad = fabsf(det);
+        const float Us = PRT_U2F(PRT_F2U(U) ^ sgn), Vs = PRT_U2F(PRT_F2U(V) ^ sgn), Ts = PRT_U2F(PRT_F2U(T) ^ sgn);
+        bool hit = (ad > 0.0f) && (Us >= 0.0f) && (Vs >= 0.0f) && (PRT_ADD(Us, Vs) <= ad) &&
+                   (Ts > PRT_MUL(tnear, ad)) && (Ts <= PRT_MUL(tfar0, ad));
+        if (hit && want_t) { t = PRT_DIV(Ts, ad); prim = a.w; }
+        return hit;
+    }
+
+    // Runs until the ray is finished, or -- when refill_thresh > 0 and more rays are waiting -- until fewer than
+    // refill_thresh lanes of the warp are still traversing.  ANY: stop at the first hit.
+    template <bool ANY>
+    PRT_HD int run(const Node8 *nodes, const Tri48 *tris, int refill_thresh, bool more) {
+        for (;;) {
+            if (ng.y > 0x00FFFFFFu) {
+                const uint32_t hits_imask = ng.y;
+                const uint32_t bit = 31u - (uint32_t)PRT_CLZ(hits_imask);
+                ng.y &= ~(1u << bit);
+                if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
+                const uint32_t slot = (bit - 24u) ^ (octinv4 & 7u);
+                const uint32_t rel = (uint32_t)PRT_POPC(hits_imask & ~(0xFFFFFFFFu << slot));
+                visit_node(nodes, ng.x + rel);
+                n_node_visits++;
+            } else {
+                tg.y = 0u; ng.y = 0u;
+            }
+            while (tg.y) {
+                const uint32_t bit = (uint32_t)PRT_FFS(tg.y) - 1u;
+                tg.y &= tg.y - 1u;
+                float t; uint32_t prim;
+                n_tri_tests++;
+                if (tri_test(tris, tg.x + bit, !ANY, t, prim)) {
+                    if (ANY) return TRAV_HIT;
+                    if (t < best_t || (t == best_t && prim < best_prim)) { best_t = t; best_prim = prim; best_tri = tg.x + bit; tbox = t; }
+                }
+            }
+            if (ng.y <= 0x00FFFFFFu) {
+                if (sp == 0) return (!ANY && best_prim != 0xFFFFFFFFu) ? TRAV_HIT : TRAV_MISS;
+                ng = stack[--sp];
+            }
+            if (refill_thresh > 0 && more && PRT_ACTIVE_LANES() < refill_thresh) return TRAV_RUNNING;
+        }
+    }
+
+    // unnormalised geometric normal (v1-v0)x(v2-v0) of the closest hit (Embree Ng convention)
+    PRT_HD f3 hit_ng(const Tri48 *tris) const {
+        const char *tp = reinterpret_cast<const char *>(tris + best_tri);
+        const u4 b = ld16(tp + 16), c = ld16(tp + 32);
+        return cross3(mk3(PRT_U2F(b.x), PRT_U2F(b.y), PRT_U2F(b.z)), mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z)));
+    }
+};
+
+}  // namespace prt

@@ -1,0 +1,49 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle
+    pyoracle.build()
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def hostcheck():
+    """Host build of the product's BVH8 builder + traversal header (test tooling, tests/hostcheck)."""
+    import ctypes as C
+    d = os.path.join(ROOT, "tests", "hostcheck")
+    so = os.path.join(d, "libhostcheck.so")
+    srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(ROOT, "prt_b200", "csrc", "bvh_build.cpp"),
+            os.path.join(ROOT, "prt_b200", "csrc", "traverse.cuh"), os.path.join(ROOT, "prt_b200", "csrc", "prt_math.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared",
+                               "-o", so, srcs[0], srcs[1], "-lpthread"])
+    L = C.CDLL(so)
+    L.hc_build.restype = C.c_void_p
+    L.hc_build.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.hc_free.argtypes = [C.c_void_p]
+    L.hc_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_any_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.hc_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+@pytest.fixture(scope="session")
+def prt():
+    """The product package with the CUDA library loaded (GPU tests)."""
+    import prt_b200
+    prt_b200.load_library()
+    return prt_b200

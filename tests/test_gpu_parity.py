@@ -1,0 +1,229 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`): the sm_100a path, called through the C ABI, against the
+CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): visibility bits and hit records bit-exact (pinned arithmetic),
+SH coefficients <= 1e-4 relative L2 per vertex.
+"""
+import numpy as np
+import pytest
+
+from prt_b200 import meshes
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-4  # north_star: "SH coefficients must match to <= 1e-4 relative L2 per vertex"
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-20)
+
+
+@pytest.fixture(scope="module")
+def torus():
+    return meshes.bumpy_torus(96, 64)
+
+
+@pytest.fixture(scope="module")
+def torus_scenes(torus, prt, oracle):
+    pos, nrm, tri = torus
+    return prt.RTScene(pos, tri), oracle.Scene(pos, tri)
+
+
+def _hemisphere_rays(pos, nrm, n, seed, eps=1e-4):
+    rng = np.random.RandomState(seed)
+    vi = rng.randint(0, len(pos), n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[np.sum(d * nrm[vi], 1) < 0] *= -1
+    return (pos[vi] + np.float32(eps) * nrm[vi]).astype(np.float32), d.astype(np.float32)
+
+
+def test_any_hit_bit_exact(torus, torus_scenes, prt):
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    org, d = _hemisphere_rays(pos, nrm, 30000, 1)
+    got = gs.any_hit(prt.RTScene.pack_rays(org, d))
+    ref = np.array([os_.any_hit(org[i], d[i:i + 1])[0] for i in range(len(d))])
+    assert 0.05 < ref.mean() < 0.95
+    assert np.array_equal(got.astype(np.int32), ref)
+
+
+def test_closest_hit_bit_exact(torus, torus_scenes, prt):
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    org, d = _hemisphere_rays(pos, nrm, 20000, 2)
+    t, prim, ng = gs.first_hit(prt.RTScene.pack_rays(org, d))
+    hit, t2, prim2, ng2 = os_.closest_hit(org, d)
+    assert np.array_equal(prim, prim2)
+    assert np.array_equal(t.view(np.uint32), t2.view(np.uint32))
+    assert np.array_equal(ng.view(np.uint32)[hit == 1], ng2.view(np.uint32)[hit == 1])
+
+
+def test_segment_rays(torus, torus_scenes, prt):
+    """unnormalised direction + tfar = 1 segment test (light_probe.cpp:250)."""
+    pos, _, _ = torus
+    gs, os_ = torus_scenes
+    rng = np.random.RandomState(3)
+    a = rng.uniform(-3.5, 3.5, (5000, 3)).astype(np.float32)
+    b = rng.uniform(-3.5, 3.5, (5000, 3)).astype(np.float32)
+    got = gs.any_hit(prt.RTScene.pack_rays(a, b - a, 0.0, 1.0))
+    ref = np.array([os_.any_hit(a[i], (b - a)[i:i + 1], 0.0, 1.0)[0] for i in range(len(a))])
+    assert np.array_equal(got.astype(np.int32), ref)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_bake_shadowed_orders(torus, torus_scenes, prt, oracle, order):
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(0, len(pos), 7)[:600]
+    gp = prt.BakeParams.make(order=order, samples_u=16, samples_v=16)
+    op = oracle.make_params(order=order, samples_u=16, samples_v=16)
+    got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], gp, want_vis=True)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(gvis, ovis), "per-ray visibility bits must agree exactly"
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+
+
+def test_bake_reference_defaults(torus, torus_scenes, prt, oracle):
+    """order 3 (9 coeffs), 32x32 jittered strata: the reference's default bake (raytracing.cpp:320, app.h:70-71)."""
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(0, len(pos), 11)[:400]
+    got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(), want_vis=True)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(), want_vis=True)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+    frac = np.unpackbits(ovis.view(np.uint8)).mean()
+    assert 0.3 < frac < 0.98  # the torus really is self-occluding
+
+
+@pytest.mark.parametrize("refill", [0, 8, 24, 32])
+def test_bake_refill_threshold_invariant(torus, torus_scenes, prt, oracle, refill):
+    """warp-level ray compaction must not change results."""
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(0, len(pos), 13)[:300]
+    gs.ctx.set_tuning(refill_thresh=refill)
+    try:
+        got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(samples_u=16, samples_v=16), want_vis=True)
+    finally:
+        gs.ctx.set_tuning(refill_thresh=24)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(samples_u=16, samples_v=16), want_vis=True)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("bounces,albedo", [(1, (1.0, 1.0, 1.0)), (3, (0.5, 0.5, 0.5)), (8, (0.5, 0.3, 0.2))])
+def test_bake_interreflect(torus, torus_scenes, prt, oracle, bounces, albedo):
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(0, len(pos), 17)[:250]
+    kw = dict(order=4, samples_u=16, samples_v=16, bounces=bounces, albedo=albedo)
+    got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(mode=prt.INTERREFLECT, **kw), want_vis=True, vertex_id_base=1000)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(mode=oracle.INTERREFLECT, **kw), want_vis=True, vertex_id_base=1000)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+    # interreflection only adds energy to the DC term
+    sh, _ = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(order=4, samples_u=16, samples_v=16))
+    assert (got[:, 0] >= sh[:, 0] - 1e-6).all()
+
+
+def test_bake_unshadowed_modes(torus, prt, oracle):
+    pos, nrm, _ = torus
+    sel = np.arange(0, len(pos), 29)[:200]
+    for mode_g, mode_o in [(prt.UNSHADOWED, oracle.UNSHADOWED), (prt.UNSHADOWED_ANALYTIC, oracle.UNSHADOWED_ANALYTIC)]:
+        got, _ = prt.bake_transfer(None, pos[sel], nrm[sel], prt.BakeParams.make(order=5, mode=mode_g))
+        ref, _, _ = oracle.bake_transfer(None, pos[sel], nrm[sel], oracle.make_params(order=5, mode=mode_o))
+        assert rel_l2(got, ref).max() <= REL_L2_TOL
+
+
+def test_cs_phase_and_centres(torus, torus_scenes, prt, oracle):
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(0, len(pos), 31)[:150]
+    kw = dict(order=5, samples_u=8, samples_v=32, cs_phase=1, jitter=0)
+    got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(**kw), want_vis=True)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(**kw), want_vis=True)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+
+
+def test_convex_sphere_known_answer(prt):
+    """SURVEY 8c KAT 2: on a convex mesh shadowed == unshadowed -> (A_l/pi) Y_lm(perm(n)); MC tolerance 1e-2."""
+    pos, nrm, tri = meshes.icosphere(4)
+    sc = prt.RTScene(pos, tri)
+    sh, vis = prt.bake_transfer(sc, pos, nrm, prt.BakeParams.make(), want_vis=True)
+    un, _ = prt.bake_transfer(None, pos, nrm, prt.BakeParams.make(mode=prt.UNSHADOWED))
+    ana, _ = prt.bake_transfer(None, pos, nrm, prt.BakeParams.make(mode=prt.UNSHADOWED_ANALYTIC))
+    assert np.unpackbits(vis.view(np.uint8)).all()
+    assert rel_l2(sh, un).max() <= 1e-6
+    assert rel_l2(sh, ana).max() <= 1e-2
+
+
+def test_closed_room_all_occluded(prt):
+    """SURVEY 8c KAT 8: rays from inside a closed box never escape."""
+    c = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32) * 3
+    f = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 4, 5], [0, 5, 1], [3, 2, 6], [3, 6, 7], [0, 3, 7], [0, 7, 4], [1, 5, 6], [1, 6, 2]], np.uint32)
+    sc = prt.RTScene(c, f)
+    rng = np.random.RandomState(5)
+    p = rng.uniform(-2.5, 2.5, (500, 3)).astype(np.float32)
+    n = rng.normal(size=(500, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    co, vis = prt.bake_transfer(sc, p, n, prt.BakeParams.make(samples_u=8, samples_v=8), want_vis=True)
+    assert not vis.any()
+    assert np.abs(co).max() == 0.0
+
+
+def test_edge_cases(prt):
+    pos, nrm, tri = meshes.icosphere(1)
+    sc = prt.RTScene(pos, tri)
+    # empty vertex range
+    co, _ = prt.bake_transfer(sc, pos[:0], nrm[:0], prt.BakeParams.make())
+    assert co.shape == (0, 9)
+    # single vertex, single sample
+    co, vis = prt.bake_transfer(sc, pos[:1], nrm[:1], prt.BakeParams.make(samples_u=1, samples_v=1), want_vis=True)
+    assert co.shape == (1, 9) and vis.shape == (1, 1)
+    # ragged sample count (not a multiple of 32) and degenerate triangles in the scene
+    tri2 = np.concatenate([tri, np.array([[0, 0, 1], [2, 2, 2]], np.uint32)])
+    sc2 = prt.RTScene(pos, tri2)
+    a, va = prt.bake_transfer(sc2, pos, nrm, prt.BakeParams.make(samples_u=5, samples_v=7), want_vis=True)
+    b, vb = prt.bake_transfer(sc, pos, nrm, prt.BakeParams.make(samples_u=5, samples_v=7), want_vis=True)
+    assert np.array_equal(va, vb) and np.allclose(a, b, atol=1e-7)
+    # bad arguments fail loudly
+    with pytest.raises(prt.PRTError):
+        prt.bake_transfer(sc, pos, nrm, prt.BakeParams.make(order=6))
+    with pytest.raises(prt.PRTError):
+        prt.bake_transfer(None, pos, nrm, prt.BakeParams.make())
+    with pytest.raises(prt.PRTError):
+        prt.RTScene(pos, np.array([[0, 1, 9999]], np.uint32))
+
+
+def test_bake_SH_mesh_vert_layout(prt, oracle):
+    """bake_SH(Mesh&): interleaved 60-byte Mesh::Vert in, sh_coeff[9] written in place (gl.h:76-80)."""
+    pos, nrm, tri = meshes.bumpy_torus(48, 32)
+    verts = np.zeros((len(pos), 15), np.float32)
+    verts[:, 0:3], verts[:, 3:6] = pos, nrm
+    out = prt.bake_SH(verts, tri)
+    assert np.array_equal(out, verts[:, 6:15])
+    ref, _, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos, nrm, oracle.make_params())
+    assert rel_l2(verts[:, 6:15], ref).max() <= REL_L2_TOL
+
+
+def test_full_size_properties(prt):
+    """BASELINE config 1 size (buddha-scale torus, S = 1024): size-independent properties instead of the oracle."""
+    pos, nrm, tri = meshes.bumpy_torus(737, 737)
+    sc = prt.RTScene(pos, tri)
+    p = prt.BakeParams.make()
+    co, vis = prt.bake_transfer(sc, pos, nrm, p, want_vis=True)
+    assert np.isfinite(co).all()
+    frac = np.unpackbits(vis.view(np.uint8)).reshape(len(pos), -1).mean(1)
+    # DC coefficient is exactly 0.282095 * visible fraction (cosine-weighted sampling: every sample weighs 1/S)
+    assert np.abs(co[:, 0] - 0.282095 * frac).max() < 2e-6
+    # shadowed <= unshadowed in the DC term, and idempotence of a second run
+    co2, vis2 = prt.bake_transfer(sc, pos, nrm, p, want_vis=True)
+    assert np.array_equal(vis, vis2)
+    assert rel_l2(co, co2).max() < 1e-5
+    # sharded bake == whole bake (vertex ranges are independent)
+    half = len(pos) // 2
+    a, _ = prt.bake_transfer(sc, pos[:half], nrm[:half], p)
+    assert rel_l2(a, co[:half]).max() < 1e-5
