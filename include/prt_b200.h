@@ -126,6 +126,7 @@ typedef struct {
     uint32_t grid, block;
     uint64_t node_visits;    /* only with tuning knob count_work=1: 80-byte node fetches ... */
     uint64_t tri_tests;      /* ... and 48-byte triangle fetches of the launch (algorithmic traversal work) */
+    uint64_t cand_tests;     /* 32-byte entry-list candidate boxes tested (shared memory) */
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
 

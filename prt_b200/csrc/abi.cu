@@ -44,7 +44,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 24, count_work = 0;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1;
     // cached sample table
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res;
@@ -108,6 +108,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "ctas_per_sm") { if (value < 0 || value > 32) return set_err(PRT_ERR_INVALID, "ctas_per_sm must be in [0,32]"); c->ctas_per_sm = value; }
     else if (n == "refill_thresh") { if (value < 0 || value > 32) return set_err(PRT_ERR_INVALID, "refill_thresh must be in [0,32]"); c->refill_thresh = value; }
     else if (n == "count_work") c->count_work = value ? 1 : 0;
+    else if (n == "entry_list") c->entry_list = value ? 1 : 0;
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
     return PRT_OK;
 }
@@ -281,6 +282,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     A.albedo[0] = p->albedo[0]; A.albedo[1] = p->albedo[1]; A.albedo[2] = p->albedo[2];
     A.origin_eps = p->origin_eps; A.bounce_eps = p->bounce_eps; A.cs_phase = p->cs_phase;
     A.refill_thresh = c->refill_thresh;
+    A.entry_list = c->entry_list;
     CU_TRY(cudaMemsetAsync(A.counter, 0, 128, st));
     if (d_vis) CU_TRY(cudaMemsetAsync(d_vis, 0, (size_t)n * A.vis_words * 4, st));
     int mode = p->mode == PRT_SHADOWED ? 0 : p->mode == PRT_INTERREFLECT ? 1 : p->mode == PRT_UNSHADOWED ? 2 : 3;
@@ -358,9 +360,9 @@ int prt_ctx_last_bake_stats(const prt_ctx *cc, prt_bake_stats *out) {
     if (c->work_pending) {
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaEventSynchronize(c->ev2));
-        unsigned long long w[2] = {0, 0};
-        CU_TRY(cudaMemcpy(w, (char *)c->counter.p + 64, 16, cudaMemcpyDeviceToHost));
-        c->stats.node_visits = w[0]; c->stats.tri_tests = w[1];
+        unsigned long long w[3] = {0, 0, 0};
+        CU_TRY(cudaMemcpy(w, (char *)c->counter.p + 64, 24, cudaMemcpyDeviceToHost));
+        c->stats.node_visits = w[0]; c->stats.tri_tests = w[1]; c->stats.cand_tests = w[2];
         c->work_pending = false;
     }
     *out = c->stats;

@@ -19,7 +19,8 @@ struct BakeArgs {
     uint32_t *vis;              // optional [n_verts][vis_words], pre-zeroed
     int vis_words;
     uint32_t *counter;          // persistent-warp work counter, pre-zeroed
-    unsigned long long *work;   // optional [2]: total node visits, triangle tests (pre-zeroed)
+    unsigned long long *work;   // optional [3]: node visits, triangle tests, candidate-box tests (pre-zeroed)
+    int entry_list;             // 1: per-origin entry lists (bake.cu), 0: every ray starts at the root
     uint32_t seed;
     int depth;                  // path segments = bounces + 1
     float albedo[3];

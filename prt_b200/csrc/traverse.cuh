@@ -39,7 +39,9 @@ PRT_HD float safe_rcp(float d) {
     return 1.0f / d;
 }
 
-enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_MISS = 2 };
+// run() results: RUNNING = interrupted for a refill (state kept); HIT = any-hit found (ANY only);
+// EMPTY = stack and current groups exhausted (closest-hit result, if any, is in best_*)
+enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_EMPTY = 2 };
 
 struct Trav {
     // ray for the pinned triangle test
@@ -57,18 +59,23 @@ struct Trav {
     uint32_t n_node_visits, n_tri_tests;   // algorithmic work counters (bench roofline)
     u2 stack[kStackEntries];
 
+    // sets up the ray; traversal starts empty (use start_root() / start_group())
     PRT_HD void init(f3 org, f3 dir, float tn, float tf) {
         o = org; d = dir; tnear = tn; tfar0 = tf; tbox = tf;
         idx = safe_rcp(dir.x); idy = safe_rcp(dir.y); idz = safe_rcp(dir.z);
         // signs are taken from the clamped reciprocals so that +-0 components stay consistent with the slab order
         uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
         octinv4 = (7u - oct) * 0x01010101u;
-        ng.x = 0u; ng.y = 0x80000000u;
+        ng.x = 0u; ng.y = 0u;
         tg.x = 0u; tg.y = 0u;
         sp = 0;
         best_t = INFINITY; best_prim = 0xFFFFFFFFu; best_tri = 0xFFFFFFFFu;
     }
     PRT_HD void reset_counters() { n_node_visits = 0u; n_tri_tests = 0u; }
+    // (x, y) is a stack-entry style group: y > 0x00FFFFFF -> node group (child base x, hit bits | imask);
+    // otherwise a triangle group (first triangle x, bit per triangle).  (node, 0x80000000) starts at `node`.
+    PRT_HD void start_group(uint32_t x, uint32_t y) { ng.x = x; ng.y = y; }
+    PRT_HD void start_root() { start_group(0u, 0x80000000u); }
 
     // Intersects the 8 quantised child boxes of `node`; fills ng/tg.
     PRT_HD void visit_node(const Node8 *nodes, uint32_t node) {
@@ -150,7 +157,7 @@ struct Trav {
                 visit_node(nodes, ng.x + rel);
                 n_node_visits++;
             } else {
-                tg.y = 0u; ng.y = 0u;
+                tg = ng; ng.y = 0u;
             }
             while (tg.y) {
                 const uint32_t bit = (uint32_t)PRT_FFS(tg.y) - 1u;
@@ -163,7 +170,7 @@ struct Trav {
                 }
             }
             if (ng.y <= 0x00FFFFFFu) {
-                if (sp == 0) return (!ANY && best_prim != 0xFFFFFFFFu) ? TRAV_HIT : TRAV_MISS;
+                if (sp == 0) return TRAV_EMPTY;
                 ng = stack[--sp];
             }
             if (refill_thresh > 0 && more && PRT_ACTIVE_LANES() < refill_thresh) return TRAV_RUNNING;

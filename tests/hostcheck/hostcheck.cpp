@@ -6,6 +6,9 @@
 #include "../../prt_b200/csrc/traverse.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <cmath>
 
 using namespace prt;
 
@@ -23,7 +26,7 @@ void hc_any_hit(void *h, const float *rays, uint32_t n, uint8_t *out) {
     HostBVH8 *b = (HostBVH8 *)h;
     for (uint32_t i = 0; i < n; i++) {
         const float *r = rays + 8 * (size_t)i;
-        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]);
+        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]); t.start_root();
         out[i] = t.run<true>(b->nodes, b->tris, 0, false) == TRAV_HIT;
     }
 }
@@ -31,9 +34,9 @@ void hc_closest_hit(void *h, const float *rays, uint32_t n, float *out_t, uint32
     HostBVH8 *b = (HostBVH8 *)h;
     for (uint32_t i = 0; i < n; i++) {
         const float *r = rays + 8 * (size_t)i;
-        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]);
-        int rc = t.run<false>(b->nodes, b->tris, 0, false);
-        if (rc == TRAV_HIT) { out_t[i] = t.best_t; out_prim[i] = t.best_prim; f3 g = t.hit_ng(b->tris); out_ng[3 * i] = g.x; out_ng[3 * i + 1] = g.y; out_ng[3 * i + 2] = g.z; }
+        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]); t.start_root();
+        t.run<false>(b->nodes, b->tris, 0, false);
+        if (t.best_prim != 0xFFFFFFFFu) { out_t[i] = t.best_t; out_prim[i] = t.best_prim; f3 g = t.hit_ng(b->tris); out_ng[3 * i] = g.x; out_ng[3 * i + 1] = g.y; out_ng[3 * i + 2] = g.z; }
         else { out_t[i] = INFINITY; out_prim[i] = 0xFFFFFFFFu; out_ng[3 * i] = out_ng[3 * i + 1] = out_ng[3 * i + 2] = 0.f; }
     }
 }
@@ -45,9 +48,119 @@ extern "C" void hc_count_work(void *h, const float *rays, uint32_t n, uint64_t *
     uint64_t nv = 0, nt = 0;
     for (uint32_t i = 0; i < n; i++) {
         const float *r = rays + 8 * (size_t)i;
-        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]);
+        Trav t; t.reset_counters(); t.init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]); t.start_root();
         t.run<true>(b->nodes, b->tris, 0, false);
         nv += t.n_node_visits; nt += t.n_tri_tests;
     }
     out[0] = nv; out[1] = nt;
+}
+
+// Experiment (design study): cost of traversing bundles of 32 same-origin rays as ONE packet with a
+// shared stack (a node is visited when any live ray hits its box) versus per-ray traversal.
+// out[0] = packet node visits, out[1] = packet triangle tests (one per triangle per packet), out[2] = sum over rays of
+// per-ray node visits, out[3] = sum of per-ray tri tests, out[4] = lane-slots doing useful tri tests in packet mode
+extern "C" void hc_packet_stats(void *h, const float *rays, uint32_t n, uint64_t *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    uint64_t pv = 0, pt = 0, rv = 0, rt = 0, useful = 0;
+    for (uint32_t base = 0; base + 32 <= n; base += 32) {
+        Trav tr[32]; bool live[32];
+        for (int l = 0; l < 32; l++) {
+            const float *r = rays + 8 * (size_t)(base + l);
+            tr[l].reset_counters(); tr[l].init(mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7]); tr[l].start_root();
+            Trav t = tr[l]; t.run<true>(b->nodes, b->tris, 0, false); rv += t.n_node_visits; rt += t.n_tri_tests;
+            live[l] = true;
+        }
+        uint32_t stack[256]; int sp = 0; stack[sp++] = 0; int nlive = 32;
+        while (sp && nlive) {
+            uint32_t node = stack[--sp];
+            pv++;
+            const Node8 &nd = b->nodes[node];
+            uint32_t inner_slots = 0, tri_bits = 0; uint32_t lane_tri[32];
+            for (int l = 0; l < 32; l++) {
+                lane_tri[l] = 0;
+                if (!live[l]) continue;
+                tr[l].visit_node(b->nodes, node);
+                uint32_t hits = tr[l].ng.y >> 24, oi = tr[l].octinv4 & 7u;
+                for (int k = 0; k < 8; k++) if (hits & (1u << k)) inner_slots |= 1u << (k ^ oi);
+                lane_tri[l] = tr[l].tg.y; tri_bits |= tr[l].tg.y;
+            }
+            for (int k = 0; k < 24 && nlive; k++) if (tri_bits & (1u << k)) {
+                pt++;
+                for (int l = 0; l < 32; l++) if (live[l] && (lane_tri[l] & (1u << k))) {
+                    useful++;
+                    float t; uint32_t prim;
+                    if (tr[l].tri_test(b->tris, nd.tri_base + k, false, t, prim)) { live[l] = false; nlive--; }
+                }
+            }
+            for (int s = 7; s >= 0; s--) if (inner_slots & (1u << s)) {
+                uint32_t rel = (uint32_t)__builtin_popcount(nd.imask & ((1u << s) - 1u));
+                if (sp < 256) stack[sp++] = nd.child_base + rel;
+            }
+        }
+    }
+    out[0] = pv; out[1] = pt; out[2] = rv; out[3] = rt; out[4] = useful;
+}
+
+// Experiment: per-origin entry list.  Descend the nodes whose box contains the origin; children that do not contain it
+// and are not entirely below the tangent plane become candidates (subtree roots or leaves).  Reports, for rays of one
+// origin: number of candidates, candidate boxes hit per ray, node visits and triangle tests left per ray.
+struct Cand { float lo[3], hi[3]; uint32_t node; uint32_t tri0, ntri; };
+static void decode_child(const Node8 &nd, int s, float lo[3], float hi[3]) {
+    const float sc[3] = { PRT_U2F((uint32_t)nd.ex << 23), PRT_U2F((uint32_t)nd.ey << 23), PRT_U2F((uint32_t)nd.ez << 23) };
+    const float p[3] = { nd.px, nd.py, nd.pz };
+    const uint8_t *ql[3] = { nd.qlox, nd.qloy, nd.qloz }, *qh[3] = { nd.qhix, nd.qhiy, nd.qhiz };
+    for (int a = 0; a < 3; a++) { lo[a] = p[a] + ql[a][s] * sc[a]; hi[a] = p[a] + qh[a][s] * sc[a]; }
+}
+extern "C" void hc_entry_stats(void *h, const float *org, const float *nrm, const float *dirs, uint32_t nrays, int max_cands, double *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    std::vector<Cand> cands; std::vector<uint32_t> queue; queue.push_back(0);
+    int expanded = 0;
+    while (!queue.empty()) {
+        uint32_t x = queue.back(); queue.pop_back(); expanded++;
+        const Node8 &nd = b->nodes[x];
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            Cand c; decode_child(nd, s, c.lo, c.hi);
+            float mx = 0.f, far2 = 0.f; bool inside = true;
+            for (int a = 0; a < 3; a++) {
+                float l = c.lo[a] - org[a], hh = c.hi[a] - org[a];
+                mx += std::max(nrm[a] * l, nrm[a] * hh);
+                far2 = std::max(far2, std::max(std::fabs(l), std::fabs(hh)));
+                if (org[a] < c.lo[a] || org[a] > c.hi[a]) inside = false;
+            }
+            if (mx < -1e-5f * far2) continue;   // wholly below the tangent plane
+            bool inner = (nd.imask >> s) & 1;
+            if (inner) {
+                uint32_t child = nd.child_base + __builtin_popcount(nd.imask & ((1u << s) - 1u));
+                if (inside && (int)(cands.size() + queue.size()) < max_cands) { queue.push_back(child); continue; }
+                c.node = child; c.ntri = 0; c.tri0 = 0;
+            } else {
+                c.node = 0xFFFFFFFFu; c.tri0 = nd.tri_base + (nd.meta[s] & 31); c.ntri = __builtin_popcount(nd.meta[s] >> 5);
+            }
+            cands.push_back(c);
+        }
+    }
+    uint64_t box_hits = 0, nv = 0, nt = 0, occl = 0;
+    for (uint32_t i = 0; i < nrays; i++) {
+        f3 o = mk3(org[0], org[1], org[2]), d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        Trav t; t.reset_counters(); t.init(o, d, 0.f, INFINITY);
+        bool hit = false;
+        for (size_t k = 0; k < cands.size() && !hit; k++) {
+            const Cand &c = cands[k];
+            float t0 = 0.f, t1 = INFINITY; const float id[3] = { t.idx, t.idy, t.idz }; const float oo[3] = { o.x, o.y, o.z };
+            for (int a = 0; a < 3; a++) { float ta = (c.lo[a] - oo[a]) * id[a], tb = (c.hi[a] - oo[a]) * id[a]; t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb)); }
+            if (!(t0 <= t1)) continue;
+            box_hits++;
+            if (c.node == 0xFFFFFFFFu) {
+                for (uint32_t j = 0; j < c.ntri && !hit; j++) { float tt; uint32_t pr; nt++; hit = t.tri_test(b->tris, c.tri0 + j, false, tt, pr); }
+            } else {
+                t.ng.x = c.node; t.ng.y = 0x80000000u; t.tg.y = 0; t.sp = 0; t.n_node_visits = 0; t.n_tri_tests = 0;
+                hit = t.run<true>(b->nodes, b->tris, 0, false) == TRAV_HIT;
+                nv += t.n_node_visits; nt += t.n_tri_tests;
+            }
+        }
+        occl += hit;
+    }
+    out[0] = (double)cands.size(); out[1] = (double)box_hits / nrays; out[2] = (double)nv / nrays; out[3] = (double)nt / nrays;
+    out[4] = (double)occl / nrays; out[5] = expanded;
 }

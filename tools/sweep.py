@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""tools/sweep.py -- times the bake kernel over tuning-knob combinations on one GPU (kernel_ms from the library's
+own CUDA events).  Usage: python tools/sweep.py [--nu 737 --nv 737] [--order 3] [--su 32 --sv 32] knob=v1,v2 ..."""
+import argparse
+import ctypes as C
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import prt_b200  # noqa: E402
+from prt_b200 import meshes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--nu", type=int, default=737)
+ap.add_argument("--nv", type=int, default=737)
+ap.add_argument("--order", type=int, default=3)
+ap.add_argument("--su", type=int, default=32)
+ap.add_argument("--sv", type=int, default=32)
+ap.add_argument("--mode", type=int, default=1)
+ap.add_argument("--bounces", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--mesh", default="torus")
+ap.add_argument("knobs", nargs="*")
+a = ap.parse_args()
+
+if a.mesh == "torus":
+    pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv)
+else:
+    pos, nrm, tri = meshes.icosphere(int(a.mesh.replace("ico", "")))
+order = meshes.morton_order(pos)
+ctx = prt_b200.Context(0)
+scene = prt_b200.RTScene(pos, tri, ctx)
+dev = torch.device("cuda", 0)
+d_pos = torch.from_numpy(np.ascontiguousarray(pos[order])).to(dev)
+d_nrm = torch.from_numpy(np.ascontiguousarray(nrm[order])).to(dev)
+n = len(pos)
+params = prt_b200.BakeParams.make(order=a.order, samples_u=a.su, samples_v=a.sv, mode=a.mode, bounces=a.bounces,
+                                  albedo=(0.5, 0.5, 0.5) if a.bounces else (1, 1, 1))
+d_out = torch.zeros((n, a.order ** 2), dtype=torch.float32, device=dev)
+L = ctx.L
+stream = torch.cuda.current_stream()
+names = [k.split("=")[0] for k in a.knobs]
+values = [[int(x) for x in k.split("=")[1].split(",")] for k in a.knobs]
+S = a.su * a.sv
+for combo in itertools.product(*values) if values else [()]:
+    kw = dict(zip(names, combo))
+    ctx.set_tuning(**kw)
+    ms = []
+    for _ in range(a.reps):
+        rc = L.prt_bake_transfer_device(ctx.h, scene.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, n, 0,
+                                        C.byref(params), C.c_void_p(d_out.data_ptr()), None, C.c_void_p(stream.cuda_stream))
+        assert rc == 0, L.prt_last_error()
+        torch.cuda.synchronize()
+        ms.append(ctx.last_bake_stats().kernel_ms)
+    st = ctx.last_bake_stats()
+    best = min(ms)
+    print(json.dumps({"knobs": kw, "kernel_ms": best, "grays_per_s": n * S / best / 1e6, "grid": st.grid, "block": st.block,
+                      "all_ms": [round(m, 2) for m in ms]}), flush=True)
