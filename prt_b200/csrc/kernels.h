@@ -32,6 +32,9 @@ struct BakeArgs {
 // mode: 0 shadowed, 1 interreflect, 2 unshadowed Monte-Carlo, 3 unshadowed analytic
 // *grid <= 0: one persistent wave, grid = n_sms x occupancy(kernel, block); the grid used is written back
 cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int block, int n_sms, cudaStream_t);
+// pair-queue kernel for the shadowed (trace = true) and unshadowed Monte-Carlo (trace = false) modes, S <= bake_shadow_max_samples()
+cudaError_t launch_bake_shadow(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
+int bake_shadow_max_samples();
 cudaError_t launch_trace_any(const Node8 *, const Tri48 *, const float *rays, uint32_t n, uint8_t *out, cudaStream_t);
 cudaError_t launch_trace_closest(const Node8 *, const Tri48 *, const float *rays, uint32_t n, float *out_t,
                                  uint32_t *out_prim, float *out_ng, cudaStream_t);

@@ -43,6 +43,29 @@ PRT_HD float safe_rcp(float d) {
 // EMPTY = stack and current groups exhausted (closest-hit result, if any, is in best_*)
 enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_EMPTY = 2 };
 
+// Pinned ray/triangle decision on triangle `ti`: hit iff tnear < t <= tfar.
+PRT_HD bool tri_hit(const Tri48 *tris, uint32_t ti, f3 o, f3 d, float tnear, float tfar, bool want_t, float &t, uint32_t &prim) {
+    const char *tp = reinterpret_cast<const char *>(tris + ti);
+    const u4 a = ld16(tp), b = ld16(tp + 16), c = ld16(tp + 32);
+    const f3 v0 = mk3(PRT_U2F(a.x), PRT_U2F(a.y), PRT_U2F(a.z));
+    const f3 e1 = mk3(PRT_U2F(b.x), PRT_U2F(b.y), PRT_U2F(b.z));
+    const f3 e2 = mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z));
+    const f3 tv = sub3(o, v0);
+    const f3 pv = cross3(d, e2);
+    const float det = dot3(e1, pv);
+    const float U = dot3(tv, pv);
+    const f3 qv = cross3(tv, e1);
+    const float V = dot3(d, qv);
+    const float T = dot3(e2, qv);
+    const uint32_t sgn = PRT_F2U(det) & 0x80000000u;
+    const float ad = fabsf(det);
+    const float Us = PRT_U2F(PRT_F2U(U) ^ sgn), Vs = PRT_U2F(PRT_F2U(V) ^ sgn), Ts = PRT_U2F(PRT_F2U(T) ^ sgn);
+    const bool hit = (ad > 0.0f) && (Us >= 0.0f) && (Vs >= 0.0f) && (PRT_ADD(Us, Vs) <= ad) &&
+                     (Ts > PRT_MUL(tnear, ad)) && (Ts <= PRT_MUL(tfar, ad));
+    if (hit && want_t) { t = PRT_DIV(Ts, ad); prim = a.w; }
+    return hit;
+}
+
 struct Trav {
     // ray for the pinned triangle test
     f3 o, d;
@@ -119,27 +142,8 @@ struct Trav {
         tg.x = n1.y; tg.y = hitmask & 0x00FFFFFFu;
     }
 
-    // Pinned triangle test. Returns true on a valid hit; t only computed when want_t.
     PRT_HD bool tri_test(const Tri48 *tris, uint32_t ti, bool want_t, float &t, uint32_t &prim) const {
-        const char *tp = reinterpret_cast<const char *>(tris + ti);
-        const u4 a = ld16(tp), b = ld16(tp + 16), c = ld16(tp + 32);
-        const f3 v0 = mk3(PRT_U2F(a.x), PRT_U2F(a.y), PRT_U2F(a.z));
-        const f3 e1 = mk3(PRT_U2F(b.x), PRT_U2F(b.y), PRT_U2F(b.z));
-        const f3 e2 = mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z));
-        const f3 tv = sub3(o, v0);
-        const f3 pv = cross3(d, e2);
-        const float det = dot3(e1, pv);
-        const float U = dot3(tv, pv);
-        const f3 qv = cross3(tv, e1);
-        const float V = dot3(d, qv);
-        const float T = dot3(e2, qv);
-        const uint32_t sgn = PRT_F2U(det) & 0x80000000u;
-        const float ad = fabsf(det);
-        const float Us = PRT_U2F(PRT_F2U(U) ^ sgn), Vs = PRT_U2F(PRT_F2U(V) ^ sgn), Ts = PRT_U2F(PRT_F2U(T) ^ sgn);
-        bool hit = (ad > 0.0f) && (Us >= 0.0f) && (Vs >= 0.0f) && (PRT_ADD(Us, Vs) <= ad) &&
-                   (Ts > PRT_MUL(tnear, ad)) && (Ts <= PRT_MUL(tfar0, ad));
-        if (hit && want_t) { t = PRT_DIV(Ts, ad); prim = a.w; }
-        return hit;
+        return tri_hit(tris, ti, o, d, tnear, tfar0, want_t, t, prim);
     }
 
     // Runs until the ray is finished, or -- when refill_thresh > 0 and more rays are waiting -- until fewer than
