@@ -44,7 +44,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 1;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2;
     // cached sample table
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res;
@@ -109,7 +109,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "refill_thresh") { if (value < 0 || value > 32) return set_err(PRT_ERR_INVALID, "refill_thresh must be in [0,32]"); c->refill_thresh = value; }
     else if (n == "count_work") c->count_work = value ? 1 : 0;
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
-    else if (n == "pair_queue") c->pair_queue = value ? 1 : 0;
+    else if (n == "pair_queue") { if (value < 0 || value > 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks), 1 (pair queues) or 2 (wavefront)"); c->pair_queue = value; }
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
     return PRT_OK;
 }
@@ -291,7 +291,10 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     const int grid = c->ctas_per_sm > 0 ? c->n_sms * c->ctas_per_sm : 0;
     if (e0) CU_TRY(cudaEventRecord(e0, st));
     int used_grid = grid;
-    if ((mode == 0 || mode == 2) && c->pair_queue && c->entry_list && S <= bake_shadow_max_samples() && c->block == 256)
+    const bool fast_ok = (mode == 0 || mode == 2) && c->entry_list && S <= bake_wave_max_samples() && c->block == 256;
+    if (fast_ok && c->pair_queue == 2)
+        CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
+    else if (fast_ok && c->pair_queue == 1)
         CU_TRY(launch_bake_shadow(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
     else
         CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));

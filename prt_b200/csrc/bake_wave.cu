@@ -1,0 +1,329 @@
+// bake_wave.cu -- warp-local wavefront kernel for shadowed per-vertex SH transfer (the headline kernel).
+//
+// Contract: reference bake_SH (src/raytracing/raytracing.cpp:320-360) with renderSH at depth 1 (:228-278); same
+// results as bake_kernel (bake.cu).  Any-hit visibility is order independent, so instead of one stack per ray the
+// warp keeps two work stacks in shared memory and runs every step in lockstep:
+//
+//   per vertex (one persistent warp):
+//     build_entry_list      chain of nodes containing the shared origin -> candidate boxes (entry_list.cuh)
+//     scan                  32 rays x all candidate boxes; every hit becomes an item
+//                             subtree candidate  -> node stack  (ray, node)
+//                             leaf candidate     -> leaf stack  (ray, first triangle, count bits)
+//     node step             pops 32 (ray, node) items: each lane decodes ONE 80-byte node, tests its 8 child boxes and
+//                           pushes (ray, child) / (ray, leaf) items (ballot/popc compaction)
+//     leaf step             pops 32 (ray, leaf) items: each lane runs <= 3 pinned triangle tests, sets the occlusion bit
+//     project               every unoccluded sample direction -> SH basis in registers, shuffle reduction, row store
+//
+// Items of rays that are already known to be occluded are dropped when popped.  If a stack is full the lane falls
+// back to an ordinary stack traversal of that subtree (Trav::run), so capacity never affects results.
+#include "kernels.h"
+#include "entry_list.cuh"
+
+namespace prt {
+
+namespace {
+
+constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples per vertex)
+constexpr int kNodeCap = 256, kLeafCap = 256;
+
+struct WaveShared {
+    EntryList el;
+    uint32_t occl[kMaxS / 32];          // bit s (reference sample index): primary ray s is occluded
+    uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
+    uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
+};
+
+__device__ __forceinline__ float fast_rcp(float d) {
+    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+    return __frcp_rn(d);
+}
+
+// Tests the 8 quantised child boxes of one node against a ray (interval [0, inf)); bit s of the result = slot s hit.
+__device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o,
+                                                   const float idx, const float idy, const float idz) {
+    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
+    const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
+    const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
+    const float ax = (__uint_as_float(n0.x) - o.x) * idx;
+    const float ay = (__uint_as_float(n0.y) - o.y) * idy;
+    const float az = (__uint_as_float(n0.z) - o.z) * idz;
+    const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+        const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+        const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
+        const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
+        const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int sh = 8 * j;
+            const float t0x = (float)((nearx >> sh) & 0xFFu) * sx + ax;
+            const float t0y = (float)((neary >> sh) & 0xFFu) * sy + ay;
+            const float t0z = (float)((nearz >> sh) & 0xFFu) * sz + az;
+            const float t1x = (float)((farx >> sh) & 0xFFu) * sx + ax;
+            const float t1y = (float)((fary >> sh) & 0xFFu) * sy + ay;
+            const float t1z = (float)((farz >> sh) & 0xFFu) * sz + az;
+            const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+            const float tmax = fminf(fminf(t1x, t1y), t1z);
+            if (tmin <= tmax) hits |= 1u << (4 * h + j);
+        }
+    }
+    return hits;
+}
+
+template <int ORDER, bool TRACE>
+__global__ void __launch_bounds__(256, 3) bake_wave_kernel(const BakeArgs A) {
+    constexpr int N2 = ORDER * ORDER;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WaveShared &W = reinterpret_cast<WaveShared *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float sgn = A.cs_phase ? -1.0f : 1.0f;
+    const int S = A.S, words = A.vis_words;
+    unsigned long long cand_tests = 0ull;
+    uint32_t node_visits = 0u, tri_tests = 0u;
+
+    for (;;) {
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(A.counter, 1u);
+        v = __shfl_sync(kFull, v, 0);
+        if (v >= A.n_verts) break;
+
+        const float *pp = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.pos) + (size_t)v * A.stride);
+        const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
+        const f3 N = mk3(__ldg(np), __ldg(np + 1), __ldg(np + 2));
+        const f3 P = mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2));
+        const Frame fr = make_frame(N);
+        const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
+
+        for (int w = lane; w < words; w += 32) W.occl[w] = 0u;
+        int n_cand = 0;
+        if (TRACE) {
+            n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
+            cand_tests += (unsigned long long)n_cand * (unsigned long long)S;
+        }
+        __syncwarp();
+
+        if (TRACE) {
+            int base = 0, nn = 0, ln = 0;             // warp-uniform: next sample, node-stack fill, leaf-stack fill
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u;       // candidate hits of the lane's scanned ray not yet queued
+            uint32_t sproc = 0u;
+            for (;;) {
+                // ---- emit pending (ray, candidate) items while one more warp-wide append fits ----------------------
+                bool pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
+                while (pending && nn <= kNodeCap - 32 && ln <= kLeafCap - 32) {
+                    int k = -1;
+                    if (m0) { k = __ffs(m0) - 1; m0 &= m0 - 1u; }
+                    else if (m1) { k = 32 + __ffs(m1) - 1; m1 &= m1 - 1u; }
+                    else if (m2) { k = 64 + __ffs(m2) - 1; m2 &= m2 - 1u; }
+                    const bool has = k >= 0;
+                    const float4 g = W.el.cb[has ? k : 0];
+                    const uint32_t gx = __float_as_uint(g.z), gy = __float_as_uint(g.w);
+                    const bool leaf = has && gy <= 0x00FFFFFFu;
+                    const unsigned hb = __ballot_sync(kFull, has), lb = __ballot_sync(kFull, leaf), ib = hb & ~lb;
+                    if (leaf) W.lq[ln + __popc(lb & lt_mask)] = make_uint2(sproc | (gy << 16), gx);
+                    else if (has) W.nq[nn + __popc(ib & lt_mask)] = make_uint2(sproc, gx);
+                    ln += __popc(lb); nn += __popc(ib);
+                    pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
+                }
+                // ---- scan the next 32 rays against the candidate boxes ------------------------------------------------
+                if (!pending && base < S && nn <= kNodeCap / 2 && ln <= kLeafCap / 2) {
+                    const int i = base + lane;
+                    base += 32;
+                    if (i < S) {
+                        const float4 smp = __ldg(&A.samples[i]);
+                        const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
+                        uint32_t cm[3];
+                        scan_entry_list(W.el, n_cand, fast_rcp(d.x), fast_rcp(d.y), fast_rcp(d.z), cm);
+                        m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
+                        sproc = (uint32_t)i;
+                    }
+                    continue;
+                }
+                if (nn == 0 && ln == 0) { if (!pending && base >= S) break; else continue; }
+                __syncwarp();
+                if (ln >= 32 || nn == 0) {
+                    // ---- leaf step ------------------------------------------------------------------------------------
+                    const int cnt = min(ln, 32);
+                    ln -= cnt;
+                    if (lane < cnt) {
+                        const uint2 it = W.lq[ln + lane];
+                        const float4 smp = __ldg(&A.samples[it.x & 0xFFFFu]);
+                        const uint32_t sref = __float_as_uint(smp.w);
+                        if (!((W.occl[sref >> 5] >> (sref & 31u)) & 1u)) {
+                            const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
+                            uint32_t bits = it.x >> 16;
+                            while (bits) {
+                                const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+                                bits &= bits - 1u;
+                                float t; uint32_t prim;
+                                tri_tests++;
+                                if (tri_hit(A.tris, it.y + b, org, d, 0.0f, INFINITY, false, t, prim)) {
+                                    atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // ---- node step ------------------------------------------------------------------------------------
+                    const int cnt = min(nn, 32);
+                    nn -= cnt;
+                    uint2 it = make_uint2(0u, 0u);
+                    bool has = lane < cnt;
+                    if (has) it = W.nq[nn + lane];
+                    __syncwarp();                   // all pops are done before anybody pushes
+                    uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
+                    f3 d = mk3(0.f, 0.f, 1.f);
+                    if (has) {
+                        const float4 smp = __ldg(&A.samples[it.x]);
+                        const uint32_t sref = __float_as_uint(smp.w);
+                        has = !((W.occl[sref >> 5] >> (sref & 31u)) & 1u);
+                        if (has) {
+                            d = to_world(fr, mk3(smp.x, smp.y, smp.z));
+                            const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
+                            const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
+                            const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, fast_rcp(d.x), fast_rcp(d.y), fast_rcp(d.z));
+                            imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
+                            inner8 = hits & imask; leaf8 = hits & ~imask;
+                            node_visits++;
+                        }
+                    }
+                    // push hit children (any order: any-hit is order independent)
+                    while (__any_sync(kFull, inner8 != 0u)) {
+                        const bool p = inner8 != 0u;
+                        uint32_t child = 0u;
+                        if (p) { const uint32_t s = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u; child = child_base + __popc(imask & ((1u << s) - 1u)); }
+                        const unsigned pb = __ballot_sync(kFull, p);
+                        const int pos = nn + __popc(pb & lt_mask);
+                        if (p) {
+                            if (pos < kNodeCap) W.nq[pos] = make_uint2(it.x, child);
+                            else {
+                                // stack full: ordinary traversal of this subtree (rare)
+                                Trav tr; tr.reset_counters();
+                                tr.init(org, d, 0.0f, INFINITY); tr.start_group(child, 0x80000000u);
+                                if (tr.template run<true>(A.nodes, A.tris, 0, false) == TRAV_HIT) {
+                                    const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w));
+                                    atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                    inner8 = 0u; leaf8 = 0u;
+                                }
+                                node_visits += tr.n_node_visits; tri_tests += tr.n_tri_tests;
+                            }
+                        }
+                        nn = min(nn + __popc(pb), kNodeCap);
+                    }
+                    while (__any_sync(kFull, leaf8 != 0u)) {
+                        const bool p = leaf8 != 0u;
+                        uint32_t tri0 = 0u, bits = 0u;
+                        if (p) {
+                            const uint32_t s = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
+                            const uint32_t meta = ((s < 4u ? meta_lo : meta_hi) >> (8u * (s & 3u))) & 0xFFu;
+                            tri0 = tri_base + (meta & 31u); bits = meta >> 5;
+                        }
+                        const unsigned pb = __ballot_sync(kFull, p);
+                        const int pos = ln + __popc(pb & lt_mask);
+                        if (p) {
+                            if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
+                            else {
+                                while (bits) {
+                                    const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+                                    bits &= bits - 1u;
+                                    float t; uint32_t prim;
+                                    tri_tests++;
+                                    if (tri_hit(A.tris, tri0 + b, org, d, 0.0f, INFINITY, false, t, prim)) {
+                                        const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w));
+                                        atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                        leaf8 = 0u;
+                                        break;
+                                    }
+                                }
+                            }
+                        }
+                        ln = min(ln + __popc(pb), kLeafCap);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- projection: L = Y_lm(dir) for every unoccluded sample (raytracing.cpp:226,257-261,348) ---------------
+        float acc[N2];
+#pragma unroll
+        for (int k = 0; k < N2; k++) acc[k] = 0.f;
+        for (int i = lane; i < S; i += 32) {
+            const float4 smp = __ldg(&A.samples[i]);
+            const uint32_t sref = __float_as_uint(smp.w);
+            if ((W.occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
+            const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
+            float y[N2];
+            sh_eval<ORDER>(d.z, d.x, d.y, sgn, y);
+#pragma unroll
+            for (int k = 0; k < N2; k++) acc[k] += y[k];
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < N2; k++) {
+            const float s = warp_sum(acc[k]);
+            if (lane == k) mine = s;
+        }
+        if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;       // raytracing.cpp:350
+        if (A.vis) {
+            for (int w = lane; w < words; w += 32) {
+                const int rem = S - 32 * w;
+                const uint32_t valid = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+                A.vis[(size_t)v * words + w] = ~W.occl[w] & valid;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.work) {
+        const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
+        if (lane == 0) { atomicAdd(&A.work[0], nv); atomicAdd(&A.work[1], nt); atomicAdd(&A.work[2], cand_tests); }
+    }
+}
+
+template <int ORDER, bool TRACE>
+cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
+    const size_t smem = sizeof(WaveShared) * (size_t)(block / 32);
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WaveShared) * 8));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (*grid <= 0) {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_wave_kernel<ORDER, TRACE>, block, smem);
+        if (e != cudaSuccess) return e;
+        *grid = n_sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int warps_per_block = block / 32;
+    const long long need = ((long long)A.n_verts + warps_per_block - 1) / warps_per_block;
+    if (need < *grid) *grid = (int)(need > 0 ? need : 1);
+    bake_wave_kernel<ORDER, TRACE><<<*grid, block, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+template <int ORDER>
+cudaError_t launch_wave_o(const BakeArgs &A, bool trace, int *grid, int block, int n_sms, cudaStream_t st) {
+    return trace ? launch_wave_t<ORDER, true>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false>(A, grid, block, n_sms, st);
+}
+
+}  // namespace
+
+int bake_wave_max_samples() { return kMaxS; }
+
+cudaError_t launch_bake_wave(const BakeArgs &A, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t st) {
+    switch (order) {
+    case 1: return launch_wave_o<1>(A, trace, grid, block, n_sms, st);
+    case 2: return launch_wave_o<2>(A, trace, grid, block, n_sms, st);
+    case 3: return launch_wave_o<3>(A, trace, grid, block, n_sms, st);
+    case 4: return launch_wave_o<4>(A, trace, grid, block, n_sms, st);
+    case 5: return launch_wave_o<5>(A, trace, grid, block, n_sms, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace prt

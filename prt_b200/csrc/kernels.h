@@ -35,6 +35,9 @@ cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int bl
 // pair-queue kernel for the shadowed (trace = true) and unshadowed Monte-Carlo (trace = false) modes, S <= bake_shadow_max_samples()
 cudaError_t launch_bake_shadow(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_shadow_max_samples();
+// warp-local wavefront kernel (bake_wave.cu), same modes / limits
+cudaError_t launch_bake_wave(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
+int bake_wave_max_samples();
 cudaError_t launch_trace_any(const Node8 *, const Tri48 *, const float *rays, uint32_t n, uint8_t *out, cudaStream_t);
 cudaError_t launch_trace_closest(const Node8 *, const Tri48 *, const float *rays, uint32_t n, float *out_t,
                                  uint32_t *out_prim, float *out_ng, cudaStream_t);
