@@ -61,7 +61,8 @@ class BakeStats(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "csrc", "libprt_b200.so")
+    # PRT_B200_LIB selects an alternative in-tree build (kernel tuning experiments)
+    return os.environ.get("PRT_B200_LIB") or os.path.join(_HERE, "csrc", "libprt_b200.so")
 
 
 def load_library():

@@ -24,7 +24,13 @@ namespace prt {
 namespace {
 
 constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples per vertex)
-constexpr int kNodeCap = 256, kLeafCap = 256;
+#ifndef PRT_WAVE_CAP
+#define PRT_WAVE_CAP 256
+#endif
+#ifndef PRT_WAVE_MINB
+#define PRT_WAVE_MINB 3
+#endif
+constexpr int kNodeCap = PRT_WAVE_CAP, kLeafCap = PRT_WAVE_CAP;
 
 struct WaveShared {
     EntryList el;
@@ -32,11 +38,6 @@ struct WaveShared {
     uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
     uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
 };
-
-__device__ __forceinline__ float fast_rcp(float d) {
-    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
-    return __frcp_rn(d);
-}
 
 // Tests the 8 quantised child boxes of one node against a ray (interval [0, inf)); bit s of the result = slot s hit.
 __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o,
@@ -74,7 +75,7 @@ __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, con
 }
 
 template <int ORDER, bool TRACE>
-__global__ void __launch_bounds__(256, 3) bake_wave_kernel(const BakeArgs A) {
+__global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WaveShared &W = reinterpret_cast<WaveShared *>(smem_raw)[threadIdx.x >> 5];
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256, 3) bake_wave_kernel(const BakeArgs A) {
                         const float4 smp = __ldg(&A.samples[i]);
                         const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
                         uint32_t cm[3];
-                        scan_entry_list(W.el, n_cand, fast_rcp(d.x), fast_rcp(d.y), fast_rcp(d.z), cm);
+                        scan_entry_list(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), cm);
                         m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
                         sproc = (uint32_t)i;
                     }
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256, 3) bake_wave_kernel(const BakeArgs A) {
                             d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                             const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
                             const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
-                            const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, fast_rcp(d.x), fast_rcp(d.y), fast_rcp(d.z));
+                            const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                             imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                             inner8 = hits & imask; leaf8 = hits & ~imask;
                             node_visits++;

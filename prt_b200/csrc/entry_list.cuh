@@ -102,6 +102,36 @@ __device__ __forceinline__ int build_entry_list(const Node8 *nodes, const f3 O, 
     return n;
 }
 
+// Bit k of the result words = candidate k is a leaf (triangle group) rather than a subtree root.
+__device__ __forceinline__ void entry_list_leaf_mask(const EntryList &W, const int n, const int lane, uint32_t lm[3]) {
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+        const int k = 32 * w + lane;
+        const bool leaf = k < n && __float_as_uint(W.cb[k].w) <= 0x00FFFFFFu;
+        lm[w] = __ballot_sync(kFull, leaf);
+    }
+}
+
+// approximate reciprocal for box tests only (never used by the pinned triangle test)
+__device__ __forceinline__ float rcp_box(float d) {
+    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+}
+
+// exclusive prefix sum over the warp of two 16-bit counters packed in one word; total returned through `total`
+__device__ __forceinline__ uint32_t warp_excl_scan_packed(uint32_t v, const int lane, uint32_t &total) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    total = __shfl_sync(kFull, incl, 31);
+    return incl - v;
+}
+
 // Tests the lane's ray (origin = list origin, interval [0, inf)) against all candidate boxes; one bit per candidate.
 __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n, const float idx, const float idy, const float idz, uint32_t m[3]) {
     const float aix = fabsf(idx), aiy = fabsf(idy), aiz = fabsf(idz);
@@ -113,9 +143,8 @@ __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n,
         for (int k = 32 * w; k < k1; k++) {
             const float4 a = W.ca[k], b = W.cb[k];
             const float tx = a.x * idx, ty = a.y * idy, tz = a.z * idz;
-            const float hx = a.w * aix, hy = b.x * aiy, hz = b.y * aiz;
-            const float tmin = fmaxf(fmaxf(tx - hx, ty - hy), tz - hz);
-            const float tmax = fminf(fminf(tx + hx, ty + hy), tz + hz);
+            const float tmin = fmaxf(fmaxf(fmaf(-a.w, aix, tx), fmaf(-b.x, aiy, ty)), fmaf(-b.y, aiz, tz));
+            const float tmax = fminf(fminf(fmaf(a.w, aix, tx), fmaf(b.x, aiy, ty)), fmaf(b.y, aiz, tz));
             if (tmin <= tmax && tmax >= 0.0f) bits |= bit;
             bit += bit;
         }

@@ -164,3 +164,70 @@ extern "C" void hc_entry_stats(void *h, const float *org, const float *nrm, cons
     out[0] = (double)cands.size(); out[1] = (double)box_hits / nrays; out[2] = (double)nv / nrays; out[3] = (double)nt / nrays;
     out[4] = (double)occl / nrays; out[5] = expanded;
 }
+
+// Experiment: directional binning of entry-list candidates.  Each candidate box is bounded by a cone (bounding sphere seen
+// from the origin) and registered in the cells of a G x G grid over the unit disk (the projected hemisphere, local frame)
+// that the cone can touch.  Reports the mean number of candidates a ray must test: (a) its own cell, (b) the union of the
+// cells of its 32-ray bundle (rays given in processing order).
+extern "C" void hc_grid_stats(void *h, const float *org, const float *nrm, const float *local_dirs, uint32_t nrays, int G, double *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    std::vector<Cand> cands; std::vector<uint32_t> queue; queue.push_back(0);
+    while (!queue.empty()) {
+        uint32_t x = queue.back(); queue.pop_back();
+        const Node8 &nd = b->nodes[x];
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            Cand c; decode_child(nd, s, c.lo, c.hi);
+            float mx = 0.f, far2 = 0.f; bool inside = true;
+            for (int a = 0; a < 3; a++) {
+                float l = c.lo[a] - org[a], hh = c.hi[a] - org[a];
+                mx += std::max(nrm[a] * l, nrm[a] * hh);
+                far2 = std::max(far2, std::max(std::fabs(l), std::fabs(hh)));
+                if (org[a] < c.lo[a] || org[a] > c.hi[a]) inside = false;
+            }
+            if (mx < -1e-5f * far2) continue;
+            bool inner = (nd.imask >> s) & 1;
+            if (inner && inside) { queue.push_back(nd.child_base + __builtin_popcount(nd.imask & ((1u << s) - 1u))); continue; }
+            cands.push_back(c);
+        }
+    }
+    // local frame
+    f3 N = mk3(nrm[0], nrm[1], nrm[2]); Frame fr = make_frame(N);
+    std::vector<std::vector<uint64_t>> cell(G * G, std::vector<uint64_t>(2, 0));
+    int n_all = 0;
+    for (size_t k = 0; k < cands.size() && k < 128; k++) {
+        const Cand &c = cands[k];
+        float cc[3], r2 = 0.f, d2 = 0.f;
+        for (int a = 0; a < 3; a++) { cc[a] = 0.5f * (c.lo[a] + c.hi[a]) - org[a]; float e = 0.5f * (c.hi[a] - c.lo[a]); r2 += e * e; d2 += cc[a] * cc[a]; }
+        int x0 = 0, x1 = G - 1, y0 = 0, y1 = G - 1;
+        if (d2 > r2 * 1.0001f) {
+            float d = std::sqrt(d2), sina = std::sqrt(r2) / d, cosa = std::sqrt(std::max(0.f, 1.f - sina * sina));
+            float rho = std::sqrt(std::max(0.f, 2.f - 2.f * cosa)) * 1.001f + 1e-4f;
+            float ax = (fr.right.x * cc[0] + fr.right.y * cc[1] + fr.right.z * cc[2]) / d, ay = (fr.up.x * cc[0] + fr.up.y * cc[1] + fr.up.z * cc[2]) / d;
+            x0 = std::max(0, (int)std::floor((ax - rho + 1.f) * 0.5f * G)); x1 = std::min(G - 1, (int)std::floor((ax + rho + 1.f) * 0.5f * G));
+            y0 = std::max(0, (int)std::floor((ay - rho + 1.f) * 0.5f * G)); y1 = std::min(G - 1, (int)std::floor((ay + rho + 1.f) * 0.5f * G));
+        } else n_all++;
+        for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) cell[y * G + x][k >> 6] |= 1ull << (k & 63);
+    }
+    double own = 0, uni = 0; uint64_t missed = 0;
+    for (uint32_t base = 0; base + 32 <= nrays; base += 32) {
+        uint64_t u[2] = {0, 0};
+        for (int l = 0; l < 32; l++) {
+            const float *d = local_dirs + 3 * (size_t)(base + l);
+            int cx = std::min(G - 1, std::max(0, (int)std::floor((d[0] + 1.f) * 0.5f * G))), cy = std::min(G - 1, std::max(0, (int)std::floor((d[1] + 1.f) * 0.5f * G)));
+            const auto &m = cell[cy * G + cx];
+            own += __builtin_popcountll(m[0]) + __builtin_popcountll(m[1]);
+            u[0] |= m[0]; u[1] |= m[1];
+            // verify conservativeness: every candidate the ray's box test hits must be in its cell mask
+            f3 wd = to_world(fr, mk3(d[0], d[1], d[2]));
+            float id[3] = { safe_rcp(wd.x), safe_rcp(wd.y), safe_rcp(wd.z) };
+            for (size_t k = 0; k < cands.size() && k < 128; k++) {
+                float t0 = 0.f, t1 = INFINITY;
+                for (int a = 0; a < 3; a++) { float ta = (cands[k].lo[a] - org[a]) * id[a], tb = (cands[k].hi[a] - org[a]) * id[a]; t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb)); }
+                if (t0 <= t1 && !((m[k >> 6] >> (k & 63)) & 1)) missed++;
+            }
+        }
+        uni += 32.0 * (__builtin_popcountll(u[0]) + __builtin_popcountll(u[1]));
+    }
+    out[0] = (double)cands.size(); out[1] = own / nrays; out[2] = uni / nrays; out[3] = (double)missed; out[4] = n_all;
+}

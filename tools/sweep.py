@@ -58,7 +58,14 @@ for combo in itertools.product(*values) if values else [()]:
         assert rc == 0, L.prt_last_error()
         torch.cuda.synchronize()
         ms.append(ctx.last_bake_stats().kernel_ms)
+    ctx.set_tuning(count_work=1)
+    L.prt_bake_transfer_device(ctx.h, scene.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, n, 0,
+                               C.byref(params), C.c_void_p(d_out.data_ptr()), None, C.c_void_p(stream.cuda_stream))
+    torch.cuda.synchronize()
     st = ctx.last_bake_stats()
+    ctx.set_tuning(count_work=0)
     best = min(ms)
     print(json.dumps({"knobs": kw, "kernel_ms": best, "grays_per_s": n * S / best / 1e6, "grid": st.grid, "block": st.block,
+                      "nodes_per_ray": round(st.node_visits / (n * S), 2), "tris_per_ray": round(st.tri_tests / (n * S), 2),
+                      "cands_per_ray": round(st.cand_tests / (n * S), 2),
                       "all_ms": [round(m, 2) for m in ms]}), flush=True)
