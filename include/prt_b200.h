@@ -130,6 +130,36 @@ typedef struct {
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
 
+/* ---- image-based lighting (BASELINE config 2) ---------------------------------------------------------------------
+ * Texture semantics the GL driver leaves open are pinned: FP32 storage, GL cube (sc,tc) table ==
+ * cubeCoordToWorld (SH_function.h:104-109), bilinear centres at (i+0.5)/N, seamless re-projection of off-face taps,
+ * 2x2-box mips, trilinear = lerp of two levels.  Cube buffers are [6][n][n][3] floats, faces +X,-X,+Y,-Y,+Z,-Z; mip
+ * chains are stored level after level. */
+typedef struct prt_env prt_env;
+
+/* load_hdr + LightProbe::equirectangular_to_cubemap + CubeMap::generateMipmap (util.cpp:6-24, gl.cpp:581-591,454-460;
+ * app.cpp:41-46): equirect RGB float image (top row first, as stb_image returns it) -> GPU-resident cube + full mip chain.
+ * cube_size = 512 in the reference (app.cpp:44). */
+int prt_env_create(prt_ctx *, const float *equirect_rgb, int w, int h, int cube_size, prt_env **out);
+void prt_env_destroy(prt_env *);
+int prt_env_levels(const prt_env *);
+int prt_env_get_cube(prt_env *, int level, float *out_rgb);
+/* LightProbe::irradiance (gl.cpp:569-579, irradiance.frag:9-43); n_out = 32 in the reference (app.cpp:55) */
+int prt_env_irradiance(prt_env *, int n_out, float *out_rgb);
+/* LightProbe::prefilter (gl.cpp:546-567, prefilter.frag:64-107); reference: n_out 256, mips 5, 1024 samples (app.cpp:58).
+ * out_rgb holds the mips one after another: sum over m of 6*(n_out>>m)^2*3 floats; roughness = m/(mips-1). */
+int prt_env_prefilter(prt_env *, int n_out, int mips, int n_samples, float *out_rgb);
+/* brdfLUT.render_to(screen_quad) with brdf.frag (app.cpp:61-63, brdf.frag:69-113): out_rg[h][w][2] = (A,B),
+ * NdotV = (x+0.5)/w, roughness = (y+0.5)/h; reference 512 x 512, 1024 samples. */
+int prt_brdf_lut(prt_ctx *, int w, int h, int n_samples, float *out_rg);
+/* environment -> SH coefficients, out_rgb_coeffs[order^2][3] (k = l(l+1)+m, sh-space (z,x,y)).
+ * method 0: lat-long quadrature of bak/projectSH.comp:63-151 (size = 256 phi columns, theta step 2pi/size);
+ * method 1: cube-texel quadrature of bak/image_projectSH.comp:64-133 (size = 64, weight |p|^-3 * 4/size^2). */
+int prt_env_project_sh(prt_env *, int order, int method, int size, float *out_rgb_coeffs);
+/* Ramamoorthi-Hanrahan polynomial pack consumed by the viewer's SH_Irad (common/SH.glsl:17-36; precomp_projectSH.comp:
+ * 23,118-139): L9_rgb[9][3] -> out28 = Ar,Ag,Ab,Br,Bg,Bb (vec4 each) then C = (rgb,1). Host helper. */
+int prt_sh_pack_rh(const float *L9_rgb, float *out28);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,17 @@ int prt_o_bake_transfer(const prt_o_scene *, const float *pos, const float *nrm,
                         uint32_t n_verts, uint32_t vertex_id_base, const prt_o_bake_params *,
                         float *out_coeffs, uint32_t *out_vis, int n_threads, int faithful, uint64_t *counters);
 
+/* ---- image-based lighting (oracle/env.c); cube buffers: levels concatenated, [6][n][n][3] floats per level ---- */
+size_t prt_o_cube_floats(int n0, int levels);
+int prt_o_cube_levels(int n0);
+void prt_o_cube_sample(const float *cube, int n0, int levels, const float d[3], float lod, float out[3]);
+void prt_o_env_equirect_to_cube(const float *eq, int w, int h, int n0, int levels, float *cube);
+void prt_o_env_irradiance(const float *cube, int n0, int levels, int n_out, float *out);
+void prt_o_env_prefilter(const float *cube, int n0, int levels, int n_out, int mips, int n_samples, float *out);
+void prt_o_brdf_lut(int w, int h, int n_samples, float *out);
+void prt_o_env_project_sh(const float *cube, int n0, int levels, int order, int method, int size, float *out);
+void prt_o_sh_pack_rh(const float *L, float *out28);
+
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void prt_o_sincos2pi(float v, float *s, float *c);

@@ -59,6 +59,17 @@ def lib():
         L.prt_o_philox.argtypes = [u32p, u32p, u32p]
         L.prt_o_sincos2pi.argtypes = [C.c_float, f32p, f32p]
         L.prt_o_hw_threads.restype = C.c_int
+        L.prt_o_cube_floats.restype = C.c_size_t
+        L.prt_o_cube_floats.argtypes = [C.c_int, C.c_int]
+        L.prt_o_cube_levels.restype = C.c_int
+        L.prt_o_cube_levels.argtypes = [C.c_int]
+        L.prt_o_cube_sample.argtypes = [vp, C.c_int, C.c_int, f32p, C.c_float, f32p]
+        L.prt_o_env_equirect_to_cube.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.prt_o_env_irradiance.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.prt_o_env_prefilter.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.prt_o_brdf_lut.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+        L.prt_o_env_project_sh.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.prt_o_sh_pack_rh.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -157,3 +168,60 @@ def sincos2pi(v: float):
 
 def hw_threads() -> int:
     return lib().prt_o_hw_threads()
+
+
+class EnvCube:
+    """oracle twin of prt_b200.LightProbe (oracle/env.c)."""
+
+    def __init__(self, equirect: np.ndarray, cube_size: int = 512):
+        eq = np.ascontiguousarray(equirect, np.float32)
+        self.n0 = cube_size
+        self.levels = lib().prt_o_cube_levels(cube_size)
+        self.data = np.zeros(lib().prt_o_cube_floats(cube_size, self.levels), np.float32)
+        lib().prt_o_env_equirect_to_cube(_ptr(eq), eq.shape[1], eq.shape[0], cube_size, self.levels, _ptr(self.data))
+
+    def cube(self, level=0) -> np.ndarray:
+        o = lib().prt_o_cube_floats(self.n0, level)
+        n = self.n0 >> level
+        return self.data[o:o + 6 * n * n * 3].reshape(6, n, n, 3)
+
+    def sample(self, d, lod=0.0) -> np.ndarray:
+        d = np.asarray(d, np.float32)
+        out = np.zeros(3, np.float32)
+        f32p = C.POINTER(C.c_float)
+        lib().prt_o_cube_sample(_ptr(self.data), self.n0, self.levels, d.ctypes.data_as(f32p), C.c_float(lod), out.ctypes.data_as(f32p))
+        return out
+
+    def irradiance(self, n_out=32) -> np.ndarray:
+        out = np.zeros((6, n_out, n_out, 3), np.float32)
+        lib().prt_o_env_irradiance(_ptr(self.data), self.n0, self.levels, n_out, _ptr(out))
+        return out
+
+    def prefilter(self, n_out=256, mips=5, n_samples=1024) -> list:
+        sizes = [n_out >> m for m in range(mips)]
+        flat = np.zeros(sum(6 * n * n * 3 for n in sizes), np.float32)
+        lib().prt_o_env_prefilter(_ptr(self.data), self.n0, self.levels, n_out, mips, n_samples, _ptr(flat))
+        out, o = [], 0
+        for n in sizes:
+            out.append(flat[o:o + 6 * n * n * 3].reshape(6, n, n, 3))
+            o += 6 * n * n * 3
+        return out
+
+    def project_sh(self, order=3, method=0, size=None) -> np.ndarray:
+        size = size or (256 if method == 0 else 64)
+        out = np.zeros((order * order, 3), np.float32)
+        lib().prt_o_env_project_sh(_ptr(self.data), self.n0, self.levels, order, method, size, _ptr(out))
+        return out
+
+
+def brdf_lut(w=512, h=512, n_samples=1024) -> np.ndarray:
+    out = np.zeros((h, w, 2), np.float32)
+    lib().prt_o_brdf_lut(w, h, n_samples, _ptr(out))
+    return out
+
+
+def sh_pack_rh(L9) -> np.ndarray:
+    L9 = np.ascontiguousarray(L9, np.float32)
+    out = np.zeros(28, np.float32)
+    lib().prt_o_sh_pack_rh(_ptr(L9), _ptr(out))
+    return out

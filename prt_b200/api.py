@@ -17,6 +17,8 @@ ABI_SYMBOLS = [
     "prt_scene_create", "prt_scene_destroy", "prt_scene_get_info", "prt_trace_any_hit", "prt_trace_closest_hit",
     "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_scatter_sh9",
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
+    "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
+    "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
 ]
 
 
@@ -96,6 +98,16 @@ def load_library():
     L.prt_scatter_sh9.argtypes = [vp, C.c_int32, u32, vp, sz, sz]
     L.prt_bake_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]
     L.prt_ctx_last_bake_stats.argtypes = [vp, C.POINTER(BakeStats)]
+    L.prt_env_create.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp)]
+    L.prt_env_destroy.argtypes = [vp]
+    L.prt_env_destroy.restype = None
+    L.prt_env_levels.argtypes = [vp]
+    L.prt_env_get_cube.argtypes = [vp, i32, vp]
+    L.prt_env_irradiance.argtypes = [vp, i32, vp]
+    L.prt_env_prefilter.argtypes = [vp, i32, i32, i32, vp]
+    L.prt_brdf_lut.argtypes = [vp, i32, i32, i32, vp]
+    L.prt_env_project_sh.argtypes = [vp, i32, i32, i32, vp]
+    L.prt_sh_pack_rh.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -243,3 +255,70 @@ def sample_table(params: BakeParams):
     uv, dirs = np.zeros((S, 2), np.float32), np.zeros((S, 3), np.float32)
     _check(load_library().prt_bake_sample_table(C.byref(params), _ptr(uv), _ptr(dirs)), "prt_bake_sample_table")
     return uv, dirs
+
+
+class LightProbe:
+    """reference ``LightProbe`` passes (src/opengl/gl.h:273-298, gl.cpp:543-591) + ``load_hdr`` upload (util.cpp:6-24) on the GPU.
+
+    ``equirect`` is the [h, w, 3] float32 image stb_image returns for data/hdr/newport_loft.hdr (top row first)."""
+
+    def __init__(self, equirect: np.ndarray, cube_size: int = 512, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.L = self.ctx.L
+        eq = np.ascontiguousarray(equirect, np.float32)
+        if eq.ndim != 3 or eq.shape[2] != 3:
+            raise PRTError("LightProbe: equirect must be [h, w, 3] float32")
+        h = C.c_void_p()
+        _check(self.L.prt_env_create(self.ctx.h, _ptr(eq), eq.shape[1], eq.shape[0], cube_size, C.byref(h)), "prt_env_create")
+        self.h, self.cube_size = h, cube_size
+        self.levels = self.L.prt_env_levels(h)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.L.prt_env_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def cube(self, level: int = 0) -> np.ndarray:
+        """equirectangular_to_cubemap (+ generateMipmap) result, [6, n, n, 3]."""
+        n = self.cube_size >> level
+        out = np.zeros((6, n, n, 3), np.float32)
+        _check(self.L.prt_env_get_cube(self.h, level, _ptr(out)), "prt_env_get_cube")
+        return out
+
+    def irradiance(self, n_out: int = 32) -> np.ndarray:
+        out = np.zeros((6, n_out, n_out, 3), np.float32)
+        _check(self.L.prt_env_irradiance(self.h, n_out, _ptr(out)), "prt_env_irradiance")
+        return out
+
+    def prefilter(self, n_out: int = 256, mips: int = 5, n_samples: int = 1024) -> list:
+        sizes = [n_out >> m for m in range(mips)]
+        flat = np.zeros(sum(6 * n * n * 3 for n in sizes), np.float32)
+        _check(self.L.prt_env_prefilter(self.h, n_out, mips, n_samples, _ptr(flat)), "prt_env_prefilter")
+        out, o = [], 0
+        for n in sizes:
+            out.append(flat[o:o + 6 * n * n * 3].reshape(6, n, n, 3))
+            o += 6 * n * n * 3
+        return out
+
+    def project_sh(self, order: int = 3, method: int = 0, size: int | None = None) -> np.ndarray:
+        size = size or (256 if method == 0 else 64)
+        out = np.zeros((order * order, 3), np.float32)
+        _check(self.L.prt_env_project_sh(self.h, order, method, size, _ptr(out)), "prt_env_project_sh")
+        return out
+
+
+def brdf_lut(w: int = 512, h: int = 512, n_samples: int = 1024, ctx: Context | None = None) -> np.ndarray:
+    """reference ``brdfLUT.render_to(screen_quad)`` with brdf.frag (app.cpp:61-63): [h, w, 2] = (A, B)."""
+    ctx = ctx or default_context()
+    out = np.zeros((h, w, 2), np.float32)
+    _check(ctx.L.prt_brdf_lut(ctx.h, w, h, n_samples, _ptr(out)), "prt_brdf_lut")
+    return out
+
+
+def sh_pack_rh(L9: np.ndarray) -> np.ndarray:
+    L9 = np.ascontiguousarray(L9, np.float32)
+    out = np.zeros(28, np.float32)
+    _check(load_library().prt_sh_pack_rh(_ptr(L9), _ptr(out)), "prt_sh_pack_rh")
+    return out

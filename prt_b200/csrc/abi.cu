@@ -5,6 +5,7 @@
 #include "bvh8.h"
 #include "kernels.h"
 #include "prt_math.cuh"
+#include "abi_internal.h"
 
 #include <algorithm>
 #include <chrono>
@@ -58,6 +59,10 @@ struct prt_scene {
     Tri48 *d_tris = nullptr;
     prt_scene_info info{};
 };
+
+int prt_set_error(int code, const std::string &msg) { return set_err(code, msg); }
+cudaStream_t prt_ctx_stream(prt_ctx *c) { return c->stream; }
+int prt_ctx_sms(const prt_ctx *c) { return c->n_sms; }
 
 extern "C" {
 
