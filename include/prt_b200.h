@@ -160,6 +160,31 @@ int prt_env_project_sh(prt_env *, int order, int method, int size, float *out_rg
  * 23,118-139): L9_rgb[9][3] -> out28 = Ar,Ag,Ab,Br,Bg,Bb (vec4 each) then C = (rgb,1). Host helper. */
 int prt_sh_pack_rh(const float *L9_rgb, float *out28);
 
+/* ---- light-probe GI: per-probe transfer capture and projection (BASELINE config 3) ----------------------------------
+ * SH_volume::precompute (volume.cpp:149-316) with the 64x64x6 G-buffer raster + readback replaced by closest-hit rays:
+ * for every probe and every direction d_i (solid angle w_i): sky and back-face hits are skipped (:246-249), the hit is
+ * binned into its surfel cluster (floor(pos), signed principal axis of the normal; :205-223) and
+ * transfer[probe][cluster] += SH9(sh-space direction) * w_i (:250-260).  Result = the CSR the viewer uploads
+ * (probe_range / ID_buffer / transfer_buffer, :265-295) plus the surfel table (primitive_buffer, :301-312), kept on the GPU.
+ * Surfel ids are the rank of the cluster key in (x,y,z,direction) lexicographic order (the reference numbers clusters
+ * first-seen, which depends on probe order; parity is defined up to that permutation).  n_dirs <= 4096. */
+typedef struct prt_csr prt_csr;
+int prt_probe_capture(prt_scene *, const float *probe_pos_xyz, uint32_t n_probes, const float *dirs_xyz, const float *solid_angles,
+                      uint32_t n_dirs, prt_csr **out);
+void prt_csr_destroy(prt_csr *);
+int prt_csr_sizes(const prt_csr *, uint32_t *n_probes, uint64_t *nnz, uint32_t *n_surfels, double *capture_kernel_ms);
+/* range[n_probes][2] (start,end), ids[nnz], transfer[nnz][9], surfels[n_surfels][6] (mean position, normalised mean normal),
+ * keys[n_surfels] (packed cluster keys, ascending); any pointer may be NULL */
+int prt_csr_download(const prt_csr *, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
+/* SH_volume::project_sh + precomp_projectSH.comp:32-143: radiance_rgba[n_surfels][4] -> out[n_probes][7][4]
+ * (Ar,Ag,Ab,Br,Bg,Bb,C of common/SH.glsl:1-7), FP32 instead of the reference's RGBA16F storage */
+int prt_probe_project(const prt_csr *, const float *radiance_rgba, float *out_sh_volumes);
+/* host helpers: probe grid positions (volume.cpp:83-90, x fastest), get_dirs (light_probe.cpp:137-152) and the cube-texel
+ * direction set of cubeCoordToWorld (SH_function.h:96-112) with the reference's solid angle 4/res^2/|c|^3 (volume.cpp:251-254) */
+int prt_probe_positions(const int32_t res[3], const float scene_size[3], float *out_pos_xyz);
+int prt_fibonacci_dirs(int32_t n, float *out_dirs_xyz);
+int prt_cube_dirs(int32_t res, float *out_dirs_xyz /*[6*res*res][3]*/, float *out_solid_angles);
+
 #ifdef __cplusplus
 }
 #endif

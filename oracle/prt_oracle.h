@@ -76,6 +76,18 @@ void prt_o_brdf_lut(int w, int h, int n_samples, float *out);
 void prt_o_env_project_sh(const float *cube, int n0, int levels, int order, int method, int size, float *out);
 void prt_o_sh_pack_rh(const float *L, float *out28);
 
+/* ---- probe capture / projection (oracle/probe.c) ---- */
+typedef struct prt_o_csr prt_o_csr;
+void prt_o_fibonacci_dirs(int n, float *dirs);
+void prt_o_cube_dirs(int res, float *dirs, float *weights);
+void prt_o_probe_positions(const int res[3], const float size[3], float *pos);
+prt_o_csr *prt_o_probe_capture(const prt_o_scene *, const float *probe_pos, uint32_t n_probes, const float *dirs,
+                               const float *weights, uint32_t n_dirs);
+void prt_o_csr_sizes(const prt_o_csr *, uint32_t *nnz, uint32_t *n_prim);
+void prt_o_csr_get(const prt_o_csr *, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
+void prt_o_csr_destroy(prt_o_csr *);
+void prt_o_probe_project(const prt_o_csr *, const float *radiance_rgba, float *out);
+
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void prt_o_sincos2pi(float v, float *s, float *c);

@@ -70,6 +70,15 @@ def lib():
         L.prt_o_brdf_lut.argtypes = [C.c_int, C.c_int, C.c_int, vp]
         L.prt_o_env_project_sh.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.prt_o_sh_pack_rh.argtypes = [vp, vp]
+        L.prt_o_fibonacci_dirs.argtypes = [C.c_int, vp]
+        L.prt_o_cube_dirs.argtypes = [C.c_int, vp, vp]
+        L.prt_o_probe_positions.argtypes = [vp, vp, vp]
+        L.prt_o_probe_capture.restype = vp
+        L.prt_o_probe_capture.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_uint32]
+        L.prt_o_csr_sizes.argtypes = [vp, u32p, u32p]
+        L.prt_o_csr_get.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.prt_o_csr_destroy.argtypes = [vp]
+        L.prt_o_probe_project.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -225,3 +234,50 @@ def sh_pack_rh(L9) -> np.ndarray:
     out = np.zeros(28, np.float32)
     lib().prt_o_sh_pack_rh(_ptr(L9), _ptr(out))
     return out
+
+
+def probe_positions(res, scene_size) -> np.ndarray:
+    res = np.asarray(res, np.int32); size = np.asarray(scene_size, np.float32)
+    out = np.zeros((int(np.prod(res)), 3), np.float32)
+    lib().prt_o_probe_positions(_ptr(res), _ptr(size), _ptr(out))
+    return out
+
+
+def fibonacci_dirs(n):
+    d = np.zeros((n, 3), np.float32)
+    lib().prt_o_fibonacci_dirs(n, _ptr(d))
+    return d, np.full(n, 4 * np.pi / n, np.float32)
+
+
+def cube_dirs(res):
+    d, w = np.zeros((6 * res * res, 3), np.float32), np.zeros(6 * res * res, np.float32)
+    lib().prt_o_cube_dirs(res, _ptr(d), _ptr(w))
+    return d, w
+
+
+class ProbeTransfer:
+    """oracle twin of prt_b200.ProbeTransfer (oracle/probe.c)."""
+
+    def __init__(self, scene: Scene, probe_pos, dirs, weights):
+        pp = np.ascontiguousarray(probe_pos, np.float32); d = np.ascontiguousarray(dirs, np.float32); w = np.ascontiguousarray(weights, np.float32)
+        self.h = lib().prt_o_probe_capture(scene.h, _ptr(pp), len(pp), _ptr(d), _ptr(w), len(d))
+        nnz, ns = C.c_uint32(), C.c_uint32()
+        lib().prt_o_csr_sizes(self.h, C.byref(nnz), C.byref(ns))
+        self.n_probes, self.nnz, self.n_surfels = len(pp), nnz.value, ns.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().prt_o_csr_destroy(self.h)
+            self.h = None
+
+    def download(self):
+        rng = np.zeros((self.n_probes, 2), np.uint32); ids = np.zeros(self.nnz, np.uint32); tr = np.zeros((self.nnz, 9), np.float32)
+        sf = np.zeros((self.n_surfels, 6), np.float32); keys = np.zeros(self.n_surfels, np.uint64)
+        lib().prt_o_csr_get(self.h, _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf), _ptr(keys))
+        return rng, ids, tr, sf, keys
+
+    def project(self, radiance_rgba) -> np.ndarray:
+        rad = np.ascontiguousarray(radiance_rgba, np.float32)
+        out = np.zeros((self.n_probes, 7, 4), np.float32)
+        lib().prt_o_probe_project(self.h, _ptr(rad), _ptr(out))
+        return out

@@ -19,6 +19,8 @@ ABI_SYMBOLS = [
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
+    "prt_probe_capture", "prt_csr_destroy", "prt_csr_sizes", "prt_csr_download", "prt_probe_project", "prt_probe_positions",
+    "prt_fibonacci_dirs", "prt_cube_dirs",
 ]
 
 
@@ -108,6 +110,15 @@ def load_library():
     L.prt_brdf_lut.argtypes = [vp, i32, i32, i32, vp]
     L.prt_env_project_sh.argtypes = [vp, i32, i32, i32, vp]
     L.prt_sh_pack_rh.argtypes = [vp, vp]
+    L.prt_probe_capture.argtypes = [vp, vp, u32, vp, vp, u32, C.POINTER(vp)]
+    L.prt_csr_destroy.argtypes = [vp]
+    L.prt_csr_destroy.restype = None
+    L.prt_csr_sizes.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(C.c_double)]
+    L.prt_csr_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.prt_probe_project.argtypes = [vp, vp, vp]
+    L.prt_probe_positions.argtypes = [vp, vp, vp]
+    L.prt_fibonacci_dirs.argtypes = [i32, vp]
+    L.prt_cube_dirs.argtypes = [i32, vp, vp]
     _LIB = L
     return L
 
@@ -322,3 +333,66 @@ def sh_pack_rh(L9: np.ndarray) -> np.ndarray:
     out = np.zeros(28, np.float32)
     _check(load_library().prt_sh_pack_rh(_ptr(L9), _ptr(out)), "prt_sh_pack_rh")
     return out
+
+
+def probe_positions(res, scene_size) -> np.ndarray:
+    """SH_volume::init probe grid (volume.cpp:83-90)."""
+    res = np.asarray(res, np.int32)
+    size = np.asarray(scene_size, np.float32)
+    out = np.zeros((int(np.prod(res)), 3), np.float32)
+    _check(load_library().prt_probe_positions(_ptr(res), _ptr(size), _ptr(out)), "prt_probe_positions")
+    return out
+
+
+def fibonacci_dirs(n: int):
+    """get_dirs (light_probe.cpp:137-152) with uniform solid angle 4 pi / n."""
+    d = np.zeros((n, 3), np.float32)
+    _check(load_library().prt_fibonacci_dirs(n, _ptr(d)), "prt_fibonacci_dirs")
+    return d, np.full(n, 4 * np.pi / n, np.float32)
+
+
+def cube_dirs(res: int):
+    d, w = np.zeros((6 * res * res, 3), np.float32), np.zeros(6 * res * res, np.float32)
+    _check(load_library().prt_cube_dirs(res, _ptr(d), _ptr(w)), "prt_cube_dirs")
+    return d, w
+
+
+class ProbeTransfer:
+    """SH_volume::precompute result (volume.cpp:149-316) on the GPU: CSR probe -> surfel transfer + surfel table."""
+
+    def __init__(self, scene: RTScene, probe_pos: np.ndarray, dirs: np.ndarray, weights: np.ndarray):
+        self.scene, self.L = scene, scene.L
+        pp = np.ascontiguousarray(probe_pos, np.float32)
+        d = np.ascontiguousarray(dirs, np.float32)
+        w = np.ascontiguousarray(weights, np.float32)
+        h = C.c_void_p()
+        _check(self.L.prt_probe_capture(scene.h, _ptr(pp), len(pp), _ptr(d), _ptr(w), len(d), C.byref(h)), "prt_probe_capture")
+        self.h = h
+        npb, nnz, ns, ms = C.c_uint32(), C.c_uint64(), C.c_uint32(), C.c_double()
+        _check(self.L.prt_csr_sizes(h, C.byref(npb), C.byref(nnz), C.byref(ns), C.byref(ms)), "prt_csr_sizes")
+        self.n_probes, self.nnz, self.n_surfels, self.capture_ms = npb.value, nnz.value, ns.value, ms.value
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.scene, "h", None):
+            self.L.prt_csr_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def download(self):
+        rng = np.zeros((self.n_probes, 2), np.uint32)
+        ids = np.zeros(self.nnz, np.uint32)
+        tr = np.zeros((self.nnz, 9), np.float32)
+        sf = np.zeros((self.n_surfels, 6), np.float32)
+        keys = np.zeros(self.n_surfels, np.uint64)
+        _check(self.L.prt_csr_download(self.h, _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf), _ptr(keys)), "prt_csr_download")
+        return rng, ids, tr, sf, keys
+
+    def project(self, radiance_rgba: np.ndarray) -> np.ndarray:
+        """SH_volume::project_sh (precomp_projectSH.comp): [n_surfels,4] radiance -> [n_probes,7,4] packed SH volumes."""
+        rad = np.ascontiguousarray(radiance_rgba, np.float32)
+        if rad.shape != (self.n_surfels, 4):
+            raise PRTError("project: radiance must be [n_surfels, 4]")
+        out = np.zeros((self.n_probes, 7, 4), np.float32)
+        _check(self.L.prt_probe_project(self.h, _ptr(rad), _ptr(out)), "prt_probe_project")
+        return out

@@ -1,9 +1,14 @@
 // abi_internal.h -- helpers shared by the translation units that implement the C ABI.
 #pragma once
 #include "../../include/prt_b200.h"
+#include "bvh8.h"
 #include <cuda_runtime.h>
 #include <string>
 
 int prt_set_error(int code, const std::string &msg);   // records the thread-local message, returns code
 cudaStream_t prt_ctx_stream(prt_ctx *);                // the context's own stream
 int prt_ctx_sms(const prt_ctx *);
+
+// device-side view of a scene for the other translation units
+struct prt_scene_view { const prt::Node8 *nodes; const prt::Tri48 *tris; prt_ctx *ctx; };
+prt_scene_view prt_scene_get_view(prt_scene *);

@@ -1,0 +1,470 @@
+// probe.cu -- sm_100a kernels + C ABI for per-probe radiance-transfer capture and projection (BASELINE config 3).
+//
+//   prt_probe_capture   reference SH_volume::precompute, src/sh/volume.cpp:149-316: for every probe and every direction of a
+//                       fixed set: closest hit (replaces the 64x64x6 G-buffer raster + glGetTexImage readback, :166-178,241-244),
+//                       sky / back-face skips (:246-249), surfel cluster key (:205-223), transfer[probe][cluster] += SH9(d)*dOmega
+//                       (:250-260); emits the CSR the viewer uploads (:265-295) and the surfel table (:301-312).
+//   prt_probe_project   reference SH_volume::project_sh + precomp_projectSH.comp:32-143: CSR SpMV with surfel radiance,
+//                       sinc window, Ramamoorthi-Hanrahan pack into 7 vec4 per probe.
+//
+// One CTA per probe (probes handed out in order by an atomic ticket): 256 threads trace the probe's <= 4096 rays, the
+// (cluster key, ray) pairs are bitonic-sorted in shared memory, segment heads reduce their rays in ray order (deterministic
+// sums) and the probe's entries are appended to the CSR through a chained prefix (each probe publishes its end offset for
+// the next one), so the output is probe-major, sorted by cluster within a probe and exactly sized.
+// Surfel ids are the rank of the cluster key among all keys (== std::map<std::array<int,4>> order of volume.cpp:204).
+#include "../../include/prt_b200.h"
+#include "abi_internal.h"
+#include "bvh8.h"
+#include "traverse.cuh"
+
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <vector>
+
+using namespace prt;
+
+
+namespace {
+
+constexpr int kMaxRays = 4096;
+constexpr int kThreads = 256;
+constexpr unsigned long long kInvalid = ~0ull;
+
+struct CaptureArgs {
+    const Node8 *nodes; const Tri48 *tris;
+    const float *probe_pos; uint32_t n_probes;
+    const float4 *dirs;          // xyz = direction, w = solid angle
+    uint32_t n_dirs;
+    uint32_t *ticket;            // [1] zeroed
+    unsigned long long *offsets; // [n_probes + 1]; offsets[0] = 1 (value + 1, 0 = not published yet)
+    unsigned long long capacity;
+    uint32_t *range;             // [n_probes][2]
+    unsigned long long *ekeys;   // [capacity]
+    float *etransfer;            // [capacity][9]
+    float *eacc;                 // [capacity][7] sum pos, sum normal, count
+    int *overflow;
+};
+
+__device__ __forceinline__ bool cluster_key(f3 pos, f3 n, unsigned long long &key) {
+    int dir = 0;
+    const float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
+    if (ax > ay && ax > az) dir = n.x > 0 ? 0 : 1;
+    if (ay > ax && ay > az) dir = n.y > 0 ? 2 : 3;
+    if (az > ax && az > ay) dir = n.z > 0 ? 4 : 5;
+    const float fx = floorf(pos.x), fy = floorf(pos.y), fz = floorf(pos.z);
+    if (!(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f && fabsf(fz) < 32768.f)) return false;
+    const unsigned long long x = (unsigned long long)((int)fx + 32768), y = (unsigned long long)((int)fy + 32768), z = (unsigned long long)((int)fz + 32768);
+    key = (x << 35) | (y << 19) | (z << 3) | (unsigned long long)dir;
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads) probe_capture_kernel(const CaptureArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem);          // [4096] (cluster key << 12) | ray
+    float *tt = reinterpret_cast<float *>(sk + kMaxRays);                          // [4096] hit distance by ray
+    uint32_t *tri = reinterpret_cast<uint32_t *>(tt + kMaxRays);                   // [4096] hit triangle slot by ray
+    __shared__ uint32_t s_probe, s_counts[kThreads], s_total;
+    __shared__ unsigned long long s_start;
+    const int tid = threadIdx.x;
+
+    for (;;) {
+        if (tid == 0) s_probe = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const uint32_t p = s_probe;
+        if (p >= A.n_probes) return;
+        const f3 P = mk3(A.probe_pos[3 * p], A.probe_pos[3 * p + 1], A.probe_pos[3 * p + 2]);
+
+        // ---- trace ------------------------------------------------------------------------------------------------------
+        for (int r = tid; r < kMaxRays; r += kThreads) {
+            unsigned long long key = kInvalid;
+            if (r < (int)A.n_dirs) {
+                const float4 dw = __ldg(&A.dirs[r]);
+                Trav tr;
+                tr.reset_counters();
+                tr.init(P, mk3(dw.x, dw.y, dw.z), 0.0f, INFINITY);
+                tr.start_root();
+                tr.run<false>(A.nodes, A.tris, 0, false);
+                if (tr.best_prim != 0xFFFFFFFFu) {                                   // sky: volume.cpp:246
+                    const f3 n = normalize3(tr.hit_ng(A.tris));
+                    const f3 pos = madd3(P, tr.best_t, tr.d);
+                    unsigned long long ck;
+                    if (!(dot3(sub3(pos, P), n) > 0.0f) && cluster_key(pos, n, ck)) {   // back face: volume.cpp:249
+                        key = (ck << 12) | (unsigned long long)r;
+                        tt[r] = tr.best_t; tri[r] = tr.best_tri;
+                    }
+                }
+            }
+            sk[r] = key;
+        }
+        __syncthreads();
+
+        // ---- bitonic sort of 4096 keys in shared memory ---------------------------------------------------------------------
+        for (int k = 2; k <= kMaxRays; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < kMaxRays; i += kThreads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = sk[i], b = sk[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+
+        // ---- segment heads, ranks --------------------------------------------------------------------------------------------
+        constexpr int kChunk = kMaxRays / kThreads;
+        uint32_t heads = 0;
+        for (int q = 0; q < kChunk; q++) {
+            const int i = tid * kChunk + q;
+            const unsigned long long a = sk[i];
+            if (a != kInvalid && (i == 0 || (sk[i - 1] >> 12) != (a >> 12))) heads++;
+        }
+        s_counts[tid] = heads;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int i = 0; i < kThreads; i++) { const uint32_t c = s_counts[i]; s_counts[i] = run; run += c; }
+            s_total = run;
+            // chained prefix: wait for the previous probe's end offset, publish ours
+            volatile unsigned long long *off = A.offsets;
+            unsigned long long v;
+            while ((v = off[p]) == 0ull) { __nanosleep(64); }
+            s_start = v - 1ull;
+            __threadfence();
+            off[p + 1] = v + (unsigned long long)run;
+            A.range[2 * p] = (uint32_t)(v - 1ull);
+            A.range[2 * p + 1] = (uint32_t)(v - 1ull + run);
+        }
+        __syncthreads();
+        const unsigned long long start = s_start;
+        if (start + s_total > A.capacity) { if (tid == 0) *A.overflow = 1; __syncthreads(); continue; }
+
+        // ---- per-cluster reduction in ray order (volume.cpp:250-260) -----------------------------------------------------------
+        uint32_t rank = s_counts[tid];
+        for (int q = 0; q < kChunk; q++) {
+            const int i = tid * kChunk + q;
+            const unsigned long long a = sk[i];
+            if (a == kInvalid || !(i == 0 || (sk[i - 1] >> 12) != (a >> 12))) continue;
+            float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float sp[3] = {0.f, 0.f, 0.f}, sn[3] = {0.f, 0.f, 0.f}, cnt = 0.f;
+            for (int j = i; j < kMaxRays && (sk[j] >> 12) == (a >> 12); j++) {
+                const uint32_t r = (uint32_t)(sk[j] & 0xFFFull);
+                const float4 dw = __ldg(&A.dirs[r]);
+                const f3 pos = madd3(P, tt[r], mk3(dw.x, dw.y, dw.z));
+                const f3 tp = sub3(pos, P);
+                const float m = fmaxf(fabsf(tp.x), fmaxf(fabsf(tp.y), fabsf(tp.z)));
+                const f3 cc = mk3(PRT_DIV(tp.x, m), PRT_DIV(tp.y, m), PRT_DIV(tp.z, m));             // volume.cpp:250
+                const f3 d = normalize3(mk3(cc.z, cc.x, cc.y));                                    // :255-256
+                float y[9];
+                sh_eval<3>(d.x, d.y, d.z, 1.0f, y);
+#pragma unroll
+                for (int c = 0; c < 9; c++) acc[c] += y[c] * dw.w;                                   // :260
+                const char *tp48 = reinterpret_cast<const char *>(A.tris + tri[r]);
+                const u4 b4 = ld16(tp48 + 16), c4 = ld16(tp48 + 32);
+                const f3 n = normalize3(cross3(mk3(PRT_U2F(b4.x), PRT_U2F(b4.y), PRT_U2F(b4.z)), mk3(PRT_U2F(c4.x), PRT_U2F(c4.y), PRT_U2F(c4.z))));
+                sp[0] += pos.x; sp[1] += pos.y; sp[2] += pos.z; sn[0] += n.x; sn[1] += n.y; sn[2] += n.z; cnt += 1.f;
+            }
+            const unsigned long long e = start + rank++;
+            A.ekeys[e] = a >> 12;
+#pragma unroll
+            for (int c = 0; c < 9; c++) A.etransfer[9 * e + c] = acc[c];
+            float *ea = A.eacc + 7 * e;
+            ea[0] = sp[0]; ea[1] = sp[1]; ea[2] = sp[2]; ea[3] = sn[0]; ea[4] = sn[1]; ea[5] = sn[2]; ea[6] = cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- global surfel ids: hash-set dedupe of cluster keys, host sort of the (few) distinct keys, rank lookup ----------------
+__device__ __forceinline__ uint32_t hash64(unsigned long long k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; return (uint32_t)k; }
+__global__ void hash_insert_kernel(const unsigned long long *keys, unsigned long long n, unsigned long long *table, uint32_t mask, int *overflow) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    uint32_t h = hash64(k) & mask;
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        const unsigned long long old = atomicCAS(&table[h], kInvalid, k);
+        if (old == kInvalid || old == k) return;
+        h = (h + 1) & mask;
+    }
+    *overflow = 1;
+}
+__global__ void hash_compact_kernel(const unsigned long long *table, uint32_t size, unsigned long long *out, uint32_t *count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const unsigned long long k = table[i];
+    if (k != kInvalid) out[atomicAdd(count, 1u)] = k;
+}
+__global__ void assign_ids_kernel(const unsigned long long *ekeys, unsigned long long n, const unsigned long long *sorted, uint32_t n_prim,
+                                  const float *eacc, uint32_t *ids, double *sacc) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = ekeys[i];
+    uint32_t lo = 0, hi = n_prim;
+    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (sorted[mid] <= k) lo = mid; else hi = mid; }
+    ids[i] = lo;
+#pragma unroll
+    for (int c = 0; c < 7; c++) atomicAdd(&sacc[7 * (size_t)lo + c], (double)eacc[7 * i + c]);
+}
+__global__ void finalize_surfels_kernel(const double *sacc, uint32_t n_prim, float *surfels) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_prim) return;
+    const double cnt = sacc[7 * (size_t)s + 6];
+    const double nx = sacc[7 * (size_t)s + 3] / cnt, ny = sacc[7 * (size_t)s + 4] / cnt, nz = sacc[7 * (size_t)s + 5] / cnt;
+    const double il = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);                                      // volume.cpp:307-308
+    float *o = surfels + 6 * (size_t)s;
+    o[0] = (float)(sacc[7 * (size_t)s] / cnt); o[1] = (float)(sacc[7 * (size_t)s + 1] / cnt); o[2] = (float)(sacc[7 * (size_t)s + 2] / cnt);
+    o[3] = (float)(nx * il); o[4] = (float)(ny * il); o[5] = (float)(nz * il);
+}
+
+// ---- projection: one warp per probe (precomp_projectSH.comp:51-139) -----------------------------------------------------------
+__global__ void __launch_bounds__(256) probe_project_kernel(const uint32_t *range, const uint32_t *ids, const float *transfer, const float4 *radiance,
+                                                            uint32_t n_probes, float4 *out) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_probes) return;
+    float L[27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) L[k] = 0.f;
+    for (uint32_t i = range[2 * p] + lane; i < range[2 * p + 1]; i += 32) {
+        const float4 rad = __ldg(&radiance[ids[i]]);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const float t = __ldg(&transfer[9 * (size_t)i + k]);
+            L[3 * k] += t * rad.x; L[3 * k + 1] += t * rad.y; L[3 * k + 2] += t * rad.z;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) L[k] += __shfl_xor_sync(0xFFFFFFFFu, L[k], o);
+    if (lane == 0) {
+        const float PI = 3.14159265359f;
+        const float w1 = 3.f / PI * sinf(PI / 3), w2 = 3.f / 2 / PI * sinf(2 * PI / 3);                // :104-113
+#pragma unroll
+        for (int k = 3; k < 12; k++) L[k] *= w1;
+#pragma unroll
+        for (int k = 12; k < 27; k++) L[k] *= w2;
+        const float c1 = 0.429043f, c2 = 0.511664f, c3 = 0.743125f, c4 = 0.886227f, c5 = 0.247708f;   // :23
+        float4 *o = out + 7 * (size_t)p;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            o[ch] = make_float4(2 * c2 * L[9 + ch], 2 * c2 * L[3 + ch], 2 * c2 * L[6 + ch], c4 * L[ch] - c5 * L[18 + ch]);      // :118-128
+            o[3 + ch] = make_float4(2 * c1 * L[12 + ch], 2 * c1 * L[21 + ch], 2 * c1 * L[15 + ch], c3 * L[18 + ch]);           // :130-136
+        }
+        o[6] = make_float4(c1 * L[24], c1 * L[25], c1 * L[26], 1.0f);                                                          // :138
+    }
+}
+
+}  // namespace
+
+struct prt_csr {
+    prt_ctx *ctx = nullptr;
+    uint32_t n_probes = 0, n_prim = 0;
+    unsigned long long nnz = 0;
+    uint32_t *range = nullptr, *ids = nullptr;
+    float *transfer = nullptr, *surfels = nullptr;
+    unsigned long long *keys = nullptr;   // sorted distinct cluster keys
+    double capture_ms = 0.0;
+};
+
+#define PB_TRY(expr)                                                                                                    \
+    do {                                                                                                                \
+        cudaError_t e_ = (expr);                                                                                        \
+        if (e_ != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+void prt_csr_destroy(prt_csr *c) {
+    if (!c) return;
+    cudaSetDevice(prt_ctx_device(c->ctx));
+    cudaFree(c->range); cudaFree(c->ids); cudaFree(c->transfer); cudaFree(c->surfels); cudaFree(c->keys);
+    delete c;
+}
+
+int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probes, const float *dirs, const float *weights,
+                      uint32_t n_dirs, prt_csr **out) {
+    if (!scene || !probe_pos || !dirs || !weights || !out || n_probes == 0 || n_dirs == 0) return prt_set_error(PRT_ERR_INVALID, "prt_probe_capture: bad argument");
+    *out = nullptr;
+    if (n_dirs > (uint32_t)kMaxRays) return prt_set_error(PRT_ERR_UNSUPPORTED, "prt_probe_capture: at most 4096 directions per probe");
+    const prt_scene_view sv = prt_scene_get_view(scene);
+    PB_TRY(cudaSetDevice(prt_ctx_device(sv.ctx)));
+    cudaStream_t st = prt_ctx_stream(sv.ctx);
+    const unsigned long long capacity = (unsigned long long)n_probes * n_dirs;
+    if (capacity >= 0xFFFFFFFFull) return prt_set_error(PRT_ERR_UNSUPPORTED, "prt_probe_capture: more than 2^32 CSR entries");
+
+    std::vector<float> dw(4 * (size_t)n_dirs);
+    for (uint32_t i = 0; i < n_dirs; i++) { dw[4 * i] = dirs[3 * i]; dw[4 * i + 1] = dirs[3 * i + 1]; dw[4 * i + 2] = dirs[3 * i + 2]; dw[4 * i + 3] = weights[i]; }
+    float *d_pos = nullptr, *d_dirs = nullptr, *etransfer = nullptr, *eacc = nullptr;
+    uint32_t *ticket = nullptr, *range = nullptr;
+    unsigned long long *offsets = nullptr, *ekeys = nullptr;
+    int *overflow = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pos); cudaFree(d_dirs); cudaFree(ticket); cudaFree(offsets); cudaFree(ekeys); cudaFree(eacc); cudaFree(overflow); };
+    cudaError_t e = cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)n_probes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dirs, sizeof(float) * 4 * (size_t)n_dirs);
+    if (e == cudaSuccess) e = cudaMalloc(&ticket, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&overflow, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&offsets, 8 * ((size_t)n_probes + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&range, 8 * (size_t)n_probes);
+    if (e == cudaSuccess) e = cudaMalloc(&ekeys, 8 * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&etransfer, 36 * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&eacc, 28 * capacity);
+    if (e != cudaSuccess) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_NOMEM, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_pos, probe_pos, sizeof(float) * 3 * (size_t)n_probes, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_dirs, dw.data(), sizeof(float) * 4 * (size_t)n_dirs, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(ticket, 0, 8, st);
+    cudaMemsetAsync(overflow, 0, 4, st);
+    cudaMemsetAsync(offsets, 0, 8 * ((size_t)n_probes + 1), st);
+    const unsigned long long one = 1ull;
+    cudaMemcpyAsync(offsets, &one, 8, cudaMemcpyHostToDevice, st);
+
+    CaptureArgs A{};
+    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs;
+    A.ticket = ticket; A.offsets = offsets; A.capacity = capacity; A.range = range; A.ekeys = ekeys; A.etransfer = etransfer; A.eacc = eacc; A.overflow = overflow;
+    const size_t smem = (size_t)kMaxRays * (8 + 4 + 4);
+    static bool configured = false;
+    if (!configured) { PB_TRY(cudaFuncSetAttribute(probe_capture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    int per_sm = 1;
+    PB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_capture_kernel, kThreads, smem));
+    // every ticket holder must be resident (chained prefix): never launch more CTAs than fit at once
+    const int grid = (int)std::min<unsigned long long>((unsigned long long)prt_ctx_sms(sv.ctx) * (unsigned long long)std::max(per_sm, 1), n_probes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    probe_capture_kernel<<<grid, kThreads, smem, st>>>(A);
+    cudaEventRecord(e1, st);
+    unsigned long long nnz_p1 = 0; int ovf = 0;
+    cudaMemcpyAsync(&nnz_p1, offsets + n_probes, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess || ovf) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_CUDA, e != cudaSuccess ? std::string("probe_capture_kernel: ") + cudaGetErrorString(e) : "prt_probe_capture: CSR capacity exceeded"); }
+    const unsigned long long nnz = nnz_p1 - 1ull;
+
+    // ---- global ids ----------------------------------------------------------------------------------------------------------
+    prt_csr *c = new prt_csr();
+    c->ctx = sv.ctx; c->n_probes = n_probes; c->nnz = nnz; c->range = range; c->transfer = etransfer; c->capture_ms = ms;
+    uint32_t tbl_bits = 16;
+    std::vector<unsigned long long> distinct;
+    for (;;) {
+        const uint32_t size = 1u << tbl_bits;
+        unsigned long long *table = nullptr, *dlist = nullptr; uint32_t *dcount = nullptr;
+        cudaMalloc(&table, 8 * (size_t)size); cudaMalloc(&dlist, 8 * (size_t)size); cudaMalloc(&dcount, 4);
+        cudaMemsetAsync(table, 0xFF, 8 * (size_t)size, st); cudaMemsetAsync(dcount, 0, 4, st); cudaMemsetAsync(overflow, 0, 4, st);
+        if (nnz) hash_insert_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ekeys, nnz, table, size - 1, overflow);
+        hash_compact_kernel<<<(size + 255) / 256, 256, 0, st>>>(table, size, dlist, dcount);
+        uint32_t cnt = 0;
+        cudaMemcpyAsync(&cnt, dcount, 4, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        const bool too_full = ovf || cnt > size / 2;
+        if (!too_full) { distinct.resize(cnt); if (cnt) cudaMemcpy(distinct.data(), dlist, 8 * (size_t)cnt, cudaMemcpyDeviceToHost); }
+        cudaFree(table); cudaFree(dlist); cudaFree(dcount);
+        if (!too_full) break;
+        if (++tbl_bits > 28) { cleanup(); prt_csr_destroy(c); return prt_set_error(PRT_ERR_NOMEM, "prt_probe_capture: too many distinct surfel clusters"); }
+    }
+    std::sort(distinct.begin(), distinct.end());
+    c->n_prim = (uint32_t)distinct.size();
+    double *sacc = nullptr;
+    const size_t np = std::max<size_t>(1, distinct.size());
+    e = cudaMalloc(&c->keys, 8 * np);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * std::max<unsigned long long>(1, nnz));
+    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
+    if (e == cudaSuccess) e = cudaMalloc(&sacc, 56 * np);
+    if (e != cudaSuccess) { cleanup(); cudaFree(sacc); prt_csr_destroy(c); return prt_set_error(PRT_ERR_NOMEM, "prt_probe_capture: cudaMalloc failed"); }
+    if (!distinct.empty()) cudaMemcpyAsync(c->keys, distinct.data(), 8 * distinct.size(), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(sacc, 0, 56 * np, st);
+    if (nnz) assign_ids_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ekeys, nnz, c->keys, c->n_prim, eacc, c->ids, sacc);
+    if (c->n_prim) finalize_surfels_kernel<<<(c->n_prim + 255) / 256, 256, 0, st>>>(sacc, c->n_prim, c->surfels);
+    e = cudaStreamSynchronize(st);
+    cudaFree(sacc);
+    cleanup();
+    if (e != cudaSuccess) { prt_csr_destroy(c); return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    *out = c;
+    return PRT_OK;
+}
+
+int prt_csr_sizes(const prt_csr *c, uint32_t *n_probes, uint64_t *nnz, uint32_t *n_surfels, double *capture_ms) {
+    if (!c) return prt_set_error(PRT_ERR_INVALID, "prt_csr_sizes: null argument");
+    if (n_probes) *n_probes = c->n_probes;
+    if (nnz) *nnz = c->nnz;
+    if (n_surfels) *n_surfels = c->n_prim;
+    if (capture_ms) *capture_ms = c->capture_ms;
+    return PRT_OK;
+}
+
+int prt_csr_download(const prt_csr *c, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys) {
+    if (!c) return prt_set_error(PRT_ERR_INVALID, "prt_csr_download: null argument");
+    PB_TRY(cudaSetDevice(prt_ctx_device(c->ctx)));
+    if (range) PB_TRY(cudaMemcpy(range, c->range, 8 * (size_t)c->n_probes, cudaMemcpyDeviceToHost));
+    if (ids && c->nnz) PB_TRY(cudaMemcpy(ids, c->ids, 4 * c->nnz, cudaMemcpyDeviceToHost));
+    if (transfer && c->nnz) PB_TRY(cudaMemcpy(transfer, c->transfer, 36 * c->nnz, cudaMemcpyDeviceToHost));
+    if (surfels && c->n_prim) PB_TRY(cudaMemcpy(surfels, c->surfels, 24 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
+    if (keys && c->n_prim) PB_TRY(cudaMemcpy(keys, c->keys, 8 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
+    return PRT_OK;
+}
+
+int prt_probe_project(const prt_csr *c, const float *radiance_rgba, float *out_sh_volumes) {
+    if (!c || !radiance_rgba || !out_sh_volumes) return prt_set_error(PRT_ERR_INVALID, "prt_probe_project: null argument");
+    PB_TRY(cudaSetDevice(prt_ctx_device(c->ctx)));
+    cudaStream_t st = prt_ctx_stream(c->ctx);
+    float4 *d_rad = nullptr, *d_out = nullptr;
+    PB_TRY(cudaMalloc(&d_rad, 16 * std::max<size_t>(1, c->n_prim)));
+    PB_TRY(cudaMalloc(&d_out, 112 * (size_t)c->n_probes));
+    if (c->n_prim) cudaMemcpyAsync(d_rad, radiance_rgba, 16 * (size_t)c->n_prim, cudaMemcpyHostToDevice, st);
+    probe_project_kernel<<<(unsigned)(((size_t)c->n_probes * 32 + 255) / 256), 256, 0, st>>>(c->range, c->ids, c->transfer, d_rad, c->n_probes, d_out);
+    cudaError_t e = cudaMemcpyAsync(out_sh_volumes, d_out, 112 * (size_t)c->n_probes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_rad); cudaFree(d_out);
+    if (e != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_project: ") + cudaGetErrorString(e));
+    return PRT_OK;
+}
+
+// probe grid (volume.cpp:83-90) and direction sets (light_probe.cpp:137-152; SH_function.h:96-112 + volume.cpp:251-254): host helpers
+int prt_probe_positions(const int32_t res[3], const float size[3], float *out_pos) {
+    if (!res || !size || !out_pos) return prt_set_error(PRT_ERR_INVALID, "prt_probe_positions: null argument");
+    size_t k = 0;
+    for (int z = 0; z < res[2]; z++)
+        for (int y = 0; y < res[1]; y++)
+            for (int x = 0; x < res[0]; x++, k++) {
+                const int id[3] = {x, y, z};
+                for (int a = 0; a < 3; a++) { const float ds = 2.0f / (float)res[a] * size[a]; out_pos[3 * k + a] = -size[a] + ds * (0.5f + (float)id[a]); }
+            }
+    return PRT_OK;
+}
+int prt_fibonacci_dirs(int32_t n, float *out_dirs) {
+    if (n < 2 || !out_dirs) return prt_set_error(PRT_ERR_INVALID, "prt_fibonacci_dirs: bad argument");
+    const double pi = 2 * acos(0.0), gold = 3 - sqrt(5.0);
+    for (int i = 0; i < n; i++) {
+        const double z = 1 - ((double)i / (double)(n - 1)) * 2, theta = pi * i * gold, r = sqrt(1 - z * z);
+        out_dirs[3 * i] = (float)(cos(theta) * r); out_dirs[3 * i + 1] = (float)(sin(theta) * r); out_dirs[3 * i + 2] = (float)z;
+    }
+    return PRT_OK;
+}
+int prt_cube_dirs(int32_t res, float *out_dirs, float *out_weights) {
+    if (res < 1 || !out_dirs || !out_weights) return prt_set_error(PRT_ERR_INVALID, "prt_cube_dirs: bad argument");
+    size_t k = 0;
+    for (int f = 0; f < 6; f++)
+        for (int y = 0; y < res; y++)
+            for (int x = 0; x < res; x++, k++) {
+                const float u = (float)(((double)x + 0.5) / (double)res) * 2.0f - 1.0f, v = (float)(((double)y + 0.5) / (double)res) * 2.0f - 1.0f;
+                float d[3];
+                switch (f) {
+                case 0: d[0] = 1.f; d[1] = -v; d[2] = -u; break;
+                case 1: d[0] = -1.f; d[1] = -v; d[2] = u; break;
+                case 2: d[0] = u; d[1] = 1.f; d[2] = v; break;
+                case 3: d[0] = u; d[1] = -1.f; d[2] = -v; break;
+                case 4: d[0] = u; d[1] = -v; d[2] = 1.f; break;
+                default: d[0] = -u; d[1] = -v; d[2] = -1.f; break;
+                }
+                float w = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                w *= sqrtf(w);
+                out_dirs[3 * k] = d[0]; out_dirs[3 * k + 1] = d[1]; out_dirs[3 * k + 2] = d[2];
+                out_weights[k] = 4.0f / (float)res / (float)res / w;
+            }
+    return PRT_OK;
+}
+
+}  // extern "C"

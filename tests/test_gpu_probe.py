@@ -1,0 +1,77 @@
+"""GPU parity tests for BASELINE config 3 (per-probe SH radiance-transfer capture + projection) against the oracle."""
+import numpy as np
+import pytest
+
+from prt_b200 import meshes
+from test_oracle_probe import room
+
+pytestmark = pytest.mark.gpu
+
+
+def scene_with_occluder():
+    """room (+-6) with a bumpy torus inside, like the reference's cube + buddha scene."""
+    rp, rt = room()
+    tp, _, tt = meshes.bumpy_torus(48, 32)
+    pos = np.concatenate([rp, tp * np.float32(1.2)]).astype(np.float32)
+    tri = np.concatenate([rt, tt + np.uint32(len(rp))]).astype(np.uint32)
+    return pos, tri
+
+
+@pytest.mark.parametrize("dirset", ["fibonacci", "cube"])
+def test_probe_capture_matches_oracle(prt, oracle, dirset):
+    pos, tri = scene_with_occluder()
+    gs, os_ = prt.RTScene(pos, tri), oracle.Scene(pos, tri)
+    probes = prt.probe_positions([4, 3, 2], [6, 6, 6])
+    assert np.array_equal(probes, oracle.probe_positions([4, 3, 2], [6, 6, 6]))
+    if dirset == "fibonacci":
+        d, w = prt.fibonacci_dirs(1500)
+        d2, w2 = oracle.fibonacci_dirs(1500)
+    else:
+        d, w = prt.cube_dirs(16)
+        d2, w2 = oracle.cube_dirs(16)
+    assert np.array_equal(d, d2) and np.array_equal(w, w2)
+    g, o = prt.ProbeTransfer(gs, probes, d, w), oracle.ProbeTransfer(os_, probes, d, w)
+    assert (g.nnz, g.n_surfels) == (o.nnz, o.n_surfels) and g.nnz > 1000
+    gr, gi, gt, gsf, gk = g.download()
+    orr, oi, ot, osf, ok = o.download()
+    assert np.array_equal(gr, orr) and np.array_equal(gi, oi) and np.array_equal(gk, ok)     # structure is exact
+    assert np.abs(gt - ot).max() <= 1e-5                                                        # SH9 * dOmega sums
+    assert np.abs(gsf - osf).max() <= 1e-4                                                      # surfel means
+    rs = np.random.RandomState(0)
+    rad = rs.rand(g.n_surfels, 4).astype(np.float32)
+    assert np.abs(g.project(rad) - o.project(rad)).max() <= 1e-4
+
+
+def test_probe_known_answers(prt):
+    """SURVEY 8c KATs 3+4 on the GPU: closed room -> sum dOmega = 4 pi; constant radiance -> SH_Irad = pi."""
+    pos, tri = room()
+    sc = prt.RTScene(pos, tri)
+    d, w = prt.fibonacci_dirs(4096)
+    g = prt.ProbeTransfer(sc, prt.probe_positions([3, 3, 3], [6, 6, 6]), d, w)
+    rng, ids, tr, sf, keys = g.download()
+    for p in range(27):
+        s = tr[rng[p, 0]:rng[p, 1]].sum(0)
+        assert abs(s[0] - 3.54491) < 2e-3 and np.abs(s[1:]).max() < 3e-2
+        assert (np.diff(ids[rng[p, 0]:rng[p, 1]].astype(np.int64)) > 0).all()
+    out = g.project(np.ones((g.n_surfels, 4), np.float32))
+    assert np.abs(out[:, 0:3, 3] - np.pi).max() < 5e-3
+    # empty result: outward facing box -> everything is a back face
+    g2 = prt.ProbeTransfer(prt.RTScene(pos, tri[:, ::-1].copy()), np.zeros((2, 3), np.float32), d, w)
+    assert g2.nnz == 0 and g2.n_surfels == 0
+    with pytest.raises(prt.PRTError):
+        prt.ProbeTransfer(sc, np.zeros((1, 3), np.float32), *prt.fibonacci_dirs(5000))
+
+
+def test_probe_grid_scale_properties(prt):
+    """a 16^3 grid (4096 probes x 4096 rays = 1.7e7 rays): every probe inside the room sees 4 pi minus nothing."""
+    pos, tri = scene_with_occluder()
+    sc = prt.RTScene(pos, tri)
+    d, w = prt.fibonacci_dirs(4096)
+    probes = prt.probe_positions([16, 16, 16], [6, 6, 6])
+    g = prt.ProbeTransfer(sc, probes, d, w)
+    rng, ids, tr, sf, keys = g.download()
+    assert rng[0, 0] == 0 and (rng[1:, 0] == rng[:-1, 1]).all() and rng[-1, 1] == g.nnz      # probe-major, contiguous
+    dc = np.add.reduceat(tr[:, 0], rng[:, 0].astype(np.int64)) if g.nnz else np.zeros(len(probes))
+    # probes inside the torus tube can see less (back faces are skipped); nobody sees more than 4 pi
+    assert dc.max() < 3.54491 * 1.001 and np.median(dc) > 3.5
+    assert ids.max() == g.n_surfels - 1 and (np.diff(keys.astype(np.int64)) > 0).all()
