@@ -185,6 +185,14 @@ int prt_probe_positions(const int32_t res[3], const float scene_size[3], float *
 int prt_fibonacci_dirs(int32_t n, float *out_dirs_xyz);
 int prt_cube_dirs(int32_t res, float *out_dirs_xyz /*[6*res*res][3]*/, float *out_solid_angles);
 
+/* Volume_weight calculate_weight(Model&, ivec3 probe_res, ivec3 volume_res, vec3 scene_size) (light_probe.h:14-18,
+ * light_probe.cpp:156-367): per voxel, the trilinear weights of its 8 surrounding probes masked by segment visibility and
+ * renormalised, after moving "inside" voxels (score > 0.2 from 100 closest-hit rays) to their least-inside neighbour.
+ * w0123 / w4567: [rx*ry*rz][4] floats, index (z*ry + y)*rx + x, corner order of the diagram at light_probe.cpp:269-294
+ * (what SH_volume::set_visibility uploads, volume.cpp:318-333).  inside_score optional [rx*ry*rz] (NaN where no ray hit). */
+int prt_volume_weights(prt_scene *, const int32_t probe_res[3], const int32_t volume_res[3], const float scene_size[3],
+                       float *w0123, float *w4567, float *inside_score);
+
 #ifdef __cplusplus
 }
 #endif

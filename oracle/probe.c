@@ -203,3 +203,84 @@ void prt_o_probe_project(const prt_o_csr *c, const float *radiance_rgba, float *
         prt_o_sh_pack_rh(L, out + 28 * (size_t)p);
     }
 }
+
+/* ---- calculate_weight (src/raytracing/light_probe.cpp:156-367): voxel -> 8-probe trilinear weights masked by visibility ----
+ * pass 1 (:207-229): 100 Fibonacci closest-hit rays per voxel; inside score = #(dot(dir, Ng) > 0.01) / #hits (0/0 = NaN, as in
+ *                    the reference; Ng is the UNNORMALISED geometric normal); score[n_voxels] = 999 for out-of-grid neighbours.
+ * pass 2 (:261-361): trilinear weights of the 8 surrounding probes (corner order of the diagram at :269-294); voxels with
+ *                    score > 0.2 are moved to the 3x3x3 neighbour with the smallest score (:320-332); each probe is tested with
+ *                    a segment any-hit ray (org = voxel, dir = probe - voxel, tfar = 1; :250-251); weights are masked and
+ *                    renormalised, or all zero when nothing is visible (:341-357).                                          */
+static void grid_pos(const int res[3], const float size[3], const int id[3], float out[3]) {
+    for (int a = 0; a < 3; a++) {
+        float ds = 2.f / (float)res[a] * size[a];
+        out[a] = -size[a] + ds * (0.5f + (float)id[a]);
+    }
+}
+void prt_o_volume_weights(const prt_o_scene *sc, const int probe_res[3], const int volume_res[3], const float scene_size[3],
+                          float *w0123, float *w4567, float *score_out) {
+    const int rx = volume_res[0], ry = volume_res[1], rz = volume_res[2];
+    const size_t nvox = (size_t)rx * ry * rz;
+    float *score = (float *)malloc(sizeof(float) * (nvox + 1));
+    float dirs[300];
+    prt_o_fibonacci_dirs(100, dirs);
+    for (int z = 0; z < rz; z++) for (int y = 0; y < ry; y++) for (int x = 0; x < rx; x++) {
+        int id[3] = { x, y, z }; float pos[3];
+        grid_pos(volume_res, scene_size, id, pos);
+        int hits = 0; float inside = 0.f;
+        for (int r = 0; r < 100; r++) {
+            float t, ng[3]; uint32_t prim;
+            if (prt_o_closest_hit(sc, pos, dirs + 3 * r, 0.f, INFINITY, 1, &t, &prim, ng)) {
+                hits++;
+                if (v3_dot(v3_make(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]), v3_make(ng[0], ng[1], ng[2])) > 0.01f) inside += 1.f;
+            }
+        }
+        score[((size_t)z * ry + y) * rx + x] = inside / (float)hits;
+    }
+    score[nvox] = 999.f;
+    if (score_out) memcpy(score_out, score, sizeof(float) * nvox);
+    for (int z = 0; z < rz; z++) for (int y = 0; y < ry; y++) for (int x = 0; x < rx; x++) {
+        const size_t index = ((size_t)z * ry + y) * rx + x;
+        int vid[3] = { x, y, z }, anchor[3]; float vpos[3], apos[3], fr[3];
+        for (int a = 0; a < 3; a++) {
+            float tc = ((float)vid[a] + 0.5f) / (float)volume_res[a];
+            tc = tc * (float)probe_res[a] - 0.5f;
+            anchor[a] = (int)floorf(tc);
+        }
+        grid_pos(volume_res, scene_size, vid, vpos);
+        grid_pos(probe_res, scene_size, anchor, apos);
+        for (int a = 0; a < 3; a++) fr[a] = (vpos[a] - apos[a]) * (float)probe_res[a] / (2.f * scene_size[a]);
+        static const int off[8][3] = { {0,0,1}, {1,0,1}, {1,0,0}, {0,0,0}, {0,1,0}, {0,1,1}, {1,1,1}, {1,1,0} };
+        float w[8] = { (1 - fr[0]) * (1 - fr[1]) * fr[2], fr[0] * (1 - fr[1]) * fr[2], fr[0] * (1 - fr[1]) * (1 - fr[2]), (1 - fr[0]) * (1 - fr[1]) * (1 - fr[2]),
+                       (1 - fr[0]) * fr[1] * (1 - fr[2]), (1 - fr[0]) * fr[1] * fr[2], fr[0] * fr[1] * fr[2], fr[0] * fr[1] * (1 - fr[2]) };
+        float vp[3] = { vpos[0], vpos[1], vpos[2] };
+        if (score[index] > 0.2f) {
+            float min_score = score[index];
+            for (int nx = -1; nx <= 1; nx++) for (int ny = -1; ny <= 1; ny++) for (int nz = -1; nz <= 1; nz++) {
+                int q[3] = { x + nx, y + ny, z + nz };
+                size_t ni = (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= rx || q[1] >= ry || q[2] >= rz) ? nvox : ((size_t)q[2] * ry + q[1]) * rx + q[0];
+                if (score[ni] < min_score) { grid_pos(volume_res, scene_size, q, vp); min_score = score[ni]; }
+            }
+        }
+        float vis[8], valid = 0.f;
+        for (int i = 0; i < 8; i++) {
+            int pid[3] = { anchor[0] + off[i][0], anchor[1] + off[i][1], anchor[2] + off[i][2] };
+            vis[i] = 0.f;
+            if (pid[0] >= 0 && pid[1] >= 0 && pid[2] >= 0 && pid[0] < probe_res[0] && pid[1] < probe_res[1] && pid[2] < probe_res[2]) {
+                float pp[3], d[3];
+                grid_pos(probe_res, scene_size, pid, pp);
+                for (int a = 0; a < 3; a++) d[a] = pp[a] - vp[a];
+                vis[i] = prt_o_any_hit(sc, vp, d, 0.f, 1.f, 1) ? 0.f : 1.f;
+            }
+            valid += vis[i];
+        }
+        if (valid > 0.f) {
+            float sum = 0.f;
+            for (int i = 0; i < 8; i++) { w[i] *= vis[i]; }
+            for (int i = 0; i < 8; i++) sum += w[i];
+            for (int i = 0; i < 8; i++) w[i] /= sum;
+        } else for (int i = 0; i < 8; i++) w[i] = 0.f;
+        memcpy(w0123 + 4 * index, w, 16); memcpy(w4567 + 4 * index, w + 4, 16);
+    }
+    free(score);
+}

@@ -87,6 +87,9 @@ void prt_o_csr_sizes(const prt_o_csr *, uint32_t *nnz, uint32_t *n_prim);
 void prt_o_csr_get(const prt_o_csr *, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
 void prt_o_csr_destroy(prt_o_csr *);
 void prt_o_probe_project(const prt_o_csr *, const float *radiance_rgba, float *out);
+/* calculate_weight (light_probe.cpp:156-367); w0123/w4567 [n_voxels][4], index (z*ry+y)*rx+x; score_out optional [n_voxels] */
+void prt_o_volume_weights(const prt_o_scene *, const int probe_res[3], const int volume_res[3], const float scene_size[3],
+                          float *w0123, float *w4567, float *score_out);
 
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -79,6 +79,7 @@ def lib():
         L.prt_o_csr_get.argtypes = [vp, vp, vp, vp, vp, vp]
         L.prt_o_csr_destroy.argtypes = [vp]
         L.prt_o_probe_project.argtypes = [vp, vp, vp]
+        L.prt_o_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -281,3 +282,12 @@ class ProbeTransfer:
         out = np.zeros((self.n_probes, 7, 4), np.float32)
         lib().prt_o_probe_project(self.h, _ptr(rad), _ptr(out))
         return out
+
+
+def volume_weights(scene: Scene, probe_res, volume_res, scene_size):
+    """calculate_weight (reference light_probe.cpp:156-367) -> (weight0123, weight4567, inside_score)."""
+    pr = np.asarray(probe_res, np.int32); vr = np.asarray(volume_res, np.int32); sz = np.asarray(scene_size, np.float32)
+    n = int(np.prod(vr))
+    w0, w1, sc = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
+    lib().prt_o_volume_weights(scene.h, _ptr(pr), _ptr(vr), _ptr(sz), _ptr(w0), _ptr(w1), _ptr(sc))
+    return w0, w1, sc

@@ -10,8 +10,8 @@ the thin Python binding used by the tests and by ``bench.py``.  It mirrors the r
 There is no CPU fallback: importing works anywhere, but creating a context without the built CUDA library or
 without a B200-class GPU raises.
 """
-from .api import (ProbeTransfer, probe_positions, fibonacci_dirs, cube_dirs, LightProbe, brdf_lut, sh_pack_rh, BakeParams, Context, PRTError, RTScene, bake_SH, bake_transfer, lib_path, load_library,  # noqa: F401
+from .api import (calculate_weight, ProbeTransfer, probe_positions, fibonacci_dirs, cube_dirs, LightProbe, brdf_lut, sh_pack_rh, BakeParams, Context, PRTError, RTScene, bake_SH, bake_transfer, lib_path, load_library,  # noqa: F401
                   SHADOWED, UNSHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC)
 
-__all__ = ["ProbeTransfer", "probe_positions", "fibonacci_dirs", "cube_dirs", "LightProbe", "brdf_lut", "sh_pack_rh", "BakeParams", "Context", "PRTError", "RTScene", "bake_SH", "bake_transfer", "lib_path", "load_library",
+__all__ = ["calculate_weight", "ProbeTransfer", "probe_positions", "fibonacci_dirs", "cube_dirs", "LightProbe", "brdf_lut", "sh_pack_rh", "BakeParams", "Context", "PRTError", "RTScene", "bake_SH", "bake_transfer", "lib_path", "load_library",
            "SHADOWED", "UNSHADOWED", "INTERREFLECT", "UNSHADOWED_ANALYTIC"]

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
     "prt_probe_capture", "prt_csr_destroy", "prt_csr_sizes", "prt_csr_download", "prt_probe_project", "prt_probe_positions",
-    "prt_fibonacci_dirs", "prt_cube_dirs",
+    "prt_fibonacci_dirs", "prt_cube_dirs", "prt_volume_weights",
 ]
 
 
@@ -119,6 +119,7 @@ def load_library():
     L.prt_probe_positions.argtypes = [vp, vp, vp]
     L.prt_fibonacci_dirs.argtypes = [i32, vp]
     L.prt_cube_dirs.argtypes = [i32, vp, vp]
+    L.prt_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -396,3 +397,13 @@ class ProbeTransfer:
         out = np.zeros((self.n_probes, 7, 4), np.float32)
         _check(self.L.prt_probe_project(self.h, _ptr(rad), _ptr(out)), "prt_probe_project")
         return out
+
+
+def calculate_weight(scene: RTScene, probe_res, volume_res, scene_size):
+    """reference ``Volume_weight calculate_weight(Model&, probe_res, volume_res, scene_size)`` (light_probe.cpp:156-367).
+    Returns (weight0123, weight4567, inside_score), each indexed (z*ry + y)*rx + x."""
+    pr = np.asarray(probe_res, np.int32); vr = np.asarray(volume_res, np.int32); sz = np.asarray(scene_size, np.float32)
+    n = int(np.prod(vr))
+    w0, w1, sc = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
+    _check(scene.L.prt_volume_weights(scene.h, _ptr(pr), _ptr(vr), _ptr(sz), _ptr(w0), _ptr(w1), _ptr(sc)), "prt_volume_weights")
+    return w0, w1, sc

@@ -75,3 +75,17 @@ def test_probe_grid_scale_properties(prt):
     # probes inside the torus tube can see less (back faces are skipped); nobody sees more than 4 pi
     assert dc.max() < 3.54491 * 1.001 and np.median(dc) > 3.5
     assert ids.max() == g.n_surfels - 1 and (np.diff(keys.astype(np.int64)) > 0).all()
+
+
+def test_calculate_weight_matches_oracle(prt, oracle):
+    """calculate_weight (light_probe.cpp:156-367): scores and weights against the oracle on a room + occluder scene."""
+    pos, tri = scene_with_occluder()
+    gs, os_ = prt.RTScene(pos, tri), oracle.Scene(pos, tri)
+    args = ([4, 4, 4], [12, 10, 8], [6, 6, 6])
+    g0, g1, gsc = prt.calculate_weight(gs, *args)
+    o0, o1, osc = oracle.volume_weights(os_, *args)
+    assert np.array_equal(np.isnan(gsc), np.isnan(osc)) and np.allclose(np.nan_to_num(gsc), np.nan_to_num(osc), atol=1e-6)
+    assert np.abs(g0 - o0).max() <= 1e-6 and np.abs(g1 - o1).max() <= 1e-6
+    s = np.concatenate([g0, g1], 1).sum(1)
+    assert np.all(np.isclose(s, 1.0, atol=1e-5) | (s == 0.0)) and (s == 0).mean() < 0.5
+    assert (osc[~np.isnan(osc)] > 0.2).any()          # the relocation branch is exercised (voxels inside the torus tube)

@@ -52,3 +52,39 @@ def test_backface_and_sky_are_skipped(oracle):
     pt = oracle.ProbeTransfer(floor_only, np.zeros((1, 3), np.float32), d, w)
     rng, ids, tr, sf, keys = pt.download()
     assert 0 < tr[:, 0].sum() < 0.282095 * 2 * np.pi
+
+
+def test_calculate_weight_known_answers(oracle):
+    """SURVEY 8c KAT 5: empty-ish scene -> pure trilinear weights that sum to 1 (light_probe.cpp:315-316); a wall between the
+    voxel and some probes zeroes exactly those weights and renormalises (:341-348)."""
+    # a tiny far-away triangle: nothing is ever occluded, no ray hits -> score NaN -> no relocation
+    far = np.array([[100, 100, 100], [101, 100, 100], [100, 101, 100]], np.float32)
+    sc = oracle.Scene(far, np.array([[0, 1, 2]], np.uint32))
+    w0, w1, score = oracle.volume_weights(sc, [2, 2, 2], [4, 4, 4], [2, 2, 2])
+    w = np.concatenate([w0, w1], 1)
+    assert np.isnan(score).all()
+    interior = np.array([(z * 4 + y) * 4 + x for z in (1, 2) for y in (1, 2) for x in (1, 2)])
+    assert np.allclose(w[interior].sum(1), 1.0, atol=1e-6)
+    # voxel (1,1,1) of a 4^3 volume over 2^3 probes: fract = 0.25 on every axis
+    f = 0.25
+    expect = [(1 - f) * (1 - f) * f, f * (1 - f) * f, f * (1 - f) * (1 - f), (1 - f) ** 3, (1 - f) * f * (1 - f), (1 - f) * f * f, f ** 3, f * f * (1 - f)]
+    assert np.allclose(w[(1 * 4 + 1) * 4 + 1], expect, atol=1e-6)
+    # border voxels only see the probes that exist; weights still renormalise to 1
+    assert np.allclose(w[0], [0, 0, 0, 0, 0, 0, 1, 0], atol=1e-6)
+    # a big wall at x = 0 separates the x<0 voxels from the x>0 probes
+    wall = np.array([[0, -50, -50], [0, 50, -50], [0, 50, 50], [0, -50, 50]], np.float32)
+    sc2 = oracle.Scene(wall, np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    w0, w1, score = oracle.volume_weights(sc2, [2, 2, 2], [4, 4, 4], [2, 2, 2])
+    w = np.concatenate([w0, w1], 1)
+    # voxel (2,1,1) at x = +0.5 faces the wall's front side (score 0, stays put): the -x probes (corners 0,3,4,5) are hidden
+    v = w[(1 * 4 + 1) * 4 + 2]
+    assert score[(1 * 4 + 1) * 4 + 2] == 0.0
+    assert np.allclose(v[[0, 3, 4, 5]], 0.0) and abs(v.sum() - 1.0) < 1e-6
+    fx = 0.75
+    e = np.array([(1 - fx) * (1 - f) * f, fx * (1 - f) * f, fx * (1 - f) * (1 - f), (1 - fx) * (1 - f) ** 2, (1 - fx) * f * (1 - f), (1 - fx) * f * f, fx * f * f, fx * f * (1 - f)])
+    e[[0, 3, 4, 5]] = 0; e /= e.sum()
+    assert np.allclose(v, e, atol=1e-6)
+    # voxel (1,1,1) at x = -0.5 sees the wall's back side (score 1 > 0.2) and is moved to its least-inside neighbour across the
+    # wall (light_probe.cpp:320-332), so it ends up with the +x probes as well
+    u = w[(1 * 4 + 1) * 4 + 1]
+    assert score[(1 * 4 + 1) * 4 + 1] == 1.0 and np.allclose(u[[0, 3, 4, 5]], 0.0) and abs(u.sum() - 1.0) < 1e-6
