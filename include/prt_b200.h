@@ -127,6 +127,7 @@ typedef struct {
     uint64_t node_visits;    /* only with tuning knob count_work=1: 80-byte node fetches ... */
     uint64_t tri_tests;      /* ... and 48-byte triangle fetches of the launch (algorithmic traversal work) */
     uint64_t cand_tests;     /* 32-byte entry-list candidate boxes tested (shared memory) */
+    uint64_t rays_traversed; /* rays NOT resolved by the horizon map (0 when the kernel variant has no horizon map) */
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -45,7 +46,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 0;
     // cached sample table
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res;
@@ -115,6 +116,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "refill_thresh") { if (value < 0 || value > 32) return set_err(PRT_ERR_INVALID, "refill_thresh must be in [0,32]"); c->refill_thresh = value; }
     else if (n == "count_work") c->count_work = value ? 1 : 0;
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
+    else if (n == "horizon") c->horizon = value ? 1 : 0;
     else if (n == "pair_queue") { if (value < 0 || value > 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks), 1 (pair queues) or 2 (wavefront)"); c->pair_queue = value; }
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
     return PRT_OK;
@@ -253,7 +255,11 @@ int ensure_samples(prt_ctx *c, const prt_bake_params *p) {
     for (int k = 0; k < S; k++) {
         const uint32_t s = key[k].second;
         tab[4 * k] = dirs[3 * s]; tab[4 * k + 1] = dirs[3 * s + 1]; tab[4 * k + 2] = dirs[3 * s + 2];
-        std::memcpy(&tab[4 * k + 3], &s, 4);
+        // w = reference sample index (24 bits) | azimuth bin of the local direction (5 bits, horizon map of bake_wave.cu)
+        int bin = (int)std::floor((std::atan2((double)dirs[3 * s + 1], (double)dirs[3 * s]) + 3.14159265358979323846) * (32.0 / 6.283185307179586));
+        bin = std::min(31, std::max(0, bin));
+        const uint32_t w = s | ((uint32_t)bin << 24);
+        std::memcpy(&tab[4 * k + 3], &w, 4);
     }
     CU_TRY(c->samples.reserve(sizeof(float) * 4 * (size_t)S));
     CU_TRY(cudaMemcpy(c->samples.p, tab.data(), sizeof(float) * 4 * (size_t)S, cudaMemcpyHostToDevice));
@@ -290,6 +296,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     A.origin_eps = p->origin_eps; A.bounce_eps = p->bounce_eps; A.cs_phase = p->cs_phase;
     A.refill_thresh = c->refill_thresh;
     A.entry_list = c->entry_list;
+    A.horizon = c->horizon;
     CU_TRY(cudaMemsetAsync(A.counter, 0, 128, st));
     if (d_vis) CU_TRY(cudaMemsetAsync(d_vis, 0, (size_t)n * A.vis_words * 4, st));
     int mode = p->mode == PRT_SHADOWED ? 0 : p->mode == PRT_INTERREFLECT ? 1 : p->mode == PRT_UNSHADOWED ? 2 : 3;
@@ -297,16 +304,18 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     const int grid = c->ctas_per_sm > 0 ? c->n_sms * c->ctas_per_sm : 0;
     if (e0) CU_TRY(cudaEventRecord(e0, st));
     int used_grid = grid;
-    const bool fast_ok = (mode == 0 || mode == 2) && c->entry_list && S <= bake_wave_max_samples() && c->block == 256;
-    if (fast_ok && c->pair_queue == 2)
-        CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
-    else if (fast_ok && c->pair_queue == 1)
+    const bool fast_ok = (mode == 0 || mode == 2) && c->entry_list && S <= bake_wave_max_samples();
+    if (fast_ok && c->pair_queue == 2) {
+        CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
+        c->stats.block = (uint32_t)bake_wave_block();
+    }
+    else if (fast_ok && c->pair_queue == 1 && c->block == 256)
         CU_TRY(launch_bake_shadow(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
     else
         CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
     if (e1) CU_TRY(cudaEventRecord(e1, st));
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;
-    c->stats.launches = 1; c->stats.grid = (uint32_t)used_grid; c->stats.block = (uint32_t)c->block;
+    c->stats.launches = 1; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
     c->stats_pending = e0 && e1;
     c->work_pending = c->count_work != 0;
     return PRT_OK;
@@ -373,9 +382,9 @@ int prt_ctx_last_bake_stats(const prt_ctx *cc, prt_bake_stats *out) {
     if (c->work_pending) {
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaEventSynchronize(c->ev2));
-        unsigned long long w[3] = {0, 0, 0};
-        CU_TRY(cudaMemcpy(w, (char *)c->counter.p + 64, 24, cudaMemcpyDeviceToHost));
-        c->stats.node_visits = w[0]; c->stats.tri_tests = w[1]; c->stats.cand_tests = w[2];
+        unsigned long long w[4] = {0, 0, 0, 0};
+        CU_TRY(cudaMemcpy(w, (char *)c->counter.p + 64, 32, cudaMemcpyDeviceToHost));
+        c->stats.node_visits = w[0]; c->stats.tri_tests = w[1]; c->stats.cand_tests = w[2]; c->stats.rays_traversed = w[3];
         c->work_pending = false;
     }
     *out = c->stats;

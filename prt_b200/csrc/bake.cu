@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
                 const int k = next + __popc(idle & lt_mask);
                 if (!active && k < A.S) {
                     const float4 smp = __ldg(&A.samples[k]);
-                    sidx = __float_as_uint(smp.w);
+                    sidx = __float_as_uint(smp.w) & 0xFFFFFFu;
                     const f3 dir = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
                     pos = org; seg = 0; Lw0 = Lw1 = Lw2 = 1.f;
                     tr.init(pos, dir, 0.0f, INFINITY);

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) bake_shadow_kernel(const BakeArgs A) {
                 for (int q = lane; q < ltail; q += 32) {
                     const uint32_t pair = W.lq[q];
                     const float4 smp = __ldg(&A.samples[pair >> 7]);
-                    const uint32_t sref = __float_as_uint(smp.w);
+                    const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
                     if ((W.occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
                     const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                     const float4 g = W.el.cb[pair & 127u];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) bake_shadow_kernel(const BakeArgs A) {
                             if (!active && q < itail) {
                                 const uint32_t pair = W.iq[q];
                                 const float4 smp = __ldg(&A.samples[pair >> 7]);
-                                sref = __float_as_uint(smp.w);
+                                sref = __float_as_uint(smp.w) & 0xFFFFFFu;
                                 if (!((W.occl[sref >> 5] >> (sref & 31u)) & 1u)) {
                                     tr.init(org, to_world(fr, mk3(smp.x, smp.y, smp.z)), 0.0f, INFINITY);
                                     const float4 g = W.el.cb[pair & 127u];
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) bake_shadow_kernel(const BakeArgs A) {
         for (int k = 0; k < N2; k++) acc[k] = 0.f;
         for (int i = lane; i < S; i += 32) {
             const float4 smp = __ldg(&A.samples[i]);
-            const uint32_t sref = __float_as_uint(smp.w);
+            const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
             if ((W.occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
             float y[N2];

@@ -25,10 +25,13 @@ namespace {
 
 constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples per vertex)
 #ifndef PRT_WAVE_CAP
-#define PRT_WAVE_CAP 256
+#define PRT_WAVE_CAP 192
 #endif
 #ifndef PRT_WAVE_MINB
-#define PRT_WAVE_MINB 3
+#define PRT_WAVE_MINB 7
+#endif
+#ifndef PRT_WAVE_BLOCK
+#define PRT_WAVE_BLOCK 128
 #endif
 constexpr int kNodeCap = PRT_WAVE_CAP, kLeafCap = PRT_WAVE_CAP;
 
@@ -37,6 +40,8 @@ struct WaveShared {
     uint32_t occl[kMaxS / 32];          // bit s (reference sample index): primary ray s is occluded
     uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
     uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
+    uint32_t hz[kHzBins];               // horizon map: float bits of the bound on sin(elevation) per azimuth bin
+    uint32_t pend[64];                  // processing indices of rays that are not above the horizon, waiting for a scan round
 };
 
 // Tests the 8 quantised child boxes of one node against a ray (interval [0, inf)); bit s of the result = slot s hit.
@@ -75,7 +80,7 @@ __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, con
 }
 
 template <int ORDER, bool TRACE>
-__global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
+__global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WaveShared &W = reinterpret_cast<WaveShared *>(smem_raw)[threadIdx.x >> 5];
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
     const unsigned lt_mask = (1u << lane) - 1u;
     const float sgn = A.cs_phase ? -1.0f : 1.0f;
     const int S = A.S, words = A.vis_words;
-    unsigned long long cand_tests = 0ull;
+    unsigned long long cand_tests = 0ull, rays_scanned = 0ull;
     uint32_t node_visits = 0u, tri_tests = 0u;
 
     for (;;) {
@@ -103,12 +108,13 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
         int n_cand = 0;
         if (TRACE) {
             n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-            cand_tests += (unsigned long long)n_cand * (unsigned long long)S;
+            if (A.horizon) build_horizon(W.el, n_cand, A.tris, org, fr, W.hz, lane);
         }
         __syncwarp();
 
         if (TRACE) {
             int base = 0, nn = 0, ln = 0;             // warp-uniform: next sample, node-stack fill, leaf-stack fill
+            int npend = 0;                            // warp-uniform: rays waiting in W.pend
             uint32_t m0 = 0u, m1 = 0u, m2 = 0u;       // candidate hits of the lane's scanned ray not yet queued
             uint32_t sproc = 0u;
             for (;;) {
@@ -129,21 +135,42 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
                     ln += __popc(lb); nn += __popc(ib);
                     pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
                 }
-                // ---- scan the next 32 rays against the candidate boxes ------------------------------------------------
-                if (!pending && base < S && nn <= kNodeCap / 2 && ln <= kLeafCap / 2) {
-                    const int i = base + lane;
-                    base += 32;
-                    if (i < S) {
-                        const float4 smp = __ldg(&A.samples[i]);
-                        const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
-                        uint32_t cm[3];
-                        scan_entry_list(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), cm);
-                        m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
-                        sproc = (uint32_t)i;
+                // ---- classify samples: a ray above the horizon of its azimuth bin is visible without any test ---------------
+                const bool room = nn <= kNodeCap / 2 && ln <= kLeafCap / 2;
+                if (!pending && room) {
+                    while (base < S && npend < 32) {
+                        const int i = base + lane;
+                        base += 32;
+                        bool need = false;
+                        if (i < S) {
+                            const float4 smp = __ldg(&A.samples[i]);
+                            need = !(A.horizon && smp.z > __uint_as_float(W.hz[__float_as_uint(smp.w) >> 24]));
+                        }
+                        const unsigned nb = __ballot_sync(kFull, need);
+                        if (need) W.pend[npend + __popc(nb & lt_mask)] = (uint32_t)i;
+                        npend += __popc(nb);
                     }
-                    continue;
+                    // ---- scan up to 32 waiting rays against the candidate boxes (lockstep) --------------------------------------
+                    if (npend >= 32 || (base >= S && npend > 0)) {
+                        __syncwarp();
+                        const int cnt = min(npend, 32);
+                        npend -= cnt;
+                        if (lane < cnt) {
+                            const uint32_t i = W.pend[npend + lane];
+                            const float4 smp = __ldg(&A.samples[i]);
+                            const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
+                            uint32_t cm[3];
+                            scan_entry_list(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), cm);
+                            m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
+                            sproc = i;
+                        }
+                        cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt;
+                        rays_scanned += (unsigned long long)cnt;
+                        __syncwarp();
+                        continue;
+                    }
                 }
-                if (nn == 0 && ln == 0) { if (!pending && base >= S) break; else continue; }
+                if (nn == 0 && ln == 0) { if (!pending && base >= S && npend == 0) break; else continue; }
                 __syncwarp();
                 if (ln >= 32 || nn == 0) {
                     // ---- leaf step ------------------------------------------------------------------------------------
@@ -152,7 +179,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
                     if (lane < cnt) {
                         const uint2 it = W.lq[ln + lane];
                         const float4 smp = __ldg(&A.samples[it.x & 0xFFFFu]);
-                        const uint32_t sref = __float_as_uint(smp.w);
+                        const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
                         if (!((W.occl[sref >> 5] >> (sref & 31u)) & 1u)) {
                             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                             uint32_t bits = it.x >> 16;
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
                     f3 d = mk3(0.f, 0.f, 1.f);
                     if (has) {
                         const float4 smp = __ldg(&A.samples[it.x]);
-                        const uint32_t sref = __float_as_uint(smp.w);
+                        const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
                         has = !((W.occl[sref >> 5] >> (sref & 31u)) & 1u);
                         if (has) {
                             d = to_world(fr, mk3(smp.x, smp.y, smp.z));
@@ -206,7 +233,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
                                 Trav tr; tr.reset_counters();
                                 tr.init(org, d, 0.0f, INFINITY); tr.start_group(child, 0x80000000u);
                                 if (tr.template run<true>(A.nodes, A.tris, 0, false) == TRAV_HIT) {
-                                    const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w));
+                                    const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
                                     atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
                                     inner8 = 0u; leaf8 = 0u;
                                 }
@@ -234,7 +261,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
                                     float t; uint32_t prim;
                                     tri_tests++;
                                     if (tri_hit(A.tris, tri0 + b, org, d, 0.0f, INFINITY, false, t, prim)) {
-                                        const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w));
+                                        const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
                                         atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
                                         leaf8 = 0u;
                                         break;
@@ -255,7 +282,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
         for (int k = 0; k < N2; k++) acc[k] = 0.f;
         for (int i = lane; i < S; i += 32) {
             const float4 smp = __ldg(&A.samples[i]);
-            const uint32_t sref = __float_as_uint(smp.w);
+            const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
             if ((W.occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
             float y[N2];
@@ -281,7 +308,7 @@ __global__ void __launch_bounds__(256, PRT_WAVE_MINB) bake_wave_kernel(const Bak
     }
     if (A.work) {
         const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
-        if (lane == 0) { atomicAdd(&A.work[0], nv); atomicAdd(&A.work[1], nt); atomicAdd(&A.work[2], cand_tests); }
+        if (lane == 0) { atomicAdd(&A.work[0], nv); atomicAdd(&A.work[1], nt); atomicAdd(&A.work[2], cand_tests); atomicAdd(&A.work[3], rays_scanned); }
     }
 }
 
@@ -290,7 +317,7 @@ cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cu
     const size_t smem = sizeof(WaveShared) * (size_t)(block / 32);
     static bool configured = false;   // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WaveShared) * 8));
+        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WaveShared) * (PRT_WAVE_BLOCK / 32)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -315,6 +342,7 @@ cudaError_t launch_wave_o(const BakeArgs &A, bool trace, int *grid, int block, i
 }  // namespace
 
 int bake_wave_max_samples() { return kMaxS; }
+int bake_wave_block() { return PRT_WAVE_BLOCK; }
 
 cudaError_t launch_bake_wave(const BakeArgs &A, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t st) {
     switch (order) {

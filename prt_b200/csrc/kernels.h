@@ -12,7 +12,7 @@ struct BakeArgs {
     const float *pos, *nrm;     // device; consecutive vertices `stride` bytes apart
     size_t stride;
     uint32_t n_verts, vid_base;
-    const float4 *samples;      // [S] (local dir xyz, bits of reference sample index s), processing order
+    const float4 *samples;      // [S] (local dir xyz, w = reference sample index s | azimuth bin << 24), processing order
     int S;
     float inv_S;
     float *out;                 // [n_verts][order^2]
@@ -21,6 +21,7 @@ struct BakeArgs {
     uint32_t *counter;          // persistent-warp work counter, pre-zeroed
     unsigned long long *work;   // optional [3]: node visits, triangle tests, candidate-box tests (pre-zeroed)
     int entry_list;             // 1: per-origin entry lists (bake.cu), 0: every ray starts at the root
+    int horizon;                // 1: per-origin horizon map (bake_wave.cu): rays above it skip traversal
     uint32_t seed;
     int depth;                  // path segments = bounces + 1
     float albedo[3];
@@ -38,6 +39,7 @@ int bake_shadow_max_samples();
 // warp-local wavefront kernel (bake_wave.cu), same modes / limits
 cudaError_t launch_bake_wave(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_wave_max_samples();
+int bake_wave_block();   // threads per CTA the wavefront kernel is compiled for
 cudaError_t launch_trace_any(const Node8 *, const Tri48 *, const float *rays, uint32_t n, uint8_t *out, cudaStream_t);
 cudaError_t launch_trace_closest(const Node8 *, const Tri48 *, const float *rays, uint32_t n, float *out_t,
                                  uint32_t *out_prim, float *out_ng, cudaStream_t);
