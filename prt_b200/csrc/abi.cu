@@ -46,10 +46,10 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 0;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 24, horizon_near = 35;
     // cached sample table
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
-    DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res;
+    DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res, need_bits, need_count;
     prt_bake_stats stats{};
     bool stats_pending = false, work_pending = false;
 };
@@ -97,7 +97,7 @@ void prt_ctx_destroy(prt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->samples.release(); c->counter.release(); c->d_pos.release(); c->d_nrm.release(); c->d_out.release();
-    c->d_vis.release(); c->d_rays.release(); c->d_res.release();
+    c->d_vis.release(); c->d_rays.release(); c->d_res.release(); c->need_bits.release(); c->need_count.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -117,6 +117,8 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "count_work") c->count_work = value ? 1 : 0;
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
     else if (n == "horizon") c->horizon = value ? 1 : 0;
+    else if (n == "horizon_near") { if (value < 5 || value > 95) return set_err(PRT_ERR_INVALID, "horizon_near (angular radius x100, rad) must be in [5,95]"); c->horizon_near = value; }
+    else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
     else if (n == "pair_queue") { if (value < 0 || value > 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks), 1 (pair queues) or 2 (wavefront)"); c->pair_queue = value; }
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
     return PRT_OK;
@@ -256,7 +258,11 @@ int ensure_samples(prt_ctx *c, const prt_bake_params *p) {
         const uint32_t s = key[k].second;
         tab[4 * k] = dirs[3 * s]; tab[4 * k + 1] = dirs[3 * s + 1]; tab[4 * k + 2] = dirs[3 * s + 2];
         // w = reference sample index (24 bits) | azimuth bin of the local direction (5 bits, horizon map of bake_wave.cu)
-        int bin = (int)std::floor((std::atan2((double)dirs[3 * s + 1], (double)dirs[3 * s]) + 3.14159265358979323846) * (32.0 / 6.283185307179586));
+        // diamond pseudo-angle in [0,4), same formula as hz_pang (entry_list.cuh); 8 bins per unit
+        const double lx = dirs[3 * s], ly = dirs[3 * s + 1], den = std::fabs(lx) + std::fabs(ly);
+        double pa = den > 0.0 ? ly / den : 0.0;
+        pa = lx < 0.0 ? 2.0 - pa : (ly < 0.0 ? 4.0 + pa : pa);
+        int bin = (int)std::floor(pa * 8.0);
         bin = std::min(31, std::max(0, bin));
         const uint32_t w = s | ((uint32_t)bin << 24);
         std::memcpy(&tab[4 * k + 3], &w, 4);
@@ -297,6 +303,8 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     A.refill_thresh = c->refill_thresh;
     A.entry_list = c->entry_list;
     A.horizon = c->horizon;
+    A.horizon_budget = c->horizon_budget;
+    { const float sn = sinf(0.01f * (float)c->horizon_near); A.horizon_near2 = 1.0f / (sn * sn); }
     CU_TRY(cudaMemsetAsync(A.counter, 0, 128, st));
     if (d_vis) CU_TRY(cudaMemsetAsync(d_vis, 0, (size_t)n * A.vis_words * 4, st));
     int mode = p->mode == PRT_SHADOWED ? 0 : p->mode == PRT_INTERREFLECT ? 1 : p->mode == PRT_UNSHADOWED ? 2 : 3;
@@ -305,7 +313,18 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     if (e0) CU_TRY(cudaEventRecord(e0, st));
     int used_grid = grid;
     const bool fast_ok = (mode == 0 || mode == 2) && c->entry_list && S <= bake_wave_max_samples();
+    uint32_t launches = 1;
     if (fast_ok && c->pair_queue == 2) {
+        A.need_bits = nullptr; A.need_count = nullptr;
+        if (mode == 0 && c->horizon) {
+            // pass 1: horizon map + classification; finishes the vertices whose samples are all provably visible
+            CU_TRY(c->need_bits.reserve((size_t)n * A.vis_words * 4));
+            CU_TRY(c->need_count.reserve((size_t)n * 4));
+            A.need_bits = (uint32_t *)c->need_bits.p; A.need_count = (uint32_t *)c->need_count.p;
+            int hgrid = 0;
+            CU_TRY(launch_horizon(A, p->order, &hgrid, c->n_sms, st));
+            launches = 2;
+        }
         CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
         c->stats.block = (uint32_t)bake_wave_block();
     }
@@ -315,7 +334,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
         CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
     if (e1) CU_TRY(cudaEventRecord(e1, st));
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;
-    c->stats.launches = 1; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
+    c->stats.launches = launches; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
     c->stats_pending = e0 && e1;
     c->work_pending = c->count_work != 0;
     return PRT_OK;

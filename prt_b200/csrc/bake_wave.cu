@@ -40,7 +40,6 @@ struct WaveShared {
     uint32_t occl[kMaxS / 32];          // bit s (reference sample index): primary ray s is occluded
     uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
     uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
-    uint32_t hz[kHzBins];               // horizon map: float bits of the bound on sin(elevation) per azimuth bin
     uint32_t pend[64];                  // processing indices of rays that are not above the horizon, waiting for a scan round
 };
 
@@ -79,6 +78,25 @@ __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, con
     return hits;
 }
 
+// rare overflow paths, kept out of line so that they do not occupy the instruction cache of the hot loop
+__device__ __noinline__ bool fallback_subtree(const Node8 *nodes, const Tri48 *tris, const f3 org, const f3 d, const uint32_t child, uint32_t &nv, uint32_t &nt) {
+    Trav tr; tr.reset_counters();
+    tr.init(org, d, 0.0f, INFINITY); tr.start_group(child, 0x80000000u);
+    const bool hit = tr.run<true>(nodes, tris, 0, false) == TRAV_HIT;
+    nv += tr.n_node_visits; nt += tr.n_tri_tests;
+    return hit;
+}
+__device__ __noinline__ bool fallback_leaf(const Tri48 *tris, const f3 org, const f3 d, const uint32_t tri0, uint32_t bits, uint32_t &nt) {
+    while (bits) {
+        const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+        bits &= bits - 1u;
+        float t; uint32_t prim;
+        nt++;
+        if (tri_hit(tris, tri0 + b, org, d, 0.0f, INFINITY, false, t, prim)) return true;
+    }
+    return false;
+}
+
 template <int ORDER, bool TRACE>
 __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
@@ -96,6 +114,8 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         if (lane == 0) v = atomicAdd(A.counter, 1u);
         v = __shfl_sync(kFull, v, 0);
         if (v >= A.n_verts) break;
+        if (TRACE && A.need_count && __ldg(&A.need_count[v]) == 0u) continue;     // finished by the horizon pass
+        const uint32_t *need_row = (TRACE && A.need_bits) ? A.need_bits + (size_t)v * A.vis_words : nullptr;
 
         const float *pp = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.pos) + (size_t)v * A.stride);
         const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
@@ -108,7 +128,6 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         int n_cand = 0;
         if (TRACE) {
             n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-            if (A.horizon) build_horizon(W.el, n_cand, A.tris, org, fr, W.hz, lane);
         }
         __syncwarp();
 
@@ -141,11 +160,9 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                     while (base < S && npend < 32) {
                         const int i = base + lane;
                         base += 32;
-                        bool need = false;
-                        if (i < S) {
-                            const float4 smp = __ldg(&A.samples[i]);
-                            need = !(A.horizon && smp.z > __uint_as_float(W.hz[__float_as_uint(smp.w) >> 24]));
-                        }
+                        // samples the horizon pass proved visible are skipped (need bit = 0)
+                        bool need = i < S;
+                        if (need_row) need = need && ((__ldg(&need_row[i >> 5]) >> lane) & 1u);
                         const unsigned nb = __ballot_sync(kFull, need);
                         if (need) W.pend[npend + __popc(nb & lt_mask)] = (uint32_t)i;
                         npend += __popc(nb);
@@ -230,14 +247,11 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             if (pos < kNodeCap) W.nq[pos] = make_uint2(it.x, child);
                             else {
                                 // stack full: ordinary traversal of this subtree (rare)
-                                Trav tr; tr.reset_counters();
-                                tr.init(org, d, 0.0f, INFINITY); tr.start_group(child, 0x80000000u);
-                                if (tr.template run<true>(A.nodes, A.tris, 0, false) == TRAV_HIT) {
+                                if (fallback_subtree(A.nodes, A.tris, org, d, child, node_visits, tri_tests)) {
                                     const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
                                     atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
                                     inner8 = 0u; leaf8 = 0u;
                                 }
-                                node_visits += tr.n_node_visits; tri_tests += tr.n_tri_tests;
                             }
                         }
                         nn = min(nn + __popc(pb), kNodeCap);
@@ -254,19 +268,10 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                         const int pos = ln + __popc(pb & lt_mask);
                         if (p) {
                             if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
-                            else {
-                                while (bits) {
-                                    const uint32_t b = (uint32_t)__ffs(bits) - 1u;
-                                    bits &= bits - 1u;
-                                    float t; uint32_t prim;
-                                    tri_tests++;
-                                    if (tri_hit(A.tris, tri0 + b, org, d, 0.0f, INFINITY, false, t, prim)) {
-                                        const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
-                                        atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
-                                        leaf8 = 0u;
-                                        break;
-                                    }
-                                }
+                            else if (fallback_leaf(A.tris, org, d, tri0, bits, tri_tests)) {
+                                const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
+                                atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                leaf8 = 0u;
                             }
                         }
                         ln = min(ln + __popc(pb), kLeafCap);

@@ -136,156 +136,263 @@ __device__ __forceinline__ uint32_t warp_excl_scan_packed(uint32_t v, const int 
 }
 
 // ---- per-origin horizon map -------------------------------------------------------------------------------------------
-// kHzBins azimuth bins (local frame of the vertex, azimuth = atan2(y, x)); hz[b] = a conservative upper bound of
-// sin(elevation above the tangent plane) of ALL geometry seen from the origin in that azimuth range.  A ray whose local z
-// exceeds hz[bin] cannot hit anything and is visible without any traversal.  Every piece of geometry is covered by exactly one
-// entry-list candidate (culled ones lie wholly below the tangent plane), so bounding every candidate bounds the scene:
+// kHzBins azimuth bins in the local frame of the vertex; hz[b] = a conservative upper bound of sin(elevation above the tangent
+// plane) of ALL geometry seen from the origin in that azimuth range.  A ray whose local z exceeds hz[bin] cannot hit anything and
+// is visible without any traversal.  Every piece of geometry is covered by exactly one entry-list candidate (culled ones lie
+// wholly below the tangent plane), so bounding every candidate bounds the scene:
 //   leaf candidate     exact maximum elevation of each of its triangles: maximum over the three edge arcs (end points and the
-//                      interior critical point, which is the root of a LINEAR equation) or 1 if the zenith pierces the triangle;
-//                      azimuth range = minimal arc containing the (non-degenerate) vertex azimuths
-//   subtree candidate  cone around the bounding sphere of its box (the builder expands any child whose sphere contains the origin)
-// Margins (2e-4 in sin-elevation, 0.02 rad in azimuth) absorb float rounding; rays inside the margin simply take the full path.
+//                      interior critical point, which is the root of a LINEAR equation) or 1 if the vertical axis pierces it
+//   subtree candidate  small angular size: cone around its bounding sphere; large angular size ("near"): the builder descends into
+//                      it -- WITHOUT adding candidates -- until the pieces are small or are triangles (budgeted)
+// Azimuth is measured by the monotone "diamond" pseudo-angle p(x,y) in [0,4) (one division, no atan2); bins are uniform in p and
+// the host bins the sample directions with the same formula.  Margins (2e-4 in sin-elevation, 0.02 in p >= 0.9 degree) absorb
+// float rounding; rays inside the margin simply take the full path.  Lane b of the warp owns bin b while the map is built.
 constexpr int kHzBins = 32;
-constexpr float kHzTwoPi = 6.283185307179586f;
 
-__device__ __forceinline__ void hz_update(uint32_t *hz, float phi_lo, float phi_hi, bool all, float sinh) {
-    if (!(sinh > 0.0f)) return;
-    const uint32_t v = __float_as_uint(fminf(sinh + 2e-4f, 2.0f));
-    if (all || !(phi_hi - phi_lo < kHzTwoPi - 0.1f)) {
-        for (int b = 0; b < kHzBins; b++) atomicMax(&hz[b], v);
-        return;
+struct HzItem { int b0, b1; float v; };          // bins b0..b1 (unwrapped, b1-b0 <= 31), value; v <= 0: empty
+
+__device__ __forceinline__ float hz_pang(float x, float y) {
+    const float p = __fdividef(y, fabsf(x) + fabsf(y));
+    return x < 0.f ? 2.f - p : (y < 0.f ? 4.f + p : p);
+}
+__device__ __forceinline__ HzItem hz_item(float lo, float hi, bool all, float sinh) {
+    HzItem it; it.b0 = 0; it.b1 = 0; it.v = 0.f;
+    if (!(sinh > 0.0f)) return it;
+    it.v = fminf(sinh + 2e-4f, 2.0f);
+    it.b1 = kHzBins - 1;
+    if (all || !(hi - lo < 3.9f)) return it;
+    const int b0 = (int)floorf((lo - 0.02f) * 8.f), b1 = (int)floorf((hi + 0.02f) * 8.f);
+    if (b1 - b0 >= kHzBins - 1) return it;
+    it.b0 = b0; it.b1 = b1;
+    return it;
+}
+// warp-collective: every lane contributes one item; lane = bin keeps the running maximum
+__device__ __forceinline__ float hz_merge(float my, const HzItem it, const int lane) {
+    unsigned m = __ballot_sync(kFull, it.v > 0.f);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1u;
+        const int b0 = __shfl_sync(kFull, it.b0, src), b1 = __shfl_sync(kFull, it.b1, src);
+        const float v = __shfl_sync(kFull, it.v, src);
+        if (((lane - b0) & (kHzBins - 1)) <= b1 - b0) my = fmaxf(my, v);
     }
-    // bins are [b, b+1) * 2pi/kHzBins - pi; walk from the bin of phi_lo - margin to the bin of phi_hi + margin (with wrap)
-    const float scale = (float)kHzBins / kHzTwoPi;
-    const int b0 = (int)floorf((phi_lo - 0.02f + 3.14159265358979f) * scale), b1 = (int)floorf((phi_hi + 0.02f + 3.14159265358979f) * scale);
-    for (int b = b0; b <= b1; b++) atomicMax(&hz[((b % kHzBins) + kHzBins) % kHzBins], v);
+    return my;
 }
 
 // maximum of (v.z / |v|) over the segment a + t (b - a), t in [0,1]  (local frame: z = height above the tangent plane)
 __device__ __forceinline__ float hz_edge_max(const f3 a, const f3 b) {
-    const float la = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), lb = sqrtf(b.x * b.x + b.y * b.y + b.z * b.z);
-    float m = fmaxf(la > 0.f ? a.z / la : 1.f, lb > 0.f ? b.z / lb : 1.f);
+    const float la2 = a.x * a.x + a.y * a.y + a.z * a.z, lb2 = b.x * b.x + b.y * b.y + b.z * b.z;
+    float m = fmaxf(la2 > 0.f ? a.z * rsqrtf(la2) : 1.f, lb2 > 0.f ? b.z * rsqrtf(lb2) : 1.f);
     const f3 e = mk3(b.x - a.x, b.y - a.y, b.z - a.z);
     const float ae = a.x * e.x + a.y * e.y + a.z * e.z, ee = e.x * e.x + e.y * e.y + e.z * e.z;
     const float den = e.z * ae - a.z * ee;
     if (fabsf(den) > 0.f) {
-        const float t = (a.z * ae - e.z * la * la) / den;
+        const float t = __fdividef(a.z * ae - e.z * la2, den);
         if (t > 0.f && t < 1.f) {
             const f3 v = mk3(a.x + t * e.x, a.y + t * e.y, a.z + t * e.z);
-            const float lv = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-            m = fmaxf(m, lv > 0.f ? v.z / lv : 1.f);
+            const float lv2 = v.x * v.x + v.y * v.y + v.z * v.z;
+            m = fmaxf(m, lv2 > 0.f ? v.z * rsqrtf(lv2) : 1.f);
         }
     }
     return m;
 }
 
-__device__ __forceinline__ void hz_triangle(uint32_t *hz, const f3 q0, const f3 q1, const f3 q2) {
+__device__ __forceinline__ HzItem hz_triangle(const f3 q0, const f3 q1, const f3 q2) {
     const float zmax = fmaxf(q0.z, fmaxf(q1.z, q2.z));
     const float scale = fmaxf(fmaxf(fabsf(q0.x) + fabsf(q0.y) + fabsf(q0.z), fabsf(q1.x) + fabsf(q1.y) + fabsf(q1.z)), fabsf(q2.x) + fabsf(q2.y) + fabsf(q2.z));
-    if (zmax < -1e-5f * scale) return;                       // wholly below the tangent plane
+    if (zmax < -1e-5f * scale) return hz_item(0.f, 0.f, false, 0.f);       // wholly below the tangent plane
     float sinh = fmaxf(hz_edge_max(q0, q1), fmaxf(hz_edge_max(q1, q2), hz_edge_max(q2, q0)));
-    // zenith inside the triangle's cone: (0,0,1) . (qi x qj) all of one sign (with tolerance) and the plane is above the origin
+    // vertical axis through the triangle: (0,0,1) . (qi x qj) all of one sign (with tolerance)
     const float c01 = q0.x * q1.y - q0.y * q1.x, c12 = q1.x * q2.y - q1.y * q2.x, c20 = q2.x * q0.y - q2.y * q0.x;
     const float tol = 1e-6f * scale * scale;
     const bool surround = (c01 >= -tol && c12 >= -tol && c20 >= -tol) || (c01 <= tol && c12 <= tol && c20 <= tol);
-    // azimuth range: minimal arc containing the azimuths of the vertices that are not (numerically) on the vertical axis
+    // azimuth range: minimal arc containing the pseudo-angles of the vertices that are not (numerically) on the vertical axis
     float ph[3]; int np = 0;
     const float rmin = 1e-4f * scale;
-    if (fabsf(q0.x) + fabsf(q0.y) > rmin) ph[np++] = atan2f(q0.y, q0.x);
-    if (fabsf(q1.x) + fabsf(q1.y) > rmin) ph[np++] = atan2f(q1.y, q1.x);
-    if (fabsf(q2.x) + fabsf(q2.y) > rmin) ph[np++] = atan2f(q2.y, q2.x);
+    if (fabsf(q0.x) + fabsf(q0.y) > rmin) ph[np++] = hz_pang(q0.x, q0.y);
+    if (fabsf(q1.x) + fabsf(q1.y) > rmin) ph[np++] = hz_pang(q1.x, q1.y);
+    if (fabsf(q2.x) + fabsf(q2.y) > rmin) ph[np++] = hz_pang(q2.x, q2.y);
     bool all = false;
     float lo = 0.f, hi = 0.f;
-    if (np == 3 && surround) { all = true; if (zmax > 0.f) sinh = 1.0f; }        // the vertical axis passes through the triangle
+    if (np == 3 && surround) { all = true; if (zmax > 0.f) sinh = 1.0f; }
     else if (np == 0) all = true;
     else if (np == 1) { lo = hi = ph[0]; }
+    else if (np == 2) { lo = fminf(ph[0], ph[1]); hi = fmaxf(ph[0], ph[1]); if (hi - lo > 2.f) { const float t = lo; lo = hi; hi = t + 4.f; } }
     else {
-        // sort, then drop the largest gap
-        if (np == 2) { lo = fminf(ph[0], ph[1]); hi = fmaxf(ph[0], ph[1]); if (hi - lo > 3.14159265358979f) { const float t = lo; lo = hi; hi = t + kHzTwoPi; } }
-        else {
-            float a = ph[0], b = ph[1], c = ph[2], t;
-            if (a > b) { t = a; a = b; b = t; } if (b > c) { t = b; b = c; c = t; } if (a > b) { t = a; a = b; b = t; }
-            const float g0 = b - a, g1 = c - b, g2 = a + kHzTwoPi - c;
-            if (g2 >= g0 && g2 >= g1) { lo = a; hi = c; }
-            else if (g0 >= g1) { lo = b; hi = a + kHzTwoPi; }
-            else { lo = c; hi = b + kHzTwoPi; }
-            if (hi - lo > 3.14159265358979f) all = true;      // cannot happen for a planar triangle that does not surround the axis; be safe
-        }
+        float a = ph[0], b = ph[1], c = ph[2], t;
+        if (a > b) { t = a; a = b; b = t; } if (b > c) { t = b; b = c; c = t; } if (a > b) { t = a; a = b; b = t; }
+        const float g0 = b - a, g1 = c - b, g2 = a + 4.f - c;
+        if (g2 >= g0 && g2 >= g1) { lo = a; hi = c; }
+        else if (g0 >= g1) { lo = b; hi = a + 4.f; }
+        else { lo = c; hi = b + 4.f; }
+        if (hi - lo > 2.f) all = true;
     }
-    hz_update(hz, lo, hi, all, sinh);
+    return hz_item(lo, hi, all, sinh);
 }
 
-__device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Tri48 *tris, const f3 O, const Frame &fr, uint32_t *hz, const int lane) {
-    hz[lane] = 0u;                                           // kHzBins == 32
-    __syncwarp();
-    for (int k = lane; k < n_cand; k += 32) {
-        const float4 ca = W.ca[k], cb = W.cb[k];
-        const uint32_t gx = __float_as_uint(cb.z), gy = __float_as_uint(cb.w);
-        if (gy > 0x00FFFFFFu) {
-            // subtree candidate: exact bound of its box.  For a convex polyhedron that the vertical axis does not pierce the
-            // maximum elevation lies on an edge (elevation is quasi-concave on every face plane), so 12 edge maxima suffice.
-            if (!(ca.w < 1e30f)) { hz_update(hz, 0.f, 0.f, true, 1.0f); continue; }      // overflow candidate: unbounded
-            {
-                // vertical ray O + t n, t >= 0, against the box (slab test)
-                float t0 = 0.f, t1 = 3.0e38f;
-                const float cc[3] = {ca.x, ca.y, ca.z}, ee[3] = {ca.w, cb.x, cb.y}, nn3[3] = {fr.n.x, fr.n.y, fr.n.z};
+// exact bound of a box (centre c relative to the origin, half extents e): 12 edge maxima, or 1 if the vertical ray pierces it
+static __device__ __noinline__ HzItem hz_box(const f3 c, const f3 e, const Frame &fr) {
+    if (!(e.x < 1e30f)) return hz_item(0.f, 0.f, true, 1.0f);               // overflow candidate: unbounded
+    {
+        float t0 = 0.f, t1 = 3.0e38f;
+        const float cc[3] = {c.x, c.y, c.z}, ee[3] = {e.x, e.y, e.z}, nn3[3] = {fr.n.x, fr.n.y, fr.n.z};
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const float inv = 1.0f / (fabsf(nn3[a]) < 1e-12f ? copysignf(1e-12f, nn3[a]) : nn3[a]);
-                    const float ta = (cc[a] - ee[a]) * inv, tb = (cc[a] + ee[a]) * inv;
-                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-                }
-                if (t0 <= t1 * 1.0001f + 1e-6f) { hz_update(hz, 0.f, 0.f, true, 1.0f); continue; }
+        for (int a = 0; a < 3; a++) {
+            const float inv = 1.0f / (fabsf(nn3[a]) < 1e-12f ? copysignf(1e-12f, nn3[a]) : nn3[a]);
+            const float ta = (cc[a] - ee[a]) * inv, tb = (cc[a] + ee[a]) * inv;
+            t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+        }
+        if (t0 <= t1 * 1.0001f + 1e-6f) return hz_item(0.f, 0.f, true, 1.0f);
+    }
+    const f3 cl = mk3(c.x * fr.right.x + c.y * fr.right.y + c.z * fr.right.z, c.x * fr.up.x + c.y * fr.up.y + c.z * fr.up.z, c.x * fr.n.x + c.y * fr.n.y + c.z * fr.n.z);
+    const f3 hx = mk3(e.x * fr.right.x, e.x * fr.up.x, e.x * fr.n.x), hy = mk3(e.y * fr.right.y, e.y * fr.up.y, e.y * fr.n.y), hzv = mk3(e.z * fr.right.z, e.z * fr.up.z, e.z * fr.n.z);
+    f3 q[8];
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        const float sx = (i & 1) ? 1.f : -1.f, sy = (i & 2) ? 1.f : -1.f, sz = (i & 4) ? 1.f : -1.f;
+        q[i] = mk3(cl.x + sx * hx.x + sy * hy.x + sz * hzv.x, cl.y + sx * hx.y + sy * hy.y + sz * hzv.y, cl.z + sx * hx.z + sy * hy.z + sz * hzv.z);
+    }
+    float sinh = -1.f;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        if (!(i & 1)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 1]));
+        if (!(i & 2)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 2]));
+        if (!(i & 4)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 4]));
+    }
+    const float rc = fabsf(cl.x) + fabsf(cl.y), sc = e.x + e.y + e.z + fabsf(c.x) + fabsf(c.y) + fabsf(c.z);
+    bool all = !(rc > 1e-4f * sc);
+    float lo = 0.f, hi = 0.f, pc = 0.f;
+    if (!all) {
+        pc = hz_pang(cl.x, cl.y);
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {
+            if (!(fabsf(q[i].x) + fabsf(q[i].y) > 1e-4f * sc)) { all = true; continue; }
+            float dl = hz_pang(q[i].x, q[i].y) - pc;
+            if (dl > 2.f) dl -= 4.f;
+            if (dl < -2.f) dl += 4.f;
+            lo = fminf(lo, dl); hi = fmaxf(hi, dl);
+        }
+        if (hi - lo >= 1.98f) all = true;                                  // the box surrounds the vertical axis
+    }
+    if (pc + lo < 0.f) pc += 4.f;
+    return hz_item(pc + lo, pc + hi, all, sinh);
+}
+
+// cone around the bounding sphere of a box (r^2 = |e|^2, d^2 = |c|^2 > r^2): cheap, slightly loose
+__device__ __forceinline__ HzItem hz_sphere(const f3 c, const float r2, const float d2, const Frame &fr) {
+    const float id = rsqrtf(d2), sina = fminf(sqrtf(r2) * id * 1.0001f + 1e-6f, 1.0f), cosa = sqrtf(fmaxf(0.f, 1.f - sina * sina));
+    const float ax = c.x * fr.right.x + c.y * fr.right.y + c.z * fr.right.z, ay = c.x * fr.up.x + c.y * fr.up.y + c.z * fr.up.z;
+    const float sinb = fminf(1.f, fmaxf(-1.f, (c.x * fr.n.x + c.y * fr.n.y + c.z * fr.n.z) * id)), cosb = sqrtf(fmaxf(0.f, 1.f - sinb * sinb));
+    float sinh = sinb * cosa + cosb * sina;
+    if (sinb >= cosa) sinh = 1.0f;                   // elevation + half angle >= 90 degrees
+    if (sina >= 0.98f * cosb || !(fabsf(ax) + fabsf(ay) > 0.f)) return hz_item(0.f, 0.f, true, sinh);
+    // asin(x) <= x (1 + 0.58 x^2) on [0,1]; d(pseudo-angle) <= d(angle), so the true half width bounds the pseudo one
+    const float x = __fdividef(sina, cosb), dphi = x * (1.f + 0.58f * x * x) + 1e-3f;
+    float p = hz_pang(ax, ay);
+    if (p - dphi < 0.f) p += 4.f;
+    return hz_item(p - dphi, p + dphi, false, sinh);
+}
+
+__device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t ti, const f3 O, const Frame &fr) {
+    const char *tp = reinterpret_cast<const char *>(tris + ti);
+    const u4 a4 = ld16(tp), b4 = ld16(tp + 16), c4 = ld16(tp + 32);
+    const f3 p0 = mk3(PRT_U2F(a4.x) - O.x, PRT_U2F(a4.y) - O.y, PRT_U2F(a4.z) - O.z);
+    const f3 p1 = mk3(p0.x + PRT_U2F(b4.x), p0.y + PRT_U2F(b4.y), p0.z + PRT_U2F(b4.z));
+    const f3 p2 = mk3(p0.x + PRT_U2F(c4.x), p0.y + PRT_U2F(c4.y), p0.z + PRT_U2F(c4.z));
+    const f3 q0 = mk3(p0.x * fr.right.x + p0.y * fr.right.y + p0.z * fr.right.z, p0.x * fr.up.x + p0.y * fr.up.y + p0.z * fr.up.z, p0.x * fr.n.x + p0.y * fr.n.y + p0.z * fr.n.z);
+    const f3 q1 = mk3(p1.x * fr.right.x + p1.y * fr.right.y + p1.z * fr.right.z, p1.x * fr.up.x + p1.y * fr.up.y + p1.z * fr.up.z, p1.x * fr.n.x + p1.y * fr.n.y + p1.z * fr.n.z);
+    const f3 q2 = mk3(p2.x * fr.right.x + p2.y * fr.right.y + p2.z * fr.right.z, p2.x * fr.up.x + p2.y * fr.up.y + p2.z * fr.up.z, p2.x * fr.n.x + p2.y * fr.n.y + p2.z * fr.n.z);
+    return hz_triangle(q0, q1, q2);
+}
+
+constexpr int kHzQueue = 64;
+// `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2))
+__device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
+                                              const Frame &fr, uint32_t *hz, uint32_t *rq, const int budget_iters, const float near2, const int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float my = 0.f;                                          // lane b owns bin b
+    int rn = 0;
+    // work item of a lane in one round: up to 3 triangles (leaf) or one box
+    // ---- pass 1: the entry-list candidates; pass 2: children of queued subtrees (4 nodes x 8 children per iteration) ------
+    int k0 = 0, budget = budget_iters;
+    for (;;) {
+        const bool pass1 = k0 < n_cand;
+        if (!pass1 && rn == 0) break;
+        bool valid = false, inner = false;
+        f3 c = mk3(0.f, 0.f, 0.f), e = mk3(0.f, 0.f, 0.f);
+        uint32_t gx = 0u, unary = 0u;
+        if (pass1) {
+            const int k = k0 + lane;
+            if (k < n_cand) {
+                const float4 ca = W.ca[k], cb = W.cb[k];
+                gx = __float_as_uint(cb.z);
+                const uint32_t gy = __float_as_uint(cb.w);
+                valid = true; inner = gy > 0x00FFFFFFu; unary = gy;
+                c = mk3(ca.x, ca.y, ca.z); e = mk3(ca.w, cb.x, cb.y);
             }
-            const f3 cl = mk3(ca.x * fr.right.x + ca.y * fr.right.y + ca.z * fr.right.z, ca.x * fr.up.x + ca.y * fr.up.y + ca.z * fr.up.z,
-                              ca.x * fr.n.x + ca.y * fr.n.y + ca.z * fr.n.z);
-            const f3 hx = mk3(ca.w * fr.right.x, ca.w * fr.up.x, ca.w * fr.n.x), hy = mk3(cb.x * fr.right.y, cb.x * fr.up.y, cb.x * fr.n.y),
-                     hzv = mk3(cb.y * fr.right.z, cb.y * fr.up.z, cb.y * fr.n.z);
-            f3 q[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float sx = (i & 1) ? 1.f : -1.f, sy = (i & 2) ? 1.f : -1.f, sz = (i & 4) ? 1.f : -1.f;
-                q[i] = mk3(cl.x + sx * hx.x + sy * hy.x + sz * hzv.x, cl.y + sx * hx.y + sy * hy.y + sz * hzv.y, cl.z + sx * hx.z + sy * hy.z + sz * hzv.z);
-            }
-            float sinh = -1.f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (!(i & 1)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 1]));
-                if (!(i & 2)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 2]));
-                if (!(i & 4)) sinh = fmaxf(sinh, hz_edge_max(q[i], q[i | 4]));
-            }
-            if (!(sinh > 0.f)) continue;
-            // azimuth range relative to the centre's azimuth; a span >= pi means the box surrounds the vertical axis
-            const float rc = fabsf(cl.x) + fabsf(cl.y), sc = fabsf(ca.w) + fabsf(cb.x) + fabsf(cb.y) + fabsf(ca.x) + fabsf(ca.y) + fabsf(ca.z);
-            bool all = !(rc > 1e-4f * sc);
-            float lo = 0.f, hi = 0.f;
-            const float phic = atan2f(cl.y, cl.x);
-            if (!all) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (!(fabsf(q[i].x) + fabsf(q[i].y) > 1e-4f * sc)) { all = true; continue; }
-                    float dl = atan2f(q[i].y, q[i].x) - phic;
-                    if (dl > 3.14159265358979f) dl -= kHzTwoPi;
-                    if (dl < -3.14159265358979f) dl += kHzTwoPi;
-                    lo = fminf(lo, dl); hi = fmaxf(hi, dl);
-                }
-                if (hi - lo >= 3.14159265358979f - 0.02f) all = true;
-            }
-            hz_update(hz, phic + lo, phic + hi, all, sinh);
+            k0 += 32;
         } else {
-            for (uint32_t bits = gy, j = 0; bits; bits >>= 1, j++) {
-                const char *tp = reinterpret_cast<const char *>(tris + gx + j);
-                const u4 a4 = ld16(tp), b4 = ld16(tp + 16), c4 = ld16(tp + 32);
-                const f3 p0 = mk3(PRT_U2F(a4.x) - O.x, PRT_U2F(a4.y) - O.y, PRT_U2F(a4.z) - O.z);
-                const f3 p1 = mk3(p0.x + PRT_U2F(b4.x), p0.y + PRT_U2F(b4.y), p0.z + PRT_U2F(b4.z));
-                const f3 p2 = mk3(p0.x + PRT_U2F(c4.x), p0.y + PRT_U2F(c4.y), p0.z + PRT_U2F(c4.z));
-                const f3 q0 = mk3(p0.x * fr.right.x + p0.y * fr.right.y + p0.z * fr.right.z, p0.x * fr.up.x + p0.y * fr.up.y + p0.z * fr.up.z, p0.x * fr.n.x + p0.y * fr.n.y + p0.z * fr.n.z);
-                const f3 q1 = mk3(p1.x * fr.right.x + p1.y * fr.right.y + p1.z * fr.right.z, p1.x * fr.up.x + p1.y * fr.up.y + p1.z * fr.up.z, p1.x * fr.n.x + p1.y * fr.n.y + p1.z * fr.n.z);
-                const f3 q2 = mk3(p2.x * fr.right.x + p2.y * fr.right.y + p2.z * fr.right.z, p2.x * fr.up.x + p2.y * fr.up.y + p2.z * fr.up.z, p2.x * fr.n.x + p2.y * fr.n.y + p2.z * fr.n.z);
-                hz_triangle(hz, q0, q1, q2);
+            const int take = min(rn, 4), g = lane >> 3, slot = lane & 7;
+            uint32_t node = 0xFFFFFFFFu;
+            if (g < take) node = rq[rn - 1 - g];
+            rn -= take;
+            budget--;
+            __syncwarp();
+            if (node != 0xFFFFFFFFu) {
+                const char *np = reinterpret_cast<const char *>(nodes + node);
+                const u4 n0 = ld16(np), n1 = ld16(np + 16), n2 = ld16(np + 32), n3 = ld16(np + 48), n4 = ld16(np + 64);
+                const int h = slot >> 2, sh = 8 * (slot & 3);
+                const uint32_t meta = ((h ? n1.w : n1.z) >> sh) & 0xFFu;
+                if (meta) {
+                    const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23), sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+                    const float lox = __uint_as_float(n0.x) + (float)(((h ? n2.y : n2.x) >> sh) & 0xFFu) * sx;
+                    const float loy = __uint_as_float(n0.y) + (float)(((h ? n2.w : n2.z) >> sh) & 0xFFu) * sy;
+                    const float loz = __uint_as_float(n0.z) + (float)(((h ? n3.y : n3.x) >> sh) & 0xFFu) * sz;
+                    const float hix = __uint_as_float(n0.x) + (float)(((h ? n3.w : n3.z) >> sh) & 0xFFu) * sx;
+                    const float hiy = __uint_as_float(n0.y) + (float)(((h ? n4.y : n4.x) >> sh) & 0xFFu) * sy;
+                    const float hiz = __uint_as_float(n0.z) + (float)(((h ? n4.w : n4.z) >> sh) & 0xFFu) * sz;
+                    c = mk3(0.5f * (lox + hix) - O.x, 0.5f * (loy + hiy) - O.y, 0.5f * (loz + hiz) - O.z);
+                    e = mk3(0.5f * (hix - lox), 0.5f * (hiy - loy), 0.5f * (hiz - loz));
+                    e.x += 4e-7f * (fabsf(c.x) + e.x); e.y += 4e-7f * (fabsf(c.y) + e.y); e.z += 4e-7f * (fabsf(c.z) + e.z);
+                    const float top = N.x * c.x + N.y * c.y + N.z * c.z + fabsf(N.x) * e.x + fabsf(N.y) * e.y + fabsf(N.z) * e.z;
+                    const float far = fmaxf(fabsf(c.x) + e.x, fmaxf(fabsf(c.y) + e.y, fabsf(c.z) + e.z));
+                    if (!(top < -1e-5f * far)) {
+                        valid = true;
+                        inner = (n0.w >> (24 + slot)) & 1u;
+                        if (inner) gx = n1.x + __popc((n0.w >> 24) & ((1u << slot) - 1u));
+                        else { gx = n1.y + (meta & 31u); unary = meta >> 5; }
+                    }
+                }
             }
         }
+        // classify boxes: far -> sphere cone, near -> refine (while budget and queue space last), else exact box bound
+        HzItem it = hz_item(0.f, 0.f, false, 0.f);
+        bool push = false;
+        if (valid && inner) {
+            const float r2 = e.x * e.x + e.y * e.y + e.z * e.z, d2 = c.x * c.x + c.y * c.y + c.z * c.z;
+            if (!(e.x < 1e30f)) it = hz_item(0.f, 0.f, true, 1.0f);
+            else if (!(d2 < near2 * r2)) it = hz_sphere(c, r2, d2, fr);
+            else push = budget > 0;
+        }
+        const unsigned pb = __ballot_sync(kFull, push);
+        const int pos = rn + __popc(pb & lt_mask);
+        if (push && pos < kHzQueue) rq[pos] = gx;
+        const bool boxed = valid && inner && (e.x < 1e30f) && (c.x * c.x + c.y * c.y + c.z * c.z < near2 * (e.x * e.x + e.y * e.y + e.z * e.z)) && !(push && pos < kHzQueue);
+        if (__any_sync(kFull, boxed)) { if (boxed) it = hz_box(c, e, fr); }
+        rn = min(rn + __popc(pb), kHzQueue);
+        my = hz_merge(my, it, lane);
+        // leaves: one merge per triangle index so that every triangle keeps its own azimuth range
+        const bool leaf = valid && !inner;
+        for (uint32_t j = 0; j < 3u; j++) {
+            const bool has = leaf && ((unary >> j) & 1u);
+            if (!__any_sync(kFull, has)) break;
+            HzItem ti = hz_item(0.f, 0.f, false, 0.f);
+            if (has) ti = hz_tri_item(tris, gx + j, O, fr);
+            my = hz_merge(my, ti, lane);
+        }
+        __syncwarp();
     }
+    hz[lane] = __float_as_uint(my);
     __syncwarp();
 }
 
@@ -296,7 +403,7 @@ __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n,
     for (int w = 0; w < 3; w++) {
         uint32_t bits = 0u, bit = 1u;
         const int k1 = min(n, 32 * (w + 1));
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 32 * w; k < k1; k++) {
             const float4 a = W.ca[k], b = W.cb[k];
             const float tx = a.x * idx, ty = a.y * idy, tz = a.z * idz;

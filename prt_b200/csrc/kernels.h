@@ -22,6 +22,11 @@ struct BakeArgs {
     unsigned long long *work;   // optional [3]: node visits, triangle tests, candidate-box tests (pre-zeroed)
     int entry_list;             // 1: per-origin entry lists (bake.cu), 0: every ray starts at the root
     int horizon;                // 1: per-origin horizon map (bake_wave.cu): rays above it skip traversal
+    int horizon_budget;         // refinement iterations (4 nodes each) the horizon builder may spend per vertex
+    float horizon_near2;        // refine boxes with d^2 < near2 * r^2 (angular radius above asin(1/sqrt(near2)))
+    uint32_t *need_bits;        // horizon pass output / traversal pass input: [n_verts][vis_words], bit i of a row = sample with
+                                // processing index i is NOT above the horizon and must be traced
+    uint32_t *need_count;       // [n_verts] number of such samples; 0 = the horizon pass already wrote the vertex's row
     uint32_t seed;
     int depth;                  // path segments = bounces + 1
     float albedo[3];
@@ -36,6 +41,8 @@ cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int bl
 // pair-queue kernel for the shadowed (trace = true) and unshadowed Monte-Carlo (trace = false) modes, S <= bake_shadow_max_samples()
 cudaError_t launch_bake_shadow(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_shadow_max_samples();
+// horizon pass (horizon.cu): per-vertex horizon map, classification of every sample, rows of fully visible vertices
+cudaError_t launch_horizon(const BakeArgs &, int order, int *grid, int n_sms, cudaStream_t);
 // warp-local wavefront kernel (bake_wave.cu), same modes / limits
 cudaError_t launch_bake_wave(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_wave_max_samples();

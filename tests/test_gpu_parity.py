@@ -97,7 +97,7 @@ def test_bake_reference_defaults(torus, torus_scenes, prt, oracle):
     assert 0.3 < frac < 0.98  # the torus really is self-occluding
 
 
-@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=1), dict(pair_queue=0), dict(pair_queue=1), dict(pair_queue=1, refill_thresh=0),
+@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4), dict(pair_queue=0), dict(pair_queue=1), dict(pair_queue=1, refill_thresh=0),
                                    dict(pair_queue=0, refill_thresh=0), dict(entry_list=0), dict(entry_list=0, refill_thresh=16)])
 def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     """ray compaction, per-origin entry lists and the pair queues only reorganise work: results must not change."""
@@ -108,7 +108,7 @@ def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     try:
         got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(samples_u=16, samples_v=16), want_vis=True)
     finally:
-        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=0)
+        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=24, horizon_near=35)
     ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(samples_u=16, samples_v=16), want_vis=True)
     assert np.array_equal(gvis, ovis)
     assert rel_l2(got, ref).max() <= REL_L2_TOL
