@@ -118,7 +118,7 @@ int prt_bake_sample_table(const prt_bake_params *, float *uv, float *local_dirs)
 
 /* Per-call statistics of the most recent bake on this context */
 typedef struct {
-    double kernel_ms;        /* traversal+projection kernel, CUDA events on the launching stream */
+    double kernel_ms;        /* all kernels of the bake (horizon pass + traversal/projection), CUDA events on the launching stream */
     double h2d_ms, d2h_ms;   /* host-pointer entry point only */
     uint64_t rays;           /* primary rays issued */
     uint64_t h2d_bytes, d2h_bytes;
@@ -128,6 +128,7 @@ typedef struct {
     uint64_t tri_tests;      /* ... and 48-byte triangle fetches of the launch (algorithmic traversal work) */
     uint64_t cand_tests;     /* 32-byte entry-list candidate boxes tested (shared memory) */
     uint64_t rays_traversed; /* rays NOT resolved by the horizon map (0 when the kernel variant has no horizon map) */
+    double horizon_ms;       /* part of kernel_ms spent in the horizon pass (0 when it did not run) */
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
 

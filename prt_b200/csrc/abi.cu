@@ -44,7 +44,7 @@ struct prt_ctx {
     int device = 0;
     int n_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
     int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 24, horizon_near = 35;
     // cached sample table
@@ -88,7 +88,7 @@ int prt_ctx_create(int device_id, prt_ctx **out) {
     c->device = device_id; c->n_sms = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0)); CU_TRY(cudaEventCreate(&c->ev1));
-    CU_TRY(cudaEventCreate(&c->ev2)); CU_TRY(cudaEventCreate(&c->ev3));
+    CU_TRY(cudaEventCreate(&c->ev2)); CU_TRY(cudaEventCreate(&c->ev3)); CU_TRY(cudaEventCreate(&c->evh));
     *out = c;
     return PRT_OK;
 }
@@ -102,6 +102,7 @@ void prt_ctx_destroy(prt_ctx *c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->evh) cudaEventDestroy(c->evh);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -323,6 +324,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
             A.need_bits = (uint32_t *)c->need_bits.p; A.need_count = (uint32_t *)c->need_count.p;
             int hgrid = 0;
             CU_TRY(launch_horizon(A, p->order, &hgrid, c->n_sms, st));
+            if (e0) CU_TRY(cudaEventRecord(c->evh, st));
             launches = 2;
         }
         CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
@@ -380,6 +382,7 @@ int prt_bake_transfer(prt_ctx *c, prt_scene *sc, const float *pos, const float *
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.h2d_ms = ms;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats.kernel_ms = ms;
+    if (c->stats.launches == 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
     CU_TRY(cudaEventElapsedTime(&ms, c->ev2, c->ev3)); c->stats.d2h_ms = ms;
     c->stats.h2d_bytes = 2 * (uint64_t)span;
     c->stats.d2h_bytes = (uint64_t)n * n2 * 4 + (out_vis ? (uint64_t)n * words * 4 : 0);
@@ -396,6 +399,7 @@ int prt_ctx_last_bake_stats(const prt_ctx *cc, prt_bake_stats *out) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->ev2));
         c->stats.kernel_ms = ms;
+        if (c->stats.launches == 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
         c->stats_pending = false;
     }
     if (c->work_pending) {

@@ -228,3 +228,59 @@ def test_full_size_properties(prt):
     half = len(pos) // 2
     a, _ = prt.bake_transfer(sc, pos[:half], nrm[:half], p)
     assert rel_l2(a, co[:half]).max() < 1e-5
+
+
+def _soup(n_tri, seed, scale=1.0, offset=(0, 0, 0), big=False):
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-1, 1, (n_tri, 1, 3))
+    size = rs.uniform(0.02, 0.6 if big else 0.15, (n_tri, 1, 1))
+    v = (c + size * rs.normal(size=(n_tri, 3, 3))).reshape(-1, 3)
+    pos = (v * scale + np.asarray(offset)).astype(np.float32)
+    tri = np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3)
+    return pos, tri
+
+
+@pytest.mark.parametrize("case", ["soup", "soup_big", "soup_offset", "soup_tiny", "room_inside", "sphere_shell"])
+def test_horizon_map_is_conservative_on_adversarial_scenes(prt, oracle, case):
+    """The horizon pass may only skip rays that provably hit nothing.  Random triangle soups with origins anywhere (not on
+    a surface), big overlapping triangles, large coordinate offsets, tiny scales, a closed room and a sphere shell seen from
+    inside: visibility words must still equal the oracle's bit for bit, with every tuning of the horizon builder."""
+    rs = np.random.RandomState(11)
+    if case == "soup":
+        pos, tri = _soup(3000, 1)
+    elif case == "soup_big":
+        pos, tri = _soup(800, 2, big=True)
+    elif case == "soup_offset":
+        pos, tri = _soup(2000, 3, scale=5.0, offset=(300.0, -150.0, 80.0))
+    elif case == "soup_tiny":
+        pos, tri = _soup(2000, 4, scale=1e-3)
+    elif case == "room_inside":
+        from test_oracle_probe import room
+        pos, tri = room(2.0)
+        extra, et = _soup(300, 5, scale=1.5)
+        pos, tri = np.concatenate([pos, extra]).astype(np.float32), np.concatenate([tri, et + np.uint32(len(pos))]).astype(np.uint32)
+    else:
+        p, n, t = meshes.icosphere(4)
+        pos, tri = (p * 2).astype(np.float32), t[:, ::-1].copy()
+    lo, hi = pos.min(0), pos.max(0)
+    n_org = 160
+    org = rs.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo), (n_org, 3)).astype(np.float32)
+    # a third of the origins sit exactly on triangle vertices (the bake's real use), with random normals
+    org[: n_org // 3] = pos[rs.randint(0, len(pos), n_org // 3)]
+    nrm = rs.normal(size=(n_org, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:8] = np.eye(3, dtype=np.float32)[[0, 1, 2, 0, 1, 2, 0, 1]] * np.array([1, 1, 1, -1, -1, -1, 1, -1], np.float32)[:, None]
+    eps = 1e-4 * (1e-3 if case == "soup_tiny" else 1.0)
+    gs, os_ = prt.RTScene(pos, tri), oracle.Scene(pos, tri)
+    kw = dict(samples_u=16, samples_v=32, origin_eps=eps)
+    ref, ovis, _ = oracle.bake_transfer(os_, org, nrm, oracle.make_params(**kw), want_vis=True)
+    frac = np.unpackbits(ovis.view(np.uint8)).mean()
+    assert 0.02 < frac < 0.99 or case in ("room_inside", "sphere_shell")
+    for knobs in (dict(), dict(horizon_budget=0), dict(horizon_budget=3, horizon_near=80), dict(horizon_budget=200, horizon_near=10)):
+        gs.ctx.set_tuning(**knobs)
+        try:
+            got, gvis = prt.bake_transfer(gs, org, nrm, prt.BakeParams.make(**kw), want_vis=True)
+        finally:
+            gs.ctx.set_tuning(horizon_budget=24, horizon_near=35)
+        assert np.array_equal(gvis, ovis), f"{case} {knobs}: {np.count_nonzero(gvis != ovis)} visibility words differ"
+        assert rel_l2(got, ref)[np.linalg.norm(ref, axis=1) > 1e-3].max(initial=0) <= REL_L2_TOL
