@@ -224,7 +224,8 @@ def run_ours(a):
     ctx.set_tuning(count_work=1)
     step_device(); torch.cuda.synchronize()
     st = ctx.last_bake_stats()
-    visits, tests = int(st.node_visits), int(st.tri_tests)
+    visits, tests, cands, traversed = int(st.node_visits), int(st.tri_tests), int(st.cand_tests), int(st.rays_traversed)
+    launches_per_step = int(st.launches)
     ctx.set_tuning(count_work=0)
 
     for _ in range(max(a.warmup, 3)):
@@ -303,16 +304,19 @@ def run_ours(a):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         k_ms_max = float(kms.item())
         rays_launch = float(n_mine) * S
-        alg_bytes = visits * 80.0 + tests * 48.0 + n_mine * (24.0 + 4.0 * n2)
+        need_bytes = n_mine * (4.0 * ((S + 31) // 32) + 4.0) if launches_per_step == 2 else 0.0
+        alg_bytes = visits * 80.0 + tests * 48.0 + cands * 32.0 + n_mine * (24.0 + 4.0 * n2) + need_bytes
         achieved = alg_bytes / (k_ms_max * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"bake_wave_kernel<{a.order},true> (traversal + projection; the horizon pass ran {hz_ms:.2f} ms before it)", "achieved": achieved, "peak": hbm_peak,
                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     "kernel_ms": k_ms_max, "rays_per_launch": rays_launch,
                     "node_visits_per_ray": visits / rays_launch, "tri_tests_per_ray": tests / rays_launch,
+                    "entry_list_box_tests_per_ray": cands / rays_launch, "rays_traversed_frac": traversed / rays_launch,
+                    "horizon_pass_ms": hz_ms,
                     "algorithmic_bytes_per_ray": alg_bytes / rays_launch,
                     "hbm_floor_bytes_per_launch": n_mine * (24.0 + 4.0 * n2) + float(info.node_bytes + info.tri_bytes),
-                    "note": "algorithmic bytes = node fetches x 80 B + triangle fetches x 48 B + 60 B/vertex I/O; the BVH "
+                    "note": "algorithmic bytes = node fetches x 80 B + triangle fetches x 48 B + entry-list boxes x 32 B (shared memory) + 60 B/vertex I/O + need bits; per-ray figures are averages over ALL rays (rays above the horizon map cost none); the BVH "
                             f"({(info.node_bytes + info.tri_bytes) / 1e6:.1f} MB) is L2-resident, so this traffic is served by L1/L2, "
                             "not HBM: the kernel is latency/issue bound, see profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
