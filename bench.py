@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--samples-u", type=int, default=32)
     ap.add_argument("--samples-v", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=16384, help="vertices of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=196608, help="vertices of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tune", default="", help="comma list name=value of prt_ctx_set_tuning knobs")
     return ap.parse_args()
@@ -87,7 +87,7 @@ def run_reference(a):
     scene_pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv)
     order = meshes.morton_order(scene_pos)
     pos, nrm = scene_pos[order], nrm[order]
-    n_sample = min(len(pos), 4096)
+    n_sample = min(len(pos), 32768)
     oscene = None
     for _ in range(max(1, min(a.warmup, 1))):
         _, _, _, cores, oscene = cpu_bake_sample(a, scene_pos, tri, pos, nrm, n_sample, oscene)

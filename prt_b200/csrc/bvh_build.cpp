@@ -210,6 +210,9 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
 
     // ---- stage 2+3: collapse to 8-wide, order slots, quantise, emit depth-first ----------------------
     const uint32_t n_bin = B.n_nodes.load();
+    // binary leaves below every binary node (children are always allocated after their parent)
+    std::vector<uint32_t> nleaves(n_bin, 1u);
+    for (uint32_t i = n_bin; i-- > 0;) if (!bn[i].count) nleaves[i] = nleaves[bn[i].left] + nleaves[bn[i].left + 1];
     std::vector<Node8> wn; wn.reserve(n_bin / 4 + 16);
     Tri48 *tris = (Tri48 *)std::malloc(sizeof(Tri48) * (size_t)nt);
     if (!tris) return fail("build_bvh8: out of memory");
@@ -229,8 +232,15 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
         if (root.count) ch[nch++] = j.bnode;
         else { ch[nch++] = root.left; ch[nch++] = root.left + 1; }
         while (nch < 8) {
-            int best = -1; float ba = -1.f;
-            for (int i = 0; i < nch; i++) if (!bn[ch[i]].count) { float a = bn[ch[i]].box.area(); if (a > ba) { ba = a; best = i; } }
+            // 1. an internal child whose whole subtree fits into the free slots is absorbed (largest first): this keeps the
+            //    bottom of the tree from degenerating into many 2-3 child nodes;  2. otherwise open the largest-area child.
+            const uint32_t free_slots = 8u - (uint32_t)nch;
+            int best = -1; uint32_t bl = 0;
+            for (int i = 0; i < nch; i++) if (!bn[ch[i]].count) { const uint32_t nl = nleaves[ch[i]]; if (nl - 1u <= free_slots && nl > bl) { bl = nl; best = i; } }
+            if (best < 0) {
+                float ba = -1.f;
+                for (int i = 0; i < nch; i++) if (!bn[ch[i]].count) { float a = bn[ch[i]].box.area(); if (a > ba) { ba = a; best = i; } }
+            }
             if (best < 0) break;
             uint32_t c = ch[best];
             ch[best] = bn[c].left; ch[nch++] = bn[c].left + 1;
