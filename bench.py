@@ -34,6 +34,10 @@ METRIC = "shadow_rays_per_sec"
 UNIT = "rays/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one bake_wave_kernel<3,true> launch on the bench workload, from the ncu --set full
+# capture summarised in profiles/r1_final_ncu_summary.txt (836.7 MB read + 292.5 MB written; includes L2-flush write-backs).
+NCU_TRAFFIC_BYTES = 1129.2e6
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,7 +312,7 @@ def run_ours(a):
         alg_bytes = visits * 80.0 + tests * 48.0 + cands * 32.0 + n_mine * (24.0 + 4.0 * n2) + need_bytes
         achieved = alg_bytes / (k_ms_max * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"bake_wave_kernel<{a.order},true> (traversal + projection; the horizon pass ran {hz_ms:.2f} ms before it)", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     "kernel_ms": k_ms_max, "rays_per_launch": rays_launch,
                     "node_visits_per_ray": visits / rays_launch, "tri_tests_per_ray": tests / rays_launch,
