@@ -178,6 +178,14 @@ int prt_csr_sizes(const prt_csr *, uint32_t *n_probes, uint64_t *nnz, uint32_t *
 /* range[n_probes][2] (start,end), ids[nnz], transfer[nnz][9], surfels[n_surfels][6] (mean position, normalised mean normal),
  * keys[n_surfels] (packed cluster keys, ascending); any pointer may be NULL */
 int prt_csr_download(const prt_csr *, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
+/* Partial captures (multi-GPU: every rank captures a slice of the probes, volume.cpp:83-90 order) are merged on the host:
+ * the union of the key sets gives the global surfel ids, and the surfel table needs the un-normalised accumulators --
+ * sums[n_surfels][7] = sum of hit positions, sum of hit normals, hit count (volume.cpp:229-236,301-312). */
+int prt_csr_surfel_sums(const prt_csr *, double *out_sums);
+/* Builds a device CSR from host arrays (a merged capture, or one read back from a cache) so prt_probe_project can run on it.
+ * keys may be NULL.  Ranges and ids are validated. */
+int prt_csr_upload(prt_ctx *, uint32_t n_probes, uint64_t nnz, uint32_t n_surfels, const uint32_t *range, const uint32_t *ids,
+                   const float *transfer, const float *surfels, const uint64_t *keys, prt_csr **out);
 /* SH_volume::project_sh + precomp_projectSH.comp:32-143: radiance_rgba[n_surfels][4] -> out[n_probes][7][4]
  * (Ar,Ag,Ab,Br,Bg,Bb,C of common/SH.glsl:1-7), FP32 instead of the reference's RGBA16F storage */
 int prt_probe_project(const prt_csr *, const float *radiance_rgba, float *out_sh_volumes);

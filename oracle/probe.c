@@ -95,6 +95,7 @@ struct prt_o_csr {
     float *transfer;     /* [nnz][9] */
     float *surfels;      /* [n_prim][6] mean position, normalised mean normal */
     uint64_t *keys;      /* [n_prim] sorted cluster keys */
+    double *sums;        /* [n_prim][7] sum of hit positions, sum of hit normals, hit count (merging partial captures) */
 };
 
 prt_o_csr *prt_o_probe_capture(const prt_o_scene *sc, const float *probe_pos, uint32_t n_probes, const float *dirs,
@@ -171,7 +172,7 @@ prt_o_csr *prt_o_probe_capture(const prt_o_scene *sc, const float *probe_pos, ui
         c->surfels[6 * s] = (float)(sacc[7 * s] / cnt); c->surfels[6 * s + 1] = (float)(sacc[7 * s + 1] / cnt); c->surfels[6 * s + 2] = (float)(sacc[7 * s + 2] / cnt);
         c->surfels[6 * s + 3] = (float)(nx * il); c->surfels[6 * s + 4] = (float)(ny * il); c->surfels[6 * s + 5] = (float)(nz * il);
     }
-    free(sacc); free(eacc); free(ekey);
+    c->sums = sacc; free(eacc); free(ekey);
     return c;
 }
 
@@ -183,9 +184,10 @@ void prt_o_csr_get(const prt_o_csr *c, uint32_t *range, uint32_t *ids, float *tr
     if (surfels) memcpy(surfels, c->surfels, (size_t)c->n_prim * 24);
     if (keys) memcpy(keys, c->keys, (size_t)c->n_prim * 8);
 }
+void prt_o_csr_get_sums(const prt_o_csr *c, double *sums) { memcpy(sums, c->sums, (size_t)c->n_prim * 56); }
 void prt_o_csr_destroy(prt_o_csr *c) {
     if (!c) return;
-    free(c->range); free(c->ids); free(c->transfer); free(c->surfels); free(c->keys); free(c);
+    free(c->sums); free(c->range); free(c->ids); free(c->transfer); free(c->surfels); free(c->keys); free(c);
 }
 
 /* precomp_projectSH.comp:51-139: L_k = sum_i transfer[9i+k] * radiance[ID[i]].rgb; window; R-H pack -> out[n_probes][7][4] */

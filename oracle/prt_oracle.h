@@ -85,6 +85,7 @@ prt_o_csr *prt_o_probe_capture(const prt_o_scene *, const float *probe_pos, uint
                                const float *weights, uint32_t n_dirs);
 void prt_o_csr_sizes(const prt_o_csr *, uint32_t *nnz, uint32_t *n_prim);
 void prt_o_csr_get(const prt_o_csr *, uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
+void prt_o_csr_get_sums(const prt_o_csr *, double *sums /*[n_prim][7]: sum pos, sum normal, count*/);
 void prt_o_csr_destroy(prt_o_csr *);
 void prt_o_probe_project(const prt_o_csr *, const float *radiance_rgba, float *out);
 /* calculate_weight (light_probe.cpp:156-367); w0123/w4567 [n_voxels][4], index (z*ry+y)*rx+x; score_out optional [n_voxels] */

@@ -77,6 +77,7 @@ def lib():
         L.prt_o_probe_capture.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_uint32]
         L.prt_o_csr_sizes.argtypes = [vp, u32p, u32p]
         L.prt_o_csr_get.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.prt_o_csr_get_sums.argtypes = [vp, vp]
         L.prt_o_csr_destroy.argtypes = [vp]
         L.prt_o_probe_project.argtypes = [vp, vp, vp]
         L.prt_o_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -276,6 +277,11 @@ class ProbeTransfer:
         sf = np.zeros((self.n_surfels, 6), np.float32); keys = np.zeros(self.n_surfels, np.uint64)
         lib().prt_o_csr_get(self.h, _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf), _ptr(keys))
         return rng, ids, tr, sf, keys
+
+    def surfel_sums(self) -> np.ndarray:
+        sums = np.zeros((self.n_surfels, 7), np.float64)
+        lib().prt_o_csr_get_sums(self.h, _ptr(sums))
+        return sums
 
     def project(self, radiance_rgba) -> np.ndarray:
         rad = np.ascontiguousarray(radiance_rgba, np.float32)

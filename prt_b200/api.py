@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
-    "prt_probe_capture", "prt_csr_destroy", "prt_csr_sizes", "prt_csr_download", "prt_probe_project", "prt_probe_positions",
+    "prt_probe_capture", "prt_csr_destroy", "prt_csr_sizes", "prt_csr_download", "prt_csr_surfel_sums", "prt_csr_upload", "prt_probe_project", "prt_probe_positions",
     "prt_fibonacci_dirs", "prt_cube_dirs", "prt_volume_weights",
 ]
 
@@ -115,6 +115,8 @@ def load_library():
     L.prt_csr_destroy.restype = None
     L.prt_csr_sizes.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(C.c_double)]
     L.prt_csr_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.prt_csr_surfel_sums.argtypes = [vp, vp]
+    L.prt_csr_upload.argtypes = [vp, u32, C.c_uint64, u32, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.prt_probe_project.argtypes = [vp, vp, vp]
     L.prt_probe_positions.argtypes = [vp, vp, vp]
     L.prt_fibonacci_dirs.argtypes = [i32, vp]
@@ -369,9 +371,29 @@ class ProbeTransfer:
         h = C.c_void_p()
         _check(self.L.prt_probe_capture(scene.h, _ptr(pp), len(pp), _ptr(d), _ptr(w), len(d), C.byref(h)), "prt_probe_capture")
         self.h = h
+        self._sizes()
+
+    def _sizes(self):
         npb, nnz, ns, ms = C.c_uint32(), C.c_uint64(), C.c_uint32(), C.c_double()
-        _check(self.L.prt_csr_sizes(h, C.byref(npb), C.byref(nnz), C.byref(ns), C.byref(ms)), "prt_csr_sizes")
+        _check(self.L.prt_csr_sizes(self.h, C.byref(npb), C.byref(nnz), C.byref(ns), C.byref(ms)), "prt_csr_sizes")
         self.n_probes, self.nnz, self.n_surfels, self.capture_ms = npb.value, nnz.value, ns.value, ms.value
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, rng, ids, transfer, surfels, keys=None) -> "ProbeTransfer":
+        """Device CSR from host arrays (a merged multi-GPU capture, ``prt_b200.dist.merge_probe_csr``, or a cached one)."""
+        self = cls.__new__(cls)
+        self.scene, self.L = ctx, ctx.L                      # keeps the context alive; `.h` doubles as the liveness check
+        rng = np.ascontiguousarray(rng, np.uint32); ids = np.ascontiguousarray(ids, np.uint32)
+        tr = np.ascontiguousarray(transfer, np.float32); sf = np.ascontiguousarray(surfels, np.float32)
+        k = None if keys is None else np.ascontiguousarray(keys, np.uint64)
+        if rng.ndim != 2 or rng.shape[1] != 2 or tr.shape != (len(ids), 9) or sf.ndim != 2 or sf.shape[1] != 6 or (k is not None and len(k) != len(sf)):
+            raise PRTError("from_arrays: expected range [P,2], ids [nnz], transfer [nnz,9], surfels [S,6], keys [S]")
+        h = C.c_void_p()
+        _check(self.L.prt_csr_upload(ctx.h, len(rng), len(ids), len(sf), _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf),
+                                     None if k is None else _ptr(k), C.byref(h)), "prt_csr_upload")
+        self.h = h
+        self._sizes()
+        return self
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.scene, "h", None):
@@ -388,6 +410,12 @@ class ProbeTransfer:
         keys = np.zeros(self.n_surfels, np.uint64)
         _check(self.L.prt_csr_download(self.h, _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf), _ptr(keys)), "prt_csr_download")
         return rng, ids, tr, sf, keys
+
+    def surfel_sums(self) -> np.ndarray:
+        """[n_surfels, 7] float64: sum of hit positions, sum of hit normals, hit count (for merging partial captures)."""
+        sums = np.zeros((self.n_surfels, 7), np.float64)
+        _check(self.L.prt_csr_surfel_sums(self.h, _ptr(sums)), "prt_csr_surfel_sums")
+        return sums
 
     def project(self, radiance_rgba: np.ndarray) -> np.ndarray:
         """SH_volume::project_sh (precomp_projectSH.comp): [n_surfels,4] radiance -> [n_probes,7,4] packed SH volumes."""

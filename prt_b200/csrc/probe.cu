@@ -265,6 +265,7 @@ struct prt_csr {
     uint32_t *range = nullptr, *ids = nullptr;
     float *transfer = nullptr, *surfels = nullptr;
     unsigned long long *keys = nullptr;   // sorted distinct cluster keys
+    double *sums = nullptr;               // [n_prim][7] sum of hit positions, sum of hit normals, hit count
     double capture_ms = 0.0;
 };
 
@@ -279,7 +280,7 @@ extern "C" {
 void prt_csr_destroy(prt_csr *c) {
     if (!c) return;
     cudaSetDevice(prt_ctx_device(c->ctx));
-    cudaFree(c->range); cudaFree(c->ids); cudaFree(c->transfer); cudaFree(c->surfels); cudaFree(c->keys);
+    cudaFree(c->range); cudaFree(c->ids); cudaFree(c->transfer); cudaFree(c->surfels); cudaFree(c->keys); cudaFree(c->sums);
     delete c;
 }
 
@@ -379,7 +380,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     if (nnz) assign_ids_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ekeys, nnz, c->keys, c->n_prim, eacc, c->ids, sacc);
     if (c->n_prim) finalize_surfels_kernel<<<(c->n_prim + 255) / 256, 256, 0, st>>>(sacc, c->n_prim, c->surfels);
     e = cudaStreamSynchronize(st);
-    cudaFree(sacc);
+    c->sums = sacc;
     cleanup();
     if (e != cudaSuccess) { prt_csr_destroy(c); return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
     *out = c;
@@ -403,6 +404,46 @@ int prt_csr_download(const prt_csr *c, uint32_t *range, uint32_t *ids, float *tr
     if (transfer && c->nnz) PB_TRY(cudaMemcpy(transfer, c->transfer, 36 * c->nnz, cudaMemcpyDeviceToHost));
     if (surfels && c->n_prim) PB_TRY(cudaMemcpy(surfels, c->surfels, 24 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
     if (keys && c->n_prim) PB_TRY(cudaMemcpy(keys, c->keys, 8 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
+    return PRT_OK;
+}
+
+int prt_csr_surfel_sums(const prt_csr *c, double *out_sums) {
+    if (!c || !out_sums) return prt_set_error(PRT_ERR_INVALID, "prt_csr_surfel_sums: null argument");
+    PB_TRY(cudaSetDevice(prt_ctx_device(c->ctx)));
+    if (c->n_prim) {
+        if (!c->sums) return prt_set_error(PRT_ERR_INVALID, "prt_csr_surfel_sums: this CSR was uploaded, not captured");
+        PB_TRY(cudaMemcpy(out_sums, c->sums, 56 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
+    }
+    return PRT_OK;
+}
+
+int prt_csr_upload(prt_ctx *ctx, uint32_t n_probes, uint64_t nnz, uint32_t n_surfels, const uint32_t *range, const uint32_t *ids,
+                   const float *transfer, const float *surfels, const uint64_t *keys, prt_csr **out) {
+    if (!ctx || !out || n_probes == 0 || !range || (nnz && (!ids || !transfer)) || (n_surfels && !surfels))
+        return prt_set_error(PRT_ERR_INVALID, "prt_csr_upload: bad argument");
+    *out = nullptr;
+    if (nnz >= 0xFFFFFFFFull) return prt_set_error(PRT_ERR_UNSUPPORTED, "prt_csr_upload: more than 2^32 CSR entries");
+    for (uint32_t p = 0; p < n_probes; p++)
+        if (range[2 * p] > range[2 * p + 1] || range[2 * p + 1] > nnz) return prt_set_error(PRT_ERR_INVALID, "prt_csr_upload: probe range outside [0, nnz]");
+    for (uint64_t i = 0; i < nnz; i++)
+        if (ids[i] >= n_surfels) return prt_set_error(PRT_ERR_INVALID, "prt_csr_upload: surfel id out of range");
+    PB_TRY(cudaSetDevice(prt_ctx_device(ctx)));
+    prt_csr *c = new prt_csr();
+    c->ctx = ctx; c->n_probes = n_probes; c->nnz = nnz; c->n_prim = n_surfels;
+    const size_t np = std::max<size_t>(1, n_surfels), nz = std::max<size_t>(1, (size_t)nnz);
+    cudaError_t e = cudaMalloc(&c->range, 8 * (size_t)n_probes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * nz);
+    if (e == cudaSuccess) e = cudaMalloc(&c->transfer, 36 * nz);
+    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
+    if (e == cudaSuccess) e = cudaMalloc(&c->keys, 8 * np);
+    if (e == cudaSuccess) e = cudaMemcpy(c->range, range, 8 * (size_t)n_probes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(c->ids, ids, 4 * (size_t)nnz, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(c->transfer, transfer, 36 * (size_t)nnz, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_surfels) e = cudaMemcpy(c->surfels, surfels, 24 * (size_t)n_surfels, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_surfels && keys) e = cudaMemcpy(c->keys, keys, 8 * (size_t)n_surfels, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_surfels && !keys) e = cudaMemset(c->keys, 0, 8 * (size_t)n_surfels);
+    if (e != cudaSuccess) { prt_csr_destroy(c); return prt_set_error(PRT_ERR_CUDA, std::string("prt_csr_upload: ") + cudaGetErrorString(e)); }
+    *out = c;
     return PRT_OK;
 }
 

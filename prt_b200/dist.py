@@ -5,6 +5,11 @@ The reference has no multi-process path at all (SURVEY.md section 2 rows 22-23);
 (``std::for_each(par, verts...)``, reference src/raytracing/raytracing.cpp:328) is embarrassingly parallel over vertices,
 which is what is sharded here.  There is no data-path collective other than the final all-gather of the
 ``[n_verts, order^2]`` coefficient rows.
+
+Probe capture (``SH_volume::precompute``, reference src/sh/volume.cpp:149-316) shards by contiguous probe ranges; the
+variable-length CSR slices, key sets and surfel accumulators are all-gathered and merged on the host
+(``merge_probe_csr``): surfel ids are the rank of the cluster key, so the union of the ranks' key sets defines them
+globally.
 """
 from __future__ import annotations
 
@@ -59,3 +64,83 @@ def sharded_bake(bake_fn, pos: np.ndarray, nrm: np.ndarray, n2: int, group=None,
     allrows = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype)
     dist.all_gather_into_tensor(allrows.view(-1), mine.reshape(-1), group=group)
     return unshard_rows(allrows.numpy(), len(pos), world, chunk)
+
+
+# ---- probe capture ---------------------------------------------------------------------------------------------------------
+
+def probe_shard_range(n_probes: int, world: int, rank: int):
+    """Contiguous probe range ``[lo, hi)`` of ``rank`` (probes keep the x-fastest order of volume.cpp:83-90, so the
+    concatenation of the ranks' CSR slices is the whole CSR)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    per = (n_probes + world - 1) // world
+    return min(rank * per, n_probes), min((rank + 1) * per, n_probes)
+
+
+def merge_probe_csr(parts):
+    """Merges per-rank captures of consecutive probe ranges.  ``parts``: list (rank order) of dicts with ``range`` [P_r,2]
+    u32, ``ids`` [nnz_r] u32, ``transfer`` [nnz_r,9] f32, ``keys`` [S_r] u64 (ascending) and ``sums`` [S_r,7] f64.
+    Returns ``(range, ids, transfer, surfels, keys)`` laid out exactly like a single capture of all probes."""
+    keys = np.unique(np.concatenate([np.asarray(p["keys"], np.uint64) for p in parts]))
+    sums = np.zeros((len(keys), 7), np.float64)
+    rng_out, ids_out, tr_out = [], [], []
+    base = 0
+    for p in parts:
+        remap = np.searchsorted(keys, np.asarray(p["keys"], np.uint64)).astype(np.uint32)
+        ids = np.asarray(p["ids"], np.uint32)
+        ids_out.append(remap[ids] if len(ids) else ids)
+        tr_out.append(np.asarray(p["transfer"], np.float32).reshape(-1, 9))
+        rng_out.append(np.asarray(p["range"], np.uint32).reshape(-1, 2) + np.uint32(base))
+        if len(remap):
+            np.add.at(sums, remap, np.asarray(p["sums"], np.float64).reshape(-1, 7))
+        base += len(ids)
+        if base >= 0xFFFFFFFF:
+            raise ValueError("merged CSR exceeds 2^32 entries")
+    cnt = sums[:, 6:7]
+    nm = sums[:, 3:6] / cnt
+    nm /= np.sqrt((nm * nm).sum(1, keepdims=True))                                   # volume.cpp:307-308
+    surfels = np.concatenate([sums[:, 0:3] / cnt, nm], 1).astype(np.float32)
+    return (np.concatenate(rng_out).astype(np.uint32), np.concatenate(ids_out).astype(np.uint32),
+            np.concatenate(tr_out).astype(np.float32), surfels, keys)
+
+
+def _all_gather_bytes(arr: np.ndarray, group, device):
+    """all-gather of one variable-length array per rank (as bytes, padded to the longest) -> list of uint8 arrays."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    raw = np.frombuffer(np.ascontiguousarray(arr).tobytes(), np.uint8)
+    n = torch.tensor([len(raw)], dtype=torch.int64, device=device)
+    sizes = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = sizes.cpu().numpy()
+    cap = max(int(sizes.max()), 1)
+    mine = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if len(raw):
+        mine[:len(raw)] = torch.from_numpy(raw.copy()).to(device)
+    out = torch.empty(world * cap, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    out = out.cpu().numpy().reshape(world, cap)
+    return [out[r, :int(sizes[r])] for r in range(world)]
+
+
+def sharded_probe_capture(capture_fn, probe_pos: np.ndarray, group=None, device="cpu"):
+    """Captures ``probe_pos`` across the ranks of ``group`` and returns the merged CSR on every rank.
+    ``capture_fn(probe_pos_slice) -> dict(range, ids, transfer, keys, sums)`` is the per-rank compute
+    (``ProbeTransfer(...)`` + ``download()`` + ``surfel_sums()`` on a GPU rank).  ``device``: where the collective's
+    buffers live ("cpu" for gloo, the rank's CUDA device for NCCL)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = probe_shard_range(len(probe_pos), world, rank)
+    empty = dict(range=np.zeros((0, 2), np.uint32), ids=np.zeros(0, np.uint32), transfer=np.zeros((0, 9), np.float32),
+                 keys=np.zeros(0, np.uint64), sums=np.zeros((0, 7), np.float64))
+    part = capture_fn(probe_pos[lo:hi]) if hi > lo else empty
+    if world == 1:
+        return merge_probe_csr([part])
+    dtypes = dict(range=np.uint32, ids=np.uint32, transfer=np.float32, keys=np.uint64, sums=np.float64)
+    gathered = {k: _all_gather_bytes(np.asarray(part[k], dt), group, device) for k, dt in dtypes.items()}
+    parts = [{k: np.frombuffer(gathered[k][r].tobytes(), dtypes[k]) for k in dtypes} for r in range(world)]
+    return merge_probe_csr(parts)

@@ -89,3 +89,37 @@ def test_calculate_weight_matches_oracle(prt, oracle):
     s = np.concatenate([g0, g1], 1).sum(1)
     assert np.all(np.isclose(s, 1.0, atol=1e-5) | (s == 0.0)) and (s == 0).mean() < 0.5
     assert (osc[~np.isnan(osc)] > 0.2).any()          # the relocation branch is exercised (voxels inside the torus tube)
+
+
+def test_split_capture_merge_upload_project(prt, oracle):
+    """multi-GPU probe path on one GPU: capture two probe slices, merge (dist.merge_probe_csr), upload the merged CSR
+    (prt_csr_upload) and project -- identical to the single capture."""
+    from prt_b200 import dist as pdist
+    pos, tri = scene_with_occluder()
+    gs = prt.RTScene(pos, tri)
+    probes = prt.probe_positions([4, 3, 2], [6, 6, 6])
+    d, w = prt.fibonacci_dirs(1200)
+    whole = prt.ProbeTransfer(gs, probes, d, w)
+    wr, wi, wt, wsf, wk = whole.download()
+    parts = []
+    for r in range(3):
+        lo, hi = pdist.probe_shard_range(len(probes), 3, r)
+        pt = prt.ProbeTransfer(gs, probes[lo:hi], d, w)
+        rng, ids, tr, _, keys = pt.download()
+        parts.append(dict(range=rng, ids=ids, transfer=tr, keys=keys, sums=pt.surfel_sums()))
+    mr, mi, mt, msf, mk = pdist.merge_probe_csr(parts)
+    assert np.array_equal(mr, wr) and np.array_equal(mi, wi) and np.array_equal(mt, wt) and np.array_equal(mk, wk)
+    assert np.abs(msf - wsf).max() <= 1e-6
+    sums = whole.surfel_sums()
+    assert sums.shape == (whole.n_surfels, 7) and (sums[:, 6] >= 1).all() and np.allclose(sums[:, :3] / sums[:, 6:7], wsf[:, :3], atol=1e-5)
+    up = prt.ProbeTransfer.from_arrays(gs.ctx, mr, mi, mt, msf, mk)
+    assert (up.n_probes, up.nnz, up.n_surfels) == (whole.n_probes, whole.nnz, whole.n_surfels)
+    rad = np.random.RandomState(3).rand(whole.n_surfels, 4).astype(np.float32)
+    assert np.array_equal(up.project(rad), whole.project(rad))
+    ur = up.download()
+    assert all(np.array_equal(a, b) for a, b in zip(ur, (mr, mi, mt, msf, mk)))
+    with pytest.raises(prt.PRTError):
+        up.surfel_sums()                                   # uploaded CSRs carry no accumulators
+    bad = mi.copy(); bad[0] = whole.n_surfels
+    with pytest.raises(prt.PRTError):
+        prt.ProbeTransfer.from_arrays(gs.ctx, mr, bad, mt, msf, mk)

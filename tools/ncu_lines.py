@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""tools/ncu_lines.py REPORT.ncu-rep [N] -- per-source-line instruction / stall-sample shares and key raw metrics."""
+"""tools/ncu_lines.py REPORT.ncu-rep [N [KERNEL_REGEX]] -- per-source-line instruction / stall-sample shares and key raw metrics."""
 import collections, csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kf = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, *kf, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
 keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
@@ -20,7 +21,7 @@ for i, h in enumerate(hdr):
         try:
             if float(vals[i]) >= 2.0: print(f"{h:75s} {vals[i]}")
         except ValueError: pass
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, *kf, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 cur = None; hdr = None; lines = []; tot = tots = 0
 for r in csv.reader(io.StringIO(src)):
     if not r: continue
