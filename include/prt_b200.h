@@ -195,6 +195,38 @@ int prt_probe_positions(const int32_t res[3], const float scene_size[3], float *
 int prt_fibonacci_dirs(int32_t n, float *out_dirs_xyz);
 int prt_cube_dirs(int32_t res, float *out_dirs_xyz /*[6*res*res][3]*/, float *out_solid_angles);
 
+/* ---- per-frame probe pipeline: SH_volume::relight + project_sh (volume.cpp:357-452) ----------------------
+ * relight.comp:68-82 lights every surfel (sky light with the shadow-map test of common/paral_shadow.glsl, spot light and point
+ * light of common/light.glsl, albedo of colored_wall.glsl unless given, optional SH_Irad feedback of common/SH.glsl from the
+ * volumes of the previous round, temporal blend temp_weight), precomp_projectSH.comp projects the radiance into per-probe SH,
+ * transfer2volume.comp:36-147 blends the 8 surrounding probes into every voxel with the calculate_weight masks.  State stays in
+ * HBM inside prt_gi; prt_gi_step runs n_rounds rounds (one round = one displayed frame of app.cpp:164-166) back to back.
+ * Storage is FP32 (reference: RGBA16F volumes).  Layouts: radiance [n_surfels][4]; probe_sh [pz][py][px][7][4];
+ * volumes [vz][vy][vx][7][4] (Ar,Ag,Ab,Br,Bg,Bb,C of common/SH.glsl:1-7). */
+typedef struct prt_relight_params {
+    float cast_intensity[3], cast_position[3], cast_direction[3], cast_cutoff;   /* CastLight  light.glsl:1-6;  volume.cpp:362-365 */
+    float ambient_intensity[3], ambient_position[3];                             /* PointLight light.glsl:8-11; volume.cpp:366-367 */
+    float sky_intensity[3], sky_direction[3];                                    /* ParalLight light.glsl:13-16; volume.cpp:374-375 */
+    float light_space_matrix[16];                                                /* column-major like glm; volume.cpp:373 */
+    int32_t multi_bounce;                                                        /* app.h:33 */
+    float atten, sh_shift, temp_weight;                                          /* app.h:34,31; relight.comp:12 (0.1) */
+} prt_relight_params;
+/* Paral_Shadow::set_dir (gl.cpp:620-631): direction and ortho(-30,30,-30,30,0.1,60) * lookAt(30 d, 0, up) from (up, dir) in [0,1]^2 */
+int prt_paral_shadow_matrix(float up, float dir, float out_direction[3], float out_matrix[16]);
+/* Paral_Shadow::render (gl.cpp:633-648) without a rasteriser: depth[j*size+i] in [0,1] = closest hit of the ray through the
+ * centre of texel (i,j) of an orthographic (affine) light matrix; 1 = nothing.  size <= 16384 (reference: 4096, gl.h:314). */
+int prt_shadow_map(prt_scene *, const float matrix[16], int32_t size, float *out_depth);
+typedef struct prt_gi prt_gi;
+/* the CSR is borrowed and must outlive the object; w0123/w4567 from prt_volume_weights; prod(probe_res) == captured probes */
+int prt_gi_create(const prt_csr *, const int32_t probe_res[3], const int32_t volume_res[3], const float scene_size[3],
+                  const float *w0123, const float *w4567, prt_gi **out);
+void prt_gi_destroy(prt_gi *);
+int prt_gi_set_shadow_map(prt_gi *, const float *depth /*NULL: unshadowed*/, int32_t size);
+int prt_gi_set_albedo(prt_gi *, const float *albedo_rgb /*[n_surfels][3]; NULL: colored_wall.glsl*/);
+int prt_gi_set_radiance(prt_gi *, const float *radiance_rgba);
+int prt_gi_step(prt_gi *, const prt_relight_params *, int32_t n_rounds);
+int prt_gi_download(const prt_gi *, float *radiance_rgba, float *probe_sh, float *volumes);   /* any pointer may be NULL */
+
 /* Volume_weight calculate_weight(Model&, ivec3 probe_res, ivec3 volume_res, vec3 scene_size) (light_probe.h:14-18,
  * light_probe.cpp:156-367): per voxel, the trilinear weights of its 8 surrounding probes masked by segment visibility and
  * renormalised, after moving "inside" voxels (score > 0.2 from 100 closest-hit rays) to their least-inside neighbour.

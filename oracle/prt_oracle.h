@@ -92,6 +92,22 @@ void prt_o_probe_project(const prt_o_csr *, const float *radiance_rgba, float *o
 void prt_o_volume_weights(const prt_o_scene *, const int probe_res[3], const int volume_res[3], const float scene_size[3],
                           float *w0123, float *w4567, float *score_out);
 
+/* ---- per-frame probe pipeline (oracle/gi.c): sky shadow map, relight.comp, transfer2volume.comp ---- */
+typedef struct {
+    float cast_intensity[3], cast_position[3], cast_direction[3], cast_cutoff;   /* CastLight   (light.glsl:1-6)  */
+    float ambient_intensity[3], ambient_position[3];                             /* PointLight  (light.glsl:8-11) */
+    float sky_intensity[3], sky_direction[3];                                    /* ParalLight  (light.glsl:13-16) */
+    float light_space_matrix[16];                                                /* column-major (glm) */
+    int32_t multi_bounce;
+    float atten, sh_shift, temp_weight;
+} prt_o_relight_params;
+void prt_o_paral_shadow_matrix(float up, float dir, float out_dir[3], float out_matrix[16]);
+int prt_o_shadow_map(const prt_o_scene *, const float matrix[16], int size, float *depth);
+void prt_o_relight(const prt_o_relight_params *, uint32_t n_surfels, const float *surfels, const float *albedo, const float *depth,
+                   int shadow_size, const float *volumes, const int volume_res[3], const float scene_size[3], float *radiance);
+void prt_o_transfer_to_volume(const float *probe_sh, const int probe_res[3], const float *w0123, const float *w4567,
+                              const int volume_res[3], float *out);
+
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void prt_o_sincos2pi(float v, float *s, float *c);

@@ -81,6 +81,10 @@ def lib():
         L.prt_o_csr_destroy.argtypes = [vp]
         L.prt_o_probe_project.argtypes = [vp, vp, vp]
         L.prt_o_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.prt_o_paral_shadow_matrix.argtypes = [C.c_float, C.c_float, vp, vp]
+        L.prt_o_shadow_map.argtypes = [vp, vp, C.c_int, vp]
+        L.prt_o_relight.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        L.prt_o_transfer_to_volume.argtypes = [vp, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -297,3 +301,41 @@ def volume_weights(scene: Scene, probe_res, volume_res, scene_size):
     w0, w1, sc = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
     lib().prt_o_volume_weights(scene.h, _ptr(pr), _ptr(vr), _ptr(sz), _ptr(w0), _ptr(w1), _ptr(sc))
     return w0, w1, sc
+
+
+def paral_shadow_matrix(up: float, direction: float):
+    """Paral_Shadow::set_dir (reference gl.cpp:620-631)."""
+    d = np.zeros(3, np.float32); m = np.zeros(16, np.float32)
+    lib().prt_o_paral_shadow_matrix(float(up), float(direction), _ptr(d), _ptr(m))
+    return d, m
+
+
+def shadow_map(scene: Scene, matrix, size: int) -> np.ndarray:
+    m = np.ascontiguousarray(np.asarray(matrix, np.float32).reshape(16))
+    out = np.zeros((size, size), np.float32)
+    if lib().prt_o_shadow_map(scene.h, _ptr(m), size, _ptr(out)) != 0:
+        raise RuntimeError("oracle shadow_map: matrix must be affine")
+    return out
+
+
+def relight(params, surfels, radiance, albedo=None, depth=None, volumes=None, volume_res=None, scene_size=None) -> np.ndarray:
+    """relight.comp:68-82 on a surfel table; ``params`` is any ctypes struct laid out like prt_o_relight_params
+    (prt_b200.RelightParams is).  Returns the new radiance [n,4]."""
+    sf = np.ascontiguousarray(surfels, np.float32); rad = np.array(radiance, np.float32, copy=True, order="C")
+    alb = None if albedo is None else np.ascontiguousarray(albedo, np.float32)
+    dep = None if depth is None else np.ascontiguousarray(depth, np.float32)
+    vol = None if volumes is None else np.ascontiguousarray(volumes, np.float32)
+    vr = np.asarray(volume_res if volume_res is not None else [1, 1, 1], np.int32)
+    sz = np.asarray(scene_size if scene_size is not None else [1, 1, 1], np.float32)
+    lib().prt_o_relight(C.cast(C.pointer(params), C.c_void_p), len(sf), _ptr(sf), _ptr(alb), _ptr(dep), 0 if dep is None else dep.shape[0],
+                        _ptr(vol), _ptr(vr), _ptr(sz), _ptr(rad))
+    return rad
+
+
+def transfer_to_volume(probe_sh, probe_res, w0123, w4567, volume_res) -> np.ndarray:
+    """transfer2volume.comp:36-147 -> [n_voxels, 7, 4]"""
+    ps = np.ascontiguousarray(probe_sh, np.float32); pr = np.asarray(probe_res, np.int32); vr = np.asarray(volume_res, np.int32)
+    w0 = np.ascontiguousarray(w0123, np.float32); w1 = np.ascontiguousarray(w4567, np.float32)
+    out = np.zeros((int(np.prod(vr)), 7, 4), np.float32)
+    lib().prt_o_transfer_to_volume(_ptr(ps), _ptr(pr), _ptr(w0), _ptr(w1), _ptr(vr), _ptr(out))
+    return out

@@ -21,6 +21,8 @@ ABI_SYMBOLS = [
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
     "prt_probe_capture", "prt_csr_destroy", "prt_csr_sizes", "prt_csr_download", "prt_csr_surfel_sums", "prt_csr_upload", "prt_probe_project", "prt_probe_positions",
     "prt_fibonacci_dirs", "prt_cube_dirs", "prt_volume_weights",
+    "prt_paral_shadow_matrix", "prt_shadow_map", "prt_gi_create", "prt_gi_destroy", "prt_gi_set_shadow_map", "prt_gi_set_albedo",
+    "prt_gi_set_radiance", "prt_gi_step", "prt_gi_download",
 ]
 
 
@@ -50,6 +52,29 @@ class BakeParams(C.Structure):
     @property
     def n_coeffs(self) -> int:
         return self.order * self.order
+
+
+class RelightParams(C.Structure):
+    """``prt_relight_params``: the uniforms SH_volume::relight sets (reference src/sh/volume.cpp:362-377)."""
+    _fields_ = [("cast_intensity", C.c_float * 3), ("cast_position", C.c_float * 3), ("cast_direction", C.c_float * 3), ("cast_cutoff", C.c_float),
+                ("ambient_intensity", C.c_float * 3), ("ambient_position", C.c_float * 3),
+                ("sky_intensity", C.c_float * 3), ("sky_direction", C.c_float * 3), ("light_space_matrix", C.c_float * 16),
+                ("multi_bounce", C.c_int32), ("atten", C.c_float), ("sh_shift", C.c_float), ("temp_weight", C.c_float)]
+
+    @classmethod
+    def make(cls, sky_direction, light_space_matrix, sky_intensity=(5, 5, 5), cast_intensity=100.0, cast_position=(4, 0, 0),
+             cast_direction=(1, 0, 0), cast_cutoff=0.9, ambient_intensity=(0, 0, 0), ambient_position=(0, 0, 0),
+             multi_bounce=True, atten=1.0, sh_shift=0.0, temp_weight=0.1):
+        """Defaults are the reference's (app.h:31-37,67-68; volume.cpp:362-367; relight.comp:12)."""
+        p = cls()
+        ci = (cast_intensity,) * 3 if np.isscalar(cast_intensity) else cast_intensity
+        p.cast_intensity[:] = [float(x) for x in ci]; p.cast_position[:] = [float(x) for x in cast_position]
+        p.cast_direction[:] = [float(x) for x in cast_direction]; p.cast_cutoff = float(cast_cutoff)
+        p.ambient_intensity[:] = [float(x) for x in ambient_intensity]; p.ambient_position[:] = [float(x) for x in ambient_position]
+        p.sky_intensity[:] = [float(x) for x in sky_intensity]; p.sky_direction[:] = [float(x) for x in sky_direction]
+        p.light_space_matrix[:] = [float(x) for x in np.asarray(light_space_matrix, np.float32).reshape(-1)]
+        p.multi_bounce = int(bool(multi_bounce)); p.atten = float(atten); p.sh_shift = float(sh_shift); p.temp_weight = float(temp_weight)
+        return p
 
 
 class SceneInfo(C.Structure):
@@ -122,6 +147,16 @@ def load_library():
     L.prt_fibonacci_dirs.argtypes = [i32, vp]
     L.prt_cube_dirs.argtypes = [i32, vp, vp]
     L.prt_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.prt_paral_shadow_matrix.argtypes = [C.c_float, C.c_float, vp, vp]
+    L.prt_shadow_map.argtypes = [vp, vp, i32, vp]
+    L.prt_gi_create.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.prt_gi_destroy.argtypes = [vp]
+    L.prt_gi_destroy.restype = None
+    L.prt_gi_set_shadow_map.argtypes = [vp, vp, i32]
+    L.prt_gi_set_albedo.argtypes = [vp, vp]
+    L.prt_gi_set_radiance.argtypes = [vp, vp]
+    L.prt_gi_step.argtypes = [vp, C.POINTER(RelightParams), i32]
+    L.prt_gi_download.argtypes = [vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -435,3 +470,75 @@ def calculate_weight(scene: RTScene, probe_res, volume_res, scene_size):
     w0, w1, sc = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
     _check(scene.L.prt_volume_weights(scene.h, _ptr(pr), _ptr(vr), _ptr(sz), _ptr(w0), _ptr(w1), _ptr(sc)), "prt_volume_weights")
     return w0, w1, sc
+
+
+def paral_shadow_matrix(up: float, direction: float):
+    """reference ``Paral_Shadow::set_dir`` (src/opengl/gl.cpp:620-631) -> (sky direction [3], lightSpaceMatrix [4,4] column-major rows)."""
+    d = np.zeros(3, np.float32); m = np.zeros(16, np.float32)
+    _check(load_library().prt_paral_shadow_matrix(float(up), float(direction), _ptr(d), _ptr(m)), "prt_paral_shadow_matrix")
+    return d, m
+
+
+def shadow_map(scene: RTScene, matrix, size: int = 4096) -> np.ndarray:
+    """reference ``Paral_Shadow::render`` (src/opengl/gl.cpp:633-648) by ray casting: [size, size] depths in [0,1]."""
+    m = np.ascontiguousarray(np.asarray(matrix, np.float32).reshape(16))
+    out = np.zeros((size, size), np.float32)
+    _check(scene.L.prt_shadow_map(scene.h, _ptr(m), size, _ptr(out)), "prt_shadow_map")
+    return out
+
+
+class SHVolume:
+    """Per-frame half of the reference's ``SH_volume`` (src/sh/volume.cpp:357-452): ``relight()`` + ``project_sh()`` on device-resident
+    state.  ``transfer``: a ``ProbeTransfer`` of prod(probe_res) probes; ``weights``: ``calculate_weight`` output."""
+
+    def __init__(self, transfer: ProbeTransfer, probe_res, volume_res, scene_size, weights):
+        self.transfer, self.L = transfer, transfer.L
+        self.probe_res = np.asarray(probe_res, np.int32); self.volume_res = np.asarray(volume_res, np.int32)
+        sz = np.asarray(scene_size, np.float32)
+        w0 = np.ascontiguousarray(weights[0], np.float32); w1 = np.ascontiguousarray(weights[1], np.float32)
+        n = int(np.prod(self.volume_res))
+        if w0.shape != (n, 4) or w1.shape != (n, 4):
+            raise PRTError("SHVolume: weights must be two [prod(volume_res), 4] arrays")
+        h = C.c_void_p()
+        _check(self.L.prt_gi_create(transfer.h, _ptr(self.probe_res), _ptr(self.volume_res), _ptr(sz), _ptr(w0), _ptr(w1), C.byref(h)), "prt_gi_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.transfer, "h", None):
+            self.L.prt_gi_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def set_shadow_map(self, depth):
+        if depth is None:
+            _check(self.L.prt_gi_set_shadow_map(self.h, None, 0), "prt_gi_set_shadow_map")
+            return
+        d = np.ascontiguousarray(depth, np.float32)
+        if d.ndim != 2 or d.shape[0] != d.shape[1]:
+            raise PRTError("set_shadow_map: depth must be square")
+        _check(self.L.prt_gi_set_shadow_map(self.h, _ptr(d), d.shape[0]), "prt_gi_set_shadow_map")
+
+    def set_albedo(self, albedo_rgb):
+        a = None if albedo_rgb is None else np.ascontiguousarray(albedo_rgb, np.float32)
+        if a is not None and a.shape != (self.transfer.n_surfels, 3):
+            raise PRTError("set_albedo: albedo must be [n_surfels, 3]")
+        _check(self.L.prt_gi_set_albedo(self.h, None if a is None else _ptr(a)), "prt_gi_set_albedo")
+
+    def set_radiance(self, radiance_rgba):
+        r = np.ascontiguousarray(radiance_rgba, np.float32)
+        if r.shape != (self.transfer.n_surfels, 4):
+            raise PRTError("set_radiance: radiance must be [n_surfels, 4]")
+        _check(self.L.prt_gi_set_radiance(self.h, _ptr(r)), "prt_gi_set_radiance")
+
+    def step(self, params: RelightParams, n_rounds: int = 1):
+        """n_rounds x (relight(); project_sh()) -- reference app.cpp:164-166 runs one round per frame."""
+        _check(self.L.prt_gi_step(self.h, C.byref(params), int(n_rounds)), "prt_gi_step")
+
+    def download(self):
+        """-> radiance [n_surfels,4], probe_sh [n_probes,7,4], volumes [n_voxels,7,4]"""
+        rad = np.zeros((self.transfer.n_surfels, 4), np.float32)
+        psh = np.zeros((self.transfer.n_probes, 7, 4), np.float32)
+        vol = np.zeros((int(np.prod(self.volume_res)), 7, 4), np.float32)
+        _check(self.L.prt_gi_download(self.h, _ptr(rad), _ptr(psh), _ptr(vol)), "prt_gi_download")
+        return rad, psh, vol

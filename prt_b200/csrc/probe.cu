@@ -258,16 +258,6 @@ __global__ void __launch_bounds__(256) probe_project_kernel(const uint32_t *rang
 
 }  // namespace
 
-struct prt_csr {
-    prt_ctx *ctx = nullptr;
-    uint32_t n_probes = 0, n_prim = 0;
-    unsigned long long nnz = 0;
-    uint32_t *range = nullptr, *ids = nullptr;
-    float *transfer = nullptr, *surfels = nullptr;
-    unsigned long long *keys = nullptr;   // sorted distinct cluster keys
-    double *sums = nullptr;               // [n_prim][7] sum of hit positions, sum of hit normals, hit count
-    double capture_ms = 0.0;
-};
 
 #define PB_TRY(expr)                                                                                                    \
     do {                                                                                                                \
@@ -406,6 +396,16 @@ int prt_csr_download(const prt_csr *c, uint32_t *range, uint32_t *ids, float *tr
     if (keys && c->n_prim) PB_TRY(cudaMemcpy(keys, c->keys, 8 * (size_t)c->n_prim, cudaMemcpyDeviceToHost));
     return PRT_OK;
 }
+
+}  // extern "C"
+
+// device-resident projection for the per-frame pipeline (gi.cu): radiance [n_surfels] float4 -> out [n_probes][7] float4
+cudaError_t prt_csr_project_device(const prt_csr *c, const float4 *d_radiance, float4 *d_out, cudaStream_t st) {
+    probe_project_kernel<<<(unsigned)(((size_t)c->n_probes * 32 + 255) / 256), 256, 0, st>>>(c->range, c->ids, c->transfer, d_radiance, c->n_probes, d_out);
+    return cudaGetLastError();
+}
+
+extern "C" {
 
 int prt_csr_surfel_sums(const prt_csr *c, double *out_sums) {
     if (!c || !out_sums) return prt_set_error(PRT_ERR_INVALID, "prt_csr_surfel_sums: null argument");
