@@ -227,6 +227,21 @@ int prt_gi_set_radiance(prt_gi *, const float *radiance_rgba);
 int prt_gi_step(prt_gi *, const prt_relight_params *, int32_t n_rounds);
 int prt_gi_download(const prt_gi *, float *radiance_rgba, float *probe_sh, float *volumes);   /* any pointer may be NULL */
 
+/* ---- progressive preview tracer: raytrace / renderAO / renderNormal (raytracing.cpp:162-222,280-317) --------
+ * The film holds App::pixels_w (sum rgb, count) and App::pixels (RGBA8) in HBM; prt_raytrace adds n_frames samples per pixel
+ * (one call of the reference's raytrace() per frame).  Camera vectors as in the reference's Camera (Front/Up/Right unit vectors,
+ * Zoom in degrees); ray (i,j) = Front - Up/2 - Right/2 + j/h Up + i/w Right with |Up| = 2 tan(Zoom/2), |Right| = |Up| w/h, row j = 0
+ * at the bottom.  Bounce randoms: Philox stream 2 keyed (seed; pixel, frame, bounce). */
+typedef struct prt_camera { float position[3], front[3], up[3], right[3], zoom_deg; } prt_camera;
+enum { PRT_RAYTRACE_AO = 0, PRT_RAYTRACE_NORMAL = 1 };
+typedef struct prt_film prt_film;
+int prt_film_create(prt_ctx *, int32_t width, int32_t height, prt_film **out);
+void prt_film_destroy(prt_film *);
+int prt_film_reset(prt_film *);                                    /* camera.dirty: clears the accumulators (raytracing.cpp:282-285) */
+int prt_raytrace(prt_scene *, prt_film *, const prt_camera *, int32_t max_path_length /*app.h: 3*/, const float albedo[3],
+                 int32_t gamma, int32_t mode, uint32_t seed, int32_t n_frames);
+int prt_film_download(const prt_film *, float *accum /*[h*w][4]*/, uint8_t *pixels_rgba8 /*[h*w][4]*/);   /* either may be NULL */
+
 /* Volume_weight calculate_weight(Model&, ivec3 probe_res, ivec3 volume_res, vec3 scene_size) (light_probe.h:14-18,
  * light_probe.cpp:156-367): per voxel, the trilinear weights of its 8 surrounding probes masked by segment visibility and
  * renormalised, after moving "inside" voxels (score > 0.2 from 100 closest-hit rays) to their least-inside neighbour.

@@ -5,6 +5,7 @@
  * section 7 "Sample-identical parity".  Integer-only, so CPU and GPU agree exactly.
  *   stream 0: strata jitter     ctr = (sample s, 0, 0, 0)          -> (xi1, xi2)
  *   stream 1: bounce randoms    ctr = (vertex, sample, bounce, 1)  -> (u, v)
+ *   stream 2: preview tracer    ctr = (pixel, frame, bounce, 2)    -> (u, v)
  *   key = (seed, 0x50525421)
  * uniform float = (x >> 8) * 2^-24 in [0,1)  (same range as uniform_real_distribution<float>(0,1))
  */

@@ -108,6 +108,12 @@ void prt_o_relight(const prt_o_relight_params *, uint32_t n_surfels, const float
 void prt_o_transfer_to_volume(const float *probe_sh, const int probe_res[3], const float *w0123, const float *w4567,
                               const int volume_res[3], float *out);
 
+/* ---- progressive AO / normal preview (oracle/raytrace.c; raytracing.cpp:162-222,280-317) ---- */
+typedef struct { float position[3], front[3], up[3], right[3], zoom_deg; } prt_o_camera;
+/* mode 0 = renderAO, 1 = renderNormal; accum [h*w][4] (sum rgb, count) is updated, pixels [h*w][4] RGBA8 written */
+void prt_o_raytrace(const prt_o_scene *, const prt_o_camera *, int w, int h, int max_path_length, const float albedo[3], int gamma,
+                    int mode, uint32_t seed, uint32_t frame, float *accum, uint8_t *pixels);
+
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void prt_o_sincos2pi(float v, float *s, float *c);

@@ -85,6 +85,7 @@ def lib():
         L.prt_o_shadow_map.argtypes = [vp, vp, C.c_int, vp]
         L.prt_o_relight.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, vp, vp, vp, vp]
         L.prt_o_transfer_to_volume.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.prt_o_raytrace.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp, vp]
         _LIB = L
     return _LIB
 
@@ -339,3 +340,15 @@ def transfer_to_volume(probe_sh, probe_res, w0123, w4567, volume_res) -> np.ndar
     out = np.zeros((int(np.prod(vr)), 7, 4), np.float32)
     lib().prt_o_transfer_to_volume(_ptr(ps), _ptr(pr), _ptr(w0), _ptr(w1), _ptr(vr), _ptr(out))
     return out
+
+
+def raytrace(scene: Scene, camera, w: int, h: int, accum=None, max_path_length=3, albedo=(1.0, 1.0, 1.0), gamma=True, mode=0,
+             seed=0x50525400, frame=0):
+    """raytrace() (reference raytracing.cpp:280-317), one frame; ``camera`` is a ctypes struct laid out like prt_o_camera
+    (prt_b200.Camera is).  Returns (accum [h,w,4], pixels [h,w,4] uint8)."""
+    acc = np.zeros((h, w, 4), np.float32) if accum is None else np.array(accum, np.float32, copy=True, order="C")
+    px = np.zeros((h, w, 4), np.uint8)
+    a = np.asarray(albedo, np.float32)
+    lib().prt_o_raytrace(scene.h, C.cast(C.pointer(camera), C.c_void_p), w, h, int(max_path_length), _ptr(a), int(bool(gamma)), int(mode),
+                         int(seed) & 0xFFFFFFFF, int(frame), _ptr(acc), _ptr(px))
+    return acc, px

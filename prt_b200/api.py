@@ -23,6 +23,7 @@ ABI_SYMBOLS = [
     "prt_fibonacci_dirs", "prt_cube_dirs", "prt_volume_weights",
     "prt_paral_shadow_matrix", "prt_shadow_map", "prt_gi_create", "prt_gi_destroy", "prt_gi_set_shadow_map", "prt_gi_set_albedo",
     "prt_gi_set_radiance", "prt_gi_step", "prt_gi_download",
+    "prt_film_create", "prt_film_destroy", "prt_film_reset", "prt_raytrace", "prt_film_download",
 ]
 
 
@@ -75,6 +76,22 @@ class RelightParams(C.Structure):
         p.light_space_matrix[:] = [float(x) for x in np.asarray(light_space_matrix, np.float32).reshape(-1)]
         p.multi_bounce = int(bool(multi_bounce)); p.atten = float(atten); p.sh_shift = float(sh_shift); p.temp_weight = float(temp_weight)
         return p
+
+
+class Camera(C.Structure):
+    """``prt_camera``: the fields of the reference's Camera that raytrace() reads (raytracing.cpp:293-299)."""
+    _fields_ = [("position", C.c_float * 3), ("front", C.c_float * 3), ("up", C.c_float * 3), ("right", C.c_float * 3), ("zoom_deg", C.c_float)]
+
+    @classmethod
+    def look_at(cls, position, target, world_up=(0, 1, 0), zoom_deg=45.0):
+        p = np.asarray(position, np.float64); f = np.asarray(target, np.float64) - p
+        f /= np.linalg.norm(f)
+        r = np.cross(f, np.asarray(world_up, np.float64)); r /= np.linalg.norm(r)
+        u = np.cross(r, f)
+        c = cls()
+        c.position[:] = [float(x) for x in p]; c.front[:] = [float(x) for x in f]; c.up[:] = [float(x) for x in u]; c.right[:] = [float(x) for x in r]
+        c.zoom_deg = float(zoom_deg)
+        return c
 
 
 class SceneInfo(C.Structure):
@@ -157,6 +174,12 @@ def load_library():
     L.prt_gi_set_radiance.argtypes = [vp, vp]
     L.prt_gi_step.argtypes = [vp, C.POINTER(RelightParams), i32]
     L.prt_gi_download.argtypes = [vp, vp, vp, vp]
+    L.prt_film_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.prt_film_destroy.argtypes = [vp]
+    L.prt_film_destroy.restype = None
+    L.prt_film_reset.argtypes = [vp]
+    L.prt_raytrace.argtypes = [vp, vp, C.POINTER(Camera), i32, vp, i32, i32, u32, i32]
+    L.prt_film_download.argtypes = [vp, vp, vp]
     _LIB = L
     return L
 
@@ -542,3 +565,41 @@ class SHVolume:
         vol = np.zeros((int(np.prod(self.volume_res)), 7, 4), np.float32)
         _check(self.L.prt_gi_download(self.h, _ptr(rad), _ptr(psh), _ptr(vol)), "prt_gi_download")
         return rad, psh, vol
+
+
+AO, NORMAL = 0, 1
+
+
+class Film:
+    """App::pixels_w / App::pixels of the reference's preview tracer (raytracing.cpp:280-317), resident on the GPU."""
+
+    def __init__(self, width: int, height: int, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.L = self.ctx.L
+        self.width, self.height = int(width), int(height)
+        h = C.c_void_p()
+        _check(self.L.prt_film_create(self.ctx.h, self.width, self.height, C.byref(h)), "prt_film_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.L.prt_film_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(self.L.prt_film_reset(self.h), "prt_film_reset")
+
+    def download(self):
+        acc = np.zeros((self.height, self.width, 4), np.float32); px = np.zeros((self.height, self.width, 4), np.uint8)
+        _check(self.L.prt_film_download(self.h, _ptr(acc), _ptr(px)), "prt_film_download")
+        return acc, px
+
+
+def raytrace(scene: RTScene, film: Film, camera: Camera, max_path_length: int = 3, albedo=(1.0, 1.0, 1.0), gamma: bool = True,
+             mode: int = AO, seed: int = 0x50525400, n_frames: int = 1):
+    """reference ``raytrace(const RTScene&)`` (raytracing.cpp:280-317): n_frames more samples per pixel into ``film``."""
+    a = np.asarray(albedo, np.float32)
+    _check(scene.L.prt_raytrace(scene.h, film.h, C.byref(camera), int(max_path_length), _ptr(a), int(bool(gamma)), int(mode),
+                                int(seed) & 0xFFFFFFFF, int(n_frames)), "prt_raytrace")
