@@ -7,10 +7,11 @@
 //   prt_probe_project   reference SH_volume::project_sh + precomp_projectSH.comp:32-143: CSR SpMV with surfel radiance,
 //                       sinc window, Ramamoorthi-Hanrahan pack into 7 vec4 per probe.
 //
-// One CTA per probe (probes handed out in order by an atomic ticket): 256 threads trace the probe's <= 4096 rays, the
+// One CTA per probe (probes handed out in order by an atomic ticket): 512 threads trace the probe's <= 4096 rays, the
 // (cluster key, ray) pairs are bitonic-sorted in shared memory, segment heads reduce their rays in ray order (deterministic
-// sums) and the probe's entries are appended to the CSR through a chained prefix (each probe publishes its end offset for
-// the next one), so the output is probe-major, sorted by cluster within a probe and exactly sized.
+// sums) into the probe's slice of a staging area; an exclusive scan of the per-probe entry counts and a compaction pass (one
+// warp per probe, coalesced copies) then give the probe-major, exactly sized CSR.  (A chained prefix inside the capture kernel
+// serialised the probes.)
 // Surfel ids are the rank of the cluster key among all keys (== std::map<std::array<int,4>> order of volume.cpp:204).
 #include "../../include/prt_b200.h"
 #include "abi_internal.h"
@@ -27,7 +28,7 @@ using namespace prt;
 namespace {
 
 constexpr int kMaxRays = 4096;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr unsigned long long kInvalid = ~0ull;
 
 struct CaptureArgs {
@@ -35,14 +36,12 @@ struct CaptureArgs {
     const float *probe_pos; uint32_t n_probes;
     const float4 *dirs;          // xyz = direction, w = solid angle
     uint32_t n_dirs;
+    const uint32_t *order;       // [n_dirs] trace slot -> ray index (directions sorted along a space-filling curve: coherent warps)
     uint32_t *ticket;            // [1] zeroed
-    unsigned long long *offsets; // [n_probes + 1]; offsets[0] = 1 (value + 1, 0 = not published yet)
-    unsigned long long capacity;
-    uint32_t *range;             // [n_probes][2]
-    unsigned long long *ekeys;   // [capacity]
-    float *etransfer;            // [capacity][9]
-    float *eacc;                 // [capacity][7] sum pos, sum normal, count
-    int *overflow;
+    uint32_t *counts;            // [n_probes] entries (clusters) of each probe
+    unsigned long long *ekeys;   // staging [n_probes][n_dirs]
+    float *etransfer;            // staging [n_probes][n_dirs][9]
+    float *eacc;                 // staging [n_probes][n_dirs][7] sum pos, sum normal, count
 };
 
 __device__ __forceinline__ bool cluster_key(f3 pos, f3 n, unsigned long long &key) {
@@ -58,13 +57,13 @@ __device__ __forceinline__ bool cluster_key(f3 pos, f3 n, unsigned long long &ke
     return true;
 }
 
-__global__ void __launch_bounds__(kThreads) probe_capture_kernel(const CaptureArgs A) {
+__global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const CaptureArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem);          // [4096] (cluster key << 12) | ray
     float *tt = reinterpret_cast<float *>(sk + kMaxRays);                          // [4096] hit distance by ray
     uint32_t *tri = reinterpret_cast<uint32_t *>(tt + kMaxRays);                   // [4096] hit triangle slot by ray
-    __shared__ uint32_t s_probe, s_counts[kThreads], s_total;
-    __shared__ unsigned long long s_start;
+    float *s_lead = reinterpret_cast<float *>(tri + kMaxRays);                      // [kThreads][16] partial sums handed to an earlier chunk
+    __shared__ uint32_t s_probe, s_counts[kThreads], s_through[kThreads];
     const int tid = threadIdx.x;
 
     for (;;) {
@@ -75,9 +74,10 @@ __global__ void __launch_bounds__(kThreads) probe_capture_kernel(const CaptureAr
         const f3 P = mk3(A.probe_pos[3 * p], A.probe_pos[3 * p + 1], A.probe_pos[3 * p + 2]);
 
         // ---- trace ------------------------------------------------------------------------------------------------------
-        for (int r = tid; r < kMaxRays; r += kThreads) {
+        for (int slot = tid; slot < kMaxRays; slot += kThreads) {
             unsigned long long key = kInvalid;
-            if (r < (int)A.n_dirs) {
+            const int r = slot < (int)A.n_dirs ? (int)__ldg(&A.order[slot]) : slot;      // results are stored by ray index, so the
+            if (slot < (int)A.n_dirs) {                                                   // trace order does not change them
                 const float4 dw = __ldg(&A.dirs[r]);
                 Trav tr;
                 tr.reset_counters();
@@ -101,13 +101,11 @@ __global__ void __launch_bounds__(kThreads) probe_capture_kernel(const CaptureAr
         // ---- bitonic sort of 4096 keys in shared memory ---------------------------------------------------------------------
         for (int k = 2; k <= kMaxRays; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < kMaxRays; i += kThreads) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const unsigned long long a = sk[i], b = sk[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
-                    }
+                for (int t = tid; t < kMaxRays / 2; t += kThreads) {                 // one compare-exchange per thread and step
+                    const int i = 2 * t - (t & (j - 1)), ixj = i + j;
+                    const unsigned long long a = sk[i], b = sk[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
                 }
                 __syncthreads();
             }
@@ -125,55 +123,109 @@ __global__ void __launch_bounds__(kThreads) probe_capture_kernel(const CaptureAr
         if (tid == 0) {
             uint32_t run = 0;
             for (int i = 0; i < kThreads; i++) { const uint32_t c = s_counts[i]; s_counts[i] = run; run += c; }
-            s_total = run;
-            // chained prefix: wait for the previous probe's end offset, publish ours
-            volatile unsigned long long *off = A.offsets;
-            unsigned long long v;
-            while ((v = off[p]) == 0ull) { __nanosleep(64); }
-            s_start = v - 1ull;
-            __threadfence();
-            off[p + 1] = v + (unsigned long long)run;
-            A.range[2 * p] = (uint32_t)(v - 1ull);
-            A.range[2 * p + 1] = (uint32_t)(v - 1ull + run);
+            A.counts[p] = run;
         }
         __syncthreads();
-        const unsigned long long start = s_start;
-        if (start + s_total > A.capacity) { if (tid == 0) *A.overflow = 1; __syncthreads(); continue; }
+        const unsigned long long start = (unsigned long long)p * A.n_dirs;          // the probe's staging slice
 
-        // ---- per-cluster reduction in ray order (volume.cpp:250-260) -----------------------------------------------------------
+        // ---- per-cluster reduction (volume.cpp:250-260) ------------------------------------------------------------------------
+        // Every thread walks its kChunk consecutive sorted slots: clusters that end inside the chunk are written directly, the
+        // slots before the first head ("lead") belong to a cluster begun in an earlier chunk and are handed over through shared
+        // memory; the thread whose last cluster runs past its chunk collects the leads of the following chunks.  All lanes stay
+        // busy whatever the cluster sizes, and the summation order is fixed by the layout (deterministic).
+        auto flush = [&](const float *acc, const unsigned long long key, const uint32_t rank) {
+            const unsigned long long e = start + rank;
+            A.ekeys[e] = key;
+#pragma unroll
+            for (int c = 0; c < 9; c++) A.etransfer[9 * e + c] = acc[c];
+#pragma unroll
+            for (int c = 0; c < 7; c++) A.eacc[7 * e + c] = acc[9 + c];
+        };
+        float lead[16], acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) { lead[c] = 0.f; acc[c] = 0.f; }
+        bool open = false, ended = false;                 // open: a cluster of this chunk is being summed; ended: ran into the invalid tail
+        unsigned long long open_key = 0ull;
         uint32_t rank = s_counts[tid];
         for (int q = 0; q < kChunk; q++) {
             const int i = tid * kChunk + q;
             const unsigned long long a = sk[i];
-            if (a == kInvalid || !(i == 0 || (sk[i - 1] >> 12) != (a >> 12))) continue;
-            float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float sp[3] = {0.f, 0.f, 0.f}, sn[3] = {0.f, 0.f, 0.f}, cnt = 0.f;
-            for (int j = i; j < kMaxRays && (sk[j] >> 12) == (a >> 12); j++) {
-                const uint32_t r = (uint32_t)(sk[j] & 0xFFFull);
-                const float4 dw = __ldg(&A.dirs[r]);
-                const f3 pos = madd3(P, tt[r], mk3(dw.x, dw.y, dw.z));
-                const f3 tp = sub3(pos, P);
-                const float m = fmaxf(fabsf(tp.x), fmaxf(fabsf(tp.y), fabsf(tp.z)));
-                const f3 cc = mk3(PRT_DIV(tp.x, m), PRT_DIV(tp.y, m), PRT_DIV(tp.z, m));             // volume.cpp:250
-                const f3 d = normalize3(mk3(cc.z, cc.x, cc.y));                                    // :255-256
-                float y[9];
-                sh_eval<3>(d.x, d.y, d.z, 1.0f, y);
+            if (a == kInvalid) { ended = true; break; }
+            const bool head = (i == 0) || ((sk[i - 1] >> 12) != (a >> 12));
+            const uint32_t r = (uint32_t)(a & 0xFFFull);
+            const float4 dw = __ldg(&A.dirs[r]);
+            const f3 pos = madd3(P, tt[r], mk3(dw.x, dw.y, dw.z));
+            const f3 tp = sub3(pos, P);
+            const float m = fmaxf(fabsf(tp.x), fmaxf(fabsf(tp.y), fabsf(tp.z)));
+            const f3 cc = mk3(PRT_DIV(tp.x, m), PRT_DIV(tp.y, m), PRT_DIV(tp.z, m));             // volume.cpp:250
+            const f3 d = normalize3(mk3(cc.z, cc.x, cc.y));                                    // :255-256
+            float c16[16];
+            sh_eval<3>(d.x, d.y, d.z, 1.0f, c16);
 #pragma unroll
-                for (int c = 0; c < 9; c++) acc[c] += y[c] * dw.w;                                   // :260
-                const char *tp48 = reinterpret_cast<const char *>(A.tris + tri[r]);
-                const u4 b4 = ld16(tp48 + 16), c4 = ld16(tp48 + 32);
-                const f3 n = normalize3(cross3(mk3(PRT_U2F(b4.x), PRT_U2F(b4.y), PRT_U2F(b4.z)), mk3(PRT_U2F(c4.x), PRT_U2F(c4.y), PRT_U2F(c4.z))));
-                sp[0] += pos.x; sp[1] += pos.y; sp[2] += pos.z; sn[0] += n.x; sn[1] += n.y; sn[2] += n.z; cnt += 1.f;
+            for (int c = 0; c < 9; c++) c16[c] *= dw.w;                                        // :260
+            const char *tp48 = reinterpret_cast<const char *>(A.tris + tri[r]);
+            const u4 b4 = ld16(tp48 + 16), c4 = ld16(tp48 + 32);
+            const f3 n = normalize3(cross3(mk3(PRT_U2F(b4.x), PRT_U2F(b4.y), PRT_U2F(b4.z)), mk3(PRT_U2F(c4.x), PRT_U2F(c4.y), PRT_U2F(c4.z))));
+            c16[9] = pos.x; c16[10] = pos.y; c16[11] = pos.z; c16[12] = n.x; c16[13] = n.y; c16[14] = n.z; c16[15] = 1.f;
+            if (head) {
+                if (open) flush(acc, open_key, rank++);
+                open = true; open_key = a >> 12;
+#pragma unroll
+                for (int c = 0; c < 16; c++) acc[c] = c16[c];
+            } else if (open) {
+#pragma unroll
+                for (int c = 0; c < 16; c++) acc[c] += c16[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; c++) lead[c] += c16[c];
             }
-            const unsigned long long e = start + rank++;
-            A.ekeys[e] = a >> 12;
+        }
 #pragma unroll
-            for (int c = 0; c < 9; c++) A.etransfer[9 * e + c] = acc[c];
-            float *ea = A.eacc + 7 * e;
-            ea[0] = sp[0]; ea[1] = sp[1]; ea[2] = sp[2]; ea[3] = sn[0]; ea[4] = sn[1]; ea[5] = sn[2]; ea[6] = cnt;
+        for (int c = 0; c < 16; c++) s_lead[tid * 16 + c] = lead[c];
+        s_through[tid] = (!open && !ended) ? 1u : 0u;      // the whole chunk continues an earlier cluster and runs on
+        __syncthreads();
+        if (open) {
+            if (!ended) {
+                for (int t = tid + 1; t < kThreads; t++) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) acc[c] += s_lead[t * 16 + c];
+                    if (!s_through[t]) break;
+                }
+            }
+            flush(acc, open_key, rank);
         }
         __syncthreads();
     }
+}
+
+// ---- exact CSR: exclusive scan of the per-probe counts (one CTA; probes are few) + compaction of the staging slices ---------
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *counts, uint32_t n, unsigned long long *offsets) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n + 1023u) / 1024u, lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long c = part[i]; part[i] = run; run += c; }
+        offsets[n] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+}
+__global__ void __launch_bounds__(256) compact_csr_kernel(const uint32_t *counts, const unsigned long long *offsets, uint32_t n_probes, uint32_t n_dirs,
+                                                          const unsigned long long *skeys, const float *stransfer, const float *sacc,
+                                                          unsigned long long *ekeys, float *etransfer, float *eacc, uint32_t *range) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_probes) return;
+    const uint32_t cnt = counts[p];
+    const unsigned long long src = (unsigned long long)p * n_dirs, dst = offsets[p];
+    if (lane == 0) { range[2 * p] = (uint32_t)dst; range[2 * p + 1] = (uint32_t)(dst + cnt); }
+    for (uint32_t i = lane; i < cnt; i += 32) ekeys[dst + i] = skeys[src + i];
+    for (uint32_t i = lane; i < 9u * cnt; i += 32) etransfer[9 * dst + i] = stransfer[9 * src + i];
+    for (uint32_t i = lane; i < 7u * cnt; i += 32) eacc[7 * dst + i] = sacc[7 * src + i];
 }
 
 // ---- global surfel ids: hash-set dedupe of cluster keys, host sort of the (few) distinct keys, rank lookup ----------------
@@ -287,53 +339,82 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
 
     std::vector<float> dw(4 * (size_t)n_dirs);
     for (uint32_t i = 0; i < n_dirs; i++) { dw[4 * i] = dirs[3 * i]; dw[4 * i + 1] = dirs[3 * i + 1]; dw[4 * i + 2] = dirs[3 * i + 2]; dw[4 * i + 3] = weights[i]; }
-    float *d_pos = nullptr, *d_dirs = nullptr, *etransfer = nullptr, *eacc = nullptr;
-    uint32_t *ticket = nullptr, *range = nullptr;
-    unsigned long long *offsets = nullptr, *ekeys = nullptr;
+    // trace order: directions sorted by the Morton code of their position on the unit sphere (10 bits per axis)
+    std::vector<uint32_t> order(n_dirs);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> mk(n_dirs);
+        auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+        for (uint32_t i = 0; i < n_dirs; i++) {
+            const float l = sqrtf(dirs[3 * i] * dirs[3 * i] + dirs[3 * i + 1] * dirs[3 * i + 1] + dirs[3 * i + 2] * dirs[3 * i + 2]);
+            uint32_t q[3];
+            for (int a = 0; a < 3; a++) {
+                const float v = l > 0.f ? dirs[3 * i + a] / l : 0.f;
+                q[a] = (uint32_t)std::min(1023.f, std::max(0.f, (v * 0.5f + 0.5f) * 1023.f));
+            }
+            mk[i] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), i};
+        }
+        std::sort(mk.begin(), mk.end());
+        for (uint32_t i = 0; i < n_dirs; i++) order[i] = mk[i].second;
+    }
+    uint32_t *d_order = nullptr;
+    float *d_pos = nullptr, *d_dirs = nullptr, *stransfer = nullptr, *sacc_stage = nullptr, *etransfer = nullptr, *eacc = nullptr;
+    uint32_t *ticket = nullptr, *range = nullptr, *counts = nullptr;
+    unsigned long long *offsets = nullptr, *skeys = nullptr, *ekeys = nullptr;
     int *overflow = nullptr;
-    auto cleanup = [&]() { cudaFree(d_pos); cudaFree(d_dirs); cudaFree(ticket); cudaFree(offsets); cudaFree(ekeys); cudaFree(eacc); cudaFree(overflow); };
+    auto free_stage = [&]() { cudaFree(skeys); cudaFree(stransfer); cudaFree(sacc_stage); skeys = nullptr; stransfer = nullptr; sacc_stage = nullptr; };
+    auto cleanup = [&]() { free_stage(); cudaFree(d_order); cudaFree(d_pos); cudaFree(d_dirs); cudaFree(ticket); cudaFree(counts); cudaFree(offsets); cudaFree(ekeys); cudaFree(eacc); cudaFree(overflow); };
     cudaError_t e = cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)n_probes);
     if (e == cudaSuccess) e = cudaMalloc(&d_dirs, sizeof(float) * 4 * (size_t)n_dirs);
+    if (e == cudaSuccess) e = cudaMalloc(&d_order, 4 * (size_t)n_dirs);
     if (e == cudaSuccess) e = cudaMalloc(&ticket, 8);
     if (e == cudaSuccess) e = cudaMalloc(&overflow, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&counts, 4 * (size_t)n_probes);
     if (e == cudaSuccess) e = cudaMalloc(&offsets, 8 * ((size_t)n_probes + 1));
     if (e == cudaSuccess) e = cudaMalloc(&range, 8 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&ekeys, 8 * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&etransfer, 36 * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&eacc, 28 * capacity);
-    if (e != cudaSuccess) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_NOMEM, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&skeys, 8 * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&stransfer, 36 * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&sacc_stage, 28 * capacity);
+    if (e != cudaSuccess) { cleanup(); cudaFree(range); return prt_set_error(PRT_ERR_NOMEM, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
     cudaMemcpyAsync(d_pos, probe_pos, sizeof(float) * 3 * (size_t)n_probes, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_dirs, dw.data(), sizeof(float) * 4 * (size_t)n_dirs, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_order, order.data(), 4 * (size_t)n_dirs, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(ticket, 0, 8, st);
     cudaMemsetAsync(overflow, 0, 4, st);
-    cudaMemsetAsync(offsets, 0, 8 * ((size_t)n_probes + 1), st);
-    const unsigned long long one = 1ull;
-    cudaMemcpyAsync(offsets, &one, 8, cudaMemcpyHostToDevice, st);
 
     CaptureArgs A{};
-    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs;
-    A.ticket = ticket; A.offsets = offsets; A.capacity = capacity; A.range = range; A.ekeys = ekeys; A.etransfer = etransfer; A.eacc = eacc; A.overflow = overflow;
-    const size_t smem = (size_t)kMaxRays * (8 + 4 + 4);
+    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order;
+    A.ticket = ticket; A.counts = counts; A.ekeys = skeys; A.etransfer = stransfer; A.eacc = sacc_stage;
+    const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + (size_t)kThreads * 16 * 4;
     static bool configured = false;
     if (!configured) { PB_TRY(cudaFuncSetAttribute(probe_capture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     int per_sm = 1;
     PB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_capture_kernel, kThreads, smem));
-    // every ticket holder must be resident (chained prefix): never launch more CTAs than fit at once
     const int grid = (int)std::min<unsigned long long>((unsigned long long)prt_ctx_sms(sv.ctx) * (unsigned long long)std::max(per_sm, 1), n_probes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
     probe_capture_kernel<<<grid, kThreads, smem, st>>>(A);
-    cudaEventRecord(e1, st);
-    unsigned long long nnz_p1 = 0; int ovf = 0;
-    cudaMemcpyAsync(&nnz_p1, offsets + n_probes, 8, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, st);
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n_probes, offsets);
+    unsigned long long nnz = 0; int ovf = 0;
+    cudaMemcpyAsync(&nnz, offsets + n_probes, 8, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+        const unsigned long long nz = std::max<unsigned long long>(1, nnz);
+        e = cudaMalloc(&ekeys, 8 * nz);
+        if (e == cudaSuccess) e = cudaMalloc(&etransfer, 36 * nz);
+        if (e == cudaSuccess) e = cudaMalloc(&eacc, 28 * nz);
+        if (e == cudaSuccess) {
+            compact_csr_kernel<<<(unsigned)(((size_t)n_probes * 32 + 255) / 256), 256, 0, st>>>(counts, offsets, n_probes, n_dirs, skeys, stransfer, sacc_stage,
+                                                                                          ekeys, etransfer, eacc, range);
+            cudaEventRecord(e1, st);
+            e = cudaStreamSynchronize(st);
+        }
+    }
     float ms = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (e != cudaSuccess || ovf) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_CUDA, e != cudaSuccess ? std::string("probe_capture_kernel: ") + cudaGetErrorString(e) : "prt_probe_capture: CSR capacity exceeded"); }
-    const unsigned long long nnz = nnz_p1 - 1ull;
+    if (e != cudaSuccess) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    free_stage();
 
     // ---- global ids ----------------------------------------------------------------------------------------------------------
     prt_csr *c = new prt_csr();
