@@ -64,6 +64,7 @@ struct prt_scene {
 int prt_set_error(int code, const std::string &msg) { return set_err(code, msg); }
 cudaStream_t prt_ctx_stream(prt_ctx *c) { return c->stream; }
 int prt_ctx_sms(const prt_ctx *c) { return c->n_sms; }
+int prt_ctx_refill_thresh(const prt_ctx *c) { return c->refill_thresh; }
 prt_scene_view prt_scene_get_view(prt_scene *s) { return prt_scene_view{s->d_nodes, s->d_tris, s->ctx}; }
 
 extern "C" {

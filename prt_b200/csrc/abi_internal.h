@@ -8,6 +8,7 @@
 int prt_set_error(int code, const std::string &msg);   // records the thread-local message, returns code
 cudaStream_t prt_ctx_stream(prt_ctx *);                // the context's own stream
 int prt_ctx_sms(const prt_ctx *);
+int prt_ctx_refill_thresh(const prt_ctx *);            // tuning knob: refill idle lanes when fewer than this many are traversing
 
 // device-side view of a scene for the other translation units
 struct prt_scene_view { const prt::Node8 *nodes; const prt::Tri48 *tris; prt_ctx *ctx; };

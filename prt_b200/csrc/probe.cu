@@ -36,6 +36,7 @@ struct CaptureArgs {
     const float *probe_pos; uint32_t n_probes;
     const float4 *dirs;          // xyz = direction, w = solid angle
     uint32_t n_dirs;
+    int refill_thresh;
     const uint32_t *order;       // [n_dirs] trace slot -> ray index (directions sorted along a space-filling curve: coherent warps)
     uint32_t *ticket;            // [1] zeroed
     uint32_t *counts;            // [n_probes] entries (clusters) of each probe
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
     float *tt = reinterpret_cast<float *>(sk + kMaxRays);                          // [4096] hit distance by ray
     uint32_t *tri = reinterpret_cast<uint32_t *>(tt + kMaxRays);                   // [4096] hit triangle slot by ray
     float *s_lead = reinterpret_cast<float *>(tri + kMaxRays);                      // [kThreads][16] partial sums handed to an earlier chunk
-    __shared__ uint32_t s_probe, s_counts[kThreads], s_through[kThreads];
+    __shared__ uint32_t s_probe, s_next, s_counts[kThreads], s_through[kThreads];
     const int tid = threadIdx.x;
 
     for (;;) {
@@ -74,41 +75,73 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
         const f3 P = mk3(A.probe_pos[3 * p], A.probe_pos[3 * p + 1], A.probe_pos[3 * p + 2]);
 
         // ---- trace ------------------------------------------------------------------------------------------------------
-        for (int slot = tid; slot < kMaxRays; slot += kThreads) {
-            unsigned long long key = kInvalid;
-            const int r = slot < (int)A.n_dirs ? (int)__ldg(&A.order[slot]) : slot;      // results are stored by ray index, so the
-            if (slot < (int)A.n_dirs) {                                                   // trace order does not change them
-                const float4 dw = __ldg(&A.dirs[r]);
-                Trav tr;
-                tr.reset_counters();
-                tr.init(P, mk3(dw.x, dw.y, dw.z), 0.0f, INFINITY);
-                tr.start_root();
-                tr.run<false>(A.nodes, A.tris, 0, false);
+        // Rays are handed out from a CTA-wide counter: a lane that finishes its ray takes the next one as soon as fewer than
+        // refill_thresh lanes of its warp are still traversing, so neither a slow ray nor a slow warp holds the others up.
+        for (int i = tid; i < kMaxRays; i += kThreads) sk[i] = kInvalid;
+        if (tid == 0) s_next = 0u;
+        __syncthreads();
+        {
+            const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+            Trav tr;
+            tr.reset_counters();
+            bool active = false, exhausted = false;
+            int r = 0;
+            for (;;) {
+                const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+                if (idle && !exhausted) {
+                    uint32_t base = 0u;
+                    if (lane == 0u) base = atomicAdd(&s_next, (uint32_t)__popc(idle));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const uint32_t slot = base + (uint32_t)__popc(idle & lt_mask);
+                    if (!active && slot < A.n_dirs) {
+                        r = (int)__ldg(&A.order[slot]);                              // results are stored by ray index, so the trace
+                        const float4 dw = __ldg(&A.dirs[r]);                         // order does not change them
+                        tr.init(P, mk3(dw.x, dw.y, dw.z), 0.0f, INFINITY);
+                        tr.start_root();
+                        active = true;
+                    }
+                    exhausted = base + (uint32_t)__popc(idle) >= A.n_dirs;
+                }
+                if (!__any_sync(0xFFFFFFFFu, active)) break;
+                if (!active) continue;
+                if (tr.run<false>(A.nodes, A.tris, A.refill_thresh, !exhausted) == TRAV_RUNNING) continue;
                 if (tr.best_prim != 0xFFFFFFFFu) {                                   // sky: volume.cpp:246
                     const f3 n = normalize3(tr.hit_ng(A.tris));
                     const f3 pos = madd3(P, tr.best_t, tr.d);
                     unsigned long long ck;
                     if (!(dot3(sub3(pos, P), n) > 0.0f) && cluster_key(pos, n, ck)) {   // back face: volume.cpp:249
-                        key = (ck << 12) | (unsigned long long)r;
+                        sk[r] = (ck << 12) | (unsigned long long)r;
                         tt[r] = tr.best_t; tri[r] = tr.best_tri;
                     }
                 }
+                active = false;
             }
-            sk[r] = key;
         }
         __syncthreads();
 
         // ---- bitonic sort of 4096 keys in shared memory ---------------------------------------------------------------------
-        for (int k = 2; k <= kMaxRays; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < kMaxRays / 2; t += kThreads) {                 // one compare-exchange per thread and step
-                    const int i = 2 * t - (t & (j - 1)), ixj = i + j;
-                    const unsigned long long a = sk[i], b = sk[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
+        // One compare-exchange per thread and step.  Warp w owns pairs [128 w, 128 w + 128): for strides j <= 128 they all lie in
+        // its own 256-key window, so only the 10 steps with j >= 256 need a block-wide barrier, the other 68 a __syncwarp.
+        {
+            constexpr int kPairsPerWarp = (kMaxRays / 2) / (kThreads / 32);
+            const int wbase = (tid >> 5) * kPairsPerWarp + (tid & 31);
+            bool prev_wide = false;                                              // (the barrier after the trace phase covers step 1)
+            for (int k = 2; k <= kMaxRays; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const bool wide = j >= 2 * kPairsPerWarp;
+                    if (wide || prev_wide) __syncthreads(); else __syncwarp();
+                    prev_wide = wide;
+#pragma unroll
+                    for (int q = 0; q < kPairsPerWarp / 32; q++) {
+                        const int t = wbase + 32 * q;
+                        const int i = 2 * t - (t & (j - 1)), ixj = i + j;
+                        const unsigned long long a = sk[i], b = sk[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
+                    }
                 }
-                __syncthreads();
-            }
+            __syncthreads();
+        }
 
         // ---- segment heads, ranks --------------------------------------------------------------------------------------------
         constexpr int kChunk = kMaxRays / kThreads;
@@ -382,7 +415,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     cudaMemsetAsync(overflow, 0, 4, st);
 
     CaptureArgs A{};
-    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order;
+    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order; A.refill_thresh = prt_ctx_refill_thresh(sv.ctx);
     A.ticket = ticket; A.counts = counts; A.ekeys = skeys; A.etransfer = stransfer; A.eacc = sacc_stage;
     const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + (size_t)kThreads * 16 * 4;
     static bool configured = false;

@@ -67,9 +67,19 @@ if want("c3"):
     res = 16 if a.quick else 32
     probes = prt_b200.probe_positions([res] * 3, [6.18] * 3)
     d, w = prt_b200.fibonacci_dirs(4096)
-    t0 = time.perf_counter()
-    pt = prt_b200.ProbeTransfer(sc, probes, d, w)
-    wall = time.perf_counter() - t0
+    prt_b200.ProbeTransfer(sc, probes[:64], d, w).close()                  # warm-up: module load, allocator
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        pt = prt_b200.ProbeTransfer(sc, probes, d, w)
+        wall = time.perf_counter() - t0
+        if best is None or pt.capture_ms < best[0].capture_ms:
+            if best is not None:
+                best[0].close()
+            best = (pt, wall)
+        else:
+            pt.close()
+    pt, wall = best
     rad = np.ones((pt.n_surfels, 4), np.float32)
     t_proj = timed(lambda: pt.project(rad))
     emit(config=f"3: probe capture {res}^3 probes x 4096 rays, room + buddha-scale torus ({len(tri)} triangles)", probes=len(probes),
