@@ -333,8 +333,20 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     }
     else if (fast_ok && c->pair_queue == 1 && c->block == 256)
         CU_TRY(launch_bake_shadow(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
-    else
+    else {
+        A.need_bits = nullptr; A.need_count = nullptr;
+        if (mode == 1 && c->horizon && c->entry_list) {
+            // interreflection: the horizon pass settles the primary rays that provably escape (and whole vertices)
+            CU_TRY(c->need_bits.reserve((size_t)n * A.vis_words * 4));
+            CU_TRY(c->need_count.reserve((size_t)n * 4));
+            A.need_bits = (uint32_t *)c->need_bits.p; A.need_count = (uint32_t *)c->need_count.p;
+            int hgrid = 0;
+            CU_TRY(launch_horizon(A, p->order, &hgrid, c->n_sms, st));
+            if (e0) CU_TRY(cudaEventRecord(c->evh, st));
+            launches = 2;
+        }
         CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
+    }
     if (e1) CU_TRY(cudaEventRecord(e1, st));
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;
     c->stats.launches = launches; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;

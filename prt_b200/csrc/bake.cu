@@ -45,13 +45,39 @@ __global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
         const Frame fr = make_frame(N);
         const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
 
+        // horizon pass ran first (interreflection): vertices with nothing to trace are finished, and of the others only the
+        // flagged samples are traced -- every other primary ray provably escapes with weight 1 (raytracing.cpp:257-261)
+        const uint32_t *need_row = (MODE == 1 && A.need_bits) ? A.need_bits + (size_t)v * A.vis_words : nullptr;
+        int n_need = A.S;
+        if (need_row) {
+            n_need = (int)__ldg(&A.need_count[v]);
+            if (n_need == 0) continue;
+        }
+
         int n_cand = 0;
         if (MODE != 2 && A.entry_list) n_cand = build_entry_list(A.nodes, org, N, W, lane);
-        cand_tests += (unsigned long long)n_cand * (unsigned long long)A.S;
+        cand_tests += (unsigned long long)n_cand * (unsigned long long)n_need;
 
         float acc[N2];
 #pragma unroll
         for (int k = 0; k < N2; k++) acc[k] = 0.f;
+
+        if (need_row) {
+            for (int base = 0; base < A.S; base += 32) {
+                const int i = base + lane;
+                if (i < A.S && !((__ldg(&need_row[base >> 5]) >> lane) & 1u)) {
+                    const float4 smp = __ldg(&A.samples[i]);
+                    const f3 dir = to_world(fr, mk3(smp.x, smp.y, smp.z));
+                    float y[N2];
+                    sh_eval<ORDER>(dir.z, dir.x, dir.y, sgn, y);
+#pragma unroll
+                    for (int k = 0; k < N2; k++) acc[k] += y[k];
+                    if (A.vis) { const uint32_t sr = __float_as_uint(smp.w) & 0xFFFFFFu; atomicOr(&A.vis[(size_t)v * A.vis_words + (sr >> 5)], 1u << (sr & 31u)); }
+                }
+            }
+        }
+        int need_word = -1, fetched = 0;      // cursor over the need bits (warp-uniform)
+        uint32_t need_cur = 0u;
 
         int next = 0;
         bool active = false;
@@ -65,6 +91,33 @@ __global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
 
         for (;;) {
             const unsigned idle = __ballot_sync(kFull, !active);
+            if (need_row) {
+                if (idle && fetched < n_need) {
+                    // hand the next popc(idle) flagged samples to the idle lanes, in processing order
+                    const int n_idle = __popc(idle), my_rank = __popc(idle & lt_mask);
+                    int taken = 0, my_k = -1;
+                    while (taken < n_idle && fetched + taken < n_need) {
+                        if (!need_cur) { need_cur = __ldg(&need_row[++need_word]); continue; }
+                        const int c = __popc(need_cur), take = min(c, n_idle - taken);
+                        if (!active && my_rank >= taken && my_rank < taken + take) my_k = need_word * 32 + (int)__fns(need_cur, 0u, my_rank - taken + 1);
+                        if (take == c) need_cur = 0u;
+                        else need_cur &= ~((2u << __fns(need_cur, 0u, take)) - 1u);
+                        taken += take;
+                    }
+                    fetched += taken;
+                    if (my_k >= 0) {
+                        const float4 smp = __ldg(&A.samples[my_k]);
+                        sidx = __float_as_uint(smp.w) & 0xFFFFFFu;
+                        const f3 dir = to_world(fr, mk3(smp.x, smp.y, smp.z));
+                        pos = org; seg = 0; Lw0 = Lw1 = Lw2 = 1.f;
+                        tr.init(pos, dir, 0.0f, INFINITY);
+                        if (n_cand) scan_entry_list(W, n_cand, tr.idx, tr.idy, tr.idz, cm);
+                        else tr.start_root();
+                        active = true;
+                    }
+                }
+                next = fetched < n_need ? 0 : A.S;               // "more samples waiting" for the refill test below
+            } else
             if (idle && next < A.S) {
                 const int k = next + __popc(idle & lt_mask);
                 if (!active && k < A.S) {

@@ -165,6 +165,79 @@ extern "C" void hc_entry_stats(void *h, const float *org, const float *nrm, cons
     out[4] = (double)occl / nrays; out[5] = expanded;
 }
 
+// Experiment: entry list expanded further by apparent size.  After the chain of nodes containing the origin, the subtree
+// candidate with the largest (radius / distance)^2 is replaced by its children until `total_max` candidates exist or no
+// candidate exceeds `min_ratio`.  Same outputs as hc_entry_stats.
+extern "C" void hc_entry_stats2(void *h, const float *org, const float *nrm, const float *dirs, uint32_t nrays, int chain_max, int total_max,
+                                float min_ratio, double *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    std::vector<Cand> cands; std::vector<uint32_t> queue; queue.push_back(0);
+    int expanded = 0;
+    auto push_children = [&](uint32_t x, bool chain) {
+        const Node8 &nd = b->nodes[x];
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            Cand c; decode_child(nd, s, c.lo, c.hi);
+            float mx = 0.f, far2 = 0.f; bool inside = true;
+            for (int a = 0; a < 3; a++) {
+                float l = c.lo[a] - org[a], hh = c.hi[a] - org[a];
+                mx += std::max(nrm[a] * l, nrm[a] * hh);
+                far2 = std::max(far2, std::max(std::fabs(l), std::fabs(hh)));
+                if (org[a] < c.lo[a] || org[a] > c.hi[a]) inside = false;
+            }
+            if (mx < -1e-5f * far2) continue;
+            bool inner = (nd.imask >> s) & 1;
+            if (inner) {
+                uint32_t child = nd.child_base + __builtin_popcount(nd.imask & ((1u << s) - 1u));
+                if (chain && inside && (int)(cands.size() + queue.size()) < chain_max) { queue.push_back(child); continue; }
+                c.node = child; c.ntri = 0; c.tri0 = 0;
+            } else {
+                c.node = 0xFFFFFFFFu; c.tri0 = nd.tri_base + (nd.meta[s] & 31); c.ntri = __builtin_popcount(nd.meta[s] >> 5);
+            }
+            cands.push_back(c);
+        }
+    };
+    while (!queue.empty()) { uint32_t x = queue.back(); queue.pop_back(); expanded++; push_children(x, true); }
+    for (;;) {
+        int best = -1; float best_ratio = min_ratio;
+        for (size_t k = 0; k < cands.size(); k++) {
+            if (cands[k].node == 0xFFFFFFFFu) continue;
+            float r2 = 0.f, d2 = 0.f;
+            for (int a = 0; a < 3; a++) { float e = 0.5f * (cands[k].hi[a] - cands[k].lo[a]), c = 0.5f * (cands[k].hi[a] + cands[k].lo[a]) - org[a]; r2 += e * e; d2 += c * c; }
+            float ratio = r2 / std::max(d2, 1e-30f);
+            if (ratio > best_ratio) { best_ratio = ratio; best = (int)k; }
+        }
+        if (best < 0 || (int)cands.size() + 7 > total_max) break;
+        uint32_t node = cands[best].node;
+        cands.erase(cands.begin() + best);
+        expanded++;
+        push_children(node, false);
+    }
+    uint64_t box_hits = 0, nv = 0, nt = 0, occl = 0;
+    for (uint32_t i = 0; i < nrays; i++) {
+        f3 o = mk3(org[0], org[1], org[2]), d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        Trav t; t.reset_counters(); t.init(o, d, 0.f, INFINITY);
+        bool hit = false;
+        for (size_t k = 0; k < cands.size() && !hit; k++) {
+            const Cand &c = cands[k];
+            float t0 = 0.f, t1 = INFINITY; const float id[3] = { t.idx, t.idy, t.idz }; const float oo[3] = { o.x, o.y, o.z };
+            for (int a = 0; a < 3; a++) { float ta = (c.lo[a] - oo[a]) * id[a], tb = (c.hi[a] - oo[a]) * id[a]; t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb)); }
+            if (!(t0 <= t1)) continue;
+            box_hits++;
+            if (c.node == 0xFFFFFFFFu) {
+                for (uint32_t j = 0; j < c.ntri && !hit; j++) { float tt; uint32_t pr; nt++; hit = t.tri_test(b->tris, c.tri0 + j, false, tt, pr); }
+            } else {
+                t.ng.x = c.node; t.ng.y = 0x80000000u; t.tg.y = 0; t.sp = 0; t.n_node_visits = 0; t.n_tri_tests = 0;
+                hit = t.run<true>(b->nodes, b->tris, 0, false) == TRAV_HIT;
+                nv += t.n_node_visits; nt += t.n_tri_tests;
+            }
+        }
+        occl += hit;
+    }
+    out[0] = (double)cands.size(); out[1] = (double)box_hits / nrays; out[2] = (double)nv / nrays; out[3] = (double)nt / nrays;
+    out[4] = (double)occl / nrays; out[5] = expanded;
+}
+
 // Experiment: directional binning of entry-list candidates.  Each candidate box is bounded by a cone (bounding sphere seen
 // from the origin) and registered in the cells of a G x G grid over the unit disk (the projected hemisphere, local frame)
 // that the cone can touch.  Reports the mean number of candidates a ray must test: (a) its own cell, (b) the union of the

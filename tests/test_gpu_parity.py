@@ -127,6 +127,14 @@ def test_bake_interreflect(torus, torus_scenes, prt, oracle, bounces, albedo):
     # interreflection only adds energy to the DC term
     sh, _ = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(order=4, samples_u=16, samples_v=16))
     assert (got[:, 0] >= sh[:, 0] - 1e-6).all()
+    # the horizon pre-pass only skips primary rays that provably escape: same visibility bits, same rows up to summation order
+    gs.ctx.set_tuning(horizon=0)
+    try:
+        got0, gvis0 = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(mode=prt.INTERREFLECT, **kw), want_vis=True, vertex_id_base=1000)
+    finally:
+        gs.ctx.set_tuning(horizon=1)
+    assert np.array_equal(gvis0, gvis) and rel_l2(got0, got).max() <= 1e-5
+    assert gs.ctx.last_bake_stats().launches == 1
 
 
 def test_bake_unshadowed_modes(torus, prt, oracle):
