@@ -345,7 +345,11 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
             if (e0) CU_TRY(cudaEventRecord(c->evh, st));
             launches = 2;
         }
-        CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
+        if (A.need_bits && c->pair_queue == 2 && S <= bake_inter_max_samples()) {
+            CU_TRY(launch_bake_inter(A, p->order, &used_grid, c->n_sms, st));
+            c->stats.block = 128;
+        } else
+            CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
     }
     if (e1) CU_TRY(cudaEventRecord(e1, st));
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;

@@ -42,6 +42,8 @@ cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int bl
 cudaError_t launch_bake_shadow(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_shadow_max_samples();
 // horizon pass (horizon.cu): per-vertex horizon map, classification of every sample, rows of fully visible vertices
+cudaError_t launch_bake_inter(const BakeArgs &, int order, int *grid, int n_sms, cudaStream_t);
+int bake_inter_max_samples();
 cudaError_t launch_horizon(const BakeArgs &, int order, int *grid, int n_sms, cudaStream_t);
 // warp-local wavefront kernel (bake_wave.cu), same modes / limits
 cudaError_t launch_bake_wave(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
