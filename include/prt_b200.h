@@ -32,7 +32,9 @@ enum {
     PRT_ERR_CUDA = -2,      /* CUDA runtime / no device */
     PRT_ERR_NOMEM = -3,
     PRT_ERR_BUILD = -4,     /* BVH build failed (bad indices, depth limit) */
-    PRT_ERR_UNSUPPORTED = -5
+    PRT_ERR_UNSUPPORTED = -5,
+    PRT_ERR_IO = -6,         /* cache file unreadable, truncated or corrupt */
+    PRT_ERR_CACHE_MISS = -7  /* no cache file for this (mesh, parameters) key: bake again */
 };
 
 typedef struct prt_ctx prt_ctx;
@@ -241,6 +243,22 @@ int prt_film_reset(prt_film *);                                    /* camera.dir
 int prt_raytrace(prt_scene *, prt_film *, const prt_camera *, int32_t max_path_length /*app.h: 3*/, const float albedo[3],
                  int32_t gamma, int32_t mode, uint32_t seed, int32_t n_frames);
 int prt_film_download(const prt_film *, float *accum /*[h*w][4]*/, uint8_t *pixels_rgba8 /*[h*w][4]*/);   /* either may be NULL */
+
+/* ---- on-disk cache of baked results --------------------------------------------------------------------
+ * The reference re-bakes at every start (app.cpp:52) and keeps results only in GL objects.  Files: 80-byte header {magic
+ * "PRTB200", version, kind, mesh hash, key hash, dims, payload bytes, payload FNV-1a} + raw rows.  Loads return
+ * PRT_ERR_CACHE_MISS when the file is absent or keyed differently (other mesh / parameters / version) and PRT_ERR_IO when it is
+ * damaged.  Host-only calls (no GPU needed). */
+uint64_t prt_hash_bytes(const void *data, size_t n_bytes, uint64_t seed /*0: FNV offset basis; chain calls by passing the last result*/);
+uint64_t prt_mesh_hash(const float *pos_xyz, size_t pos_stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris);
+int prt_cache_save_transfer(const char *path, uint64_t mesh_hash, uint32_t n_verts, const prt_bake_params *, const float *coeffs);
+int prt_cache_load_transfer(const char *path, uint64_t mesh_hash, uint32_t n_verts, const prt_bake_params *, float *out_coeffs);
+/* config_hash: the caller's hash of everything else the capture depends on (probe positions, directions, solid angles) */
+int prt_cache_save_csr(const char *path, uint64_t mesh_hash, uint64_t config_hash, uint32_t n_probes, uint64_t nnz, uint32_t n_surfels,
+                       const uint32_t *range, const uint32_t *ids, const float *transfer, const float *surfels, const uint64_t *keys);
+int prt_cache_csr_sizes(const char *path, uint64_t mesh_hash, uint64_t config_hash, uint32_t *n_probes, uint64_t *nnz, uint32_t *n_surfels);
+int prt_cache_load_csr(const char *path, uint64_t mesh_hash, uint64_t config_hash, uint32_t n_probes, uint64_t nnz, uint32_t n_surfels,
+                       uint32_t *range, uint32_t *ids, float *transfer, float *surfels, uint64_t *keys);
 
 /* Volume_weight calculate_weight(Model&, ivec3 probe_res, ivec3 volume_res, vec3 scene_size) (light_probe.h:14-18,
  * light_probe.cpp:156-367): per voxel, the trilinear weights of its 8 surrounding probes masked by segment visibility and

@@ -24,6 +24,8 @@ ABI_SYMBOLS = [
     "prt_paral_shadow_matrix", "prt_shadow_map", "prt_gi_create", "prt_gi_destroy", "prt_gi_set_shadow_map", "prt_gi_set_albedo",
     "prt_gi_set_radiance", "prt_gi_step", "prt_gi_download",
     "prt_film_create", "prt_film_destroy", "prt_film_reset", "prt_raytrace", "prt_film_download",
+    "prt_hash_bytes", "prt_mesh_hash", "prt_cache_save_transfer", "prt_cache_load_transfer", "prt_cache_save_csr", "prt_cache_csr_sizes",
+    "prt_cache_load_csr",
 ]
 
 
@@ -180,6 +182,16 @@ def load_library():
     L.prt_film_reset.argtypes = [vp]
     L.prt_raytrace.argtypes = [vp, vp, C.POINTER(Camera), i32, vp, i32, i32, u32, i32]
     L.prt_film_download.argtypes = [vp, vp, vp]
+    u64 = C.c_uint64
+    L.prt_hash_bytes.restype = u64
+    L.prt_hash_bytes.argtypes = [vp, sz, u64]
+    L.prt_mesh_hash.restype = u64
+    L.prt_mesh_hash.argtypes = [vp, sz, u32, vp, u32]
+    L.prt_cache_save_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
+    L.prt_cache_load_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
+    L.prt_cache_save_csr.argtypes = [C.c_char_p, u64, u64, u32, u64, u32, vp, vp, vp, vp, vp]
+    L.prt_cache_csr_sizes.argtypes = [C.c_char_p, u64, u64, C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]
+    L.prt_cache_load_csr.argtypes = [C.c_char_p, u64, u64, u32, u64, u32, vp, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -603,3 +615,60 @@ def raytrace(scene: RTScene, film: Film, camera: Camera, max_path_length: int = 
     a = np.asarray(albedo, np.float32)
     _check(scene.L.prt_raytrace(scene.h, film.h, C.byref(camera), int(max_path_length), _ptr(a), int(bool(gamma)), int(mode),
                                 int(seed) & 0xFFFFFFFF, int(n_frames)), "prt_raytrace")
+
+
+# ---- on-disk cache (host only) -----------------------------------------------------------------------------
+ERR_IO, ERR_CACHE_MISS = -6, -7
+
+
+def mesh_hash(pos: np.ndarray, tri: np.ndarray) -> int:
+    p = np.ascontiguousarray(pos, np.float32); t = np.ascontiguousarray(tri, np.uint32)
+    return int(load_library().prt_mesh_hash(_ptr(p), 12, len(p), _ptr(t), len(t)))
+
+
+def hash_arrays(*arrays) -> int:
+    """FNV-1a over the bytes of the arrays, chained (the ``config_hash`` of a probe capture: positions, directions, weights)."""
+    h = 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h = int(load_library().prt_hash_bytes(_ptr(a), a.nbytes, h))
+    return h
+
+
+def cache_save_transfer(path: str, mhash: int, params: BakeParams, coeffs: np.ndarray):
+    c = np.ascontiguousarray(coeffs, np.float32)
+    if c.ndim != 2 or c.shape[1] != params.n_coeffs:
+        raise PRTError("cache_save_transfer: coeffs must be [n_verts, order^2]")
+    _check(load_library().prt_cache_save_transfer(os.fsencode(path), mhash, len(c), C.byref(params), _ptr(c)), "prt_cache_save_transfer")
+
+
+def cache_load_transfer(path: str, mhash: int, n_verts: int, params: BakeParams):
+    """-> [n_verts, order^2] rows, or None on a cache miss (no file, or baked from another mesh / with other parameters)."""
+    out = np.zeros((n_verts, params.n_coeffs), np.float32)
+    rc = load_library().prt_cache_load_transfer(os.fsencode(path), mhash, n_verts, C.byref(params), _ptr(out))
+    if rc == ERR_CACHE_MISS:
+        return None
+    _check(rc, "prt_cache_load_transfer")
+    return out
+
+
+def cache_save_csr(path: str, mhash: int, config_hash: int, rng, ids, transfer, surfels, keys):
+    rng = np.ascontiguousarray(rng, np.uint32); ids = np.ascontiguousarray(ids, np.uint32); tr = np.ascontiguousarray(transfer, np.float32)
+    sf = np.ascontiguousarray(surfels, np.float32); k = np.ascontiguousarray(keys, np.uint64)
+    _check(load_library().prt_cache_save_csr(os.fsencode(path), mhash, config_hash, len(rng), len(ids), len(sf), _ptr(rng), _ptr(ids), _ptr(tr),
+                                             _ptr(sf), _ptr(k)), "prt_cache_save_csr")
+
+
+def cache_load_csr(path: str, mhash: int, config_hash: int):
+    """-> (range, ids, transfer, surfels, keys) or None on a cache miss; feed to ``ProbeTransfer.from_arrays``."""
+    L = load_library()
+    npb, nnz, ns = C.c_uint32(), C.c_uint64(), C.c_uint32()
+    rc = L.prt_cache_csr_sizes(os.fsencode(path), mhash, config_hash, C.byref(npb), C.byref(nnz), C.byref(ns))
+    if rc == ERR_CACHE_MISS:
+        return None
+    _check(rc, "prt_cache_csr_sizes")
+    rng = np.zeros((npb.value, 2), np.uint32); ids = np.zeros(nnz.value, np.uint32); tr = np.zeros((nnz.value, 9), np.float32)
+    sf = np.zeros((ns.value, 6), np.float32); keys = np.zeros(ns.value, np.uint64)
+    _check(L.prt_cache_load_csr(os.fsencode(path), mhash, config_hash, npb.value, nnz.value, ns.value, _ptr(rng), _ptr(ids), _ptr(tr), _ptr(sf),
+                                _ptr(keys)), "prt_cache_load_csr")
+    return rng, ids, tr, sf, keys
