@@ -35,9 +35,10 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #endif
 constexpr int kNodeCap = PRT_WAVE_CAP, kLeafCap = PRT_WAVE_CAP;
 
+// per-warp shared memory: this struct followed by the occlusion bitset (vis_words words rounded up to 16 bytes; bit s, reference
+// sample index: primary ray s is occluded) -- sized per launch so that 1024-sample bakes fit 8 CTAs per SM
 struct WaveShared {
     EntryList el;
-    uint32_t occl[kMaxS / 32];          // bit s (reference sample index): primary ray s is occluded
     uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
     uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
     uint32_t pend[64];                  // processing indices of rays that are not above the horizon, waiting for a scan round
@@ -101,11 +102,13 @@ template <int ORDER, bool TRACE>
 __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WaveShared &W = reinterpret_cast<WaveShared *>(smem_raw)[threadIdx.x >> 5];
+    const int S = A.S, words = A.vis_words;
+    const size_t wstride = sizeof(WaveShared) + 4 * (size_t)((words + 3) & ~3);
+    WaveShared &W = *reinterpret_cast<WaveShared *>(smem_raw + wstride * (threadIdx.x >> 5));
+    uint32_t *const occl = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(&W) + sizeof(WaveShared));
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float sgn = A.cs_phase ? -1.0f : 1.0f;
-    const int S = A.S, words = A.vis_words;
     unsigned long long cand_tests = 0ull, rays_scanned = 0ull;
     uint32_t node_visits = 0u, tri_tests = 0u;
 
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         const Frame fr = make_frame(N);
         const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
 
-        for (int w = lane; w < words; w += 32) W.occl[w] = 0u;
+        for (int w = lane; w < words; w += 32) occl[w] = 0u;
         int n_cand = 0;
         if (TRACE) {
             n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                         const uint2 it = W.lq[ln + lane];
                         const float4 smp = __ldg(&A.samples[it.x & 0xFFFFu]);
                         const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-                        if (!((W.occl[sref >> 5] >> (sref & 31u)) & 1u)) {
+                        if (!((occl[sref >> 5] >> (sref & 31u)) & 1u)) {
                             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                             uint32_t bits = it.x >> 16;
                             while (bits) {
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                                 float t; uint32_t prim;
                                 tri_tests++;
                                 if (tri_hit(A.tris, it.y + b, org, d, 0.0f, INFINITY, false, t, prim)) {
-                                    atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                    atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
                                     break;
                                 }
                             }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                     if (has) {
                         const float4 smp = __ldg(&A.samples[it.x]);
                         const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-                        has = !((W.occl[sref >> 5] >> (sref & 31u)) & 1u);
+                        has = !((occl[sref >> 5] >> (sref & 31u)) & 1u);
                         if (has) {
                             d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                             const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                                 // stack full: ordinary traversal of this subtree (rare)
                                 if (fallback_subtree(A.nodes, A.tris, org, d, child, node_visits, tri_tests)) {
                                     const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
-                                    atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                    atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
                                     inner8 = 0u; leaf8 = 0u;
                                 }
                             }
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                             else if (fallback_leaf(A.tris, org, d, tri0, bits, tri_tests)) {
                                 const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
-                                atomicOr(&W.occl[sref >> 5], 1u << (sref & 31u));
+                                atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
                                 leaf8 = 0u;
                             }
                         }
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         for (int i = lane; i < S; i += 32) {
             const float4 smp = __ldg(&A.samples[i]);
             const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-            if ((W.occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
+            if ((occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
             float y[N2];
             sh_eval<ORDER>(d.z, d.x, d.y, sgn, y);
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
             for (int w = lane; w < words; w += 32) {
                 const int rem = S - 32 * w;
                 const uint32_t valid = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-                A.vis[(size_t)v * words + w] = ~W.occl[w] & valid;
+                A.vis[(size_t)v * words + w] = ~occl[w] & valid;
             }
         }
         __syncwarp();
@@ -319,10 +322,10 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
 
 template <int ORDER, bool TRACE>
 cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
-    const size_t smem = sizeof(WaveShared) * (size_t)(block / 32);
+    const size_t smem = (sizeof(WaveShared) + 4 * (size_t)((A.vis_words + 3) & ~3)) * (size_t)(block / 32);
     static bool configured = false;   // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WaveShared) * (PRT_WAVE_BLOCK / 32)));
+        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
