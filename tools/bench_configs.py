@@ -121,3 +121,42 @@ for name, order, su, sv, mode, bounces, nu, nv, nsub in [
          kernel_ms=min(ms), primary_grays_per_s=len(sel) * S / min(ms) / 1e6, vertices_per_s=len(sel) / min(ms) * 1e3,
          full_mesh_seconds_extrapolated=len(pos) / (len(sel) / min(ms) * 1e3), finite=bool(torch.isfinite(d_out).all().item()))
     sc.close()
+
+if want("f"):
+    # SURVEY 8 rows f1 / f2 / f4 at the reference's default sizes (app.cpp:50-51: scene_size 12, probes 3.0 apart -> 8^3, volume 0.25 -> 96^3;
+    # gl.h:314: 4096^2 shadow map; 1920x1080 preview)
+    rp = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32) * 6.18
+    rt = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 4, 5], [0, 5, 1], [3, 2, 6], [3, 6, 7], [0, 3, 7], [0, 7, 4], [1, 5, 6], [1, 6, 2]], np.uint32)
+    nu = 200 if a.quick else 737
+    tp, _, tt = meshes.bumpy_torus(nu, nu)
+    pos = np.concatenate([rp, tp]).astype(np.float32)
+    tri = np.concatenate([rt, tt + np.uint32(8)]).astype(np.uint32)
+    sc = prt_b200.RTScene(pos, tri, ctx)
+    pres, vres, size = [8] * 3, [24 if a.quick else 96] * 3, [12.0] * 3
+    prt_b200.calculate_weight(sc, [2] * 3, [4] * 3, size)
+    t_w = timed(lambda: prt_b200.calculate_weight(sc, pres, vres, size), 2)
+    weights = prt_b200.calculate_weight(sc, pres, vres, size)
+    nvox = int(np.prod(vres))
+    emit(config=f"f1: calculate_weight, {pres[0]}^3 probes, {vres[0]}^3 voxels x (100 closest-hit + 8 any-hit rays)", rays=nvox * 108,
+         seconds_incl_copies=t_w, grays_per_s=nvox * 108 / t_w / 1e9)
+    d, w = prt_b200.cube_dirs(26)
+    pt = prt_b200.ProbeTransfer(sc, prt_b200.probe_positions(pres, size), d, w)
+    sky, M = prt_b200.paral_shadow_matrix(0.17, 0.84)
+    smap = 1024 if a.quick else 4096
+    prt_b200.shadow_map(sc, M, 64)
+    t_sm = timed(lambda: prt_b200.shadow_map(sc, M, smap), 2)
+    vol = prt_b200.SHVolume(pt, pres, vres, size, weights)
+    vol.set_shadow_map(prt_b200.shadow_map(sc, M, smap))
+    P = prt_b200.RelightParams.make(sky, M)
+    vol.step(P, 1)
+    t_gi = timed(lambda: vol.step(P, 100), 2) / 100
+    emit(config=f"f2: per-frame probe pipeline, {pt.n_surfels} surfels, {pt.nnz} CSR entries, {pres[0]}^3 probes -> {vres[0]}^3 voxels",
+         shadow_map=f"{smap}^2 texels by ray casting", shadow_map_seconds_incl_copy=t_sm, shadow_grays_per_s=smap * smap / t_sm / 1e9,
+         seconds_per_round_relight_project_blend=t_gi, rounds_per_second=1.0 / t_gi)
+    W_, H_ = (480, 270) if a.quick else (1920, 1080)
+    film = prt_b200.Film(W_, H_, ctx)
+    cam = prt_b200.Camera.look_at((5.5, 3.0, 5.0), (0, -0.3, 0), zoom_deg=45)
+    prt_b200.raytrace(sc, film, cam, max_path_length=3, albedo=(0.7, 0.7, 0.7), n_frames=1)
+    t_rt = timed(lambda: prt_b200.raytrace(sc, film, cam, max_path_length=3, albedo=(0.7, 0.7, 0.7), n_frames=16), 2) / 16
+    emit(config=f"f4: AO preview {W_}x{H_}, max_path_length 3 (inside the closed room: every path runs its full length)",
+         seconds_per_frame=t_rt, mpaths_per_s=W_ * H_ / t_rt / 1e6)
