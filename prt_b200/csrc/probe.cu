@@ -58,6 +58,78 @@ __device__ __forceinline__ bool cluster_key(f3 pos, f3 n, unsigned long long &ke
     return true;
 }
 
+// ---- warp-local asynchronous closest-hit wavefront (same scheme as bake_inter.cu, one ray slot per lane) ---------------------
+constexpr int kWaveCap = 96;
+constexpr unsigned long long kNoHit = 0x7F800000FFFFFFFFull;        // (+inf, invalid prim)
+struct TraceShared {
+    float4 dir[32];                     // direction of the slot's ray (origin = the probe, tnear = 0)
+    unsigned long long best[32];        // (closest t bits << 32) | prim
+    uint32_t btri[32];                  // triangle slot of `best`
+    int refc[32];                       // outstanding work items
+    uint32_t ray[32];                   // ray index, kFreeSlot = empty
+    uint2 nq[kWaveCap];                 // (slot, node)
+    uint2 lq[kWaveCap];                 // (slot | triangle bits << 16, first triangle)
+};
+constexpr uint32_t kFreeSlot = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float rcp_dir(float d) {
+    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+}
+// 8 quantised child boxes of one node against the ray interval [0, tfar]; bit s = slot s hit
+__device__ __forceinline__ uint32_t node_hits(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx, const float idy,
+                                              const float idz, const float tfar) {
+    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx, sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy, sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
+    const float ax = (__uint_as_float(n0.x) - o.x) * idx, ay = (__uint_as_float(n0.y) - o.y) * idy, az = (__uint_as_float(n0.z) - o.z) * idz;
+    const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+        const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+        const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx, neary = ny ? qhy : qly, fary = ny ? qly : qhy, nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int sh = 8 * j;
+            const float t0x = (float)((nearx >> sh) & 0xFFu) * sx + ax, t0y = (float)((neary >> sh) & 0xFFu) * sy + ay, t0z = (float)((nearz >> sh) & 0xFFu) * sz + az;
+            const float t1x = (float)((farx >> sh) & 0xFFu) * sx + ax, t1y = (float)((fary >> sh) & 0xFFu) * sy + ay, t1z = (float)((farz >> sh) & 0xFFu) * sz + az;
+            if (fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f)) <= fminf(fminf(t1x, t1y), fminf(t1z, tfar))) hits |= 1u << (4 * h + j);
+        }
+    }
+    return hits;
+}
+// rare paths, out of line: queue overflow (plain stack traversal of a subtree / leaf) and repair of a stale triangle slot
+__device__ __noinline__ void wave_fallback_subtree(const Node8 *nodes, const Tri48 *tris, TraceShared &W, const f3 P, const uint32_t slot, const uint32_t child) {
+    const float4 b = W.dir[slot];
+    Trav tr; tr.reset_counters();
+    tr.init(P, mk3(b.x, b.y, b.z), 0.0f, INFINITY); tr.start_group(child, 0x80000000u);
+    tr.run<false>(nodes, tris, 0, false);
+    if (tr.best_prim != 0xFFFFFFFFu) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(tr.best_t) << 32) | (unsigned long long)tr.best_prim;
+        if (key <= atomicMin(&W.best[slot], key)) W.btri[slot] = tr.best_tri;
+    }
+}
+__device__ __noinline__ void wave_fallback_leaf(const Tri48 *tris, TraceShared &W, const f3 P, const uint32_t slot, const uint32_t tri0, uint32_t bits) {
+    const float4 b = W.dir[slot];
+    while (bits) {
+        const uint32_t bb = (uint32_t)__ffs(bits) - 1u;
+        bits &= bits - 1u;
+        float t; uint32_t prim;
+        if (tri_hit(tris, tri0 + bb, P, mk3(b.x, b.y, b.z), 0.0f, INFINITY, true, t, prim)) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)prim;
+            if (key <= atomicMin(&W.best[slot], key)) W.btri[slot] = tri0 + bb;
+        }
+    }
+}
+__device__ __noinline__ uint32_t wave_repair_triangle(const Node8 *nodes, const Tri48 *tris, const f3 P, const float4 b) {
+    Trav tr; tr.reset_counters();
+    tr.init(P, mk3(b.x, b.y, b.z), 0.0f, INFINITY); tr.start_root();
+    tr.run<false>(nodes, tris, 0, false);
+    return tr.best_tri;
+}
+
 __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const CaptureArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *sk = reinterpret_cast<unsigned long long *>(smem);          // [4096] (cluster key << 12) | ray
@@ -74,47 +146,150 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
         if (p >= A.n_probes) return;
         const f3 P = mk3(A.probe_pos[3 * p], A.probe_pos[3 * p + 1], A.probe_pos[3 * p + 2]);
 
-        // ---- trace ------------------------------------------------------------------------------------------------------
-        // Rays are handed out from a CTA-wide counter: a lane that finishes its ray takes the next one as soon as fewer than
-        // refill_thresh lanes of its warp are still traversing, so neither a slow ray nor a slow warp holds the others up.
+        // ---- trace: asynchronous wavefront, one ray slot per lane -------------------------------------------------------------
+        // Rays are handed out from a CTA-wide counter (Morton order of their directions).  Work is (slot, node) / (slot, leaf) items
+        // on two warp-local stacks: a node step decodes one node per lane and pushes the child boxes the ray hits inside
+        // [0, closest t], a leaf step runs the pinned triangle tests and lowers the slot's (t, prim) key with a 64-bit atomicMin;
+        // a slot whose outstanding-item count reaches zero is finished, stored and refilled.  Per-ray stacks ran this phase at
+        // 12.5 of 32 active lanes (profiles/r1_probe_capture_ncu_summary.txt).
         for (int i = tid; i < kMaxRays; i += kThreads) sk[i] = kInvalid;
         if (tid == 0) s_next = 0u;
         __syncthreads();
         {
-            const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
-            Trav tr;
-            tr.reset_counters();
-            bool active = false, exhausted = false;
-            int r = 0;
-            for (;;) {
-                const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-                if (idle && !exhausted) {
+            const int lane = tid & 31;
+            const unsigned lt_mask = (1u << lane) - 1u;
+            TraceShared &W = reinterpret_cast<TraceShared *>(s_lead)[tid >> 5];      // aliases the hand-over area of the reduction
+            W.ray[lane] = kFreeSlot; W.refc[lane] = 0;
+            __syncwarp();
+            int nn = 0, ln = 0;
+            bool exhausted = false;
+            for (uint32_t guard = 0; guard < (1u << 22); guard++) {               // (bounded: a logic error must not hang the device)
+                // finished slots: store the hit, free the slot
+                const uint32_t myray = W.ray[lane];
+                if (myray != kFreeSlot && W.refc[lane] == 0) {
+                    const unsigned long long key = W.best[lane];
+                    if (key != kNoHit) {                                              // sky otherwise: volume.cpp:246
+                        const float4 b = W.dir[lane];
+                        uint32_t bt = W.btri[lane];
+                        if (ld16(reinterpret_cast<const char *>(A.tris + bt)).w != (uint32_t)key) bt = wave_repair_triangle(A.nodes, A.tris, P, b);
+                        const char *tp = reinterpret_cast<const char *>(A.tris + bt);
+                        const u4 b4 = ld16(tp + 16), c4 = ld16(tp + 32);
+                        const f3 n = normalize3(cross3(mk3(PRT_U2F(b4.x), PRT_U2F(b4.y), PRT_U2F(b4.z)), mk3(PRT_U2F(c4.x), PRT_U2F(c4.y), PRT_U2F(c4.z))));
+                        const float t = __uint_as_float((uint32_t)(key >> 32));
+                        const f3 pos = madd3(P, t, mk3(b.x, b.y, b.z));
+                        unsigned long long ck;
+                        if (!(dot3(sub3(pos, P), n) > 0.0f) && cluster_key(pos, n, ck)) {   // back face: volume.cpp:249
+                            sk[myray] = (ck << 12) | (unsigned long long)myray;
+                            tt[myray] = t; tri[myray] = bt;
+                        }
+                    }
+                    W.ray[lane] = kFreeSlot;
+                }
+                __syncwarp();
+                // refill free slots while rays remain and one warp-wide push fits
+                const unsigned freeb = __ballot_sync(0xFFFFFFFFu, W.ray[lane] == kFreeSlot);
+                if (freeb && !exhausted && nn <= kWaveCap - 32) {
                     uint32_t base = 0u;
-                    if (lane == 0u) base = atomicAdd(&s_next, (uint32_t)__popc(idle));
+                    if (lane == 0) base = atomicAdd(&s_next, (uint32_t)__popc(freeb));
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    const uint32_t slot = base + (uint32_t)__popc(idle & lt_mask);
-                    if (!active && slot < A.n_dirs) {
-                        r = (int)__ldg(&A.order[slot]);                              // results are stored by ray index, so the trace
-                        const float4 dw = __ldg(&A.dirs[r]);                         // order does not change them
-                        tr.init(P, mk3(dw.x, dw.y, dw.z), 0.0f, INFINITY);
-                        tr.start_root();
-                        active = true;
+                    const uint32_t slot_rank = (uint32_t)__popc(freeb & lt_mask);
+                    const bool take = ((freeb >> lane) & 1u) && base + slot_rank < A.n_dirs;
+                    if (take) {
+                        const uint32_t r = __ldg(&A.order[base + slot_rank]);          // results are stored by ray index, so the
+                        const float4 dw = __ldg(&A.dirs[r]);                           // trace order does not change them
+                        W.dir[lane] = make_float4(dw.x, dw.y, dw.z, 0.f);
+                        W.best[lane] = kNoHit; W.refc[lane] = 1; W.ray[lane] = r;
                     }
-                    exhausted = base + (uint32_t)__popc(idle) >= A.n_dirs;
+                    const unsigned tb = __ballot_sync(0xFFFFFFFFu, take);
+                    if (take) W.nq[nn + __popc(tb & lt_mask)] = make_uint2((uint32_t)lane, 0u);      // start at the root
+                    nn += __popc(tb);
+                    exhausted = base + (uint32_t)__popc(freeb) >= A.n_dirs;
                 }
-                if (!__any_sync(0xFFFFFFFFu, active)) break;
-                if (!active) continue;
-                if (tr.run<false>(A.nodes, A.tris, A.refill_thresh, !exhausted) == TRAV_RUNNING) continue;
-                if (tr.best_prim != 0xFFFFFFFFu) {                                   // sky: volume.cpp:246
-                    const f3 n = normalize3(tr.hit_ng(A.tris));
-                    const f3 pos = madd3(P, tr.best_t, tr.d);
-                    unsigned long long ck;
-                    if (!(dot3(sub3(pos, P), n) > 0.0f) && cluster_key(pos, n, ck)) {   // back face: volume.cpp:249
-                        sk[r] = (ck << 12) | (unsigned long long)r;
-                        tt[r] = tr.best_t; tri[r] = tr.best_tri;
+                __syncwarp();
+                if (nn == 0 && ln == 0) {
+                    if (exhausted && __all_sync(0xFFFFFFFFu, W.ray[lane] == kFreeSlot)) break;
+                    if (exhausted && !__any_sync(0xFFFFFFFFu, W.ray[lane] != kFreeSlot && W.refc[lane] != 0)) continue;   // only finished slots left
+                    continue;
+                }
+                if (ln >= 32 || nn == 0) {
+                    // ---- leaf step ----
+                    const int cnt = min(ln, 32);
+                    ln -= cnt;
+                    uint32_t slot = 0u, mytri = 0u;
+                    unsigned long long mykey = kNoHit;
+                    if (lane < cnt) {
+                        const uint2 it = W.lq[ln + lane];
+                        slot = it.x & 0xFFFFu;
+                        const float4 b = W.dir[slot];
+                        const f3 d = mk3(b.x, b.y, b.z);
+                        uint32_t bits = it.x >> 16;
+                        while (bits) {
+                            const uint32_t bb = (uint32_t)__ffs(bits) - 1u;
+                            bits &= bits - 1u;
+                            float t; uint32_t prim;
+                            if (tri_hit(A.tris, it.y + bb, P, d, 0.0f, INFINITY, true, t, prim)) {
+                                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)prim;
+                                if (key < mykey) { mykey = key; mytri = it.y + bb; }
+                            }
+                        }
+                        if (mykey != kNoHit) atomicMin(&W.best[slot], mykey);
+                    }
+                    __syncwarp();
+                    if (lane < cnt) {
+                        if (mykey != kNoHit && W.best[slot] == mykey) W.btri[slot] = mytri;      // the holder of the final key records its triangle
+                        atomicSub(&W.refc[slot], 1);
+                    }
+                } else {
+                    // ---- node step ----
+                    const int cnt = min(nn, 32);
+                    nn -= cnt;
+                    uint2 it = make_uint2(0u, 0u);
+                    const bool has = lane < cnt;
+                    if (has) it = W.nq[nn + lane];
+                    __syncwarp();                   // all pops are done before anybody pushes
+                    uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
+                    if (has) {
+                        const float4 b = W.dir[it.x];
+                        const float tfar = __uint_as_float((uint32_t)(W.best[it.x] >> 32));
+                        const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
+                        const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
+                        const uint32_t hits = node_hits(n0, n2, n3, n4, P, rcp_dir(b.x), rcp_dir(b.y), rcp_dir(b.z), tfar);
+                        imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
+                        inner8 = hits & imask; leaf8 = hits & ~imask;
+                        const int delta = __popc(hits) - 1;
+                        if (delta) atomicAdd(&W.refc[it.x], delta);       // before the pushes: the count never reaches zero early
+                    }
+                    __syncwarp();
+                    while (__any_sync(0xFFFFFFFFu, inner8 != 0u)) {
+                        const bool pp = inner8 != 0u;
+                        uint32_t child = 0u;
+                        if (pp) { const uint32_t sl = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u; child = child_base + __popc(imask & ((1u << sl) - 1u)); }
+                        const unsigned pb = __ballot_sync(0xFFFFFFFFu, pp);
+                        const int pos = nn + __popc(pb & lt_mask);
+                        if (pp) {
+                            if (pos < kWaveCap) W.nq[pos] = make_uint2(it.x, child);
+                            else { wave_fallback_subtree(A.nodes, A.tris, W, P, it.x, child); atomicSub(&W.refc[it.x], 1); }
+                        }
+                        nn = min(nn + __popc(pb), kWaveCap);
+                    }
+                    while (__any_sync(0xFFFFFFFFu, leaf8 != 0u)) {
+                        const bool pp = leaf8 != 0u;
+                        uint32_t tri0 = 0u, bits = 0u;
+                        if (pp) {
+                            const uint32_t sl = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
+                            const uint32_t meta = ((sl < 4u ? meta_lo : meta_hi) >> (8u * (sl & 3u))) & 0xFFu;
+                            tri0 = tri_base + (meta & 31u); bits = meta >> 5;
+                        }
+                        const unsigned pb = __ballot_sync(0xFFFFFFFFu, pp);
+                        const int pos = ln + __popc(pb & lt_mask);
+                        if (pp) {
+                            if (pos < kWaveCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
+                            else { wave_fallback_leaf(A.tris, W, P, it.x, tri0, bits); atomicSub(&W.refc[it.x], 1); }
+                        }
+                        ln = min(ln + __popc(pb), kWaveCap);
                     }
                 }
-                active = false;
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -417,7 +592,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     CaptureArgs A{};
     A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order; A.refill_thresh = prt_ctx_refill_thresh(sv.ctx);
     A.ticket = ticket; A.counts = counts; A.ekeys = skeys; A.etransfer = stransfer; A.eacc = sacc_stage;
-    const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + (size_t)kThreads * 16 * 4;
+    const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + std::max((size_t)kThreads * 16 * 4, sizeof(TraceShared) * (size_t)(kThreads / 32));
     static bool configured = false;
     if (!configured) { PB_TRY(cudaFuncSetAttribute(probe_capture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     int per_sm = 1;
