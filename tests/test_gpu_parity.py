@@ -284,11 +284,11 @@ def test_horizon_map_is_conservative_on_adversarial_scenes(prt, oracle, case):
     ref, ovis, _ = oracle.bake_transfer(os_, org, nrm, oracle.make_params(**kw), want_vis=True)
     frac = np.unpackbits(ovis.view(np.uint8)).mean()
     assert 0.02 < frac < 0.99 or case in ("room_inside", "sphere_shell")
-    for knobs in (dict(), dict(horizon_budget=0), dict(horizon_budget=3, horizon_near=80), dict(horizon_budget=200, horizon_near=10)):
+    for knobs in (dict(), dict(horizon=0), dict(horizon_budget=0), dict(horizon_budget=3, horizon_near=80), dict(horizon_budget=200, horizon_near=10)):
         gs.ctx.set_tuning(**knobs)
         try:
             got, gvis = prt.bake_transfer(gs, org, nrm, prt.BakeParams.make(**kw), want_vis=True)
         finally:
-            gs.ctx.set_tuning(horizon_budget=24, horizon_near=35)
+            gs.ctx.set_tuning(horizon=1, horizon_budget=24, horizon_near=35)
         assert np.array_equal(gvis, ovis), f"{case} {knobs}: {np.count_nonzero(gvis != ovis)} visibility words differ"
         assert rel_l2(got, ref)[np.linalg.norm(ref, axis=1) > 1e-3].max(initial=0) <= REL_L2_TOL
