@@ -98,7 +98,8 @@ __device__ __noinline__ bool fallback_leaf(const Tri48 *tris, const f3 org, cons
     return false;
 }
 
-template <int ORDER, bool TRACE>
+// COUNT: carry the work counters (an instrumented, untimed launch of bench.py); the timed variant keeps those registers free
+template <int ORDER, bool TRACE, bool COUNT>
 __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -184,8 +185,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
                             sproc = i;
                         }
-                        cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt;
-                        rays_scanned += (unsigned long long)cnt;
+                        if (COUNT) { cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt; rays_scanned += (unsigned long long)cnt; }
                         __syncwarp();
                         continue;
                     }
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                                 const uint32_t b = (uint32_t)__ffs(bits) - 1u;
                                 bits &= bits - 1u;
                                 float t; uint32_t prim;
-                                tri_tests++;
+                                if (COUNT) tri_tests++;
                                 if (tri_hit(A.tris, it.y + b, org, d, 0.0f, INFINITY, false, t, prim)) {
                                     atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
                                     break;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                             imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                             inner8 = hits & imask; leaf8 = hits & ~imask;
-                            node_visits++;
+                            if (COUNT) node_visits++;
                         }
                     }
                     // push hit children (any order: any-hit is order independent)
@@ -314,37 +314,38 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         }
         __syncwarp();
     }
-    if (A.work) {
+    if (COUNT && A.work) {
         const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
         if (lane == 0) { atomicAdd(&A.work[0], nv); atomicAdd(&A.work[1], nt); atomicAdd(&A.work[2], cand_tests); atomicAdd(&A.work[3], rays_scanned); }
     }
 }
 
-template <int ORDER, bool TRACE>
+template <int ORDER, bool TRACE, bool COUNT>
 cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
     const size_t smem = (sizeof(WaveShared) + 4 * (size_t)((A.vis_words + 3) & ~3)) * (size_t)(block / 32);
     static bool configured = false;   // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)));
+        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (*grid <= 0) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_wave_kernel<ORDER, TRACE>, block, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_wave_kernel<ORDER, TRACE, COUNT>, block, smem);
         if (e != cudaSuccess) return e;
         *grid = n_sms * (per_sm > 0 ? per_sm : 1);
     }
     const int warps_per_block = block / 32;
     const long long need = ((long long)A.n_verts + warps_per_block - 1) / warps_per_block;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
-    bake_wave_kernel<ORDER, TRACE><<<*grid, block, smem, st>>>(A);
+    bake_wave_kernel<ORDER, TRACE, COUNT><<<*grid, block, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 template <int ORDER>
 cudaError_t launch_wave_o(const BakeArgs &A, bool trace, int *grid, int block, int n_sms, cudaStream_t st) {
-    return trace ? launch_wave_t<ORDER, true>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false>(A, grid, block, n_sms, st);
+    if (A.work) return trace ? launch_wave_t<ORDER, true, true>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false, true>(A, grid, block, n_sms, st);
+    return trace ? launch_wave_t<ORDER, true, false>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false, false>(A, grid, block, n_sms, st);
 }
 
 }  // namespace
