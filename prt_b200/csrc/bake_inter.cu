@@ -121,7 +121,8 @@ __device__ __noinline__ uint32_t repair_hit_triangle(const Node8 *nodes, const T
     return tr.best_tri;
 }
 
-template <int ORDER>
+// COUNT: carry the work counters (instrumented launches only; the timed variant keeps those registers free)
+template <int ORDER, bool COUNT>
 __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -294,8 +295,7 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
                     W.refc[slot] = __popc(m0) + __popc(m1) + __popc(m2);
                 }
                 nfree -= cnt;
-                cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt;
-                rays_scanned += (unsigned long long)cnt;
+                if (COUNT) { cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt; rays_scanned += (unsigned long long)cnt; }
                 __syncwarp();
                 continue;
             }
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
                         const uint32_t bb = (uint32_t)__ffs(bits) - 1u;
                         bits &= bits - 1u;
                         float t; uint32_t prim;
-                        tri_tests++;
+                        if (COUNT) tri_tests++;
                         if (tri_hit(A.tris, it.y + bb, o, d, a.w, INFINITY, true, t, prim)) {
                             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)prim;
                             if (key < mykey) { mykey = key; mytri = it.y + bb; }
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
                     const uint32_t hits = node_slots_hit_range(n0, n2, n3, n4, mk3(a.x, a.y, a.z), rcp_box(b.x), rcp_box(b.y), rcp_box(b.z), a.w, tfar);
                     imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                     inner8 = hits & imask; leaf8 = hits & ~imask;
-                    node_visits++;
+                    if (COUNT) node_visits++;
                     delta = __popc(hits) - 1;
                     if (delta) atomicAdd(&W.refc[it.x], delta);       // before the pushes: the count never reaches zero early
                 }
@@ -404,32 +404,37 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
         if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
         __syncwarp();
     }
-    if (A.work) {
+    if (COUNT && A.work) {
         const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
         if (lane == 0) { atomicAdd(&A.work[0], nv); atomicAdd(&A.work[1], nt); atomicAdd(&A.work[2], cand_tests); atomicAdd(&A.work[3], rays_scanned); }
     }
 }
 
-template <int ORDER>
-cudaError_t launch_inter_t(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
+template <int ORDER, bool COUNT>
+cudaError_t launch_inter_tc(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
     const int block = 128;
     const size_t smem = sizeof(InterShared) * (size_t)(block / 32);
     static bool configured = false;   // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_inter_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bake_inter_kernel<ORDER, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (*grid <= 0) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_inter_kernel<ORDER>, block, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_inter_kernel<ORDER, COUNT>, block, smem);
         if (e != cudaSuccess) return e;
         *grid = n_sms * (per_sm > 0 ? per_sm : 1);
     }
     const long long need = ((long long)A.n_verts + 3) / 4;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
-    bake_inter_kernel<ORDER><<<*grid, block, smem, st>>>(A);
+    bake_inter_kernel<ORDER, COUNT><<<*grid, block, smem, st>>>(A);
     return cudaGetLastError();
+}
+
+template <int ORDER>
+cudaError_t launch_inter_t(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
+    return A.work ? launch_inter_tc<ORDER, true>(A, grid, n_sms, st) : launch_inter_tc<ORDER, false>(A, grid, n_sms, st);
 }
 
 }  // namespace
