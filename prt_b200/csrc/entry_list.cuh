@@ -166,9 +166,18 @@ __device__ __forceinline__ HzItem hz_item(float lo, float hi, bool all, float si
     it.b0 = b0; it.b1 = b1;
     return it;
 }
-// warp-collective: every lane contributes one item; lane = bin keeps the running maximum
-__device__ __forceinline__ float hz_merge(float my, const HzItem it, const int lane) {
-    unsigned m = __ballot_sync(kFull, it.v > 0.f);
+// warp-collective: every lane contributes one item; lane = bin keeps the running maximum.  The running map is first published
+// to shared memory so that each lane can drop an item that does not raise the horizon in any bin it spans (most far boxes do
+// not, once the near geometry is in): only the useful items go through the serial broadcast loop.
+__device__ __forceinline__ float hz_merge(float my, const HzItem it, const int lane, uint32_t *hz) {
+    hz[lane] = __float_as_uint(my);
+    __syncwarp();
+    bool useful = false;
+    if (it.v > 0.f) {
+        for (int b = it.b0; b <= it.b1; b++)
+            if (it.v > __uint_as_float(hz[b & (kHzBins - 1)])) { useful = true; break; }
+    }
+    unsigned m = __ballot_sync(kFull, useful);
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1u;
@@ -380,7 +389,7 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         const bool boxed = valid && inner && (e.x < 1e30f) && (c.x * c.x + c.y * c.y + c.z * c.z < near2 * (e.x * e.x + e.y * e.y + e.z * e.z)) && !(push && pos < kHzQueue);
         if (__any_sync(kFull, boxed)) { if (boxed) it = hz_box(c, e, fr); }
         rn = min(rn + __popc(pb), kHzQueue);
-        my = hz_merge(my, it, lane);
+        my = hz_merge(my, it, lane, hz);
         // leaves: one merge per triangle index so that every triangle keeps its own azimuth range
         const bool leaf = valid && !inner;
         for (uint32_t j = 0; j < 3u; j++) {
@@ -388,7 +397,7 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
             if (!__any_sync(kFull, has)) break;
             HzItem ti = hz_item(0.f, 0.f, false, 0.f);
             if (has) ti = hz_tri_item(tris, gx + j, O, fr);
-            my = hz_merge(my, ti, lane);
+            my = hz_merge(my, ti, lane, hz);
         }
         __syncwarp();
     }
