@@ -315,12 +315,13 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
 }
 
 constexpr int kHzQueue = 64;
+constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
 // `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2))
 __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
-                                              const Frame &fr, uint32_t *hz, uint32_t *rq, const int budget_iters, const float near2, const int lane) {
+                                              const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
     float my = 0.f;                                          // lane b owns bin b
-    int rn = 0;
+    int rn = 0, tn = 0;
     // work item of a lane in one round: up to 3 triangles (leaf) or one box
     // ---- pass 1: the entry-list candidates; pass 2: children of queued subtrees (4 nodes x 8 children per iteration) ------
     int k0 = 0, budget = budget_iters;
@@ -390,16 +391,28 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         if (__any_sync(kFull, boxed)) { if (boxed) it = hz_box(c, e, fr); }
         rn = min(rn + __popc(pb), kHzQueue);
         my = hz_merge(my, it, lane, hz);
-        // leaves: one merge per triangle index so that every triangle keeps its own azimuth range
+        // leaves: their triangles are queued and bounded 32 at a time, so the (long) triangle bound always runs on a full warp;
+        // every triangle keeps its own azimuth range
         const bool leaf = valid && !inner;
         for (uint32_t j = 0; j < 3u; j++) {
             const bool has = leaf && ((unary >> j) & 1u);
-            if (!__any_sync(kFull, has)) break;
-            HzItem ti = hz_item(0.f, 0.f, false, 0.f);
-            if (has) ti = hz_tri_item(tris, gx + j, O, fr);
+            const unsigned tb = __ballot_sync(kFull, has);
+            if (!tb) break;
+            if (has) tq[tn + __popc(tb & lt_mask)] = gx + j;
+            tn += __popc(tb);
+        }
+        __syncwarp();
+        while (tn >= 32) {
+            tn -= 32;
+            const HzItem ti = hz_tri_item(tris, tq[tn + lane], O, fr);
             my = hz_merge(my, ti, lane, hz);
         }
         __syncwarp();
+    }
+    if (tn > 0) {
+        HzItem ti = hz_item(0.f, 0.f, false, 0.f);
+        if (lane < tn) ti = hz_tri_item(tris, tq[lane], O, fr);
+        my = hz_merge(my, ti, lane, hz);
     }
     hz[lane] = __float_as_uint(my);
     __syncwarp();

@@ -22,6 +22,7 @@ struct HorizonShared {
     EntryList el;
     uint32_t hz[kHzBins];
     uint32_t rq[kHzQueue];
+    uint32_t tq[kHzTriQueue];
 };
 
 template <int ORDER>
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(128) horizon_kernel(const BakeArgs A) {
         const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
 
         const int n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, A.horizon_budget, A.horizon_near2, lane);
+        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane);
 
         uint32_t *row = A.need_bits + (size_t)v * words;
         uint32_t total = 0u;
