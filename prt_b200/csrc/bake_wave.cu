@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples per vertex)
 #ifndef PRT_WAVE_CAP
-#define PRT_WAVE_CAP 192
+#define PRT_WAVE_CAP 256
 #endif
 #ifndef PRT_WAVE_MINB
 #define PRT_WAVE_MINB 7
@@ -33,7 +33,16 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_BLOCK
 #define PRT_WAVE_BLOCK 128
 #endif
-constexpr int kNodeCap = PRT_WAVE_CAP, kLeafCap = PRT_WAVE_CAP;
+#ifndef PRT_WAVE_NCAP
+#define PRT_WAVE_NCAP PRT_WAVE_CAP
+#endif
+#ifndef PRT_WAVE_LCAP
+#define PRT_WAVE_LCAP PRT_WAVE_CAP
+#endif
+#ifndef PRT_WAVE_ROOM8
+#define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
+#endif
+constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP;
 
 // per-warp shared memory: this struct followed by the occlusion bitset (vis_words words rounded up to 16 bytes; bit s, reference
 // sample index: primary ray s is occluded) -- sized per launch so that 1024-sample bakes fit 8 CTAs per SM
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                     pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
                 }
                 // ---- classify samples: a ray above the horizon of its azimuth bin is visible without any test ---------------
-                const bool room = nn <= kNodeCap / 2 && ln <= kLeafCap / 2;
+                const bool room = nn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;
                 if (!pending && room) {
                     while (base < S && npend < 32) {
                         const int i = base + lane;
