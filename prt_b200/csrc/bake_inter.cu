@@ -32,6 +32,9 @@ namespace {
 #ifndef PRT_INTER_CAP
 #define PRT_INTER_CAP 192
 #endif
+#ifndef PRT_INTER_ROOM8
+#define PRT_INTER_ROOM8 4          // new primary rays are scanned while both stacks are at most ROOM8/8 full
+#endif
 constexpr int kSlots = 64;
 constexpr int kCap = PRT_INTER_CAP;
 constexpr uint32_t kFree = 0xFFFFFFFFu;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
             }
 
             // ---- refill: the next flagged samples take free slots, 32 at a time (lockstep entry-list scan) ------------------------
-            if (!pending && fetched < n_need && nn <= kCap / 2 && ln <= kCap / 2 && (nfree >= 32 || (nn == 0 && ln == 0 && nfree > 0))) {
+            if (!pending && fetched < n_need && nn <= kCap * PRT_INTER_ROOM8 / 8 && ln <= kCap * PRT_INTER_ROOM8 / 8 && (nfree >= 32 || (nn == 0 && ln == 0 && nfree > 0))) {
                 const int cnt = min(min(32, nfree), n_need - fetched);
                 // the cnt next flagged samples, in processing order
                 int taken = 0, my_k = -1;
