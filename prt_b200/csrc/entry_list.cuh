@@ -177,6 +177,7 @@ __device__ __forceinline__ float hz_merge(float my, const HzItem it, const int l
         for (int b = it.b0; b <= it.b1; b++)
             if (it.v > __uint_as_float(hz[b & (kHzBins - 1)])) { useful = true; break; }
     }
+    __syncwarp();                                              // all reads of hz[] are done before the next call overwrites it
     unsigned m = __ballot_sync(kFull, useful);
     while (m) {
         const int src = __ffs(m) - 1;
