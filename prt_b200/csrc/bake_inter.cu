@@ -32,6 +32,9 @@ namespace {
 #ifndef PRT_INTER_CAP
 #define PRT_INTER_CAP 192
 #endif
+#ifndef PRT_INTER_SHADE_MIN
+#define PRT_INTER_SHADE_MIN 32
+#endif
 #ifndef PRT_INTER_ROOM8
 #define PRT_INTER_ROOM8 4          // new primary rays are scanned while both stacks are at most ROOM8/8 full
 #endif
@@ -202,7 +205,16 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
             __syncwarp();
 
             // ---- shade: slots whose segment is finished (no outstanding item) ----------------------------------------------------
+            // (batched: shading a couple of slots per iteration would run the long bounce code on a few lanes each time, so it waits
+            //  until PRT_INTER_SHADE_MIN slots are finished or the stacks run low)
+            bool shade_now = false;
             if (!pending && nn <= kCap - 64) {
+                const unsigned f0 = __ballot_sync(kFull, W.info[lane] != kFree && W.refc[lane] == 0);
+                const unsigned f1 = __ballot_sync(kFull, W.info[lane + 32] != kFree && W.refc[lane + 32] == 0);
+                const int nfin = __popc(f0) + __popc(f1);
+                shade_now = nfin > 0 && (nfin >= PRT_INTER_SHADE_MIN || nn + ln < 32);
+            }
+            if (shade_now) {
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const uint32_t slot = (uint32_t)(lane + 32 * h);
