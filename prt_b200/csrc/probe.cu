@@ -59,6 +59,9 @@ __device__ __forceinline__ bool cluster_key(f3 pos, f3 n, unsigned long long &ke
 }
 
 // ---- warp-local asynchronous closest-hit wavefront (same scheme as bake_inter.cu, one ray slot per lane) ---------------------
+#ifndef PRT_PROBE_FIN_MIN
+#define PRT_PROBE_FIN_MIN 16
+#endif
 constexpr int kWaveCap = 96;
 constexpr unsigned long long kNoHit = 0x7F800000FFFFFFFFull;        // (+inf, invalid prim)
 struct TraceShared {
@@ -166,7 +169,9 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
             for (uint32_t guard = 0; guard < (1u << 22); guard++) {               // (bounded: a logic error must not hang the device)
                 // finished slots: store the hit, free the slot
                 const uint32_t myray = W.ray[lane];
-                if (myray != kFreeSlot && W.refc[lane] == 0) {
+                const bool fin = myray != kFreeSlot && W.refc[lane] == 0;
+                const int nfin = __popc(__ballot_sync(0xFFFFFFFFu, fin));
+                if (fin && (nfin >= PRT_PROBE_FIN_MIN || nn + ln < 32)) {          // batched: the store code runs on many lanes at once
                     const unsigned long long key = W.best[lane];
                     if (key != kNoHit) {                                              // sky otherwise: volume.cpp:246
                         const float4 b = W.dir[lane];
