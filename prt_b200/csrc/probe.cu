@@ -7,9 +7,10 @@
 //   prt_probe_project   reference SH_volume::project_sh + precomp_projectSH.comp:32-143: CSR SpMV with surfel radiance,
 //                       sinc window, Ramamoorthi-Hanrahan pack into 7 vec4 per probe.
 //
-// One CTA per probe (probes handed out in order by an atomic ticket): 512 threads trace the probe's <= 4096 rays, the
-// (cluster key, ray) pairs are bitonic-sorted in shared memory, segment heads reduce their rays in ray order (deterministic
-// sums) into the probe's slice of a staging area; an exclusive scan of the per-probe entry counts and a compaction pass (one
+// One CTA per probe (probes handed out in order by an atomic ticket): 512 threads trace the probe's <= 4096 rays (warp-local
+// asynchronous wavefront, rays taken from a CTA-wide counter), the (cluster key, ray) pairs are bitonic-sorted in shared memory,
+// every thread reduces a chunk of consecutive sorted slots (clusters spanning chunks are handed over through shared memory;
+// fixed summation order) into the probe's slice of a staging area; an exclusive scan of the per-probe entry counts and a compaction pass (one
 // warp per probe, coalesced copies) then give the probe-major, exactly sized CSR.  (A chained prefix inside the capture kernel
 // serialised the probes.)
 // Surfel ids are the rank of the cluster key among all keys (== std::map<std::array<int,4>> order of volume.cpp:204).
