@@ -32,6 +32,9 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_CAP
 #define PRT_WAVE_CAP 256
 #endif
+#ifndef PRT_WAVE_SCAN_PUSH
+#define PRT_WAVE_SCAN_PUSH 1
+#endif
 #ifndef PRT_WAVE_MINB
 #define PRT_WAVE_MINB 7
 #endif
@@ -254,6 +257,26 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                         }
                     }
                     // push hit children (any order: any-hit is order independent)
+#if PRT_WAVE_SCAN_PUSH
+                    uint32_t tot;
+                    const uint32_t ex = warp_excl_scan_packed((uint32_t)__popc(inner8) | ((uint32_t)__popc(leaf8) << 16), lane, tot);
+                    if (nn + (int)(tot & 0xFFFFu) <= kNodeCap && ln + (int)(tot >> 16) <= kLeafCap) {
+                        // everything fits (the common case): one packed warp scan gave every lane its write positions on both
+                        // stacks, the lanes store their own children without further votes
+                        int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
+                        while (inner8) {
+                            const uint32_t s = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u;
+                            W.nq[pi++] = make_uint2(it.x, child_base + __popc(imask & ((1u << s) - 1u)));
+                        }
+                        while (leaf8) {
+                            const uint32_t s = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
+                            const uint32_t meta = ((s < 4u ? meta_lo : meta_hi) >> (8u * (s & 3u))) & 0xFFu;
+                            W.lq[pl++] = make_uint2(it.x | ((meta >> 5) << 16), tri_base + (meta & 31u));
+                        }
+                        nn += (int)(tot & 0xFFFFu); ln += (int)(tot >> 16);
+                    } else
+#endif
+                    {
                     while (__any_sync(kFull, inner8 != 0u)) {
                         const bool p = inner8 != 0u;
                         uint32_t child = 0u;
@@ -292,6 +315,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             }
                         }
                         ln = min(ln + __popc(pb), kLeafCap);
+                    }
                     }
                 }
                 __syncwarp();

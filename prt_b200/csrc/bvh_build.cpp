@@ -39,7 +39,7 @@ struct BNode {
     uint32_t count;  // 0 = internal
 };
 
-constexpr int kBins = 16;
+constexpr int kBins = 32;
 constexpr uint32_t kLeafMax = 3;
 constexpr int kMedianDepth = 36;   // beyond this binary depth fall back to median splits (bounds the stack)
 
