@@ -371,6 +371,22 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
                     if (delta) atomicAdd(&W.refc[it.x], delta);       // before the pushes: the count never reaches zero early
                 }
                 __syncwarp();
+                uint32_t tot;
+                const uint32_t ex = warp_excl_scan_packed((uint32_t)__popc(inner8) | ((uint32_t)__popc(leaf8) << 16), lane, tot);
+                if (nn + (int)(tot & 0xFFFFu) <= kCap && ln + (int)(tot >> 16) <= kCap) {
+                    // everything fits (the common case): one packed warp scan gave every lane its write positions on both stacks
+                    int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
+                    while (inner8) {
+                        const uint32_t s = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u;
+                        W.nq[pi++] = make_uint2(it.x, child_base + __popc(imask & ((1u << s) - 1u)));
+                    }
+                    while (leaf8) {
+                        const uint32_t s = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
+                        const uint32_t meta = ((s < 4u ? meta_lo : meta_hi) >> (8u * (s & 3u))) & 0xFFu;
+                        W.lq[pl++] = make_uint2(it.x | ((meta >> 5) << 16), tri_base + (meta & 31u));
+                    }
+                    nn += (int)(tot & 0xFFFFu); ln += (int)(tot >> 16);
+                }
                 while (__any_sync(kFull, inner8 != 0u)) {
                     const bool p = inner8 != 0u;
                     uint32_t child = 0u;

@@ -266,6 +266,27 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
                         if (delta) atomicAdd(&W.refc[it.x], delta);       // before the pushes: the count never reaches zero early
                     }
                     __syncwarp();
+                    {
+                        // positions on both stacks from one packed warp scan; when everything fits the lanes store their own children
+                        uint32_t incl = (uint32_t)__popc(inner8) | ((uint32_t)__popc(leaf8) << 16);
+                        const uint32_t mine = incl;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), ex = incl - mine;
+                        if (nn + (int)(tot & 0xFFFFu) <= kWaveCap && ln + (int)(tot >> 16) <= kWaveCap) {
+                            int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
+                            while (inner8) {
+                                const uint32_t sl = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u;
+                                W.nq[pi++] = make_uint2(it.x, child_base + __popc(imask & ((1u << sl) - 1u)));
+                            }
+                            while (leaf8) {
+                                const uint32_t sl = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
+                                const uint32_t meta = ((sl < 4u ? meta_lo : meta_hi) >> (8u * (sl & 3u))) & 0xFFu;
+                                W.lq[pl++] = make_uint2(it.x | ((meta >> 5) << 16), tri_base + (meta & 31u));
+                            }
+                            nn += (int)(tot & 0xFFFFu); ln += (int)(tot >> 16);
+                        }
+                    }
                     while (__any_sync(0xFFFFFFFFu, inner8 != 0u)) {
                         const bool pp = inner8 != 0u;
                         uint32_t child = 0u;
