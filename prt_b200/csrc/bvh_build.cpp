@@ -39,7 +39,7 @@ struct BNode {
     uint32_t count;  // 0 = internal
 };
 
-constexpr int kBins = 32;
+constexpr int kBins = 64;
 constexpr uint32_t kLeafMax = 3;
 constexpr int kMedianDepth = 36;   // beyond this binary depth fall back to median splits (bounds the stack)
 
@@ -68,24 +68,26 @@ struct Builder {
         if (count <= kLeafMax) return 0;
         int best_axis = -1, best_bin = -1;
         float best_cost = 3.0e38f;
+        const int nbin = (int)std::min<uint32_t>((uint32_t)kBins, std::max<uint32_t>(4u, 2u * count));     // few primitives need few bins
         if (depth < kMedianDepth) {
             for (int a = 0; a < 3; a++) {
                 float ext = cb.hi[a] - cb.lo[a];
                 if (!(ext > 0.f)) continue;
-                float scale = (float)kBins / ext;
-                uint32_t cnt[kBins] = {0};
+                float scale = (float)nbin / ext;
+                uint32_t cnt[kBins];
+                for (int b = 0; b < nbin; b++) cnt[b] = 0;
                 Box bb[kBins];
-                for (int b = 0; b < kBins; b++) bb[b].reset();
+                for (int b = 0; b < nbin; b++) bb[b].reset();
                 for (uint32_t i = first; i < first + count; i++) {
                     uint32_t t = ids[i];
-                    int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * (size_t)t + a] - cb.lo[a]) * scale)));
+                    int b = std::min(nbin - 1, std::max(0, (int)((cent[3 * (size_t)t + a] - cb.lo[a]) * scale)));
                     cnt[b]++; bb[b].grow(tb[t]);
                 }
                 float ra[kBins]; uint32_t rc[kBins];
                 Box acc; acc.reset(); uint32_t c = 0;
-                for (int b = kBins - 1; b >= 0; b--) { acc.grow(bb[b]); c += cnt[b]; rc[b] = c; ra[b] = c ? acc.area() : 0.f; }
+                for (int b = nbin - 1; b >= 0; b--) { acc.grow(bb[b]); c += cnt[b]; rc[b] = c; ra[b] = c ? acc.area() : 0.f; }
                 acc.reset(); c = 0;
-                for (int b = 0; b < kBins - 1; b++) {
+                for (int b = 0; b < nbin - 1; b++) {
                     acc.grow(bb[b]); c += cnt[b];
                     if (!c || !rc[b + 1]) continue;
                     float cost = acc.area() * (float)c + ra[b + 1] * (float)rc[b + 1];
@@ -96,10 +98,10 @@ struct Builder {
         uint32_t mid;
         if (best_axis >= 0) {
             int a = best_axis;
-            float scale = (float)kBins / (cb.hi[a] - cb.lo[a]);
+            float scale = (float)nbin / (cb.hi[a] - cb.lo[a]);
             uint32_t i = first, k = first + count;
             while (i < k) {
-                int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * (size_t)ids[i] + a] - cb.lo[a]) * scale)));
+                int b = std::min(nbin - 1, std::max(0, (int)((cent[3 * (size_t)ids[i] + a] - cb.lo[a]) * scale)));
                 if (b <= best_bin) i++; else std::swap(ids[i], ids[--k]);
             }
             mid = i;
