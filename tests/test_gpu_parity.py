@@ -137,6 +137,23 @@ def test_bake_interreflect(torus, torus_scenes, prt, oracle, bounces, albedo):
     assert gs.ctx.last_bake_stats().launches == 1
 
 
+@pytest.mark.parametrize("su,sv,mode,bounces", [(128, 64, "shadowed", 0), (96, 96, "shadowed", 0), (64, 64, "interreflect", 2), (96, 96, "interreflect", 1)])
+def test_bake_large_sample_counts(torus, torus_scenes, prt, oracle, su, sv, mode, bounces):
+    """BASELINE configs 4/5 sample counts: 8192 = the wavefront kernels' occlusion-bitset limit (config 5), 9216 takes the
+    per-ray fallback kernel, 4096-sample interreflection (config 4) runs the asynchronous wavefront."""
+    pos, nrm, _ = torus
+    gs, os_ = torus_scenes
+    sel = np.arange(7, len(pos), 97)[:24]
+    kw = dict(order=5 if mode == "shadowed" else 4, samples_u=su, samples_v=sv, bounces=bounces, albedo=(0.6, 0.5, 0.4))
+    gm = prt.SHADOWED if mode == "shadowed" else prt.INTERREFLECT
+    om = oracle.SHADOWED if mode == "shadowed" else oracle.INTERREFLECT
+    got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(mode=gm, **kw), want_vis=True, vertex_id_base=5)
+    ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(mode=om, **kw), want_vis=True, vertex_id_base=5)
+    assert gvis.shape == ovis.shape == (len(sel), (su * sv + 31) // 32)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+
+
 def test_bake_unshadowed_modes(torus, prt, oracle):
     pos, nrm, _ = torus
     sel = np.arange(0, len(pos), 29)[:200]
