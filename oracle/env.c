@@ -55,8 +55,8 @@ static const float *texel(const float *cube, int n0, int l, int f, int i, int j)
         face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n - 1.0f, d);
         dir_face(d, &f, &s, &t);
         i = (int)floorf(s * (float)n); j = (int)floorf(t * (float)n);
-        if (i < 0) i = 0; if (i > n - 1) i = n - 1;
-        if (j < 0) j = 0; if (j > n - 1) j = n - 1;
+        i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+        j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
     }
     return cube + level_offset(n0, l) + ((size_t)f * n * n + (size_t)j * n + i) * 3;
 }
@@ -101,8 +101,8 @@ void prt_o_env_equirect_to_cube(const float *eq, int w, int h, int n0, int level
                 float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
                 float x0 = floorf(x), y0 = floorf(y), fx = x - x0, fy = y - y0;
                 int i0 = (int)x0, j0 = (int)y0, i1 = i0 + 1, j1 = j0 + 1;
-                if (i0 < 0) i0 = 0; if (i0 > w - 1) i0 = w - 1; if (i1 < 0) i1 = 0; if (i1 > w - 1) i1 = w - 1;
-                if (j0 < 0) j0 = 0; if (j0 > h - 1) j0 = h - 1; if (j1 < 0) j1 = 0; if (j1 > h - 1) j1 = h - 1;
+                i0 = i0 < 0 ? 0 : (i0 > w - 1 ? w - 1 : i0); i1 = i1 < 0 ? 0 : (i1 > w - 1 ? w - 1 : i1);
+                j0 = j0 < 0 ? 0 : (j0 > h - 1 ? h - 1 : j0); j1 = j1 < 0 ? 0 : (j1 > h - 1 ? h - 1 : j1);
                 float *o = cube + ((size_t)f * n0 * n0 + (size_t)j * n0 + i) * 3;
                 for (int k = 0; k < 3; k++) {
                     float a = eq[((size_t)j0 * w + i0) * 3 + k], b = eq[((size_t)j0 * w + i1) * 3 + k];
