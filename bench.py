@@ -311,7 +311,7 @@ def run_ours(a):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         k_ms_max = float(kms.item())
         rays_launch = float(n_mine) * S
-        need_bytes = n_mine * (4.0 * ((S + 31) // 32) + 4.0) if launches_per_step == 2 else 0.0
+        need_bytes = n_mine * (4.0 * ((S + 31) // 32) + 4.0) if launches_per_step >= 2 else 0.0
         alg_bytes = visits * 80.0 + tests * 48.0 + cands * 32.0 + n_mine * (24.0 + 4.0 * n2) + need_bytes
         achieved = alg_bytes / (k_ms_max * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"bake_wave_kernel<{a.order},true> (traversal + projection; the horizon pass ran {hz_ms:.2f} ms before it)", "achieved": achieved, "peak": hbm_peak,

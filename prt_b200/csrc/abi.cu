@@ -46,10 +46,10 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 32, horizon_near = 38;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 32, horizon_near = 38, work_list_on = 0;
     // cached sample table
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
-    DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res, need_bits, need_count;
+    DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res, need_bits, need_count, work_list;
     prt_bake_stats stats{};
     bool stats_pending = false, work_pending = false;
 };
@@ -98,7 +98,7 @@ void prt_ctx_destroy(prt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->samples.release(); c->counter.release(); c->d_pos.release(); c->d_nrm.release(); c->d_out.release();
-    c->d_vis.release(); c->d_rays.release(); c->d_res.release(); c->need_bits.release(); c->need_count.release();
+    c->d_vis.release(); c->d_rays.release(); c->d_res.release(); c->need_bits.release(); c->need_count.release(); c->work_list.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -119,6 +119,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "count_work") c->count_work = value ? 1 : 0;
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
     else if (n == "horizon") c->horizon = value ? 1 : 0;
+    else if (n == "work_list") c->work_list_on = value ? 1 : 0;
     else if (n == "horizon_near") { if (value < 5 || value > 95) return set_err(PRT_ERR_INVALID, "horizon_near (angular radius x100, rad) must be in [5,95]"); c->horizon_near = value; }
     else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
     else if (n == "pair_queue") { if (value < 0 || value > 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks), 1 (pair queues) or 2 (wavefront)"); c->pair_queue = value; }
@@ -259,13 +260,13 @@ int ensure_samples(prt_ctx *c, const prt_bake_params *p) {
     for (int k = 0; k < S; k++) {
         const uint32_t s = key[k].second;
         tab[4 * k] = dirs[3 * s]; tab[4 * k + 1] = dirs[3 * s + 1]; tab[4 * k + 2] = dirs[3 * s + 2];
-        // w = reference sample index (24 bits) | azimuth bin of the local direction (5 bits, horizon map of bake_wave.cu)
-        // diamond pseudo-angle in [0,4), same formula as hz_pang (entry_list.cuh); 8 bins per unit
+        // w = reference sample index (24 bits) | azimuth bin of the local direction (5-6 bits, horizon map of horizon.cu)
+        // diamond pseudo-angle in [0,4), same formula as hz_pang (entry_list.cuh); kHzBins / 4 bins per unit
         const double lx = dirs[3 * s], ly = dirs[3 * s + 1], den = std::fabs(lx) + std::fabs(ly);
         double pa = den > 0.0 ? ly / den : 0.0;
         pa = lx < 0.0 ? 2.0 - pa : (ly < 0.0 ? 4.0 + pa : pa);
-        int bin = (int)std::floor(pa * 8.0);
-        bin = std::min(31, std::max(0, bin));
+        int bin = (int)std::floor(pa * (double)(prt::kHzBins / 4));
+        bin = std::min(prt::kHzBins - 1, std::max(0, bin));
         const uint32_t w = s | ((uint32_t)bin << 24);
         std::memcpy(&tab[4 * k + 3], &w, 4);
     }
@@ -323,10 +324,14 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
             CU_TRY(c->need_bits.reserve((size_t)n * A.vis_words * 4));
             CU_TRY(c->need_count.reserve((size_t)n * 4));
             A.need_bits = (uint32_t *)c->need_bits.p; A.need_count = (uint32_t *)c->need_count.p;
+            if (c->work_list_on) {
+                CU_TRY(c->work_list.reserve((size_t)n * 16));
+                A.work_list = (uint32_t *)c->work_list.p;
+            }
             int hgrid = 0;
             CU_TRY(launch_horizon(A, p->order, &hgrid, c->n_sms, st));
             if (e0) CU_TRY(cudaEventRecord(c->evh, st));
-            launches = 2;
+            launches = A.work_list ? 3 : 2;        // horizon_kernel (+ work_list_kernel) + bake_wave_kernel
         }
         CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
         c->stats.block = (uint32_t)bake_wave_block();
@@ -399,7 +404,7 @@ int prt_bake_transfer(prt_ctx *c, prt_scene *sc, const float *pos, const float *
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->stats.h2d_ms = ms;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats.kernel_ms = ms;
-    if (c->stats.launches == 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
+    if (c->stats.launches >= 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
     CU_TRY(cudaEventElapsedTime(&ms, c->ev2, c->ev3)); c->stats.d2h_ms = ms;
     c->stats.h2d_bytes = 2 * (uint64_t)span;
     c->stats.d2h_bytes = (uint64_t)n * n2 * 4 + (out_vis ? (uint64_t)n * words * 4 : 0);
@@ -416,7 +421,7 @@ int prt_ctx_last_bake_stats(const prt_ctx *cc, prt_bake_stats *out) {
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->ev2));
         c->stats.kernel_ms = ms;
-        if (c->stats.launches == 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
+        if (c->stats.launches >= 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
         c->stats_pending = false;
     }
     if (c->work_pending) {

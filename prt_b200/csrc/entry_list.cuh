@@ -147,9 +147,11 @@ __device__ __forceinline__ uint32_t warp_excl_scan_packed(uint32_t v, const int 
 // Azimuth is measured by the monotone "diamond" pseudo-angle p(x,y) in [0,4) (one division, no atan2); bins are uniform in p and
 // the host bins the sample directions with the same formula.  Margins (2e-4 in sin-elevation, 0.02 in p >= 0.9 degree) absorb
 // float rounding; rays inside the margin simply take the full path.  Lane b of the warp owns bin b while the map is built.
-constexpr int kHzBins = 32;
+constexpr int kHzPerLane = kHzBins / 32;         // lane l owns bins l, l + 32, ...
+constexpr float kHzPerUnit = (float)(kHzBins / 4);   // bins per unit of pseudo-angle
+struct HzMap { float v[kHzPerLane]; };
 
-struct HzItem { int b0, b1; float v; };          // bins b0..b1 (unwrapped, b1-b0 <= 31), value; v <= 0: empty
+struct HzItem { int b0, b1; float v; };          // bins b0..b1 (unwrapped, b1-b0 <= kHzBins-1), value; v <= 0: empty
 
 __device__ __forceinline__ float hz_pang(float x, float y) {
     const float p = __fdividef(y, fabsf(x) + fabsf(y));
@@ -161,7 +163,7 @@ __device__ __forceinline__ HzItem hz_item(float lo, float hi, bool all, float si
     it.v = fminf(sinh + 2e-4f, 2.0f);
     it.b1 = kHzBins - 1;
     if (all || !(hi - lo < 3.9f)) return it;
-    const int b0 = (int)floorf((lo - 0.02f) * 8.f), b1 = (int)floorf((hi + 0.02f) * 8.f);
+    const int b0 = (int)floorf((lo - 0.02f) * kHzPerUnit), b1 = (int)floorf((hi + 0.02f) * kHzPerUnit);
     if (b1 - b0 >= kHzBins - 1) return it;
     it.b0 = b0; it.b1 = b1;
     return it;
@@ -169,8 +171,9 @@ __device__ __forceinline__ HzItem hz_item(float lo, float hi, bool all, float si
 // warp-collective: every lane contributes one item; lane = bin keeps the running maximum.  The running map is first published
 // to shared memory so that each lane can drop an item that does not raise the horizon in any bin it spans (most far boxes do
 // not, once the near geometry is in): only the useful items go through the serial broadcast loop.
-__device__ __forceinline__ float hz_merge(float my, const HzItem it, const int lane, uint32_t *hz) {
-    hz[lane] = __float_as_uint(my);
+__device__ __forceinline__ HzMap hz_merge(HzMap my, const HzItem it, const int lane, uint32_t *hz) {
+#pragma unroll
+    for (int j = 0; j < kHzPerLane; j++) hz[lane + 32 * j] = __float_as_uint(my.v[j]);
     __syncwarp();
     bool useful = false;
     if (it.v > 0.f) {
@@ -184,7 +187,9 @@ __device__ __forceinline__ float hz_merge(float my, const HzItem it, const int l
         m &= m - 1u;
         const int b0 = __shfl_sync(kFull, it.b0, src), b1 = __shfl_sync(kFull, it.b1, src);
         const float v = __shfl_sync(kFull, it.v, src);
-        if (((lane - b0) & (kHzBins - 1)) <= b1 - b0) my = fmaxf(my, v);
+#pragma unroll
+        for (int j = 0; j < kHzPerLane; j++)
+            if (((lane + 32 * j - b0) & (kHzBins - 1)) <= b1 - b0) my.v[j] = fmaxf(my.v[j], v);
     }
     return my;
 }
@@ -315,13 +320,18 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
     return hz_triangle(q0, q1, q2);
 }
 
+#ifndef PRT_HZ_SLAB
+#define PRT_HZ_SLAB 0
+#endif
 constexpr int kHzQueue = 64;
 constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
 // `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2))
 __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
                                               const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    float my = 0.f;                                          // lane b owns bin b
+    HzMap my;                                                // lane b owns bins b (+ 32)
+#pragma unroll
+    for (int j = 0; j < kHzPerLane; j++) my.v[j] = 0.f;
     int rn = 0, tn = 0;
     // work item of a lane in one round: up to 3 triangles (leaf) or one box
     // ---- pass 1: the entry-list candidates; pass 2: children of queued subtrees (4 nodes x 8 children per iteration) ------
@@ -382,7 +392,20 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         if (valid && inner) {
             const float r2 = e.x * e.x + e.y * e.y + e.z * e.z, d2 = c.x * c.x + c.y * c.y + c.z * c.z;
             if (!(e.x < 1e30f)) it = hz_item(0.f, 0.f, true, 1.0f);
-            else if (!(d2 < near2 * r2)) it = hz_sphere(c, r2, d2, fr);
+            else if (!(d2 < near2 * r2)) {
+                it = hz_sphere(c, r2, d2, fr);
+#if PRT_HZ_SLAB
+                // second bound of sin(elevation) = z / |p| over the box: (largest height above the tangent plane) / (smallest
+                // distance from the origin).  Much tighter than the cone for the flat, surface-hugging boxes of a mesh, whose
+                // bounding sphere lifts the horizon by their whole angular radius.  d_min > 0: the origin is outside the sphere.
+                if (it.v > 0.f) {
+                    const float zt = c.x * fr.n.x + c.y * fr.n.y + c.z * fr.n.z + fabsf(fr.n.x) * e.x + fabsf(fr.n.y) * e.y + fabsf(fr.n.z) * e.z;
+                    const float mx = fmaxf(fabsf(c.x) - e.x, 0.f), my_ = fmaxf(fabsf(c.y) - e.y, 0.f), mz = fmaxf(fabsf(c.z) - e.z, 0.f);
+                    const float dm2 = mx * mx + my_ * my_ + mz * mz;
+                    if (dm2 > 0.f) it.v = fminf(it.v, fmaxf(zt, 0.f) * rsqrtf(dm2) * 1.0001f + (1e-6f + 2e-4f));
+                }
+#endif
+            }
             else push = budget > 0;
         }
         const unsigned pb = __ballot_sync(kFull, push);
@@ -415,7 +438,8 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         if (lane < tn) ti = hz_tri_item(tris, tq[lane], O, fr);
         my = hz_merge(my, ti, lane, hz);
     }
-    hz[lane] = __float_as_uint(my);
+#pragma unroll
+    for (int j = 0; j < kHzPerLane; j++) hz[lane + 32 * j] = __float_as_uint(my.v[j]);
     __syncwarp();
 }
 

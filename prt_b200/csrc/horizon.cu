@@ -2,7 +2,7 @@
 //
 // One persistent warp per vertex:
 //   1. build_entry_list   candidate boxes for the shared ray origin (entry_list.cuh)
-//   2. build_horizon      conservative bound of sin(elevation) of all geometry per azimuth bin (32 bins), refined through near
+//   2. build_horizon      conservative bound of sin(elevation) of all geometry per azimuth bin (kHzBins = 32 or 64), refined through near
 //                         subtrees down to exact triangle bounds
 //   3. classify           sample i needs tracing iff its local z does not exceed the horizon of its bin; the need bits of the
 //                         vertex (processing order) and their count go to global memory for the traversal pass
@@ -94,6 +94,29 @@ __global__ void __launch_bounds__(128) horizon_kernel(const BakeArgs A) {
     }
 }
 
+// Files every unfinished vertex under one of four cost classes (the quartile of S its need count falls in).  The traversal pass
+// walks the classes heaviest first, so that the warps still busy when the work runs out hold cheap vertices (shorter tail).
+// Thread per vertex, one atomic per warp and class; the order inside a class stays close to the (Morton) vertex order.
+__global__ void __launch_bounds__(256) work_list_kernel(const uint32_t *need_count, const uint32_t n, const uint32_t S, uint32_t *list, uint32_t *class_count) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t cls = 4u;
+    if (v < n) {
+        const uint32_t q = 4u * need_count[v];
+        if (q) cls = q > 3u * S ? 0u : q > 2u * S ? 1u : q > S ? 2u : 3u;
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < 4u; c++) {
+        const unsigned m = __ballot_sync(kFull, cls == c);
+        if (!m) continue;
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0u;
+        if (lane == leader) base = atomicAdd(class_count + c, (uint32_t)__popc(m));
+        base = __shfl_sync(kFull, base, leader);
+        if (cls == c) list[(size_t)c * n + base + __popc(m & ((1u << lane) - 1u))] = v;
+    }
+}
+
 template <int ORDER>
 cudaError_t launch_horizon_t(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
     const int block = 128;
@@ -107,6 +130,7 @@ cudaError_t launch_horizon_t(const BakeArgs &A, int *grid, int n_sms, cudaStream
     const long long need = ((long long)A.n_verts + 3) / 4;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
     horizon_kernel<ORDER><<<*grid, block, smem, st>>>(A);
+    if (A.work_list) work_list_kernel<<<(A.n_verts + 255u) / 256u, 256, 0, st>>>(A.need_count, A.n_verts, (uint32_t)A.S, A.work_list, A.counter + 4);
     return cudaGetLastError();
 }
 

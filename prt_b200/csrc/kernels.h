@@ -6,6 +6,14 @@
 
 namespace prt {
 
+// azimuth bins of the per-origin horizon map (entry_list.cuh): 32 or 64, i.e. one or two bins per lane of the building warp.
+// The host bins the sample directions with the same constant (abi.cu, ensure_samples).
+#ifndef PRT_HZ_BINS
+#define PRT_HZ_BINS 32
+#endif
+constexpr int kHzBins = PRT_HZ_BINS;
+static_assert(kHzBins == 32 || kHzBins == 64, "the horizon map has one or two bins per lane");
+
 struct BakeArgs {
     const Node8 *nodes;
     const Tri48 *tris;
@@ -27,6 +35,9 @@ struct BakeArgs {
     uint32_t *need_bits;        // horizon pass output / traversal pass input: [n_verts][vis_words], bit i of a row = sample with
                                 // processing index i is NOT above the horizon and must be traced
     uint32_t *need_count;       // [n_verts] number of such samples; 0 = the horizon pass already wrote the vertex's row
+    uint32_t *work_list;        // optional [4][n_verts]: the horizon pass files every unfinished vertex under one of four cost
+                                // classes (quartile of S its need count falls in; class sizes in counter[4..7]) and the traversal
+                                // pass walks the classes heaviest first, so the warps that finish last hold cheap vertices
     uint32_t seed;
     int depth;                  // path segments = bounces + 1
     float albedo[3];

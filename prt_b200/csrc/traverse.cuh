@@ -44,9 +44,9 @@ PRT_HD float safe_rcp(float d) {
 enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_EMPTY = 2 };
 
 // Pinned ray/triangle decision on triangle `ti`: hit iff tnear < t <= tfar.
-PRT_HD bool tri_hit(const Tri48 *tris, uint32_t ti, f3 o, f3 d, float tnear, float tfar, bool want_t, float &t, uint32_t &prim) {
-    const char *tp = reinterpret_cast<const char *>(tris + ti);
-    const u4 a = ld16(tp), b = ld16(tp + 16), c = ld16(tp + 32);
+// tri_hit_regs: the same decision on a triangle whose three 16-byte words are already in registers (lets a caller issue the
+// fetch before the ray direction is known)
+PRT_HD bool tri_hit_regs(const u4 a, const u4 b, const u4 c, f3 o, f3 d, float tnear, float tfar, bool want_t, float &t, uint32_t &prim) {
     const f3 v0 = mk3(PRT_U2F(a.x), PRT_U2F(a.y), PRT_U2F(a.z));
     const f3 e1 = mk3(PRT_U2F(b.x), PRT_U2F(b.y), PRT_U2F(b.z));
     const f3 e2 = mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z));
@@ -64,6 +64,11 @@ PRT_HD bool tri_hit(const Tri48 *tris, uint32_t ti, f3 o, f3 d, float tnear, flo
                      (Ts > PRT_MUL(tnear, ad)) && (Ts <= PRT_MUL(tfar, ad));
     if (hit && want_t) { t = PRT_DIV(Ts, ad); prim = a.w; }
     return hit;
+}
+PRT_HD bool tri_hit(const Tri48 *tris, uint32_t ti, f3 o, f3 d, float tnear, float tfar, bool want_t, float &t, uint32_t &prim) {
+    const char *tp = reinterpret_cast<const char *>(tris + ti);
+    const u4 a = ld16(tp), b = ld16(tp + 16), c = ld16(tp + 32);
+    return tri_hit_regs(a, b, c, o, d, tnear, tfar, want_t, t, prim);
 }
 
 struct Trav {
