@@ -139,17 +139,27 @@ __device__ __forceinline__ uint32_t warp_excl_scan_packed(uint32_t v, const int 
 // kHzBins azimuth bins in the local frame of the vertex; hz[b] = a conservative upper bound of sin(elevation above the tangent
 // plane) of ALL geometry seen from the origin in that azimuth range.  A ray whose local z exceeds hz[bin] cannot hit anything and
 // is visible without any traversal.  Every piece of geometry is covered by exactly one entry-list candidate (culled ones lie
-// wholly below the tangent plane), so bounding every candidate bounds the scene:
-//   leaf candidate     exact maximum elevation of each of its triangles: maximum over the three edge arcs (end points and the
+// wholly below the tangent plane), so bounding every candidate bounds the scene.  The builder works *lazily*, nearest geometry
+// first: every box (subtree or leaf) first gets a cheap bound --
+//   cone around its bounding sphere, clamped by the slab bound z_max / d_min (largest height above the tangent plane over the
+//   smallest distance from the origin: much tighter for the flat, surface-hugging boxes of a mesh, whose bounding sphere lifts
+//   the horizon by their whole angular radius)
+// -- and a box whose cheap bound cannot raise the map in any bin it spans is dropped at once, whatever its size (no refinement,
+// no triangle bounds).  Of the boxes that could raise it:
+//   leaf               exact maximum elevation of each of its triangles: maximum over the three edge arcs (end points and the
 //                      interior critical point, which is the root of a LINEAR equation) or 1 if the vertical axis pierces it
-//   subtree candidate  small angular size: cone around its bounding sphere; large angular size ("near"): the builder descends into
-//                      it -- WITHOUT adding candidates -- until the pieces are small or are triangles (budgeted)
+//   far subtree        (small angular size) the cheap bound is merged
+//   near subtree       the builder descends into it -- WITHOUT adding candidates -- until the pieces are small, are dropped or are
+//                      triangles (budgeted; afterwards the exact box bound)
+// "Cannot raise the map" is one range-minimum query: the map is published to shared memory together with its minima over 2, 4, 8
+// and 16 consecutive bins (a sparse table, kHzLevels x 32 words), so the test is two loads whatever the azimuth span of the item.
 // Azimuth is measured by the monotone "diamond" pseudo-angle p(x,y) in [0,4) (one division, no atan2); bins are uniform in p and
 // the host bins the sample directions with the same formula.  Margins (2e-4 in sin-elevation, 0.02 in p >= 0.9 degree) absorb
 // float rounding; rays inside the margin simply take the full path.  Lane b of the warp owns bin b while the map is built.
-constexpr int kHzPerLane = kHzBins / 32;         // lane l owns bins l, l + 32, ...
+// Dropping only ever uses a published (possibly stale, i.e. lower) copy of the map, so it is conservative by construction.
 constexpr float kHzPerUnit = (float)(kHzBins / 4);   // bins per unit of pseudo-angle
-struct HzMap { float v[kHzPerLane]; };
+constexpr int kHzLevels = 5;                          // published map: level k = minima over 2^k consecutive bins (circular)
+constexpr int kHzWords = kHzLevels * kHzBins;
 
 struct HzItem { int b0, b1; float v; };          // bins b0..b1 (unwrapped, b1-b0 <= kHzBins-1), value; v <= 0: empty
 
@@ -168,29 +178,38 @@ __device__ __forceinline__ HzItem hz_item(float lo, float hi, bool all, float si
     it.b0 = b0; it.b1 = b1;
     return it;
 }
-// warp-collective: every lane contributes one item; lane = bin keeps the running maximum.  The running map is first published
-// to shared memory so that each lane can drop an item that does not raise the horizon in any bin it spans (most far boxes do
-// not, once the near geometry is in): only the useful items go through the serial broadcast loop.
-__device__ __forceinline__ HzMap hz_merge(HzMap my, const HzItem it, const int lane, uint32_t *hz) {
+// warp-collective: publishes the map (lane = bin) and its range minima
+__device__ __forceinline__ void hz_publish(const float my, const int lane, uint32_t *hz) {
+    float t = my;
+    hz[lane] = __float_as_uint(t);
 #pragma unroll
-    for (int j = 0; j < kHzPerLane; j++) hz[lane + 32 * j] = __float_as_uint(my.v[j]);
-    __syncwarp();
-    bool useful = false;
-    if (it.v > 0.f) {
-        for (int b = it.b0; b <= it.b1; b++)
-            if (it.v > __uint_as_float(hz[b & (kHzBins - 1)])) { useful = true; break; }
+    for (int k = 1; k < kHzLevels; k++) {
+        t = fminf(t, __shfl_sync(kFull, t, (lane + (1 << (k - 1))) & 31));
+        hz[kHzBins * k + lane] = __float_as_uint(t);
     }
-    __syncwarp();                                              // all reads of hz[] are done before the next call overwrites it
-    unsigned m = __ballot_sync(kFull, useful);
+    __syncwarp();
+}
+// could the item raise the published map in any bin it spans?  (two loads: the range b0..b1 is covered by two table entries)
+__device__ __forceinline__ bool hz_useful(const HzItem it, const uint32_t *hz) {
+    if (!(it.v > 0.f)) return false;
+    const int k = min(31 - __clz(it.b1 - it.b0 + 1), kHzLevels - 1);
+    const float m = fminf(__uint_as_float(hz[kHzBins * k + (it.b0 & (kHzBins - 1))]),
+                          __uint_as_float(hz[kHzBins * k + ((it.b1 - (1 << k) + 1) & (kHzBins - 1))]));
+    return it.v > m;
+}
+// warp-collective: every lane contributes one item (if `useful`); lane = bin keeps the running maximum.  Only the useful items
+// go through the serial broadcast loop; the map is re-published when it may have changed.
+__device__ __forceinline__ float hz_merge(float my, const HzItem it, const bool useful, const int lane, uint32_t *hz) {
+    unsigned m = __ballot_sync(kFull, useful);              // also: every lane has finished its reads of hz[]
+    if (!m) return my;
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1u;
         const int b0 = __shfl_sync(kFull, it.b0, src), b1 = __shfl_sync(kFull, it.b1, src);
         const float v = __shfl_sync(kFull, it.v, src);
-#pragma unroll
-        for (int j = 0; j < kHzPerLane; j++)
-            if (((lane + 32 * j - b0) & (kHzBins - 1)) <= b1 - b0) my.v[j] = fmaxf(my.v[j], v);
+        if (((lane - b0) & (kHzBins - 1)) <= b1 - b0) my = fmaxf(my, v);
     }
+    hz_publish(my, lane, hz);
     return my;
 }
 
@@ -320,21 +339,19 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
     return hz_triangle(q0, q1, q2);
 }
 
-#ifndef PRT_HZ_SLAB
-#define PRT_HZ_SLAB 0
-#endif
 constexpr int kHzQueue = 64;
 constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
-// `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2))
+// `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2)).
+// hz: kHzWords words of shared memory; on return hz[0..kHzBins) is the map.
 __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
                                               const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    HzMap my;                                                // lane b owns bins b (+ 32)
-#pragma unroll
-    for (int j = 0; j < kHzPerLane; j++) my.v[j] = 0.f;
+    float my = 0.f;                                          // lane b owns bin b
     int rn = 0, tn = 0;
-    // work item of a lane in one round: up to 3 triangles (leaf) or one box
-    // ---- pass 1: the entry-list candidates; pass 2: children of queued subtrees (4 nodes x 8 children per iteration) ------
+    hz_publish(my, lane, hz);
+    // work item of a lane in one round: one box (subtree or leaf)
+    // ---- pass 1: the entry-list candidates, deepest (nearest) first: they establish the horizon that lets the far boxes be
+    //      dropped; pass 2: children of queued subtrees (4 nodes x 8 children per iteration) ---------------------------------
     int k0 = 0, budget = budget_iters;
     for (;;) {
         const bool pass1 = k0 < n_cand;
@@ -343,8 +360,8 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         f3 c = mk3(0.f, 0.f, 0.f), e = mk3(0.f, 0.f, 0.f);
         uint32_t gx = 0u, unary = 0u;
         if (pass1) {
-            const int k = k0 + lane;
-            if (k < n_cand) {
+            const int k = n_cand - 1 - (k0 + lane);
+            if (k >= 0) {
                 const float4 ca = W.ca[k], cb = W.cb[k];
                 gx = __float_as_uint(cb.z);
                 const uint32_t gy = __float_as_uint(cb.w);
@@ -386,38 +403,37 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
                 }
             }
         }
-        // classify boxes: far -> sphere cone, near -> refine (while budget and queue space last), else exact box bound
+        // ---- classify the lane's box ------------------------------------------------------------------------------------
         HzItem it = hz_item(0.f, 0.f, false, 0.f);
-        bool push = false;
-        if (valid && inner) {
+        bool merge = false, push = false, leaf = false, nearb = false;
+        if (valid && !(e.x < 1e30f)) { it = hz_item(0.f, 0.f, true, 1.0f); merge = true; }      // overflow candidate: unbounded
+        else if (valid) {
             const float r2 = e.x * e.x + e.y * e.y + e.z * e.z, d2 = c.x * c.x + c.y * c.y + c.z * c.z;
-            if (!(e.x < 1e30f)) it = hz_item(0.f, 0.f, true, 1.0f);
-            else if (!(d2 < near2 * r2)) {
-                it = hz_sphere(c, r2, d2, fr);
-#if PRT_HZ_SLAB
-                // second bound of sin(elevation) = z / |p| over the box: (largest height above the tangent plane) / (smallest
-                // distance from the origin).  Much tighter than the cone for the flat, surface-hugging boxes of a mesh, whose
-                // bounding sphere lifts the horizon by their whole angular radius.  d_min > 0: the origin is outside the sphere.
-                if (it.v > 0.f) {
-                    const float zt = c.x * fr.n.x + c.y * fr.n.y + c.z * fr.n.z + fabsf(fr.n.x) * e.x + fabsf(fr.n.y) * e.y + fabsf(fr.n.z) * e.z;
-                    const float mx = fmaxf(fabsf(c.x) - e.x, 0.f), my_ = fmaxf(fabsf(c.y) - e.y, 0.f), mz = fmaxf(fabsf(c.z) - e.z, 0.f);
-                    const float dm2 = mx * mx + my_ * my_ + mz * mz;
-                    if (dm2 > 0.f) it.v = fminf(it.v, fmaxf(zt, 0.f) * rsqrtf(dm2) * 1.0001f + (1e-6f + 2e-4f));
-                }
-#endif
+            // cheap bound: cone around the bounding sphere (needs the origin outside it) ...
+            HzItem cb = d2 > 1.05f * r2 ? hz_sphere(c, r2, d2, fr) : hz_item(0.f, 0.f, true, 1.0f);
+            if (cb.v > 0.f) {
+                // ... clamped by z_max / d_min over the box (d_min > 0: the origin is outside the box)
+                const float zt = c.x * fr.n.x + c.y * fr.n.y + c.z * fr.n.z + fabsf(fr.n.x) * e.x + fabsf(fr.n.y) * e.y + fabsf(fr.n.z) * e.z;
+                const float mx = fmaxf(fabsf(c.x) - e.x, 0.f), my_ = fmaxf(fabsf(c.y) - e.y, 0.f), mz = fmaxf(fabsf(c.z) - e.z, 0.f);
+                const float dm2 = mx * mx + my_ * my_ + mz * mz;
+                if (dm2 > 0.f) cb.v = fminf(cb.v, fmaxf(zt, 0.f) * rsqrtf(dm2) * 1.0001f + (1e-6f + 2e-4f));
             }
-            else push = budget > 0;
+            if (hz_useful(cb, hz)) {
+                if (!inner) leaf = true;
+                else if (!(d2 < near2 * r2)) { it = cb; merge = true; }
+                else { nearb = true; push = budget > 0; }
+            }
         }
         const unsigned pb = __ballot_sync(kFull, push);
         const int pos = rn + __popc(pb & lt_mask);
         if (push && pos < kHzQueue) rq[pos] = gx;
-        const bool boxed = valid && inner && (e.x < 1e30f) && (c.x * c.x + c.y * c.y + c.z * c.z < near2 * (e.x * e.x + e.y * e.y + e.z * e.z)) && !(push && pos < kHzQueue);
-        if (__any_sync(kFull, boxed)) { if (boxed) it = hz_box(c, e, fr); }
+        // near, but no budget / queue space left: exact bound of the box itself
+        const bool boxed = nearb && !(push && pos < kHzQueue);
+        if (__any_sync(kFull, boxed)) { if (boxed) { it = hz_box(c, e, fr); merge = hz_useful(it, hz); } }
         rn = min(rn + __popc(pb), kHzQueue);
-        my = hz_merge(my, it, lane, hz);
+        my = hz_merge(my, it, merge, lane, hz);
         // leaves: their triangles are queued and bounded 32 at a time, so the (long) triangle bound always runs on a full warp;
         // every triangle keeps its own azimuth range
-        const bool leaf = valid && !inner;
         for (uint32_t j = 0; j < 3u; j++) {
             const bool has = leaf && ((unary >> j) & 1u);
             const unsigned tb = __ballot_sync(kFull, has);
@@ -429,17 +445,16 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         while (tn >= 32) {
             tn -= 32;
             const HzItem ti = hz_tri_item(tris, tq[tn + lane], O, fr);
-            my = hz_merge(my, ti, lane, hz);
+            my = hz_merge(my, ti, hz_useful(ti, hz), lane, hz);
         }
         __syncwarp();
     }
     if (tn > 0) {
         HzItem ti = hz_item(0.f, 0.f, false, 0.f);
         if (lane < tn) ti = hz_tri_item(tris, tq[lane], O, fr);
-        my = hz_merge(my, ti, lane, hz);
+        my = hz_merge(my, ti, hz_useful(ti, hz), lane, hz);
     }
-#pragma unroll
-    for (int j = 0; j < kHzPerLane; j++) hz[lane + 32 * j] = __float_as_uint(my.v[j]);
+    hz[lane] = __float_as_uint(my);
     __syncwarp();
 }
 

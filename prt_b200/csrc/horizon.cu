@@ -18,15 +18,19 @@ namespace prt {
 
 namespace {
 
+#ifndef PRT_HZ_MINB
+#define PRT_HZ_MINB 9               // CTAs per SM the register allocation aims at (56 registers; 10 CTAs at 48 registers measured 3 % slower)
+#endif
+
 struct HorizonShared {
     EntryList el;
-    uint32_t hz[kHzBins];
+    uint32_t hz[kHzWords];             // the map (first kHzBins words) and its range-minimum table
     uint32_t rq[kHzQueue];
     uint32_t tq[kHzTriQueue];
 };
 
 template <int ORDER>
-__global__ void __launch_bounds__(128) horizon_kernel(const BakeArgs A) {
+__global__ void __launch_bounds__(128, PRT_HZ_MINB) horizon_kernel(const BakeArgs A) {
     constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HorizonShared &W = reinterpret_cast<HorizonShared *>(smem_raw)[threadIdx.x >> 5];

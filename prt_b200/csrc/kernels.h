@@ -6,13 +6,9 @@
 
 namespace prt {
 
-// azimuth bins of the per-origin horizon map (entry_list.cuh): 32 or 64, i.e. one or two bins per lane of the building warp.
-// The host bins the sample directions with the same constant (abi.cu, ensure_samples).
-#ifndef PRT_HZ_BINS
-#define PRT_HZ_BINS 32
-#endif
-constexpr int kHzBins = PRT_HZ_BINS;
-static_assert(kHzBins == 32 || kHzBins == 64, "the horizon map has one or two bins per lane");
+// azimuth bins of the per-origin horizon map (entry_list.cuh): one bin per lane of the building warp.  The host bins the
+// sample directions with the same constant (abi.cu, ensure_samples).
+constexpr int kHzBins = 32;
 
 struct BakeArgs {
     const Node8 *nodes;

@@ -19,6 +19,8 @@ from prt_b200 import hdr, meshes  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--only", default="")
+ap.add_argument("--budget", type=int, default=0, help="horizon_budget for configs 4/5 (0: library default)")
+ap.add_argument("--near", default="", help="comma list of horizon_near values to time configs 4/5 with (default: the library default)")
 a = ap.parse_args()
 ctx = prt_b200.Context(0)
 dev = torch.device("cuda", 0)
@@ -108,18 +110,24 @@ for name, order, su, sv, mode, bounces, nu, nv, nsub in [
     params = prt_b200.BakeParams.make(order=order, samples_u=su, samples_v=sv, mode=mode, bounces=bounces,
                                       albedo=(0.5, 0.5, 0.5) if bounces else (1, 1, 1))
     stream = torch.cuda.current_stream()
-    ms = []
-    for _ in range(2):
-        rc = ctx.L.prt_bake_transfer_device(ctx.h, sc.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, len(sel), 0,
-                                            C.byref(params), C.c_void_p(d_out.data_ptr()), None, C.c_void_p(stream.cuda_stream))
-        assert rc == 0, ctx.L.prt_last_error()
-        torch.cuda.synchronize()
-        ms.append(ctx.last_bake_stats().kernel_ms)
     S = su * sv
-    emit(config=name, vertices_total=len(pos), triangles=len(tri), bvh_build_s=info.build_seconds, bvh_mb=(info.node_bytes + info.tri_bytes) / 1e6,
-         bvh_depth=info.max_depth, vertices_timed=len(sel), sample=f"every {stride}-th vertex in Morton order", samples_per_vertex=S,
-         kernel_ms=min(ms), primary_grays_per_s=len(sel) * S / min(ms) / 1e6, vertices_per_s=len(sel) / min(ms) * 1e3,
-         full_mesh_seconds_extrapolated=len(pos) / (len(sel) / min(ms) * 1e3), finite=bool(torch.isfinite(d_out).all().item()))
+    for near in ([int(x) for x in a.near.split(",")] if a.near else [None]):
+        if near is not None:
+            ctx.set_tuning(horizon_near=near)
+        if a.budget:
+            ctx.set_tuning(horizon_budget=a.budget)
+        ms = []
+        for _ in range(2):
+            rc = ctx.L.prt_bake_transfer_device(ctx.h, sc.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, len(sel), 0,
+                                                C.byref(params), C.c_void_p(d_out.data_ptr()), None, C.c_void_p(stream.cuda_stream))
+            assert rc == 0, ctx.L.prt_last_error()
+            torch.cuda.synchronize()
+            ms.append(ctx.last_bake_stats().kernel_ms)
+        emit(config=name, horizon_near=near, horizon_budget=a.budget or None, horizon_ms=ctx.last_bake_stats().horizon_ms, vertices_total=len(pos), triangles=len(tri), bvh_build_s=info.build_seconds,
+             bvh_mb=(info.node_bytes + info.tri_bytes) / 1e6,
+             bvh_depth=info.max_depth, vertices_timed=len(sel), sample=f"every {stride}-th vertex in Morton order", samples_per_vertex=S,
+             kernel_ms=min(ms), primary_grays_per_s=len(sel) * S / min(ms) / 1e6, vertices_per_s=len(sel) / min(ms) * 1e3,
+             full_mesh_seconds_extrapolated=len(pos) / (len(sel) / min(ms) * 1e3), finite=bool(torch.isfinite(d_out).all().item()))
     sc.close()
 
 if want("f"):
