@@ -111,7 +111,7 @@ def run_reference(a):
                              "note": "CPU oracle (binary SAH BVH + scalar pinned Moeller-Trumbore, one trace per sample); "
                                      "the reference's Embree path cannot be built here"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -124,7 +124,7 @@ class ClockSampler:
     def __init__(self, dev):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(dev)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40", "-i", str(dev)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -159,7 +159,7 @@ class ClockSampler:
         return out
 
 
-def shard_indices(n_verts, world, rank, chunk=2048):
+def shard_indices(n_verts, world, rank, chunk=64):
     """Interleaved chunks of the Morton-ordered vertex list; padded so every rank owns the same count."""
     n_chunks = (n_verts + chunk - 1) // chunk
     n_chunks_pad = ((n_chunks + world - 1) // world) * world
@@ -258,7 +258,6 @@ def run_ours(a):
     last = ctx.last_bake_stats()
     k_ms = last.kernel_ms - last.horizon_ms        # the dominant kernel (traversal + projection) alone
     hz_ms = last.horizon_ms
-    clk = clocks.stop() if clocks else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     kms = torch.tensor([k_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -294,6 +293,8 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = rays_per_step * a.steps / float(e2e_s.item())
+    # the clock sampler (40 ms period) ran through both timed regions: at N = 8 the device-timed one alone lasts 35 ms
+    clk = clocks.stop() if clocks else None
     h2d = world * n_mine * 24
     d2h = (world * n_mine * n2 * 4) + (world - 1) * n_mine * n2 * 4 if world > 1 else n_mine * n2 * 4
 
@@ -341,14 +342,31 @@ def run_ours(a):
             rps, n_sel, dt, cores, _ = cpu_bake_sample(a, pos, tri, pos_m, nrm_m, a.cpu_sample)
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_sel} Morton-strided vertices x {S} rays ({dt:.1f} s of CPU work)"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit_line(line):
+    """The one JSON line of the contract goes to the process's ORIGINAL stdout (see main)."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write there behind Python's back (NCCL prints its version banner with
+    # printf when NCCL_DEBUG is VERSION/INFO in the environment), so file descriptor 1 is pointed at stderr for the whole run and
+    # the JSON line is written to a private duplicate of the original stdout.
+    global _JSON_OUT
     a = parse()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

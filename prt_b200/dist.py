@@ -15,7 +15,8 @@ from __future__ import annotations
 
 import numpy as np
 
-CHUNK = 2048
+CHUNK = 64        # vertices per interleaved chunk: 2048 left the slowest of 8 ranks 4 % behind the mean, 64 leaves 0.5 %
+                  # (tools/shard_balance.py); a chunk is still two 32-vertex Morton runs, enough for L1/L2 locality
 
 
 def shard_indices(n_verts: int, world: int, rank: int, chunk: int = CHUNK):

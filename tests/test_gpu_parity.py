@@ -97,7 +97,7 @@ def test_bake_reference_defaults(torus, torus_scenes, prt, oracle):
     assert 0.3 < frac < 0.98  # the torus really is self-occluding
 
 
-@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4), dict(work_list=1), dict(pair_queue=0), dict(pair_queue=1), dict(pair_queue=1, refill_thresh=0),
+@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4), dict(work_list=0), dict(work_list=1), dict(pair_queue=0), dict(pair_queue=1), dict(pair_queue=1, refill_thresh=0),
                                    dict(pair_queue=0, refill_thresh=0), dict(entry_list=0), dict(entry_list=0, refill_thresh=16)])
 def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     """ray compaction, per-origin entry lists and the pair queues only reorganise work: results must not change."""
@@ -108,7 +108,7 @@ def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     try:
         got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(samples_u=16, samples_v=16), want_vis=True)
     finally:
-        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, horizon_near=30, work_list=0)
+        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, horizon_near=30, work_list=-1)
     ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(samples_u=16, samples_v=16), want_vis=True)
     assert np.array_equal(gvis, ovis)
     assert rel_l2(got, ref).max() <= REL_L2_TOL
@@ -120,15 +120,16 @@ def test_work_list_order_independent(torus, torus_scenes, prt):
     pos, nrm, _ = torus
     gs, _ = torus_scenes
     gp = prt.BakeParams.make(order=3, samples_u=32, samples_v=32)
-    off, voff = prt.bake_transfer(gs, pos, nrm, gp, want_vis=True)
-    assert gs.ctx.last_bake_stats().launches == 2
-    gs.ctx.set_tuning(work_list=1)
     try:
+        gs.ctx.set_tuning(work_list=0)
+        off, voff = prt.bake_transfer(gs, pos, nrm, gp, want_vis=True)
+        assert gs.ctx.last_bake_stats().launches == 2
+        gs.ctx.set_tuning(work_list=1)
         on, von = prt.bake_transfer(gs, pos, nrm, gp, want_vis=True)
         assert gs.ctx.last_bake_stats().launches == 3
         on_novis = prt.bake_transfer(gs, pos, nrm, gp)[0]
     finally:
-        gs.ctx.set_tuning(work_list=0)
+        gs.ctx.set_tuning(work_list=-1)         # auto: on for small vertex counts (a shard of a multi-GPU bake)
     assert np.array_equal(von, voff)
     assert np.array_equal(on.view(np.uint32), off.view(np.uint32))
     assert np.array_equal(on.view(np.uint32), on_novis.view(np.uint32))

@@ -26,6 +26,10 @@ ap.add_argument("--mode", type=int, default=1)
 ap.add_argument("--bounces", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--mesh", default="torus")
+ap.add_argument("--world", type=int, default=1, help="time the shard rank --rank of a --world-way split (bench.py's interleaved chunks)")
+ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--chunk", type=int, default=2048)
+ap.add_argument("--flush", action="store_true", help="flush L2 between repetitions, as bench.py does")
 ap.add_argument("knobs", nargs="*")
 a = ap.parse_args()
 
@@ -34,16 +38,20 @@ if a.mesh == "torus":
 else:
     pos, nrm, tri = meshes.icosphere(int(a.mesh.replace("ico", "")))
 order = meshes.morton_order(pos)
+if a.world > 1:
+    n_chunks = (len(order) + a.chunk - 1) // a.chunk
+    order = np.concatenate([order[c * a.chunk:(c + 1) * a.chunk] for c in range(a.rank, n_chunks, a.world)])
 ctx = prt_b200.Context(0)
 scene = prt_b200.RTScene(pos, tri, ctx)
 dev = torch.device("cuda", 0)
 d_pos = torch.from_numpy(np.ascontiguousarray(pos[order])).to(dev)
 d_nrm = torch.from_numpy(np.ascontiguousarray(nrm[order])).to(dev)
-n = len(pos)
+n = len(order)
 params = prt_b200.BakeParams.make(order=a.order, samples_u=a.su, samples_v=a.sv, mode=a.mode, bounces=a.bounces,
                                   albedo=(0.5, 0.5, 0.5) if a.bounces else (1, 1, 1))
 d_out = torch.zeros((n, a.order ** 2), dtype=torch.float32, device=dev)
 L = ctx.L
+flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if a.flush else None
 stream = torch.cuda.current_stream()
 names = [k.split("=")[0] for k in a.knobs]
 values = [[int(x) for x in k.split("=")[1].split(",")] for k in a.knobs]
@@ -53,6 +61,8 @@ for combo in itertools.product(*values) if values else [()]:
     ctx.set_tuning(**kw)
     ms = []
     for _ in range(a.reps):
+        if a.flush:
+            flush_buf.zero_()
         rc = L.prt_bake_transfer_device(ctx.h, scene.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, n, 0,
                                         C.byref(params), C.c_void_p(d_out.data_ptr()), None, C.c_void_p(stream.cuda_stream))
         assert rc == 0, L.prt_last_error()
