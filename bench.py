@@ -121,10 +121,10 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, dev):
+    def __init__(self, dev, period_ms=100):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40", "-i", str(dev)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(period_ms), "-i", str(dev)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -240,7 +240,9 @@ def run_ours(a):
     barrier()
 
     # --- device-resident timing: K steps, CUDA events per step, L2 flushed between steps ----------------------
-    clocks = ClockSampler(local) if rank == 0 else None
+    # every NVML query costs the running kernel ~0.1 ms (measured: 20 ms sampling made a 50 ms step 0.6 % slower), so the period is
+    # 100 ms where the timed regions are long enough for that and 30 ms for the short steps of 4 and 8 GPUs
+    clocks = ClockSampler(local, 100 if world <= 2 else 30) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -293,7 +295,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = rays_per_step * a.steps / float(e2e_s.item())
-    # the clock sampler (40 ms period) ran through both timed regions: at N = 8 the device-timed one alone lasts 35 ms
+    # the clock sampler ran through both timed regions: at N = 8 the device-timed one alone lasts 35 ms
     clk = clocks.stop() if clocks else None
     h2d = world * n_mine * 24
     d2h = (world * n_mine * n2 * 4) + (world - 1) * n_mine * n2 * 4 if world > 1 else n_mine * n2 * 4
