@@ -48,7 +48,14 @@ int prt_abi_version(void);
 int prt_ctx_create(int device_id, prt_ctx **out);
 void prt_ctx_destroy(prt_ctx *);
 int prt_ctx_device(const prt_ctx *);
-/* name/value tuning knobs for experiments (block size, occupancy, refill threshold); unknown names fail */
+/* name/value tuning knobs for experiments; unknown names and out-of-range values fail.  None of them changes a result
+ * (tests/test_gpu_parity.py), only how the work is organised:
+ *   horizon 0/1 (1)            per-origin horizon pass before the shadowed / interreflected bake
+ *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
+ *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
+ *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first; -1 = only for small vertex counts
+ *   entry_list, pair_queue, refill_thresh, block, ctas_per_sm   kernel selection / occupancy of the older kernel variants
+ *   count_work 0/1 (0)         instrumented launch filling the work counters of prt_bake_stats */
 int prt_ctx_set_tuning(prt_ctx *, const char *name, int value);
 
 /* RTScene::RTScene(Mesh&) / RTScene(Model&) (raytracing.cpp:58-94, light_probe.cpp:44-87): copies

@@ -50,9 +50,6 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif
-#ifndef PRT_WAVE_OCCL_PROC
-#define PRT_WAVE_OCCL_PROC 1        // occlusion bitset indexed by processing index (1) or by reference sample index (0)
-#endif
 constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP;
 static_assert(kNodeCap * 64 >= kMaxS, "the node stack doubles as the visibility permutation buffer");
 
@@ -122,7 +119,6 @@ __device__ __noinline__ bool fallback_leaf(const Tri48 *tris, const f3 org, cons
     return false;
 }
 
-#if PRT_WAVE_OCCL_PROC
 // The visibility words of the C ABI are in reference order, the occlusion bitset in processing order: permute through `perm`
 // (the node stack, empty by then).  Out of line: only callers that ask for visibility words pay for it, and its registers
 // stay out of the traversal loop's allocation.
@@ -137,7 +133,6 @@ __device__ __noinline__ void write_vis_permuted(const float4 *samples, const uin
     __syncwarp();
     for (int w = lane; w < words; w += 32) row[w] = perm[w];
 }
-#endif
 
 // COUNT: carry the work counters (an instrumented, untimed launch of bench.py); the timed variant keeps those registers free
 template <int ORDER, bool TRACE, bool COUNT>
@@ -255,7 +250,6 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                     ln -= cnt;
                     if (lane < cnt) {
                         const uint2 it = W.lq[ln + lane];
-#if PRT_WAVE_OCCL_PROC
                         const uint32_t oi = it.x & 0xFFFFu;
                         uint32_t bits = it.x >> 16;
                         if (bits && !((occl[oi >> 5] >> (oi & 31u)) & 1u)) {
@@ -280,24 +274,6 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                                 ta = ld16(tp); tb = ld16(tp + 16); tc = ld16(tp + 32);
                             }
                         }
-#else
-                        const float4 smp = __ldg(&A.samples[it.x & 0xFFFFu]);
-                        const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-                        if (!((occl[sref >> 5] >> (sref & 31u)) & 1u)) {
-                            const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
-                            uint32_t bits = it.x >> 16;
-                            while (bits) {
-                                const uint32_t b = (uint32_t)__ffs(bits) - 1u;
-                                bits &= bits - 1u;
-                                float t; uint32_t prim;
-                                if (COUNT) tri_tests++;
-                                if (tri_hit(A.tris, it.y + b, org, d, 0.0f, INFINITY, false, t, prim)) {
-                                    atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
-                                    break;
-                                }
-                            }
-                        }
-#endif
                     }
                 } else {
                     // ---- node step ------------------------------------------------------------------------------------
@@ -310,19 +286,11 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                     uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
                     f3 d = mk3(0.f, 0.f, 1.f);
                     if (has) {
-#if PRT_WAVE_OCCL_PROC
                         has = !((occl[it.x >> 5] >> (it.x & 31u)) & 1u);
-#else
-                        const float4 smp = __ldg(&A.samples[it.x]);
-                        const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-                        has = !((occl[sref >> 5] >> (sref & 31u)) & 1u);
-#endif
                         if (has) {
                             const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
                             const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
-#if PRT_WAVE_OCCL_PROC
                             const float4 smp = __ldg(&A.samples[it.x]);       // issued together with the node fetch
-#endif
                             d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                             const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                             imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
@@ -362,12 +330,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                             else {
                                 // stack full: ordinary traversal of this subtree (rare)
                                 if (fallback_subtree(A.nodes, A.tris, org, d, child, node_visits, tri_tests)) {
-#if PRT_WAVE_OCCL_PROC
-                                    const uint32_t sref = it.x;
-#else
-                                    const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
-#endif
-                                    atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
+                                    atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
                                     inner8 = 0u; leaf8 = 0u;
                                 }
                             }
@@ -387,12 +350,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
                         if (p) {
                             if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                             else if (fallback_leaf(A.tris, org, d, tri0, bits, tri_tests)) {
-#if PRT_WAVE_OCCL_PROC
-                                const uint32_t sref = it.x;
-#else
-                                const uint32_t sref = __float_as_uint(__ldg(&A.samples[it.x].w)) & 0xFFFFFFu;
-#endif
-                                atomicOr(&occl[sref >> 5], 1u << (sref & 31u));
+                                atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
                                 leaf8 = 0u;
                             }
                         }
@@ -409,14 +367,8 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
 #pragma unroll
         for (int k = 0; k < N2; k++) acc[k] = 0.f;
         for (int i = lane; i < S; i += 32) {
-#if PRT_WAVE_OCCL_PROC
             if (TRACE && ((occl[i >> 5] >> lane) & 1u)) continue;           // one broadcast word per 32 samples
             const float4 smp = __ldg(&A.samples[i]);
-#else
-            const float4 smp = __ldg(&A.samples[i]);
-            const uint32_t sref = __float_as_uint(smp.w) & 0xFFFFFFu;
-            if ((occl[sref >> 5] >> (sref & 31u)) & 1u) continue;
-#endif
             const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
             float y[N2];
             sh_eval<ORDER>(d.z, d.x, d.y, sgn, y);
@@ -431,10 +383,8 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         }
         if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;       // raytracing.cpp:350
         if (A.vis) {
-#if PRT_WAVE_OCCL_PROC
             if (TRACE) write_vis_permuted(A.samples, occl, reinterpret_cast<uint32_t *>(W.nq), A.vis + (size_t)v * words, S, words, lane);
             else
-#endif
             for (int w = lane; w < words; w += 32) {
                 const int rem = S - 32 * w;
                 const uint32_t valid = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
