@@ -1,14 +1,11 @@
 // kernels.h -- launch interface between the C-ABI layer (abi.cu) and the kernel translation units.
 #pragma once
 #include "bvh8.h"
+#include "horizon_math.cuh"     // kHzBins
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace prt {
-
-// azimuth bins of the per-origin horizon map (entry_list.cuh): one bin per lane of the building warp.  The host bins the
-// sample directions with the same constant (abi.cu, ensure_samples).
-constexpr int kHzBins = 32;
 
 struct BakeArgs {
     const Node8 *nodes;

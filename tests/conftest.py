@@ -27,7 +27,8 @@ def hostcheck():
     d = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(d, "libhostcheck.so")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(ROOT, "prt_b200", "csrc", "bvh_build.cpp"),
-            os.path.join(ROOT, "prt_b200", "csrc", "traverse.cuh"), os.path.join(ROOT, "prt_b200", "csrc", "prt_math.cuh")]
+            os.path.join(ROOT, "prt_b200", "csrc", "traverse.cuh"), os.path.join(ROOT, "prt_b200", "csrc", "prt_math.cuh"),
+            os.path.join(ROOT, "prt_b200", "csrc", "horizon_math.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared",
                                "-o", so, srcs[0], srcs[1], "-lpthread"])
@@ -38,6 +39,11 @@ def hostcheck():
     L.hc_info.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_any_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.hc_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hc_frame.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_hz_pang.restype = C.c_float
+    L.hc_hz_pang.argtypes = [C.c_float, C.c_float]
+    L.hc_hz_triangle.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.hc_hz_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 

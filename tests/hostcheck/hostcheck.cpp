@@ -4,6 +4,7 @@
 // (compared with the oracle's brute force) and that any-hit / closest-hit answers equal the oracle's.
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/traverse.cuh"
+#include "../../prt_b200/csrc/horizon_math.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -303,4 +304,35 @@ extern "C" void hc_grid_stats(void *h, const float *org, const float *nrm, const
         uni += 32.0 * (__builtin_popcountll(u[0]) + __builtin_popcountll(u[1]));
     }
     out[0] = (double)cands.size(); out[1] = own / nrays; out[2] = uni / nrays; out[3] = (double)missed; out[4] = n_all;
+}
+
+// ---- per-item bounds of the horizon map (prt_b200/csrc/horizon_math.cuh compiled as plain C++) ----------------------------------
+// out[0] = first bin, out[1] = last bin (unwrapped), value = bound of sin(elevation) incl. margin (<= 0: the item is empty)
+extern "C" void hc_frame(const float *n, float *out9) {
+    const Frame f = make_frame(mk3(n[0], n[1], n[2]));
+    out9[0] = f.right.x; out9[1] = f.right.y; out9[2] = f.right.z; out9[3] = f.up.x; out9[4] = f.up.y; out9[5] = f.up.z;
+    out9[6] = f.n.x; out9[7] = f.n.y; out9[8] = f.n.z;
+}
+extern "C" float hc_hz_pang(float x, float y) { return hz_pang(x, y); }
+// triangle given in the LOCAL frame of the origin (z = height above the tangent plane)
+extern "C" void hc_hz_triangle(const float *q, uint32_t n, int *bins, float *val) {
+    for (uint32_t i = 0; i < n; i++) {
+        const float *t = q + 9 * (size_t)i;
+        const HzItem it = hz_triangle(mk3(t[0], t[1], t[2]), mk3(t[3], t[4], t[5]), mk3(t[6], t[7], t[8]));
+        bins[2 * i] = it.b0; bins[2 * i + 1] = it.b1; val[i] = it.v;
+    }
+}
+// boxes in WORLD space relative to the origin: centre c, half extents e; n = vertex normal (unit).  which: 0 cheap (cone clamped
+// by the slab bound), 1 exact box bound, 2 cone alone (only defined for d2 > 1.05 r2; otherwise the unbounded item)
+extern "C" void hc_hz_box(const float *c, const float *e, const float *nrm, uint32_t n, int which, int *bins, float *val) {
+    for (uint32_t i = 0; i < n; i++) {
+        const f3 cc = mk3(c[3 * i], c[3 * i + 1], c[3 * i + 2]), ee = mk3(e[3 * i], e[3 * i + 1], e[3 * i + 2]);
+        const Frame fr = make_frame(mk3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+        const float r2 = ee.x * ee.x + ee.y * ee.y + ee.z * ee.z, d2 = cc.x * cc.x + cc.y * cc.y + cc.z * cc.z;
+        HzItem it;
+        if (which == 0) it = hz_cheap_box(cc, ee, r2, d2, fr);
+        else if (which == 1) it = hz_box(cc, ee, fr);
+        else it = d2 > 1.05f * r2 ? hz_sphere(cc, r2, d2, fr) : hz_item(0.f, 0.f, true, 1.0f);
+        bins[2 * i] = it.b0; bins[2 * i + 1] = it.b1; val[i] = it.v;
+    }
 }

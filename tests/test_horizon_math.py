@@ -1,0 +1,165 @@
+"""CPU property tests of the horizon map's per-item bounds (prt_b200/csrc/horizon_math.cuh compiled as plain C++ by
+tests/hostcheck): every bound must be CONSERVATIVE -- for any point p of the triangle / box that lies above the tangent plane,
+sin(elevation) = p.z / |p| does not exceed the item's value and p's azimuth bin lies inside the item's bin range.  A ray the
+horizon pass frees is never traced, so a bound that is too low would silently turn occluded rays into visible ones; the GPU
+parity tests catch that end to end, these tests pin the formulas themselves without a GPU.
+
+The host build uses exact division / square roots where the device uses __fdividef / rsqrtf (2 ulp); the items carry margins
+(2e-4 in sin-elevation, 0.02 in pseudo-angle) that are orders of magnitude above that difference."""
+import numpy as np
+import pytest
+
+BINS = 32
+
+
+def pang(x, y):
+    """diamond pseudo-angle in [0,4) -- the formula of hz_pang / the host sample table (abi.cu)"""
+    p = y / (np.abs(x) + np.abs(y))
+    return np.where(x < 0, 2.0 - p, np.where(y < 0, 4.0 + p, p))
+
+
+def check_points(pts, b0, b1, v, what):
+    """pts: [k,3] local-frame points of one primitive; asserts the conservativeness of the item (b0, b1, v)."""
+    z = pts[:, 2]
+    r = np.linalg.norm(pts, axis=1)
+    up = (z > 0) & (r > 0)
+    if not up.any():
+        return
+    sin_el = z[up] / r[up]
+    assert v > 0, f"{what}: geometry above the tangent plane but the item is empty"
+    assert sin_el.max() <= v + 1e-6, f"{what}: sin(elevation) {sin_el.max():.6f} above the bound {v:.6f}"
+    if b1 - b0 >= BINS - 1:
+        return
+    q = pts[up]
+    planar = np.abs(q[:, 0]) + np.abs(q[:, 1])
+    ok = planar > 1e-3 * r[up]           # azimuth is undefined on the vertical axis
+    if not ok.any():
+        return
+    bins = np.floor(pang(q[ok, 0].astype(np.float64), q[ok, 1].astype(np.float64)) * (BINS / 4)).astype(int) % BINS
+    inside = ((bins - b0) % BINS) <= (b1 - b0)
+    assert inside.all(), f"{what}: azimuth bins {sorted(set(bins[~inside]))} outside [{b0},{b1}]"
+
+
+def test_pseudo_angle_matches_python(hostcheck):
+    rng = np.random.RandomState(0)
+    xy = rng.normal(size=(2000, 2)).astype(np.float32)
+    got = np.array([hostcheck.hc_hz_pang(float(x), float(y)) for x, y in xy])
+    ref = pang(xy[:, 0].astype(np.float64), xy[:, 1].astype(np.float64))
+    assert np.abs(got - ref).max() < 1e-5
+    assert (got >= 0).all() and (got <= 4.0).all()
+    # monotone in the true angle
+    a = np.linspace(-np.pi, np.pi, 4001)[1:-1]
+    p = pang(np.cos(a), np.sin(a))
+    p = np.where(a < 0, p - 4.0, p)
+    assert (np.diff(p) > 0).all()
+
+
+def _tri_points(t, n=24):
+    """barycentric grid over one triangle [3,3] (edges and interior)"""
+    u, w = np.meshgrid(np.linspace(0, 1, n), np.linspace(0, 1, n))
+    m = u + w <= 1.0 + 1e-12
+    u, w = u[m], w[m]
+    return (1 - u - w)[:, None] * t[0] + u[:, None] * t[1] + w[:, None] * t[2]
+
+
+@pytest.mark.parametrize("kind", ["generic", "near_axis", "crossing_plane", "sliver", "far_small"])
+def test_triangle_bound_is_conservative(hostcheck, kind):
+    rng = np.random.RandomState({"generic": 1, "near_axis": 2, "crossing_plane": 3, "sliver": 4, "far_small": 5}[kind])
+    n = 400
+    tri = rng.normal(size=(n, 3, 3))
+    if kind == "near_axis":            # triangles around / close to the vertical through the origin
+        tri[:, :, :2] *= 0.2
+        tri[:, :, 2] = np.abs(tri[:, :, 2]) + 0.05
+    elif kind == "crossing_plane":     # one vertex below, two above the tangent plane
+        tri[:, 0, 2] = -np.abs(tri[:, 0, 2])
+        tri[:, 1:, 2] = np.abs(tri[:, 1:, 2])
+    elif kind == "sliver":             # long thin triangles at grazing elevation
+        c = rng.normal(size=(n, 1, 3)) * 3
+        d = rng.normal(size=(n, 1, 3))
+        tri = c + d * np.array([0.0, 1.0, 1.0])[None, :, None] * np.array([[0], [5.0], [5.001]])[None] + rng.normal(size=(n, 3, 3)) * 1e-3
+        tri[:, :, 2] = np.abs(tri[:, :, 2]) * 0.02
+    elif kind == "far_small":
+        tri = rng.normal(size=(n, 1, 3)) * 20 + rng.normal(size=(n, 3, 3)) * 0.05
+    tri = tri.astype(np.float32)
+    bins = np.zeros((n, 2), np.int32)
+    val = np.zeros(n, np.float32)
+    q = np.ascontiguousarray(tri.reshape(n, 9))
+    hostcheck.hc_hz_triangle(q.ctypes.data, n, bins.ctypes.data, val.ctypes.data)
+    for i in range(n):
+        check_points(_tri_points(tri[i].astype(np.float64)), int(bins[i, 0]), int(bins[i, 1]), float(val[i]), f"{kind} triangle {i}")
+    if kind == "far_small":            # and the bound is tight where it can be: within 2e-3 of the true maximum
+        for i in range(0, n, 7):
+            p = _tri_points(tri[i].astype(np.float64), 64)
+            true = max(0.0, (p[:, 2] / np.linalg.norm(p, axis=1)).max())
+            if true > 0:
+                assert val[i] - true < 2e-3
+
+
+def _box_points(c, e, rng, k=400):
+    s = rng.uniform(-1, 1, size=(k, 3))
+    # push a third of the samples onto faces / edges / corners, where the extrema are
+    s[: k // 3] = np.sign(s[: k // 3])
+    s[k // 3: 2 * k // 3, rng.randint(0, 3)] = np.sign(s[k // 3: 2 * k // 3, 0])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float64)
+    s = np.concatenate([s, corners])
+    return c + s * e
+
+
+@pytest.mark.parametrize("which,name", [(0, "cheap (cone clamped by the slab bound)"), (1, "exact box"), (2, "cone")])
+@pytest.mark.parametrize("kind", ["far", "near", "flat_on_surface", "overhead"])
+def test_box_bounds_are_conservative(hostcheck, which, name, kind):
+    rng = np.random.RandomState(10 * which + {"far": 1, "near": 2, "flat_on_surface": 3, "overhead": 4}[kind])
+    n = 500
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    c = rng.normal(size=(n, 3))
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    if kind == "far":
+        c *= rng.uniform(3, 30, size=(n, 1)); e = rng.uniform(0.01, 1.0, size=(n, 3))
+    elif kind == "near":
+        c *= rng.uniform(0.3, 2.0, size=(n, 1)); e = rng.uniform(0.05, 1.0, size=(n, 3))
+    elif kind == "flat_on_surface":    # thin slabs hugging the tangent plane: the case the slab bound is made for
+        nrm[:] = 0.0
+        ax = rng.randint(0, 3, n)
+        nrm[np.arange(n), ax] = rng.choice([-1.0, 1.0], n)
+        c *= rng.uniform(1.0, 8.0, size=(n, 1))
+        c[np.arange(n), ax] = rng.uniform(-0.02, 0.05, n) * nrm[np.arange(n), ax]
+        e = rng.uniform(0.2, 1.5, size=(n, 3))
+        e[np.arange(n), ax] = rng.uniform(0.005, 0.05, n)
+    else:                              # boxes over the vertex
+        c = nrm * rng.uniform(0.5, 5.0, size=(n, 1)) + rng.normal(size=(n, 3)) * 0.1
+        e = rng.uniform(0.05, 1.0, size=(n, 3))
+    c32, e32, n32 = (np.ascontiguousarray(a, np.float32) for a in (c, e, nrm))
+    bins = np.zeros((n, 2), np.int32)
+    val = np.zeros(n, np.float32)
+    hostcheck.hc_hz_box(c32.ctypes.data, e32.ctypes.data, n32.ctypes.data, n, which, bins.ctypes.data, val.ctypes.data)
+    fr = np.zeros(9, np.float32)
+    tighter = 0
+    for i in range(n):
+        hostcheck.hc_frame(n32[i].ctypes.data, fr.ctypes.data)
+        R = fr.reshape(3, 3).astype(np.float64)                      # rows: right, up, n
+        pts = _box_points(c32[i].astype(np.float64), e32[i].astype(np.float64), rng) @ R.T
+        check_points(pts, int(bins[i, 0]), int(bins[i, 1]), float(val[i]), f"{name}, {kind} box {i}")
+        tighter += 1
+    assert tighter == n
+
+
+def test_slab_clamp_tightens_flat_boxes(hostcheck):
+    """The reason the cheap bound exists: for a thin box lying in the tangent plane the cone around the bounding sphere lifts
+    the horizon by the box's angular radius, z_max / d_min does not."""
+    n = 200
+    rng = np.random.RandomState(7)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (n, 1))
+    c = np.zeros((n, 3), np.float32)
+    c[:, 0] = rng.uniform(3, 6, n)
+    e = np.zeros((n, 3), np.float32)
+    e[:, 0] = e[:, 1] = rng.uniform(0.5, 1.0, n)
+    e[:, 2] = 0.01
+    out = {}
+    for which in (0, 2):
+        bins = np.zeros((n, 2), np.int32)
+        val = np.zeros(n, np.float32)
+        hostcheck.hc_hz_box(c.ctypes.data, e.ctypes.data, nrm.ctypes.data, n, which, bins.ctypes.data, val.ctypes.data)
+        out[which] = val.copy()
+    assert (out[0] <= out[2] + 1e-7).all()
+    assert np.median(out[2] / out[0]) > 10          # cone: ~0.2, slab: ~0.005
