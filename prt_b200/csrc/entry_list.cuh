@@ -119,9 +119,13 @@ __device__ __forceinline__ void entry_list_leaf_mask(const EntryList &W, const i
 // approximate reciprocal for box tests only (never used by the pinned triangle test)
 __device__ __forceinline__ float rcp_box(float d) {
     if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+#if defined(__CUDA_ARCH__)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
     return r;
+#else
+    return 1.0f / d;            // host build of the CPU test harness (tests/hostcheck)
+#endif
 }
 
 // exclusive prefix sum over the warp of two 16-bit counters packed in one word; total returned through `total`

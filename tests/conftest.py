@@ -26,12 +26,14 @@ def hostcheck():
     import ctypes as C
     d = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(d, "libhostcheck.so")
-    srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(ROOT, "prt_b200", "csrc", "bvh_build.cpp"),
-            os.path.join(ROOT, "prt_b200", "csrc", "traverse.cuh"), os.path.join(ROOT, "prt_b200", "csrc", "prt_math.cuh"),
-            os.path.join(ROOT, "prt_b200", "csrc", "horizon_math.cuh")]
+    csrc = os.path.join(ROOT, "prt_b200", "csrc")
+    srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck_warp.cpp"), os.path.join(csrc, "bvh_build.cpp"),
+            os.path.join(d, "warp_emu.h")] + [os.path.join(csrc, f) for f in ("traverse.cuh", "prt_math.cuh", "horizon_math.cuh",
+                                                                              "entry_list.cuh", "bvh8.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared",
-                               "-o", so, srcs[0], srcs[1], "-lpthread"])
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # float4 & co. for entry_list.cuh
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-I", cuda_inc,
+                               "-o", so, srcs[0], srcs[1], srcs[2], "-lpthread"])
     L = C.CDLL(so)
     L.hc_build.restype = C.c_void_p
     L.hc_build.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -44,6 +46,7 @@ def hostcheck():
     L.hc_hz_pang.argtypes = [C.c_float, C.c_float]
     L.hc_hz_triangle.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.hc_hz_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.hc_horizon_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 

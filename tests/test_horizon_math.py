@@ -163,3 +163,90 @@ def test_slab_clamp_tightens_flat_boxes(hostcheck):
         out[which] = val.copy()
     assert (out[0] <= out[2] + 1e-7).all()
     assert np.median(out[2] / out[0]) > 10          # cone: ~0.2, slab: ~0.005
+
+
+# ---- the warp-cooperative builder itself, run on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) --------------------
+def _maps(hostcheck, h, pos, nrm, budget=64, near=30, eps=1e-4):
+    n = len(pos)
+    hz = np.zeros((n, BINS), np.float32)
+    ncand = np.zeros(n, np.int32)
+    p32, n32 = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32)
+    hostcheck.hc_horizon_maps(h, p32.ctypes.data, n32.ctypes.data, n, eps, budget, near, hz.ctypes.data, ncand.ctypes.data)
+    return hz, ncand
+
+
+def _free_mask(dirs, hz):
+    """classification of horizon_kernel (horizon.cu): a sample is free iff its local z exceeds the map in its azimuth bin; the
+    bin is the one abi.cu's ensure_samples stores in the sample table"""
+    den = np.abs(dirs[:, 0].astype(np.float64)) + np.abs(dirs[:, 1].astype(np.float64))
+    pa = np.where(den > 0, pang(dirs[:, 0].astype(np.float64), dirs[:, 1].astype(np.float64)), 0.0)
+    bins = np.clip(np.floor(pa * (BINS / 4)).astype(int), 0, BINS - 1)
+    return dirs[None, :, 2] > hz[:, bins]
+
+
+@pytest.mark.parametrize("knobs", [dict(), dict(budget=0), dict(near=60, budget=4), dict(near=12, budget=256)])
+def test_horizon_map_never_frees_an_occluded_ray(hostcheck, oracle, knobs):
+    """build_entry_list + build_horizon (the product's device code, unmodified, on the warp emulator) against the oracle's
+    per-ray visibility on a self-occluding mesh: every freed sample must be visible -- and the map must be worth having."""
+    from prt_b200 import meshes
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    try:
+        sel = np.arange(3, len(pos), 41)[:150]
+        hz, ncand = _maps(hostcheck, h, pos[sel], nrm[sel], **knobs)
+    finally:
+        hostcheck.hc_free(h)
+    assert (ncand > 0).all() and (ncand <= 96).all()
+    assert np.isfinite(hz).all() and (hz >= 0).all() and (hz <= 2.0).all()
+    op = oracle.make_params(order=3, samples_u=32, samples_v=32)
+    _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
+    visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
+    _, dirs = oracle.sample_table(op)
+    free = _free_mask(dirs, hz)
+    assert not (free & ~visible).any(), "the horizon pass would free an occluded ray"
+    occluded = 1.0 - visible.mean()
+    traversed = 1.0 - free.mean()
+    assert 0.05 < occluded < 0.6
+    # tightness (regression guard, not a correctness bar): the default builder leaves fewer than 2.2x the occluded share to trace
+    if not knobs:
+        assert traversed < 2.2 * occluded + 0.05, (traversed, occluded)
+    assert traversed >= occluded - 1e-9
+
+
+def test_horizon_map_adversarial_geometry(hostcheck, oracle):
+    """thin sliver at grazing elevation, an overhang, a wall crossing the tangent plane and a far big occluder around one vertex"""
+    rng = np.random.RandomState(5)
+    base = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32) * 4
+    verts = [base]
+    tris = [np.array([[0, 1, 2], [0, 2, 3]], np.uint32)]
+
+    def add(tv):
+        off = sum(len(v) for v in verts)
+        verts.append(np.asarray(tv, np.float32))
+        tris.append(np.array([[0, 1, 2]], np.uint32) + off)
+    add([[1.0, -2.0, 0.02], [1.0, 2.0, 0.02], [1.0005, 0.0, 0.06]])            # sliver just above the plane
+    add([[-0.5, -0.5, 0.8], [0.5, -0.5, 0.8], [0.0, 0.6, 0.8]])                # overhang above the vertex
+    add([[0.3, 0.4, -0.5], [0.9, 0.4, 0.7], [0.3, 1.0, 0.7]])                  # crosses the tangent plane
+    add([[-30.0, -40.0, 1.0], [-30.0, 40.0, 1.0], [-30.0, 0.0, 25.0]])         # far, large
+    for _ in range(40):                                                        # clutter so that the BVH has inner nodes
+        c = rng.uniform(-3, 3, 3); c[2] = rng.uniform(0.05, 2.0)
+        add(c + rng.normal(size=(3, 3)) * 0.15)
+    pos = np.concatenate(verts).astype(np.float32)
+    tri = np.concatenate(tris).astype(np.uint32)
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    p = np.array([[0.0, 0.0, 0.0], [0.5, 0.2, 0.0], [-1.0, 1.0, 0.0]], np.float32)
+    n = np.array([[0, 0, 1]] * 3, np.float32)
+    op = oracle.make_params(order=3, samples_u=32, samples_v=32)
+    _, dirs = oracle.sample_table(op)
+    _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), p, n, op, want_vis=True)
+    visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
+    try:
+        for knobs in (dict(), dict(budget=0), dict(near=90, budget=1)):
+            hz, _ = _maps(hostcheck, h, p, n, **knobs)
+            free = _free_mask(dirs, hz)
+            assert not (free & ~visible).any(), knobs
+    finally:
+        hostcheck.hc_free(h)
+    assert 0.02 < 1.0 - visible.mean() < 0.9
