@@ -209,6 +209,10 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
     return hz_triangle(q0, q1, q2);
 }
 
+// host-side work counters of the CPU study harness (tests/hostcheck, tools/horizon_study.py); nothing in a product build
+#ifndef PRT_HZ_STAT
+#define PRT_HZ_STAT(counter, n)
+#endif
 constexpr int kHzQueue = 64;
 constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
 // `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2)).
@@ -245,8 +249,10 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
             if (g < take) node = rq[rn - 1 - g];
             rn -= take;
             budget--;
+            PRT_HZ_STAT(iterations, 1);
             __syncwarp();
             if (node != 0xFFFFFFFFu) {
+                if (slot == 0) PRT_HZ_STAT(nodes_expanded, 1);
                 const char *np = reinterpret_cast<const char *>(nodes + node);
                 const u4 n0 = ld16(np), n1 = ld16(np + 16), n2 = ld16(np + 32), n3 = ld16(np + 48), n4 = ld16(np + 64);
                 const int h = slot >> 2, sh = 8 * (slot & 3);
@@ -276,6 +282,7 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         // ---- classify the lane's box ------------------------------------------------------------------------------------
         HzItem it = hz_item(0.f, 0.f, false, 0.f);
         bool merge = false, push = false, leaf = false, nearb = false;
+        if (valid) PRT_HZ_STAT(boxes_bounded, 1);
         if (valid && !(e.x < 1e30f)) { it = hz_item(0.f, 0.f, true, 1.0f); merge = true; }      // overflow candidate: unbounded
         else if (valid) {
             const float r2 = e.x * e.x + e.y * e.y + e.z * e.z, d2 = c.x * c.x + c.y * c.y + c.z * c.z;
@@ -306,12 +313,14 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         __syncwarp();
         while (tn >= 32) {
             tn -= 32;
+            PRT_HZ_STAT(triangle_rounds, 1);
             const HzItem ti = hz_tri_item(tris, tq[tn + lane], O, fr);
             my = hz_merge(my, ti, hz_useful(ti, hz), lane, hz);
         }
         __syncwarp();
     }
     if (tn > 0) {
+        PRT_HZ_STAT(triangle_rounds, 1);
         HzItem ti = hz_item(0.f, 0.f, false, 0.f);
         if (lane < tn) ti = hz_tri_item(tris, tq[lane], O, fr);
         my = hz_merge(my, ti, hz_useful(ti, hz), lane, hz);

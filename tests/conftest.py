@@ -20,8 +20,7 @@ def oracle():
     return pyoracle
 
 
-@pytest.fixture(scope="session")
-def hostcheck():
+def load_hostcheck():
     """Host build of the product's BVH8 builder + traversal header (test tooling, tests/hostcheck)."""
     import ctypes as C
     d = os.path.join(ROOT, "tests", "hostcheck")
@@ -46,8 +45,13 @@ def hostcheck():
     L.hc_hz_pang.argtypes = [C.c_float, C.c_float]
     L.hc_hz_triangle.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.hc_hz_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
-    L.hc_horizon_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hc_horizon_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
+
+
+@pytest.fixture(scope="session")
+def hostcheck():
+    return load_hostcheck()
 
 
 @pytest.fixture(scope="session")

@@ -7,6 +7,10 @@
 #define __forceinline__ inline
 #define __noinline__
 #include "warp_emu.h"
+#include <atomic>
+// work counters of the builder (entry_list.cuh calls PRT_HZ_STAT from the lanes that do the work)
+namespace { struct HzStats { std::atomic<uint64_t> iterations{0}, nodes_expanded{0}, boxes_bounded{0}, triangle_rounds{0}; } g_hz_stats; }
+#define PRT_HZ_STAT(counter, n) (g_hz_stats.counter.fetch_add((n), std::memory_order_relaxed))
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/entry_list.cuh"
 #include <thread>
@@ -25,12 +29,14 @@ struct HorizonSharedHost {          // HorizonShared of horizon.cu
 
 // h: HostBVH8* from hc_build.  pos / nrm: n x 3 floats.  near100: horizon_near (angular radius x 100, rad); budget: horizon_budget.
 // out_hz: n x kHzBins floats (the map), out_ncand: n (entry-list candidates).
+// stats (optional, 4 x uint64): refinement iterations, nodes expanded, boxes bounded, triangle rounds -- summed over the n vertices.
 extern "C" void hc_horizon_maps(void *h, const float *pos, const float *nrm, uint32_t n, float origin_eps, int budget, int near100,
-                                float *out_hz, int *out_ncand) {
+                                float *out_hz, int *out_ncand, uint64_t *stats) {
     HostBVH8 *b = (HostBVH8 *)h;
     warp_emu::State state;
     warp_emu::g_state = &state;
     HorizonSharedHost W;
+    g_hz_stats.iterations = 0; g_hz_stats.nodes_expanded = 0; g_hz_stats.boxes_bounded = 0; g_hz_stats.triangle_rounds = 0;
     const float sn = sinf(0.01f * (float)near100), near2 = 1.0f / (sn * sn);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; lane++) {
@@ -51,4 +57,9 @@ extern "C" void hc_horizon_maps(void *h, const float *pos, const float *nrm, uin
     }
     for (auto &t : lanes) t.join();
     warp_emu::g_state = nullptr;
+    if (stats) {
+        // iterations and triangle rounds are counted by all 32 lanes of the warp
+        stats[0] = g_hz_stats.iterations / 32; stats[1] = g_hz_stats.nodes_expanded; stats[2] = g_hz_stats.boxes_bounded;
+        stats[3] = g_hz_stats.triangle_rounds / 32;
+    }
 }

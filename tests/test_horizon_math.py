@@ -166,12 +166,13 @@ def test_slab_clamp_tightens_flat_boxes(hostcheck):
 
 
 # ---- the warp-cooperative builder itself, run on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) --------------------
-def _maps(hostcheck, h, pos, nrm, budget=64, near=30, eps=1e-4):
+def _maps(hostcheck, h, pos, nrm, budget=64, near=30, eps=1e-4, stats=None):
     n = len(pos)
     hz = np.zeros((n, BINS), np.float32)
     ncand = np.zeros(n, np.int32)
     p32, n32 = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32)
-    hostcheck.hc_horizon_maps(h, p32.ctypes.data, n32.ctypes.data, n, eps, budget, near, hz.ctypes.data, ncand.ctypes.data)
+    hostcheck.hc_horizon_maps(h, p32.ctypes.data, n32.ctypes.data, n, eps, budget, near, hz.ctypes.data, ncand.ctypes.data,
+                              stats.ctypes.data if stats is not None else None)
     return hz, ncand
 
 
@@ -243,7 +244,7 @@ def test_horizon_map_adversarial_geometry(hostcheck, oracle):
     _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), p, n, op, want_vis=True)
     visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
     try:
-        for knobs in (dict(), dict(budget=0), dict(near=90, budget=1)):
+        for knobs in (dict(), dict(budget=0), dict(near=90, budget=1), dict(near=10, budget=256)):
             hz, _ = _maps(hostcheck, h, p, n, **knobs)
             free = _free_mask(dirs, hz)
             assert not (free & ~visible).any(), knobs
