@@ -37,6 +37,8 @@ UNIT = "rays/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one bake_wave_kernel<3,true> launch on the bench workload, from the ncu --set full
 # capture summarised in profiles/r1_final_ncu_summary.txt (259.8 MB read + 46.5 MB written).
 NCU_TRAFFIC_BYTES = 305.0e6
+# the resource that actually binds that kernel (same capture): smsp__issue_active.avg.pct_of_peak_sustained_active
+NCU_ISSUE_ACTIVE_FRAC = 0.728
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -324,6 +326,8 @@ def run_ours(a):
                     "node_visits_per_ray": visits / rays_launch, "tri_tests_per_ray": tests / rays_launch,
                     "entry_list_box_tests_per_ray": cands / rays_launch, "rays_traversed_frac": traversed / rays_launch,
                     "horizon_pass_ms": hz_ms,
+                    "binding_resource": {"name": "instruction issue slots", "frac": NCU_ISSUE_ACTIVE_FRAC,
+                                         "source": "ncu smsp__issue_active of the same launch, profiles/r1_final_ncu_summary.txt"},
                     "algorithmic_bytes_per_ray": alg_bytes / rays_launch,
                     "hbm_floor_bytes_per_launch": n_mine * (24.0 + 4.0 * n2) + float(info.node_bytes + info.tri_bytes),
                     "note": "algorithmic bytes = node fetches x 80 B + triangle fetches x 48 B + entry-list boxes x 32 B (shared memory) + 60 B/vertex I/O + need bits; per-ray figures are averages over ALL rays (rays above the horizon map cost none); the BVH "
