@@ -213,6 +213,9 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
 #ifndef PRT_HZ_STAT
 #define PRT_HZ_STAT(counter, n)
 #endif
+#ifndef PRT_HZ_TRACE_FAR
+#define PRT_HZ_TRACE_FAR(c, e, item)
+#endif
 constexpr int kHzQueue = 64;
 constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
 // `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2)).
@@ -289,7 +292,7 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
             const HzItem cb = hz_cheap_box(c, e, r2, d2, fr);
             if (hz_useful(cb, hz)) {
                 if (!inner) leaf = true;
-                else if (!(d2 < near2 * r2)) { it = cb; merge = true; }
+                else if (!(d2 < near2 * r2)) { it = cb; merge = true; PRT_HZ_TRACE_FAR(c, e, cb); }
                 else { nearb = true; push = budget > 0; }
             }
         }

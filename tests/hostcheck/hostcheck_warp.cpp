@@ -11,6 +11,12 @@
 // work counters of the builder (entry_list.cuh calls PRT_HZ_STAT from the lanes that do the work)
 namespace { struct HzStats { std::atomic<uint64_t> iterations{0}, nodes_expanded{0}, boxes_bounded{0}, triangle_rounds{0}; } g_hz_stats; }
 #define PRT_HZ_STAT(counter, n) (g_hz_stats.counter.fetch_add((n), std::memory_order_relaxed))
+// far boxes whose cheap bound was merged into the map: (centre, half extents, value, first bin, last bin), for the bound studies
+#include <mutex>
+#include <vector>
+namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on = false; }
+#define PRT_HZ_TRACE_FAR(c, e, item) do { if (g_trace_on) { std::lock_guard<std::mutex> lk(g_trace_mu); \
+    const float rec[9] = {(c).x, (c).y, (c).z, (e).x, (e).y, (e).z, (item).v, (float)(item).b0, (float)(item).b1}; g_trace.insert(g_trace.end(), rec, rec + 9); } } while (0)
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/entry_list.cuh"
 #include <thread>
@@ -62,4 +68,15 @@ extern "C" void hc_horizon_maps(void *h, const float *pos, const float *nrm, uin
         stats[0] = g_hz_stats.iterations / 32; stats[1] = g_hz_stats.nodes_expanded; stats[2] = g_hz_stats.boxes_bounded;
         stats[3] = g_hz_stats.triangle_rounds / 32;
     }
+}
+
+// bound study: the far boxes merged while building the map of ONE vertex; returns the number of records (9 floats each) written
+extern "C" uint32_t hc_horizon_trace_far(void *h, const float *pos, const float *nrm, float origin_eps, int budget, int near100, float *out, uint32_t cap) {
+    g_trace.clear(); g_trace_on = true;
+    float hz[kHzBins]; int nc;
+    hc_horizon_maps(h, pos, nrm, 1, origin_eps, budget, near100, hz, &nc, nullptr);
+    g_trace_on = false;
+    const uint32_t n = (uint32_t)std::min<size_t>(g_trace.size() / 9, cap);
+    std::memcpy(out, g_trace.data(), (size_t)n * 9 * sizeof(float));
+    return n;
 }
