@@ -19,6 +19,7 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
     const float rec[9] = {(c).x, (c).y, (c).z, (e).x, (e).y, (e).z, (item).v, (float)(item).b0, (float)(item).b1}; g_trace.insert(g_trace.end(), rec, rec + 9); } } while (0)
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/entry_list.cuh"
+#include "../../prt_b200/csrc/bake_wave.cuh"
 #include <thread>
 #include <vector>
 
@@ -79,4 +80,52 @@ extern "C" uint32_t hc_horizon_trace_far(void *h, const float *pos, const float 
     const uint32_t n = (uint32_t)std::min<size_t>(g_trace.size() / 9, cap);
     std::memcpy(out, g_trace.data(), (size_t)n * 9 * sizeof(float));
     return n;
+}
+
+// ---- the traversal pass: bake_wave_vertex of prt_b200/csrc/bake_wave.cuh (what one persistent warp of bake_wave_kernel does for
+// one vertex), unmodified, on the warp emulator.  samples: S x 4 floats in PROCESSING order (local direction, w = reference sample
+// index | azimuth bin << 24 -- the table abi.cu uploads); need_bits: optional [n][words] flags of the horizon pass (processing
+// order); out: [n][order^2] rows; vis: optional [n][words] visibility words (reference order, pre-zeroed).
+namespace {
+struct WaveSharedHost { WaveShared W; uint32_t occl[kMaxS / 32]; };
+
+template <int ORDER>
+void run_wave(const BakeArgs &A) {
+    warp_emu::State state;
+    warp_emu::g_state = &state;
+    static WaveSharedHost sh;
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++) {
+        lanes.emplace_back([&, lane]() {
+            warp_emu::t_lane = lane;
+            unsigned long long cand = 0ull, scanned = 0ull;
+            uint32_t nv = 0u, nt = 0u;
+            const float sgn = A.cs_phase ? -1.0f : 1.0f;
+            for (uint32_t v = 0; v < A.n_verts; v++)
+                bake_wave_vertex<ORDER, true, false>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+        });
+    }
+    for (auto &t : lanes) t.join();
+    warp_emu::g_state = nullptr;
+}
+}
+
+extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_t n, const float *samples, int S, int order,
+                            const uint32_t *need_bits, float origin_eps, int cs_phase, float *out, uint32_t *vis) {
+    if (S < 1 || S > kMaxS || order < 1 || order > 5) return -1;
+    HostBVH8 *b = (HostBVH8 *)h;
+    BakeArgs A{};
+    A.nodes = b->nodes; A.tris = b->tris; A.pos = pos; A.nrm = nrm; A.stride = 12; A.n_verts = n;
+    A.samples = reinterpret_cast<const float4 *>(samples); A.S = S; A.inv_S = 1.0f / (float)S;
+    A.out = out; A.vis = vis; A.vis_words = (S + 31) / 32;
+    A.need_bits = const_cast<uint32_t *>(need_bits);
+    A.origin_eps = origin_eps; A.cs_phase = cs_phase;
+    switch (order) {
+    case 1: run_wave<1>(A); break;
+    case 2: run_wave<2>(A); break;
+    case 3: run_wave<3>(A); break;
+    case 4: run_wave<4>(A); break;
+    default: run_wave<5>(A); break;
+    }
+    return 0;
 }

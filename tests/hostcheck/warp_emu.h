@@ -48,4 +48,5 @@ inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <class T> inline T __ldg(const T *p) { return *p; }
+inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 namespace prt { using std::max; using std::min; }

@@ -1,0 +1,94 @@
+"""The headline traversal kernel's per-vertex code -- bake_wave_vertex (prt_b200/csrc/bake_wave.cuh: entry list, lockstep candidate
+scan, node / leaf wavefront steps, projection, visibility permutation), exactly what one persistent warp of bake_wave_kernel runs --
+executed UNMODIFIED on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) and compared with the oracle: visibility bits
+bit for bit, SH rows within 1e-4 relative L2 (north_star).  Also the two-pass pipeline: horizon maps from the emulated horizon
+builder -> need bits -> traversal of the flagged samples only, which must give the same bits."""
+import numpy as np
+import pytest
+
+from prt_b200 import meshes
+from test_horizon_math import BINS, _maps, pang
+
+REL_L2_TOL = 1e-4
+
+
+def processing_table(oracle, params):
+    """The sample table abi.cu (ensure_samples) uploads: strata in Morton order over (i, j); w = reference index | bin << 24."""
+    _, dirs = oracle.sample_table(params)
+    ru, rv = params.samples_u, params.samples_v
+
+    def spread(x):
+        x &= 0xFFFF; x = (x | (x << 8)) & 0x00FF00FF; x = (x | (x << 4)) & 0x0F0F0F0F
+        x = (x | (x << 2)) & 0x33333333; x = (x | (x << 1)) & 0x55555555
+        return x
+    keys = sorted((spread(j) | (spread(i) << 1), i * rv + j) for i in range(ru) for j in range(rv))
+    sref = np.array([s for _, s in keys], np.uint32)
+    d = dirs[sref]
+    den = np.abs(d[:, 0].astype(np.float64)) + np.abs(d[:, 1].astype(np.float64))
+    pa = np.where(den > 0, pang(d[:, 0].astype(np.float64), d[:, 1].astype(np.float64)), 0.0)
+    bins = np.clip(np.floor(pa * (BINS / 4)).astype(np.int64), 0, BINS - 1).astype(np.uint32)
+    tab = np.zeros((len(sref), 4), np.float32)
+    tab[:, :3] = d
+    tab[:, 3] = (sref | (bins << 24)).view(np.float32)
+    return tab, bins
+
+
+def run_wave(hostcheck, h, pos, nrm, tab, order, need=None, want_vis=True, cs_phase=0):
+    n, S = len(pos), len(tab)
+    words = (S + 31) // 32
+    out = np.zeros((n, order * order), np.float32)
+    vis = np.zeros((n, words), np.uint32) if want_vis else None
+    p32, n32 = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32)
+    rc = hostcheck.hc_bake_wave(h, p32.ctypes.data, n32.ctypes.data, n, tab.ctypes.data, S, order,
+                                need.ctypes.data if need is not None else None, 1e-4, cs_phase, out.ctypes.data,
+                                vis.ctypes.data if vis is not None else None)
+    assert rc == 0
+    return out, vis
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-20)
+
+
+@pytest.fixture(scope="module")
+def scene(hostcheck, oracle):
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    yield pos, nrm, tri, h, oracle.Scene(pos, tri)
+    hostcheck.hc_free(h)
+
+
+@pytest.mark.parametrize("order,su,sv", [(3, 16, 16), (5, 8, 32), (2, 5, 7), (3, 32, 32)])
+def test_wave_vertex_matches_oracle(hostcheck, oracle, scene, order, su, sv):
+    pos, nrm, tri, h, osc = scene
+    sel = np.arange(5, len(pos), 53)[:40 if su * sv <= 256 else 16]
+    op = oracle.make_params(order=order, samples_u=su, samples_v=sv)
+    tab, _ = processing_table(oracle, op)
+    got, gvis = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, order)
+    ref, ovis, _ = oracle.bake_transfer(osc, pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(gvis, ovis), "per-ray visibility bits must agree exactly"
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+    frac = np.unpackbits(ovis.view(np.uint8)).sum() / (len(sel) * su * sv)
+    assert 0.3 < frac < 0.99
+    # rows do not depend on whether the caller asks for the visibility words
+    got2, _ = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, order, want_vis=False)
+    assert np.array_equal(got.view(np.uint32), got2.view(np.uint32))
+
+
+def test_two_pass_pipeline_on_the_emulator(hostcheck, oracle, scene):
+    """horizon maps (emulated horizon builder) -> need bits in processing order -> traversal of the flagged samples only"""
+    pos, nrm, tri, h, osc = scene
+    sel = np.arange(11, len(pos), 67)[:24]
+    op = oracle.make_params(order=3, samples_u=32, samples_v=32)
+    tab, bins = processing_table(oracle, op)
+    hz, _ = _maps(hostcheck, h, pos[sel], nrm[sel])
+    need = ~(tab[None, :, 2] > hz[:, bins])                               # horizon_kernel's classification (horizon.cu)
+    need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
+    assert 0.05 < need.mean() < 0.95
+    got, gvis = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, 3, need=need_words)
+    ref, ovis, _ = oracle.bake_transfer(osc, pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(gvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL
+    full, fvis = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, 3)
+    assert np.array_equal(fvis, gvis) and np.array_equal(full.view(np.uint32), got.view(np.uint32))
