@@ -47,7 +47,7 @@ def load_hostcheck():
     L.hc_hz_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     L.hc_horizon_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_bake_wave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int,
-                               C.c_void_p, C.c_void_p]
+                               C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_horizon_trace_far.restype = C.c_uint32
     L.hc_horizon_trace_far.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     return L

@@ -89,11 +89,14 @@ extern "C" uint32_t hc_horizon_trace_far(void *h, const float *pos, const float 
 namespace {
 struct WaveSharedHost { WaveShared W; uint32_t occl[kMaxS / 32]; };
 
-template <int ORDER>
-void run_wave(const BakeArgs &A) {
+// work (optional, 4 x uint64): node visits, triangle tests, entry-list box tests, rays scanned -- the counters of an instrumented
+// launch (COUNT variant of the kernel), summed over lanes as the kernel does
+template <int ORDER, bool COUNT>
+void run_wave(const BakeArgs &A, uint64_t *work) {
     warp_emu::State state;
     warp_emu::g_state = &state;
     static WaveSharedHost sh;
+    std::atomic<uint64_t> w_nv{0}, w_nt{0}, w_cand{0}, w_scanned{0};
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; lane++) {
         lanes.emplace_back([&, lane]() {
@@ -102,16 +105,19 @@ void run_wave(const BakeArgs &A) {
             uint32_t nv = 0u, nt = 0u;
             const float sgn = A.cs_phase ? -1.0f : 1.0f;
             for (uint32_t v = 0; v < A.n_verts; v++)
-                bake_wave_vertex<ORDER, true, false>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                bake_wave_vertex<ORDER, true, COUNT>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+            w_nv += nv; w_nt += nt;
+            if (lane == 0) { w_cand += cand; w_scanned += scanned; }      // warp-uniform counters
         });
     }
     for (auto &t : lanes) t.join();
     warp_emu::g_state = nullptr;
+    if (work) { work[0] = w_nv; work[1] = w_nt; work[2] = w_cand; work[3] = w_scanned; }
 }
 }
 
 extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_t n, const float *samples, int S, int order,
-                            const uint32_t *need_bits, float origin_eps, int cs_phase, float *out, uint32_t *vis) {
+                            const uint32_t *need_bits, float origin_eps, int cs_phase, float *out, uint32_t *vis, uint64_t *work) {
     if (S < 1 || S > kMaxS || order < 1 || order > 5) return -1;
     HostBVH8 *b = (HostBVH8 *)h;
     BakeArgs A{};
@@ -121,11 +127,11 @@ extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_
     A.need_bits = const_cast<uint32_t *>(need_bits);
     A.origin_eps = origin_eps; A.cs_phase = cs_phase;
     switch (order) {
-    case 1: run_wave<1>(A); break;
-    case 2: run_wave<2>(A); break;
-    case 3: run_wave<3>(A); break;
-    case 4: run_wave<4>(A); break;
-    default: run_wave<5>(A); break;
+    case 1: run_wave<1, false>(A, nullptr); break;
+    case 2: run_wave<2, false>(A, nullptr); break;
+    case 3: if (work) run_wave<3, true>(A, work); else run_wave<3, false>(A, nullptr); break;
+    case 4: run_wave<4, false>(A, nullptr); break;
+    default: run_wave<5, false>(A, nullptr); break;
     }
     return 0;
 }

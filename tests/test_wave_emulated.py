@@ -33,7 +33,7 @@ def processing_table(oracle, params):
     return tab, bins
 
 
-def run_wave(hostcheck, h, pos, nrm, tab, order, need=None, want_vis=True, cs_phase=0):
+def run_wave(hostcheck, h, pos, nrm, tab, order, need=None, want_vis=True, cs_phase=0, work=None):
     n, S = len(pos), len(tab)
     words = (S + 31) // 32
     out = np.zeros((n, order * order), np.float32)
@@ -41,7 +41,7 @@ def run_wave(hostcheck, h, pos, nrm, tab, order, need=None, want_vis=True, cs_ph
     p32, n32 = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32)
     rc = hostcheck.hc_bake_wave(h, p32.ctypes.data, n32.ctypes.data, n, tab.ctypes.data, S, order,
                                 need.ctypes.data if need is not None else None, 1e-4, cs_phase, out.ctypes.data,
-                                vis.ctypes.data if vis is not None else None)
+                                vis.ctypes.data if vis is not None else None, work.ctypes.data if work is not None else None)
     assert rc == 0
     return out, vis
 
