@@ -28,7 +28,7 @@ def load_hostcheck():
     csrc = os.path.join(ROOT, "prt_b200", "csrc")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck_warp.cpp"), os.path.join(csrc, "bvh_build.cpp"),
             os.path.join(d, "warp_emu.h")] + [os.path.join(csrc, f) for f in ("traverse.cuh", "prt_math.cuh", "horizon_math.cuh",
-                                                                              "entry_list.cuh", "bvh8.h", "bake_wave.cuh", "kernels.h")]
+                                                                              "entry_list.cuh", "bvh8.h", "bake_wave.cuh", "bake_inter.cuh", "kernels.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # float4 & co. for entry_list.cuh
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-I", cuda_inc,
@@ -48,6 +48,8 @@ def load_hostcheck():
     L.hc_horizon_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_bake_wave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hc_bake_inter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_uint32, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.hc_horizon_trace_far.restype = C.c_uint32
     L.hc_horizon_trace_far.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     return L

@@ -20,6 +20,7 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/entry_list.cuh"
 #include "../../prt_b200/csrc/bake_wave.cuh"
+#include "../../prt_b200/csrc/bake_inter.cuh"
 #include <thread>
 #include <vector>
 
@@ -132,6 +133,56 @@ extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_
     case 3: if (work) run_wave<3, true>(A, work); else run_wave<3, false>(A, nullptr); break;
     case 4: run_wave<4, false>(A, nullptr); break;
     default: run_wave<5, false>(A, nullptr); break;
+    }
+    return 0;
+}
+
+// ---- interreflection: bake_inter_vertex of prt_b200/csrc/bake_inter.cuh (one persistent warp of bake_inter_kernel, one vertex),
+// unmodified, on the warp emulator.  need_bits [n][words] / need_count [n]: output of the horizon pass (or all samples flagged).
+namespace {
+template <int ORDER>
+void run_inter(const BakeArgs &A) {
+    warp_emu::State state;
+    warp_emu::g_state = &state;
+    static InterShared W;
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++) {
+        lanes.emplace_back([&, lane]() {
+            warp_emu::t_lane = lane;
+            unsigned long long cand = 0ull, scanned = 0ull;
+            uint32_t nv = 0u, nt = 0u;
+            const float sgn = A.cs_phase ? -1.0f : 1.0f;
+            for (uint32_t v = 0; v < A.n_verts; v++) {
+                const int n_need = (int)A.need_count[v];
+                if (n_need == 0) continue;                      // the kernel skips the vertices the horizon pass finished
+                bake_inter_vertex<ORDER, false>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+            }
+        });
+    }
+    for (auto &t : lanes) t.join();
+    warp_emu::g_state = nullptr;
+}
+}
+
+extern "C" int hc_bake_inter(void *h, const float *pos, const float *nrm, uint32_t n, uint32_t vid_base, const float *samples, int S, int order,
+                             const uint32_t *need_bits, const uint32_t *need_count, uint32_t seed, int bounces, const float *albedo,
+                             float origin_eps, float bounce_eps, float *out, uint32_t *vis) {
+    if (S < 1 || S > 4096 || order < 1 || order > 5 || !need_bits || !need_count) return -1;
+    HostBVH8 *b = (HostBVH8 *)h;
+    BakeArgs A{};
+    A.nodes = b->nodes; A.tris = b->tris; A.pos = pos; A.nrm = nrm; A.stride = 12; A.n_verts = n; A.vid_base = vid_base;
+    A.samples = reinterpret_cast<const float4 *>(samples); A.S = S; A.inv_S = 1.0f / (float)S;
+    A.out = out; A.vis = vis; A.vis_words = (S + 31) / 32;
+    A.need_bits = const_cast<uint32_t *>(need_bits); A.need_count = const_cast<uint32_t *>(need_count);
+    A.seed = seed; A.depth = bounces + 1;
+    A.albedo[0] = albedo[0]; A.albedo[1] = albedo[1]; A.albedo[2] = albedo[2];
+    A.origin_eps = origin_eps; A.bounce_eps = bounce_eps;
+    switch (order) {
+    case 1: run_inter<1>(A); break;
+    case 2: run_inter<2>(A); break;
+    case 3: run_inter<3>(A); break;
+    case 4: run_inter<4>(A); break;
+    default: run_inter<5>(A); break;
     }
     return 0;
 }

@@ -49,4 +49,22 @@ inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicSub(int *p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_RELAXED); }
+// position of the offset-th set bit of mask counted from bit `base` (PTX fns.b32); 0xFFFFFFFF when there is none
+inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+    if (offset == 0) return ((mask >> base) & 1u) ? base : 0xFFFFFFFFu;
+    if (offset > 0) {
+        for (unsigned b = base; b < 32u; b++) if (((mask >> b) & 1u) && --offset == 0) return b;
+        return 0xFFFFFFFFu;
+    }
+    for (int b = (int)base; b >= 0; b--) if (((mask >> b) & 1u) && ++offset == 0) return (unsigned)b;
+    return 0xFFFFFFFFu;
+}
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 namespace prt { using std::max; using std::min; }
