@@ -50,6 +50,8 @@ def load_hostcheck():
                                C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_bake_inter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_uint32, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.hc_entry_list.restype = C.c_int
+    L.hc_entry_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
     L.hc_horizon_trace_far.restype = C.c_uint32
     L.hc_horizon_trace_far.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     return L

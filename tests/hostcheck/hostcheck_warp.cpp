@@ -186,3 +186,25 @@ extern "C" int hc_bake_inter(void *h, const float *pos, const float *nrm, uint32
     }
     return 0;
 }
+
+// study helper: the entry list of ONE vertex (candidate boxes relative to the ray origin): out = n_cand x 8 floats
+// (centre xyz, half extents xyz, group x, group y as raw bits); returns n_cand
+extern "C" int hc_entry_list(void *h, const float *pos, const float *nrm, float origin_eps, float *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    warp_emu::State state;
+    warp_emu::g_state = &state;
+    static EntryList el;
+    int n_cand = 0;
+    const f3 N = mk3(nrm[0], nrm[1], nrm[2]);
+    const f3 org = madd3(mk3(pos[0], pos[1], pos[2]), origin_eps, N);
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++)
+        lanes.emplace_back([&, lane]() { warp_emu::t_lane = lane; const int n = build_entry_list(b->nodes, org, N, el, lane); if (lane == 0) n_cand = n; });
+    for (auto &t : lanes) t.join();
+    warp_emu::g_state = nullptr;
+    for (int k = 0; k < n_cand; k++) {
+        const float rec[8] = {el.ca[k].x, el.ca[k].y, el.ca[k].z, el.ca[k].w, el.cb[k].x, el.cb[k].y, el.cb[k].z, el.cb[k].w};
+        std::memcpy(out + 8 * k, rec, sizeof rec);
+    }
+    return n_cand;
+}
