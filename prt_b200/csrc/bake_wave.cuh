@@ -28,6 +28,9 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_LCAP
 #define PRT_WAVE_LCAP PRT_WAVE_CAP
 #endif
+#ifndef PRT_WAVE_CULL
+#define PRT_WAVE_CULL 0             // 1 (experimental, CPU-validated only): the candidate scan skips, warp-uniformly, the candidates whose
+#endif                              // elevation bound lies below the lowest ray of the round (tools/entry_list_culling_study.py)
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif
@@ -136,6 +139,9 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
     int n_cand = 0;
     if (TRACE) {
         n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
+#if PRT_WAVE_CULL
+        entry_list_elevation_bounds(W.el, n_cand, fr, lane);
+#endif
     }
     __syncwarp();
 
@@ -180,6 +186,22 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     __syncwarp();
                     const int cnt = min(npend, 32);
                     npend -= cnt;
+#if PRT_WAVE_CULL
+                    // candidates whose elevation bound lies below the lowest ray of the round are skipped by the whole warp
+                    uint32_t ci = 0u;
+                    float4 csmp = make_float4(0.f, 0.f, 1.f, 0.f);
+                    if (lane < cnt) { ci = W.pend[npend + lane]; csmp = __ldg(&A.samples[ci]); }
+                    float zmin = lane < cnt ? csmp.z : 2.0f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) zmin = fminf(zmin, __shfl_xor_sync(kFull, zmin, o));
+                    if (lane < cnt) {
+                        const f3 d = to_world(fr, mk3(csmp.x, csmp.y, csmp.z));   // raytracing.cpp:340
+                        uint32_t cm[3];
+                        scan_entry_list_culled(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), zmin, cm);
+                        m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
+                        sproc = ci;
+                    }
+#else
                     if (lane < cnt) {
                         const uint32_t i = W.pend[npend + lane];
                         const float4 smp = __ldg(&A.samples[i]);
@@ -189,6 +211,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
                         sproc = i;
                     }
+#endif
                     if (COUNT) { cand_tests += (unsigned long long)n_cand * (unsigned long long)cnt; rays_scanned += (unsigned long long)cnt; }
                     __syncwarp();
                     continue;

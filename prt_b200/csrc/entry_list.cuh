@@ -332,6 +332,39 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
     __syncwarp();
 }
 
+// Optional culling data for the candidate scan: the cheap elevation bound (hz_cheap_box: no ray from the origin whose local z exceeds
+// it can hit the box) of every candidate, stored as float bits in the build queue, which is free once the list is built.
+__device__ __forceinline__ void entry_list_elevation_bounds(EntryList &W, const int n, const Frame &fr, const int lane) {
+    for (int k = lane; k < n; k += 32) {
+        const float4 a = W.ca[k], b = W.cb[k];
+        float v = 2.0f;                                            // overflow candidate (unbounded): never skipped
+        if (a.w < 1e30f) {
+            const f3 c = mk3(a.x, a.y, a.z), e = mk3(a.w, b.x, b.y);
+            v = hz_cheap_box(c, e, e.x * e.x + e.y * e.y + e.z * e.z, c.x * c.x + c.y * c.y + c.z * c.z, fr).v;
+        }
+        W.queue[k] = __float_as_uint(v);
+    }
+    __syncwarp();
+}
+// scan_entry_list with the warp-uniform skip: zmin = the lowest local z of the rays of this round
+__device__ __forceinline__ void scan_entry_list_culled(const EntryList &W, const int n, const float idx, const float idy, const float idz, const float zmin, uint32_t m[3]) {
+    const float aix = fabsf(idx), aiy = fabsf(idy), aiz = fabsf(idz);
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+        uint32_t bits = 0u, bit = 1u;
+        const int k1 = min(n, 32 * (w + 1));
+        for (int k = 32 * w; k < k1; k++, bit += bit) {
+            if (__uint_as_float(W.queue[k]) < zmin) continue;
+            const float4 a = W.ca[k], b = W.cb[k];
+            const float tx = a.x * idx, ty = a.y * idy, tz = a.z * idz;
+            const float tmin = fmaxf(fmaxf(fmaf(-a.w, aix, tx), fmaf(-b.x, aiy, ty)), fmaf(-b.y, aiz, tz));
+            const float tmax = fminf(fminf(fmaf(a.w, aix, tx), fmaf(b.x, aiy, ty)), fmaf(b.y, aiz, tz));
+            if (tmin <= tmax && tmax >= 0.0f) bits |= bit;
+        }
+        m[w] = bits;
+    }
+}
+
 // Tests the lane's ray (origin = list origin, interval [0, inf)) against all candidate boxes; one bit per candidate.
 __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n, const float idx, const float idy, const float idz, uint32_t m[3]) {
     const float aix = fabsf(idx), aiy = fabsf(idy), aiz = fabsf(idz);

@@ -20,18 +20,21 @@ def oracle():
     return pyoracle
 
 
-def load_hostcheck():
+def load_hostcheck(extra_flags=None):
     """Host build of the product's BVH8 builder + traversal header (test tooling, tests/hostcheck)."""
     import ctypes as C
     d = os.path.join(ROOT, "tests", "hostcheck")
-    so = os.path.join(d, "libhostcheck.so")
+    # PRT_HOSTCHECK_FLAGS: extra compile flags (e.g. -DPRT_WAVE_CULL=1 to run the suite on an experimental build variant of the kernels)
+    extra = list(extra_flags) if extra_flags else os.environ.get("PRT_HOSTCHECK_FLAGS", "").split()
+    import hashlib
+    so = os.path.join(d, "libhostcheck.so" if not extra else "libhostcheck_variant_%s.so" % hashlib.md5(" ".join(extra).encode()).hexdigest()[:8])
     csrc = os.path.join(ROOT, "prt_b200", "csrc")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck_warp.cpp"), os.path.join(csrc, "bvh_build.cpp"),
             os.path.join(d, "warp_emu.h")] + [os.path.join(csrc, f) for f in ("traverse.cuh", "prt_math.cuh", "horizon_math.cuh",
                                                                               "entry_list.cuh", "bvh8.h", "bake_wave.cuh", "bake_inter.cuh", "kernels.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # float4 & co. for entry_list.cuh
-        subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-I", cuda_inc,
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-I", cuda_inc, *extra,
                                "-o", so, srcs[0], srcs[1], srcs[2], "-lpthread"])
     L = C.CDLL(so)
     L.hc_build.restype = C.c_void_p

@@ -136,3 +136,27 @@ def test_inter_vertex_matches_oracle(hostcheck, oracle, scene, bounces, albedo, 
     # interreflection only adds energy to the DC term of the shadowed transfer
     sh, _, _ = oracle.bake_transfer(osc, pos[sel], nrm[sel], oracle.make_params(order=4, samples_u=16, samples_v=16))
     assert (got[live, 0] >= sh[live, 0] - 1e-6).all()
+
+
+def test_wave_cull_variant_matches_oracle(oracle):
+    """Experimental build variant PRT_WAVE_CULL=1 (candidate scan skips, warp-uniformly, the candidates whose elevation bound lies below
+    the lowest ray of the round): results must not change.  CPU-validated here so that a later round only has to time it."""
+    import conftest
+    hc = conftest.load_hostcheck(["-DPRT_WAVE_CULL=1"])
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    h = hc.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    try:
+        sel = np.arange(2, len(pos), 47)[:40]
+        op = oracle.make_params(order=3, samples_u=16, samples_v=16)
+        tab, bins = processing_table(oracle, op)
+        hz, _ = _maps(hc, h, pos[sel], nrm[sel])
+        need = ~(tab[None, :, 2] > hz[:, bins])
+        need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
+        got, gvis = run_wave(hc, h, pos[sel], nrm[sel], tab, 3, need=need_words)
+        full, fvis = run_wave(hc, h, pos[sel], nrm[sel], tab, 3)
+    finally:
+        hc.hc_free(h)
+    ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(gvis, ovis) and np.array_equal(fvis, ovis)
+    assert rel_l2(got, ref).max() <= REL_L2_TOL and rel_l2(full, ref).max() <= REL_L2_TOL
