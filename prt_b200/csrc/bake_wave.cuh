@@ -28,9 +28,6 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_LCAP
 #define PRT_WAVE_LCAP PRT_WAVE_CAP
 #endif
-#ifndef PRT_WAVE_CULL
-#define PRT_WAVE_CULL 0             // 1 (experimental, CPU-validated only): the candidate scan skips, warp-uniformly, the candidates whose
-#endif                              // elevation bound lies below the lowest ray of the round (tools/entry_list_culling_study.py)
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif

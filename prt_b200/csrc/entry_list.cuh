@@ -332,9 +332,13 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
     __syncwarp();
 }
 
+#ifndef PRT_WAVE_CULL
+#define PRT_WAVE_CULL 0             // 1 (experimental, CPU-validated only): the candidate scan of bake_wave.cuh skips, warp-uniformly, the
+#endif                              // candidates whose elevation bound lies below the lowest ray of the round (tools/entry_list_culling_study.py)
+#if PRT_WAVE_CULL
 // Optional culling data for the candidate scan: the cheap elevation bound (hz_cheap_box: no ray from the origin whose local z exceeds
 // it can hit the box) of every candidate, stored as float bits in the build queue, which is free once the list is built.
-__device__ __forceinline__ void entry_list_elevation_bounds(EntryList &W, const int n, const Frame &fr, const int lane) {
+static __device__ __noinline__ void entry_list_elevation_bounds(EntryList &W, const int n, const Frame &fr, const int lane) {
     for (int k = lane; k < n; k += 32) {
         const float4 a = W.ca[k], b = W.cb[k];
         float v = 2.0f;                                            // overflow candidate (unbounded): never skipped
@@ -364,6 +368,8 @@ __device__ __forceinline__ void scan_entry_list_culled(const EntryList &W, const
         m[w] = bits;
     }
 }
+
+#endif  // PRT_WAVE_CULL
 
 // Tests the lane's ray (origin = list origin, interval [0, inf)) against all candidate boxes; one bit per candidate.
 __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n, const float idx, const float idy, const float idz, uint32_t m[3]) {
