@@ -25,7 +25,6 @@ namespace {
 // COUNT: carry the work counters (instrumented launches only; the timed variant keeps those registers free)
 template <int ORDER, bool COUNT>
 __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const BakeArgs A) {
-    constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     InterShared &W = reinterpret_cast<InterShared *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;

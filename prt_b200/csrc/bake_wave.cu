@@ -31,7 +31,6 @@ namespace {
 // COUNT: carry the work counters (an instrumented, untimed launch of bench.py); the timed variant keeps those registers free
 template <int ORDER, bool TRACE, bool COUNT>
 __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
-    constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = A.S, words = A.vis_words;
     const size_t wstride = sizeof(WaveShared) + 4 * (size_t)((words + 3) & ~3);
