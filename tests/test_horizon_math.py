@@ -251,3 +251,42 @@ def test_horizon_map_adversarial_geometry(hostcheck, oracle):
     finally:
         hostcheck.hc_free(h)
     assert 0.02 < 1.0 - visible.mean() < 0.9
+
+
+@pytest.mark.parametrize("scene_kind", ["sphere_in_sphere", "triangle_soup"])
+def test_horizon_map_other_scenes(hostcheck, oracle, scene_kind):
+    """the same end-to-end check on geometry that is not a smooth surface seen from itself: a small sphere inside a big inverted
+    one (everything is far field, every ray is occluded or escapes through nothing) and an unstructured triangle soup with
+    arbitrary vertex normals (origins inside bounding boxes, geometry on both sides of every tangent plane)"""
+    from prt_b200 import meshes
+    rng = np.random.RandomState(11)
+    if scene_kind == "sphere_in_sphere":
+        p0, n0, t0 = meshes.icosphere(3)
+        p1, n1, t1 = meshes.icosphere(2)
+        pos = np.concatenate([p0 * 0.5, p1 * 3.0]).astype(np.float32)
+        nrm = np.concatenate([n0, -n1]).astype(np.float32)
+        tri = np.concatenate([t0, t1[:, ::-1] + len(p0)]).astype(np.uint32)
+        sel = np.concatenate([np.arange(0, len(p0), 9)[:40], len(p0) + np.arange(0, len(p1), 5)[:20]])
+    else:
+        k = 600
+        c = rng.uniform(-2, 2, size=(k, 1, 3))
+        pos = (c + rng.normal(size=(k, 3, 3)) * 0.25).reshape(-1, 3).astype(np.float32)
+        tri = np.arange(3 * k, dtype=np.uint32).reshape(k, 3)
+        nrm = rng.normal(size=(3 * k, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        sel = np.arange(0, 3 * k, 31)[:60]
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    op = oracle.make_params(order=3, samples_u=32, samples_v=32)
+    _, dirs = oracle.sample_table(op)
+    _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
+    visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
+    try:
+        for knobs in (dict(), dict(near=15, budget=200), dict(budget=1)):
+            hz, _ = _maps(hostcheck, h, pos[sel], nrm[sel], **knobs)
+            free = _free_mask(dirs, hz)
+            assert not (free & ~visible).any(), (scene_kind, knobs)
+    finally:
+        hostcheck.hc_free(h)
+    if scene_kind == "sphere_in_sphere":
+        assert visible.mean() < 0.05            # a closed room: (almost) nothing escapes

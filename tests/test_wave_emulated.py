@@ -160,3 +160,32 @@ def test_wave_cull_variant_matches_oracle(oracle):
     ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
     assert np.array_equal(gvis, ovis) and np.array_equal(fvis, ovis)
     assert rel_l2(got, ref).max() <= REL_L2_TOL and rel_l2(full, ref).max() <= REL_L2_TOL
+
+
+def test_wave_vertex_on_triangle_soup(hostcheck, oracle):
+    """unstructured soup, arbitrary normals, ray origins on the geometry itself: deep entry chains, rays that start inside many
+    boxes, hits at t ~ 0 -- the traversal pass must still agree with the oracle bit for bit (full and with need bits)"""
+    rng = np.random.RandomState(12)
+    k = 500
+    c = rng.uniform(-1.5, 1.5, size=(k, 1, 3))
+    pos = (c + rng.normal(size=(k, 3, 3)) * 0.3).reshape(-1, 3).astype(np.float32)
+    tri = np.arange(3 * k, dtype=np.uint32).reshape(k, 3)
+    nrm = rng.normal(size=(3 * k, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    sel = np.arange(1, 3 * k, 37)[:40]
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    try:
+        op = oracle.make_params(order=3, samples_u=16, samples_v=16)
+        tab, bins = processing_table(oracle, op)
+        full, fvis = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, 3)
+        hz, _ = _maps(hostcheck, h, pos[sel], nrm[sel])
+        need = ~(tab[None, :, 2] > hz[:, bins])
+        need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
+        got, gvis = run_wave(hostcheck, h, pos[sel], nrm[sel], tab, 3, need=need_words)
+    finally:
+        hostcheck.hc_free(h)
+    ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(fvis, ovis) and np.array_equal(gvis, ovis)
+    assert rel_l2(full, ref).max() <= REL_L2_TOL and rel_l2(got, ref).max() <= REL_L2_TOL
+    assert 0.2 < np.unpackbits(ovis.view(np.uint8)).mean() < 0.95
