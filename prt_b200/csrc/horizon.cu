@@ -11,8 +11,7 @@
 //
 // The pass is a pure culling device: a ray it marks "free" provably cannot hit anything, every other ray goes through the pinned
 // triangle test in the traversal pass, so results are identical with or without it (tests/test_gpu_parity.py).
-#include "kernels.h"
-#include "entry_list.cuh"
+#include "horizon.cuh"
 
 namespace prt {
 
@@ -22,16 +21,8 @@ namespace {
 #define PRT_HZ_MINB 9               // CTAs per SM the register allocation aims at (56 registers; 10 CTAs at 48 registers measured 3 % slower)
 #endif
 
-struct HorizonShared {
-    EntryList el;
-    uint32_t hz[kHzWords];             // the map (first kHzBins words) and its range-minimum table
-    uint32_t rq[kHzQueue];
-    uint32_t tq[kHzTriQueue];
-};
-
 template <int ORDER>
 __global__ void __launch_bounds__(128, PRT_HZ_MINB) horizon_kernel(const BakeArgs A) {
-    constexpr int N2 = ORDER * ORDER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HorizonShared &W = reinterpret_cast<HorizonShared *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -43,58 +34,7 @@ __global__ void __launch_bounds__(128, PRT_HZ_MINB) horizon_kernel(const BakeArg
         if (lane == 0) v = atomicAdd(A.counter + 1, 1u);          // counter[1]: this pass, counter[0]: traversal pass
         v = __shfl_sync(kFull, v, 0);
         if (v >= A.n_verts) break;
-
-        const float *pp = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.pos) + (size_t)v * A.stride);
-        const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
-        const f3 N = mk3(__ldg(np), __ldg(np + 1), __ldg(np + 2));
-        const f3 P = mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2));
-        const Frame fr = make_frame(N);
-        const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
-
-        const int n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane);
-
-        uint32_t *row = A.need_bits + (size_t)v * words;
-        uint32_t total = 0u;
-        for (int base = 0; base < S; base += 32) {
-            const int i = base + lane;
-            bool need = false;
-            if (i < S) {
-                const float4 smp = __ldg(&A.samples[i]);
-                need = !(smp.z > __uint_as_float(W.hz[__float_as_uint(smp.w) >> 24]));
-            }
-            const unsigned nb = __ballot_sync(kFull, need);
-            if (lane == 0) row[base >> 5] = nb;
-            total += __popc(nb);
-        }
-        if (lane == 0) A.need_count[v] = total;
-        if (total == 0u) {
-            float acc[N2];
-#pragma unroll
-            for (int k = 0; k < N2; k++) acc[k] = 0.f;
-            for (int i = lane; i < S; i += 32) {
-                const float4 smp = __ldg(&A.samples[i]);
-                const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
-                float y[N2];
-                sh_eval<ORDER>(d.z, d.x, d.y, sgn, y);
-#pragma unroll
-                for (int k = 0; k < N2; k++) acc[k] += y[k];
-            }
-            float mine = 0.f;
-#pragma unroll
-            for (int k = 0; k < N2; k++) {
-                const float s = warp_sum(acc[k]);
-                if (lane == k) mine = s;
-            }
-            if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
-            if (A.vis) {
-                for (int w = lane; w < words; w += 32) {
-                    const int rem = S - 32 * w;
-                    A.vis[(size_t)v * words + w] = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-                }
-            }
-        }
-        __syncwarp();
+        horizon_vertex<ORDER>(A, W, v, lane, S, words, sgn);
     }
 }
 

@@ -31,7 +31,7 @@ def load_hostcheck(extra_flags=None):
     csrc = os.path.join(ROOT, "prt_b200", "csrc")
     srcs = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck_warp.cpp"), os.path.join(csrc, "bvh_build.cpp"),
             os.path.join(d, "warp_emu.h")] + [os.path.join(csrc, f) for f in ("traverse.cuh", "prt_math.cuh", "horizon_math.cuh",
-                                                                              "entry_list.cuh", "bvh8.h", "bake_wave.cuh", "bake_inter.cuh", "kernels.h")]
+                                                                              "entry_list.cuh", "bvh8.h", "bake_wave.cuh", "bake_inter.cuh", "horizon.cuh", "kernels.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # float4 & co. for entry_list.cuh
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-I", cuda_inc, *extra,
@@ -53,6 +53,8 @@ def load_hostcheck(extra_flags=None):
                                C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_bake_inter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_uint32, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.hc_horizon_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_entry_list.restype = C.c_int
     L.hc_entry_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
     L.hc_horizon_trace_far.restype = C.c_uint32

@@ -19,6 +19,7 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
     const float rec[9] = {(c).x, (c).y, (c).z, (e).x, (e).y, (e).z, (item).v, (float)(item).b0, (float)(item).b1}; g_trace.insert(g_trace.end(), rec, rec + 9); } } while (0)
 #include "../../prt_b200/csrc/bvh8.h"
 #include "../../prt_b200/csrc/entry_list.cuh"
+#include "../../prt_b200/csrc/horizon.cuh"
 #include "../../prt_b200/csrc/bake_wave.cuh"
 #include "../../prt_b200/csrc/bake_inter.cuh"
 #include <thread>
@@ -207,4 +208,47 @@ extern "C" int hc_entry_list(void *h, const float *pos, const float *nrm, float 
         std::memcpy(out + 8 * k, rec, sizeof rec);
     }
     return n_cand;
+}
+
+// ---- the horizon pass as the kernel runs it: horizon_vertex of prt_b200/csrc/horizon.cuh (entry list, map, need bits and counts,
+// rows + visibility words of the vertices it finishes), unmodified, on the warp emulator
+namespace {
+template <int ORDER>
+void run_horizon(const BakeArgs &A) {
+    warp_emu::State state;
+    warp_emu::g_state = &state;
+    static HorizonShared W;
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++) {
+        lanes.emplace_back([&, lane]() {
+            warp_emu::t_lane = lane;
+            const float sgn = A.cs_phase ? -1.0f : 1.0f;
+            for (uint32_t v = 0; v < A.n_verts; v++) horizon_vertex<ORDER>(A, W, v, lane, A.S, A.vis_words, sgn);
+        });
+    }
+    for (auto &t : lanes) t.join();
+    warp_emu::g_state = nullptr;
+}
+}
+
+extern "C" int hc_horizon_pass(void *h, const float *pos, const float *nrm, uint32_t n, const float *samples, int S, int order, int budget,
+                               int near100, float origin_eps, int cs_phase, float *out, uint32_t *vis, uint32_t *need_bits, uint32_t *need_count) {
+    if (S < 1 || order < 1 || order > 5 || !need_bits || !need_count) return -1;
+    HostBVH8 *b = (HostBVH8 *)h;
+    BakeArgs A{};
+    A.nodes = b->nodes; A.tris = b->tris; A.pos = pos; A.nrm = nrm; A.stride = 12; A.n_verts = n;
+    A.samples = reinterpret_cast<const float4 *>(samples); A.S = S; A.inv_S = 1.0f / (float)S;
+    A.out = out; A.vis = vis; A.vis_words = (S + 31) / 32;
+    A.need_bits = need_bits; A.need_count = need_count;
+    A.origin_eps = origin_eps; A.cs_phase = cs_phase;
+    A.horizon_budget = budget;
+    { const float sn = sinf(0.01f * (float)near100); A.horizon_near2 = 1.0f / (sn * sn); }
+    switch (order) {
+    case 1: run_horizon<1>(A); break;
+    case 2: run_horizon<2>(A); break;
+    case 3: run_horizon<3>(A); break;
+    case 4: run_horizon<4>(A); break;
+    default: run_horizon<5>(A); break;
+    }
+    return 0;
 }

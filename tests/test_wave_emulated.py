@@ -189,3 +189,40 @@ def test_wave_vertex_on_triangle_soup(hostcheck, oracle):
     assert np.array_equal(fvis, ovis) and np.array_equal(gvis, ovis)
     assert rel_l2(full, ref).max() <= REL_L2_TOL and rel_l2(got, ref).max() <= REL_L2_TOL
     assert 0.2 < np.unpackbits(ovis.view(np.uint8)).mean() < 0.95
+
+
+@pytest.mark.parametrize("order,su,sv", [(3, 32, 32), (4, 5, 7)])
+def test_both_passes_as_the_kernels_run_them(hostcheck, oracle, order, su, sv):
+    """horizon_vertex (horizon.cuh) writes need bits / counts and finishes the fully visible vertices; bake_wave_vertex traces the
+    rest from those bits -- the bake exactly as the two kernels run it, on the emulator, against the oracle for EVERY vertex.  A
+    smooth sphere next to the torus makes sure some vertices are finished by the first pass."""
+    p0, n0, t0 = meshes.bumpy_torus(64, 48)
+    p1, n1, t1 = meshes.icosphere(3)
+    pos = np.concatenate([p0, p1 * 0.4 + np.float32([6.0, 0.0, 0.0])]).astype(np.float32)
+    nrm = np.concatenate([n0, n1]).astype(np.float32)
+    tri = np.concatenate([t0, t1 + len(p0)]).astype(np.uint32)
+    sel = np.concatenate([np.arange(3, len(p0), 61)[:30], len(p0) + np.arange(0, len(p1), 13)[:20]])
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    op = oracle.make_params(order=order, samples_u=su, samples_v=sv)
+    tab, _ = processing_table(oracle, op)
+    S, n, words = len(tab), len(sel), (len(tab) + 31) // 32
+    out = np.zeros((n, order * order), np.float32)
+    vis = np.zeros((n, words), np.uint32)
+    need_bits = np.zeros((n, words), np.uint32)
+    need_count = np.zeros(n, np.uint32)
+    p32, n32 = np.ascontiguousarray(pos[sel]), np.ascontiguousarray(nrm[sel])
+    try:
+        rc = hostcheck.hc_horizon_pass(h, p32.ctypes.data, n32.ctypes.data, n, tab.ctypes.data, S, order, 64, 30, 1e-4, 0, out.ctypes.data,
+                                       vis.ctypes.data, need_bits.ctypes.data, need_count.ctypes.data)
+        assert rc == 0
+        live = need_count > 0
+        assert live.any() and (~live).any(), "the scene is meant to exercise both ways a vertex can be finished"
+        assert np.array_equal(need_count, np.unpackbits(need_bits.view(np.uint8), axis=1, bitorder="little")[:, :S].sum(axis=1))
+        o2, v2 = run_wave(hostcheck, h, p32[live], n32[live], tab, order, need=np.ascontiguousarray(need_bits[live]))
+        out[live], vis[live] = o2, v2
+    finally:
+        hostcheck.hc_free(h)
+    ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
+    assert np.array_equal(vis, ovis)
+    assert rel_l2(out, ref).max() <= REL_L2_TOL
