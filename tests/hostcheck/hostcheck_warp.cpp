@@ -27,6 +27,32 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
 
 using namespace prt;
 
+// h: HostBVH8* from hc_build.  pos / nrm: n x 3 floats.  near100: horizon_near (angular radius x 100, rad); budget: horizon_budget.
+// out_hz: n x kHzBins floats (the map), out_ncand: n (entry-list candidates).
+// stats (optional, 4 x uint64): refinement iterations, nodes expanded, boxes bounded, triangle rounds -- summed over the n vertices.
+extern "C" void hc_horizon_maps(void *h, const float *pos, const float *nrm, uint32_t n, float origin_eps, int budget, int near100,
+                                float *out_hz, int *out_ncand, uint64_t *stats) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    warp_emu::State state;
+    warp_emu::g_state = &state;
+    static HorizonShared W;                 // the per-warp shared memory of horizon_kernel (horizon.cuh)
+    g_hz_stats.iterations = 0; g_hz_stats.nodes_expanded = 0; g_hz_stats.boxes_bounded = 0; g_hz_stats.triangle_rounds = 0;
+    const float sn = sinf(0.01f * (float)near100), near2 = 1.0f / (sn * sn);
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++) {
+        lanes.emplace_back([&, lane]() {
+            warp_emu::t_lane = lane;
+            for (uint32_t v = 0; v < n; v++) {
+                const f3 N = mk3(nrm[3 * v], nrm[3 * v + 1], nrm[3 * v + 2]);
+                const f3 P = mk3(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2]);
+                const Frame fr = make_frame(N);
+                const f3 org = madd3(P, origin_eps, N);
+                const int n_cand = build_entry_list(b->nodes, org, N, W.el, lane);
+                build_horizon(W.el, n_cand, b->nodes, b->tris, org, N, fr, W.hz, W.rq, W.tq, budget, near2, lane);
+                out_hz[(size_t)v * kHzBins + lane] = __uint_as_float(W.hz[lane]);
+                if (lane == 0) out_ncand[v] = n_cand;
+                __syncwarp();
+            }
         });
     }
     for (auto &t : lanes) t.join();
