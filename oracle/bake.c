@@ -23,6 +23,16 @@
 void prt_o_sh_eval(int order, int cs_phase, const float d[3], float *out) { prt_sh_eval(order, cs_phase, d[0], d[1], d[2], out); }
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { prt_philox4x32_10(ctr, key, out); }
 void prt_o_sincos2pi(float v, float *s, float *c) { prt_sincos2pi(v, s, c); }
+void prt_o_cosine_world(float u, float v, const float N[3], float local[3], float world[3], float frame9[9], float *pdf) {
+    v3 l = prt_cosine_local(u, v);
+    frame3 f = prt_frame(v3_make(N[0], N[1], N[2]));
+    v3 w = prt_to_world(&f, l);
+    local[0] = l.x; local[1] = l.y; local[2] = l.z;
+    world[0] = w.x; world[1] = w.y; world[2] = w.z;
+    frame9[0] = f.right.x; frame9[1] = f.right.y; frame9[2] = f.right.z; frame9[3] = f.up.x; frame9[4] = f.up.y; frame9[5] = f.up.z;
+    frame9[6] = f.n.x; frame9[7] = f.n.y; frame9[8] = f.n.z;
+    *pdf = l.z / PRT_PI_F;
+}
 int prt_o_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
 
 void prt_o_sample_table(const prt_o_bake_params *p, float *uv, float *dirs) {

@@ -87,6 +87,12 @@ void prt_o_cube_sample(const float *cube, int n0, int levels, const float d[3], 
     }
 }
 
+/* SampleSphericalMap (rectangle2cube.frag:7-15) of a normalised direction; acos argument clamped against rounding */
+void prt_o_equirect_uv(const float v[3], float uv[2]) {
+    uv[0] = atan2f(-v[0], -v[2]) * 0.1591f + 0.5f;
+    uv[1] = acosf(fminf(1.0f, fmaxf(-1.0f, v[1]))) * 0.3183f;
+}
+
 /* rectangle2cube.frag:7-22 + Tex2D bilinear, CLAMP_TO_EDGE (gl.cpp:375-380); then 2x2 box mips */
 void prt_o_env_equirect_to_cube(const float *eq, int w, int h, int n0, int levels, float *cube) {
     for (int f = 0; f < 6; f++)
@@ -95,9 +101,9 @@ void prt_o_env_equirect_to_cube(const float *eq, int w, int h, int n0, int level
                 float d[3];
                 face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n0 - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n0 - 1.0f, d);
                 float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                float vx = d[0] * inv, vy = d[1] * inv, vz = d[2] * inv;
-                float u = atan2f(-vx, -vz) * 0.1591f + 0.5f;
-                float v = acosf(fminf(1.0f, fmaxf(-1.0f, vy))) * 0.3183f;
+                float vn[3] = { d[0] * inv, d[1] * inv, d[2] * inv }, uvq[2];
+                prt_o_equirect_uv(vn, uvq);
+                float u = uvq[0], v = uvq[1];
                 float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
                 float x0 = floorf(x), y0 = floorf(y), fx = x - x0, fy = y - y0;
                 int i0 = (int)x0, j0 = (int)y0, i1 = i0 + 1, j1 = j0 + 1;
@@ -134,13 +140,9 @@ static void tangent_frame(const float N[3], float thr, float right[3], float up[
     up[0] = N[1] * right[2] - N[2] * right[1]; up[1] = N[2] * right[0] - N[0] * right[2]; up[2] = N[0] * right[1] - N[1] * right[0];
 }
 
-/* irradiance.frag:9-43 */
-void prt_o_env_irradiance(const float *cube, int n0, int levels, int n_out, float *out) {
-    for (int f = 0; f < 6; f++)
-        for (int j = 0; j < n_out; j++)
-            for (int i = 0; i < n_out; i++) {
-                float N[3], right[3], up[3];
-                face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n_out - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n_out - 1.0f, N);
+/* irradiance.frag:9-43 for one fragment: P = CubeTexPos (un-normalised position on the cube) */
+void prt_o_env_irradiance_dir(const float *cube, int n0, int levels, const float P[3], float o[3]) {
+                float N[3] = { P[0], P[1], P[2] }, right[3], up[3];
                 float inv = 1.0f / sqrtf(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
                 N[0] *= inv; N[1] *= inv; N[2] *= inv;
                 tangent_frame(N, 0.99f, right, up);
@@ -154,8 +156,15 @@ void prt_o_env_irradiance(const float *cube, int n0, int levels, int n_out, floa
                         for (int k = 0; k < 3; k++) acc[k] += c[k] * ct * st;
                         nr += 1.0f;
                     }
-                float *o = out + ((size_t)f * n_out * n_out + (size_t)j * n_out + i) * 3;
                 for (int k = 0; k < 3; k++) o[k] = PIF * PIF * acc[k] * (1.0f / nr);
+}
+void prt_o_env_irradiance(const float *cube, int n0, int levels, int n_out, float *out) {
+    for (int f = 0; f < 6; f++)
+        for (int j = 0; j < n_out; j++)
+            for (int i = 0; i < n_out; i++) {
+                float P[3];
+                face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n_out - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n_out - 1.0f, P);
+                prt_o_env_irradiance_dir(cube, n0, levels, P, out + ((size_t)f * n_out * n_out + (size_t)j * n_out + i) * 3);
             }
 }
 
@@ -181,17 +190,9 @@ static void sample_ggx(float xi_x, float xi_y, const float N[3], float roughness
     H[0] = s[0] * inv; H[1] = s[1] * inv; H[2] = s[2] * inv;
 }
 
-/* prefilter.frag:64-107; out: levels concatenated like the cube storage, n_out >> mip, roughness = mip/(mips-1) */
-void prt_o_env_prefilter(const float *cube, int n0, int levels, int n_out, int mips, int n_samples, float *out) {
-    for (int mip = 0; mip < mips; mip++) {
-        int n = n_out >> mip;
-        float roughness = (float)mip / (float)(mips - 1);
-        float *dst = out + level_offset(n_out, mip);
-        for (int f = 0; f < 6; f++)
-            for (int j = 0; j < n; j++)
-                for (int i = 0; i < n; i++) {
-                    float N[3];
-                    face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n - 1.0f, N);
+/* prefilter.frag:64-107 for one fragment: P = CubeTexPos (un-normalised position on the cube) */
+void prt_o_env_prefilter_dir(const float *cube, int n0, int levels, const float P[3], float roughness, int n_samples, float o[3]) {
+                    float N[3] = { P[0], P[1], P[2] };
                     float inv = 1.0f / sqrtf(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
                     N[0] *= inv; N[1] *= inv; N[2] *= inv;
                     float acc[3] = { 0, 0, 0 }, wsum = 0.0f;
@@ -217,8 +218,20 @@ void prt_o_env_prefilter(const float *cube, int n0, int levels, int n_out, int m
                             wsum += ndl;
                         }
                     }
-                    float *o = dst + ((size_t)f * n * n + (size_t)j * n + i) * 3;
                     for (int k = 0; k < 3; k++) o[k] = acc[k] / wsum;
+}
+/* out: levels concatenated like the cube storage, n_out >> mip, roughness = mip/(mips-1) (gl.cpp:556-566) */
+void prt_o_env_prefilter(const float *cube, int n0, int levels, int n_out, int mips, int n_samples, float *out) {
+    for (int mip = 0; mip < mips; mip++) {
+        int n = n_out >> mip;
+        float roughness = (float)mip / (float)(mips - 1);
+        float *dst = out + level_offset(n_out, mip);
+        for (int f = 0; f < 6; f++)
+            for (int j = 0; j < n; j++)
+                for (int i = 0; i < n; i++) {
+                    float P[3];
+                    face_dir(f, 2.0f * ((float)i + 0.5f) / (float)n - 1.0f, 2.0f * ((float)j + 0.5f) / (float)n - 1.0f, P);
+                    prt_o_env_prefilter_dir(cube, n0, levels, P, roughness, n_samples, dst + ((size_t)f * n * n + (size_t)j * n + i) * 3);
                 }
     }
 }

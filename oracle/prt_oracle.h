@@ -70,6 +70,9 @@ size_t prt_o_cube_floats(int n0, int levels);
 int prt_o_cube_levels(int n0);
 void prt_o_cube_sample(const float *cube, int n0, int levels, const float d[3], float lod, float out[3]);
 void prt_o_env_equirect_to_cube(const float *eq, int w, int h, int n0, int levels, float *cube);
+void prt_o_equirect_uv(const float v[3], float uv[2]);
+void prt_o_env_irradiance_dir(const float *cube, int n0, int levels, const float P[3], float out[3]);
+void prt_o_env_prefilter_dir(const float *cube, int n0, int levels, const float P[3], float roughness, int n_samples, float out[3]);
 void prt_o_env_irradiance(const float *cube, int n0, int levels, int n_out, float *out);
 void prt_o_env_prefilter(const float *cube, int n0, int levels, int n_out, int mips, int n_samples, float *out);
 void prt_o_brdf_lut(int w, int h, int n_samples, float *out);
@@ -117,6 +120,9 @@ void prt_o_raytrace(const prt_o_scene *, const prt_o_camera *, int w, int h, int
 void prt_o_sh_eval(int order, int cs_phase, const float dir_sh[3], float *out);
 void prt_o_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void prt_o_sincos2pi(float v, float *s, float *c);
+/* frame(N) and cosineSampleHemisphere(u, v, N) (raytracing.cpp:101-107,130-160): local direction, world direction,
+ * frame columns (right, up, N) and the pdf z / PI */
+void prt_o_cosine_world(float u, float v, const float N[3], float local[3], float world[3], float frame9[9], float *pdf);
 int prt_o_hw_threads(void);
 
 #ifdef __cplusplus

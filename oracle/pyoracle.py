@@ -59,6 +59,10 @@ def lib():
         L.prt_o_philox.argtypes = [u32p, u32p, u32p]
         L.prt_o_sincos2pi.argtypes = [C.c_float, f32p, f32p]
         L.prt_o_hw_threads.restype = C.c_int
+        L.prt_o_cosine_world.argtypes = [C.c_float, C.c_float, f32p, f32p, f32p, f32p, f32p]
+        L.prt_o_equirect_uv.argtypes = [f32p, f32p]
+        L.prt_o_env_irradiance_dir.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
+        L.prt_o_env_prefilter_dir.argtypes = [vp, C.c_int, C.c_int, f32p, C.c_float, C.c_int, f32p]
         L.prt_o_cube_floats.restype = C.c_size_t
         L.prt_o_cube_floats.argtypes = [C.c_int, C.c_int]
         L.prt_o_cube_levels.restype = C.c_int
@@ -182,6 +186,24 @@ def sincos2pi(v: float):
     return s.value, c.value
 
 
+def cosine_world(u: float, v: float, N):
+    """frame(N) + cosineSampleHemisphere(u, v, N) (reference raytracing.cpp:101-107,130-160) -> (local, world, frame [3,3] rows =
+    right, up, N, pdf)."""
+    f32p = C.POINTER(C.c_float)
+    n = np.asarray(N, np.float32); l = np.zeros(3, np.float32); w = np.zeros(3, np.float32); fr = np.zeros(9, np.float32); pdf = C.c_float()
+    lib().prt_o_cosine_world(C.c_float(u), C.c_float(v), n.ctypes.data_as(f32p), l.ctypes.data_as(f32p), w.ctypes.data_as(f32p),
+                             fr.ctypes.data_as(f32p), C.byref(pdf))
+    return l, w, fr.reshape(3, 3), pdf.value
+
+
+def equirect_uv(d) -> np.ndarray:
+    """SampleSphericalMap (reference rectangle2cube.frag:7-15) of a normalised direction."""
+    f32p = C.POINTER(C.c_float)
+    v = np.asarray(d, np.float32); uv = np.zeros(2, np.float32)
+    lib().prt_o_equirect_uv(v.ctypes.data_as(f32p), uv.ctypes.data_as(f32p))
+    return uv
+
+
 def hw_threads() -> int:
     return lib().prt_o_hw_threads()
 
@@ -206,6 +228,21 @@ class EnvCube:
         out = np.zeros(3, np.float32)
         f32p = C.POINTER(C.c_float)
         lib().prt_o_cube_sample(_ptr(self.data), self.n0, self.levels, d.ctypes.data_as(f32p), C.c_float(lod), out.ctypes.data_as(f32p))
+        return out
+
+    def irradiance_dir(self, P) -> np.ndarray:
+        """irradiance.frag main() for one fragment, P = CubeTexPos."""
+        f32p = C.POINTER(C.c_float)
+        p = np.asarray(P, np.float32); out = np.zeros(3, np.float32)
+        lib().prt_o_env_irradiance_dir(_ptr(self.data), self.n0, self.levels, p.ctypes.data_as(f32p), out.ctypes.data_as(f32p))
+        return out
+
+    def prefilter_dir(self, P, roughness: float, n_samples: int = 1024) -> np.ndarray:
+        """prefilter.frag main() for one fragment, P = CubeTexPos."""
+        f32p = C.POINTER(C.c_float)
+        p = np.asarray(P, np.float32); out = np.zeros(3, np.float32)
+        lib().prt_o_env_prefilter_dir(_ptr(self.data), self.n0, self.levels, p.ctypes.data_as(f32p), C.c_float(roughness), n_samples,
+                                      out.ctypes.data_as(f32p))
         return out
 
     def irradiance(self, n_out=32) -> np.ndarray:

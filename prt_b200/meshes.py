@@ -7,9 +7,9 @@ bench generates meshes of the named sizes instead:
 * ``bumpy_torus(nu,nv)``-- self-occluding; V = nu*nv, F = 2*nu*nv; 737x737 is "buddha-scale"
   (543 169 V / 1 086 338 F; Stanford Happy Buddha: 543 652 V / 1 087 716 F)
 
-A vertex is (pos, normal) as in the reference's Mesh::Vert (src/opengl/gl.h:76-80); normals are smooth
-area-weighted vertex normals, i.e. what assimp's GenNormals + JoinIdenticalVertices (src/scene/model.cpp:72)
-would not change for meshes that already carry normals.
+A vertex is (pos, normal) as in the reference's Mesh::Vert (src/opengl/gl.h:76-80).  The synthetic meshes carry smooth
+area-weighted vertex normals (an OBJ with normals passes through assimp unchanged); ``load_obj_assimp`` reproduces what the
+reference's import flags (src/scene/model.cpp:72) make of an OBJ without normals: flat normals, vertices split per face.
 """
 from __future__ import annotations
 
@@ -129,6 +129,65 @@ def load_obj(path: str):
             t.append(lut[c])
         tri.append(t)
     return np.asarray(pos, np.float32), np.asarray(nrm, np.float32), np.asarray(tri, np.uint32)
+
+
+def load_obj_assimp(path: str):
+    """What a vertex IS in the reference: ``Model(path)`` imports with ``aiProcess_Triangulate | aiProcess_GenNormals |
+    aiProcess_JoinIdenticalVertices`` (reference src/scene/model.cpp:72) and ``processMesh`` copies ``mVertices`` / ``mNormals`` into
+    ``Mesh::Vert`` (model.cpp:14-47).  assimp's OBJ importer emits one vertex per face corner; for a file WITHOUT normals (the
+    reference's data/cube.obj and data/sphere.obj) GenNormals gives every corner the FLAT normal of its face, normalize((v1-v0)x(v2-v0))
+    in float, and JoinIdenticalVertices then merges corners whose position, normal and texture coordinate are all identical, keeping
+    first occurrences in order -- so coplanar neighbours share vertices and everything else is split per face.  A file WITH normals
+    keeps them and only the join applies.  Returns (pos [V,3] f32, nrm [V,3] f32, tri [F,3] u32); polygons are fan-triangulated
+    (assimp's ear clipping differs only for non-convex polygons; the reference's assets are triangles)."""
+    vs, vns, vts, faces = [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            s = line.split()
+            if not s:
+                continue
+            if s[0] == "v":
+                vs.append([float(x) for x in s[1:4]])
+            elif s[0] == "vn":
+                vns.append([float(x) for x in s[1:4]])
+            elif s[0] == "vt":
+                vts.append([float(x) for x in (s[1:3] + ["0"])[:2]])
+            elif s[0] == "f":
+                c = []
+                for tok in s[1:]:
+                    q = (tok.split("/") + ["", ""])[:3]
+                    idx = [int(x) if x else 0 for x in q]
+                    c.append(tuple(i - 1 if i > 0 else (n + i if i < 0 else -1) for i, n in zip(idx, (len(vs), len(vts), len(vns)))))
+                for k in range(1, len(c) - 1):
+                    faces.append((c[0], c[k], c[k + 1]))
+    vs = np.asarray(vs, np.float32)
+    vns = np.asarray(vns, np.float32).reshape(-1, 3)
+    vts = np.asarray(vts, np.float32).reshape(-1, 2)
+    fv = np.asarray([[c[0] for c in f] for f in faces], np.int64)
+    corner_pos = vs[fv]                                                           # [F,3,3]
+    if len(vns):
+        fn = np.asarray([[c[2] for c in f] for f in faces], np.int64)
+        corner_nrm = np.where((fn >= 0)[..., None], vns[np.maximum(fn, 0)], np.float32(0))
+    else:
+        e1, e2 = corner_pos[:, 1] - corner_pos[:, 0], corner_pos[:, 2] - corner_pos[:, 0]
+        n = np.cross(e1, e2).astype(np.float32)
+        ln = np.sqrt((n * n).sum(1, keepdims=True, dtype=np.float32))
+        n = np.where(ln > 0, n / np.where(ln > 0, ln, 1), n).astype(np.float32)   # NormalizeSafe
+        corner_nrm = np.repeat(n[:, None, :], 3, axis=1)
+    if len(vts):
+        ft = np.asarray([[c[1] for c in f] for f in faces], np.int64)
+        corner_uv = np.where((ft >= 0)[..., None], vts[np.maximum(ft, 0)], np.float32(0))
+    else:
+        corner_uv = np.zeros(corner_pos.shape[:2] + (2,), np.float32)
+    rec = np.concatenate([corner_pos, corner_nrm, corner_uv], -1).reshape(-1, 8).astype(np.float32) + np.float32(0)   # -0 -> +0
+    # (assimp joins with an epsilon of 1e-5 on every component; exact equality is used here -- it differs only for corners whose
+    # face normals agree to 1e-5 without being equal)
+    _, first, inv = np.unique(rec.view(np.uint32), axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")                                      # first occurrences, in file order
+    rank = np.empty(len(order), np.int64)
+    rank[order] = np.arange(len(order))
+    keep = first[order]
+    return rec[keep, 0:3].copy(), rec[keep, 3:6].copy(), rank[inv.reshape(-1)].reshape(-1, 3).astype(np.uint32)
 
 
 def morton_order(pos: np.ndarray) -> np.ndarray:

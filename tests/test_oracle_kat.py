@@ -174,3 +174,33 @@ def test_interreflection_properties(oracle):
     assert np.allclose(dark, sh, atol=1e-7)                          # Lw < 0.01 cut (raytracing.cpp:249)
     f1, _, _ = oracle.bake_transfer(sc, pos[sel][:8], nrm[sel][:8], oracle.make_params(**kw), faithful=True)
     assert np.allclose(f1, sh[:8], atol=1e-7)                        # per-coefficient re-tracing gives the same numbers
+
+
+def test_reference_assets_vertex_semantics():
+    """data/cube.obj and data/sphere.obj carry no normals: under the reference's import flags (model.cpp:72) every face corner gets
+    its face's flat normal and only identical (pos, normal, uv) corners are joined."""
+    import os
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    pos, nrm, tri = meshes.load_obj_assimp(os.path.join(g, "sphere.obj"))
+    assert tri.shape == (5120, 3) and len(pos) == 3 * 5120          # no two facets of the icosphere are coplanar
+    fn = np.cross(pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    for k in range(3):
+        assert np.abs(nrm[tri[:, k]] - fn).max() < 1e-6
+    pos, nrm, tri = meshes.load_obj_assimp(os.path.join(g, "cube.obj"))
+    assert tri.shape == (820, 3) and 416 < len(pos) < 3 * 820        # coplanar neighbours of the room's walls share vertices
+    assert len(np.unique(np.concatenate([pos, nrm], 1), axis=0)) == len(pos)
+    assert np.abs(np.abs(pos).max(0) - 6.18).max() < 1e-3
+    # a file with normals keeps them (smooth normals survive the import)
+    import tempfile
+    p, n, t = meshes.icosphere(1)
+    with tempfile.NamedTemporaryFile("w", suffix=".obj", delete=False) as f:
+        for v in p:
+            f.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for v in n:
+            f.write("vn %.9g %.9g %.9g\n" % tuple(v))
+        for a, b, c in t + 1:
+            f.write(f"f {a}//{a} {b}//{b} {c}//{c}\n")
+    p2, n2, t2 = meshes.load_obj_assimp(f.name)
+    os.unlink(f.name)
+    assert len(p2) == len(p) and np.allclose(p2[t2], p[t]) and np.allclose(n2[t2], n[t])
