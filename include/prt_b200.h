@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PRT_B200_ABI_VERSION 1
+#define PRT_B200_ABI_VERSION 2
 
 enum {
     PRT_OK = 0,
@@ -48,13 +48,16 @@ int prt_abi_version(void);
 int prt_ctx_create(int device_id, prt_ctx **out);
 void prt_ctx_destroy(prt_ctx *);
 int prt_ctx_device(const prt_ctx *);
+/* CUDA-event duration of the kernels of the most recent prt_env_* / prt_brdf_lut / prt_volume_weights call on this context (those
+ * entry points also accept NULL host outputs: the result then stays in the context's device scratch -- timing runs) */
+int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
 /* name/value tuning knobs for experiments; unknown names and out-of-range values fail.  None of them changes a result
  * (tests/test_gpu_parity.py), only how the work is organised:
  *   horizon 0/1 (1)            per-origin horizon pass before the shadowed / interreflected bake
  *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
  *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
  *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first; -1 = only for small vertex counts
- *   entry_list, pair_queue, refill_thresh, block, ctas_per_sm   kernel selection / occupancy of the older kernel variants
+ *   entry_list, pair_queue (0 per-ray stacks / 2 wavefront), refill_thresh, block, ctas_per_sm   the per-ray fallback kernel (S > 8192, horizon off)
  *   count_work 0/1 (0)         instrumented launch filling the work counters of prt_bake_stats */
 int prt_ctx_set_tuning(prt_ctx *, const char *name, int value);
 
@@ -97,10 +100,14 @@ typedef struct {
     float origin_eps;     /* 1e-4 (raytracing.cpp:343) */
     float bounce_eps;     /* 1e-5 (raytracing.cpp:235) */
     int32_t mode;         /* PRT_SHADOWED etc. */
-    int32_t cs_phase;     /* 0: SH_function.h convention; 1: google/spherical-harmonics sign */
+    int32_t cs_phase;     /* 1 (default): Condon-Shortley sign (-1)^m on the basis, as google/spherical-harmonics' sh::EvalSH has it --
+                             what bake_SH itself computes (raytracing.cpp:226); 0: the sign-free convention of the reference's own
+                             SH_function.h / common/SH.glsl, which the probe path and the viewer's SH_Irad() use */
     int32_t jitter;       /* 1: jittered strata (raytracing.cpp:338-339); 0: stratum centres */
 } prt_bake_params;
 
+/* The reference's defaults: order 3, 32 x 32 jittered strata, no bounce (max_path_length 2), albedo 1, eps 1e-4 / 1e-5, shadowed,
+ * cs_phase 1 (bake_SH evaluates the basis with sh::EvalSH). */
 void prt_bake_params_default(prt_bake_params *);
 
 /* Host buffers in, host buffers out.  pos/nrm point at the first vertex's position / normal, consecutive
@@ -116,6 +123,13 @@ int prt_bake_transfer(prt_ctx *, prt_scene *, const float *pos, const float *nrm
 int prt_bake_transfer_device(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes,
                              uint32_t n_verts, uint32_t vertex_id_base, const prt_bake_params *,
                              float *d_out_coeffs, uint32_t *d_out_vis, void *stream);
+
+/* Same, with the rows written out_stride_bytes apart instead of packed: d_out_coeffs + 24 bytes into a device-resident Mesh::Vert
+ * array with out_stride_bytes = 60 and order 3 fills sh_coeff[9] of every vertex in place (gl.h:76-80) -- the device-side half of
+ * Mesh::update (gl.cpp:255-268) for a VBO mapped with cudaGraphicsGLRegisterBuffer: no host hop, no scatter pass. */
+int prt_bake_transfer_device_strided(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes,
+                                     uint32_t n_verts, uint32_t vertex_id_base, const prt_bake_params *,
+                                     float *d_out_coeffs, size_t out_stride_bytes, uint32_t *d_out_vis, void *stream);
 
 /* Mesh::Vert scatter for the viewer (gl.h:76-80, gl.cpp:255-268): writes order-3 rows into sh_coeff[9] of an
  * interleaved 60-byte vertex array on the host. */
@@ -140,6 +154,52 @@ typedef struct {
     double horizon_ms;       /* part of kernel_ms spent in the horizon pass (0 when it did not run) */
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
+
+/* ---- multi-GPU driver: one process, 1..8 GPUs of one box (BASELINE config 5) ---------------------------------
+ * The reference's per-vertex loop (std::for_each(par, verts...), raytracing.cpp:328) sharded over GPUs: one context per device, the
+ * BVH built once and replicated, the vertex list dealt out in interleaved 64-vertex chunks (callers should pass vertices in a
+ * space-filling-curve order), coefficient rows gathered on every GPU and returned to the host in the caller's vertex order.
+ * Results are bit-identical to a single-GPU prt_bake_transfer of the same list (each vertex is reduced by one warp in a fixed order;
+ * the bounce RNG is keyed by the position in the list). */
+typedef struct prt_group prt_group;
+typedef struct prt_group_scene prt_group_scene;
+enum {
+    PRT_GATHER_NONE = 0,   /* rows stay on the GPU that baked them (the host still receives all rows) */
+    PRT_GATHER_NCCL = 1,   /* in-place ncclAllGather (ncclCommInitAll communicator over the group) + permutation to vertex order */
+    PRT_GATHER_P2P = 2,    /* fused: the bake kernels store every finished row into every peer GPU's buffer (P2P over NVLink) */
+    PRT_GATHER_AUTO = -1   /* P2P if every pair has peer access, else NCCL, else NONE */
+};
+/* contexts on the listed devices, peer access between every pair, an NCCL communicator over them (NCCL is loaded at run time with
+ * dlopen; without it, or with a device listed twice, only the P2P / NONE modes work -- prt_group_capabilities says which and why) */
+int prt_group_create(const int *device_ids, int n_devices, prt_group **out);
+void prt_group_destroy(prt_group *);
+int prt_group_size(const prt_group *);
+prt_ctx *prt_group_ctx(prt_group *, int member);
+int prt_group_capabilities(const prt_group *, int *p2p, int *nccl, int *nccl_version, char *why, size_t why_len);
+int prt_group_set_tuning(prt_group *, const char *name, int value);            /* prt_ctx_set_tuning on every member */
+/* RTScene(Mesh&) once for the whole group: ONE host BVH build, one upload per GPU (parallel over the PCIe links) */
+int prt_group_scene_create(prt_group *, const float *pos_xyz, size_t pos_stride_bytes, uint32_t n_verts,
+                           const uint32_t *tri_idx, uint32_t n_tris, prt_group_scene **out);
+void prt_group_scene_destroy(prt_group_scene *);
+int prt_group_scene_get_info(const prt_group_scene *, prt_scene_info *out);      /* upload_seconds = slowest GPU */
+prt_scene *prt_group_scene_member(prt_group_scene *, int member);
+typedef struct {
+    uint32_t n_devices; int32_t gather_mode;     /* the mode used (AUTO resolved) */
+    double wall_ms;                              /* host clock around the whole call */
+    double kernel_ms_max, gather_ms_max;         /* slowest GPU: bake kernels; collective + permutation (NCCL mode; ~0 otherwise) */
+    double h2d_ms[8], kernel_ms[8], gather_ms[8];/* per GPU, CUDA events on its stream */
+    uint32_t vertices[8];                        /* vertices baked per GPU */
+    uint64_t gather_bytes_per_gpu;               /* row bytes every GPU receives from its peers */
+    uint64_t h2d_bytes, d2h_bytes;               /* summed over the GPUs */
+} prt_group_stats;
+/* bake_SH over all GPUs of the group: host vertices in (layout as prt_bake_transfer; an interleaved Mesh::Vert array is uploaded
+ * once), out_coeffs [n_verts][order^2] on the host (may be NULL: rows stay on the GPUs).  Every GPU uploads its own shard and
+ * downloads its own rows over its own PCIe link; pinned host buffers make those copies asynchronous.  stats may be NULL. */
+int prt_group_bake_transfer(prt_group *, prt_group_scene *, const float *pos, const float *nrm, size_t stride_bytes, uint32_t n_verts,
+                            const prt_bake_params *, float *out_coeffs, int gather_mode, prt_group_stats *stats);
+/* the full [n_verts][order^2] rows as gathered on one member GPU by the last bake (modes NCCL / P2P): device pointer / host copy */
+const float *prt_group_rows_device(prt_group *, int member);
+int prt_group_download_rows(prt_group *, int member, float *out_coeffs);
 
 /* ---- image-based lighting (BASELINE config 2) ---------------------------------------------------------------------
  * Texture semantics the GL driver leaves open are pinned: FP32 storage, GL cube (sc,tc) table ==
@@ -257,7 +317,7 @@ int prt_film_download(const prt_film *, float *accum /*[h*w][4]*/, uint8_t *pixe
  * PRT_ERR_CACHE_MISS when the file is absent or keyed differently (other mesh / parameters / version) and PRT_ERR_IO when it is
  * damaged.  Host-only calls (no GPU needed). */
 uint64_t prt_hash_bytes(const void *data, size_t n_bytes, uint64_t seed /*0: FNV offset basis; chain calls by passing the last result*/);
-uint64_t prt_mesh_hash(const float *pos_xyz, size_t pos_stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris);
+uint64_t prt_mesh_hash(const float *pos_xyz, const float *nrm_xyz, size_t stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris);
 int prt_cache_save_transfer(const char *path, uint64_t mesh_hash, uint32_t n_verts, const prt_bake_params *, const float *coeffs);
 int prt_cache_load_transfer(const char *path, uint64_t mesh_hash, uint32_t n_verts, const prt_bake_params *, float *out_coeffs);
 /* config_hash: the caller's hash of everything else the capture depends on (probe positions, directions, solid angles) */

@@ -13,9 +13,9 @@ UNSHADOWED, SHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC = 0, 1, 2, 3
 
 # every symbol include/prt_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "prt_last_error", "prt_abi_version", "prt_ctx_create", "prt_ctx_destroy", "prt_ctx_device", "prt_ctx_set_tuning",
+    "prt_last_error", "prt_abi_version", "prt_ctx_create", "prt_ctx_destroy", "prt_ctx_device", "prt_ctx_last_kernel_ms", "prt_ctx_set_tuning",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_get_info", "prt_trace_any_hit", "prt_trace_closest_hit",
-    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_scatter_sh9",
+    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_bake_transfer_device_strided", "prt_scatter_sh9",
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
@@ -26,6 +26,9 @@ ABI_SYMBOLS = [
     "prt_film_create", "prt_film_destroy", "prt_film_reset", "prt_raytrace", "prt_film_download",
     "prt_hash_bytes", "prt_mesh_hash", "prt_cache_save_transfer", "prt_cache_load_transfer", "prt_cache_save_csr", "prt_cache_csr_sizes",
     "prt_cache_load_csr",
+    "prt_group_create", "prt_group_destroy", "prt_group_size", "prt_group_ctx", "prt_group_capabilities", "prt_group_set_tuning",
+    "prt_group_scene_create", "prt_group_scene_destroy", "prt_group_scene_get_info", "prt_group_scene_member", "prt_group_bake_transfer",
+    "prt_group_rows_device", "prt_group_download_rows",
 ]
 
 
@@ -108,6 +111,15 @@ class BakeStats(C.Structure):
                 ("block", C.c_uint32), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("cand_tests", C.c_uint64), ("rays_traversed", C.c_uint64), ("horizon_ms", C.c_double)]
 
 
+class GroupStats(C.Structure):
+    _fields_ = [("n_devices", C.c_uint32), ("gather_mode", C.c_int32), ("wall_ms", C.c_double), ("kernel_ms_max", C.c_double),
+                ("gather_ms_max", C.c_double), ("h2d_ms", C.c_double * 8), ("kernel_ms", C.c_double * 8), ("gather_ms", C.c_double * 8),
+                ("vertices", C.c_uint32 * 8), ("gather_bytes_per_gpu", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+GATHER_NONE, GATHER_NCCL, GATHER_P2P, GATHER_AUTO = 0, 1, 2, -1
+
+
 def lib_path() -> str:
     # PRT_B200_LIB selects an alternative in-tree build (kernel tuning experiments)
     return os.environ.get("PRT_B200_LIB") or os.path.join(_HERE, "csrc", "libprt_b200.so")
@@ -131,6 +143,7 @@ def load_library():
     L.prt_ctx_destroy.restype = None
     L.prt_ctx_device.argtypes = [vp]
     L.prt_ctx_set_tuning.argtypes = [vp, C.c_char_p, i32]
+    L.prt_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.prt_scene_create.argtypes = [vp, vp, sz, u32, vp, u32, C.POINTER(vp)]
     L.prt_scene_destroy.argtypes = [vp]
     L.prt_scene_destroy.restype = None
@@ -141,6 +154,7 @@ def load_library():
     L.prt_bake_params_default.restype = None
     L.prt_bake_transfer.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp]
     L.prt_bake_transfer_device.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
+    L.prt_bake_transfer_device_strided.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, sz, vp, vp]
     L.prt_scatter_sh9.argtypes = [vp, C.c_int32, u32, vp, sz, sz]
     L.prt_bake_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]
     L.prt_ctx_last_bake_stats.argtypes = [vp, C.POINTER(BakeStats)]
@@ -186,7 +200,25 @@ def load_library():
     L.prt_hash_bytes.restype = u64
     L.prt_hash_bytes.argtypes = [vp, sz, u64]
     L.prt_mesh_hash.restype = u64
-    L.prt_mesh_hash.argtypes = [vp, sz, u32, vp, u32]
+    L.prt_mesh_hash.argtypes = [vp, vp, sz, u32, vp, u32]
+    L.prt_group_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.prt_group_destroy.argtypes = [vp]
+    L.prt_group_destroy.restype = None
+    L.prt_group_size.argtypes = [vp]
+    L.prt_group_ctx.argtypes = [vp, i32]
+    L.prt_group_ctx.restype = vp
+    L.prt_group_capabilities.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p, sz]
+    L.prt_group_set_tuning.argtypes = [vp, C.c_char_p, i32]
+    L.prt_group_scene_create.argtypes = [vp, vp, sz, u32, vp, u32, C.POINTER(vp)]
+    L.prt_group_scene_destroy.argtypes = [vp]
+    L.prt_group_scene_destroy.restype = None
+    L.prt_group_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    L.prt_group_scene_member.argtypes = [vp, i32]
+    L.prt_group_scene_member.restype = vp
+    L.prt_group_bake_transfer.argtypes = [vp, vp, vp, vp, sz, u32, C.POINTER(BakeParams), vp, i32, C.POINTER(GroupStats)]
+    L.prt_group_rows_device.argtypes = [vp, i32]
+    L.prt_group_rows_device.restype = vp
+    L.prt_group_download_rows.argtypes = [vp, i32, vp]
     L.prt_cache_save_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
     L.prt_cache_load_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
     L.prt_cache_save_csr.argtypes = [C.c_char_p, u64, u64, u32, u64, u32, vp, vp, vp, vp, vp]
@@ -228,6 +260,11 @@ class Context:
     def set_tuning(self, **kw):
         for k, v in kw.items():
             _check(self.L.prt_ctx_set_tuning(self.h, k.encode(), int(v)), f"prt_ctx_set_tuning({k})")
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_double()
+        _check(self.L.prt_ctx_last_kernel_ms(self.h, C.byref(ms)), "prt_ctx_last_kernel_ms")
+        return ms.value
 
     def last_bake_stats(self) -> BakeStats:
         s = BakeStats()
@@ -315,8 +352,11 @@ def bake_SH(verts: np.ndarray, indices: np.ndarray, params: BakeParams | None = 
 
     ``verts`` is the reference's interleaved Mesh::Vert array, shape [V, 15] float32 = pos(3) norm(3) sh_coeff(9)
     (gl.h:76-80); it is updated in place (sh_coeff columns) exactly like ``edit_verts()`` and also returned.
+    Default parameters are ``prt_bake_params_default`` (the reference's, with the Condon-Shortley sign of ``sh::EvalSH``).
     """
-    params = params or BakeParams.make()
+    if params is None:
+        params = BakeParams()
+        load_library().prt_bake_params_default(C.byref(params))    # incl. cs_phase = 1: bake_SH evaluates sh::EvalSH
     verts = np.asarray(verts)
     if verts.dtype != np.float32 or verts.ndim != 2 or verts.shape[1] != 15 or not verts.flags.c_contiguous:
         raise PRTError("bake_SH: verts must be a C-contiguous [V,15] float32 Mesh::Vert array")
@@ -332,6 +372,67 @@ def bake_SH(verts: np.ndarray, indices: np.ndarray, params: BakeParams | None = 
         _check(L.prt_scatter_sh9(_ptr(out), params.order, n, C.c_void_p(base), 60, 24), "prt_scatter_sh9")
     scene.close()
     return out
+
+
+class Group:
+    """Multi-GPU driver in ONE process (``prt_group_*``): the reference's ``bake_SH`` vertex loop (raytracing.cpp:328) sharded over the
+    listed GPUs, BVH replicated, rows gathered on every GPU (fused P2P stores or NCCL all-gather)."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _check(self.L.prt_group_create(ids, len(devices), C.byref(h)), "prt_group_create")
+        self.h, self.n = h, len(devices)
+        self.scene_h = None
+
+    def close(self):
+        if getattr(self, "scene_h", None):
+            self.L.prt_group_scene_destroy(self.scene_h)
+            self.scene_h = None
+        if getattr(self, "h", None):
+            self.L.prt_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def capabilities(self) -> dict:
+        p2p, nccl, ver = C.c_int(), C.c_int(), C.c_int()
+        why = C.create_string_buffer(512)
+        _check(self.L.prt_group_capabilities(self.h, C.byref(p2p), C.byref(nccl), C.byref(ver), why, 512), "prt_group_capabilities")
+        return {"p2p": bool(p2p.value), "nccl": bool(nccl.value), "nccl_version": ver.value, "why": why.value.decode()}
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            _check(self.L.prt_group_set_tuning(self.h, k.encode(), int(v)), f"prt_group_set_tuning({k})")
+
+    def set_scene(self, pos: np.ndarray, tri: np.ndarray) -> SceneInfo:
+        pos = np.ascontiguousarray(pos, np.float32); tri = np.ascontiguousarray(tri, np.uint32)
+        if self.scene_h:
+            self.L.prt_group_scene_destroy(self.scene_h)
+            self.scene_h = None
+        h = C.c_void_p()
+        _check(self.L.prt_group_scene_create(self.h, _ptr(pos), 12, len(pos), _ptr(tri), len(tri), C.byref(h)), "prt_group_scene_create")
+        self.scene_h = h
+        info = SceneInfo()
+        _check(self.L.prt_group_scene_get_info(h, C.byref(info)), "prt_group_scene_get_info")
+        return info
+
+    def bake_transfer(self, pos, nrm, params: BakeParams, gather: int = GATHER_AUTO, out: np.ndarray | None = None, want_host: bool = True):
+        """-> (rows [n, order^2] in the order of ``pos`` (or None), GroupStats)."""
+        pos = np.ascontiguousarray(pos, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
+        n = len(pos)
+        if want_host and out is None:
+            out = np.zeros((n, params.n_coeffs), np.float32)
+        st = GroupStats()
+        _check(self.L.prt_group_bake_transfer(self.h, self.scene_h, _ptr(pos), _ptr(nrm), 12, n, C.byref(params),
+                                              _ptr(out) if want_host else None, gather, C.byref(st)), "prt_group_bake_transfer")
+        return (out if want_host else None), st
+
+    def download_rows(self, member: int, n: int, n2: int) -> np.ndarray:
+        out = np.zeros((n, n2), np.float32)
+        _check(self.L.prt_group_download_rows(self.h, member, _ptr(out)), "prt_group_download_rows")
+        return out
 
 
 def sample_table(params: BakeParams):
@@ -621,9 +722,14 @@ def raytrace(scene: RTScene, film: Film, camera: Camera, max_path_length: int = 
 ERR_IO, ERR_CACHE_MISS = -6, -7
 
 
-def mesh_hash(pos: np.ndarray, tri: np.ndarray) -> int:
+def mesh_hash(pos: np.ndarray, tri: np.ndarray, nrm: np.ndarray | None = None) -> int:
+    """Key of a baked result: positions, triangles and -- for per-vertex transfer, whose rays start at P + eps N in the frame of N --
+    the vertex normals (pass ``nrm``); a probe capture does not depend on them."""
     p = np.ascontiguousarray(pos, np.float32); t = np.ascontiguousarray(tri, np.uint32)
-    return int(load_library().prt_mesh_hash(_ptr(p), 12, len(p), _ptr(t), len(t)))
+    n = None if nrm is None else np.ascontiguousarray(nrm, np.float32)
+    if n is not None and n.shape != p.shape:
+        raise PRTError("mesh_hash: nrm must have the shape of pos")
+    return int(load_library().prt_mesh_hash(_ptr(p), _ptr(n), 12, len(p), _ptr(t), len(t)))
 
 
 def hash_arrays(*arrays) -> int:

@@ -47,11 +47,16 @@ struct prt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
     int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 30, work_list_on = -1 /* -1 = auto */;
-    // cached sample table
+    // cached sample table (the device copy is only replaced after the bake that last read it has finished: ev_tab)
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
+    std::vector<float> h_samples;
+    cudaEvent_t ev_tab = nullptr; bool tab_in_use = false;
     DevBuf counter, d_pos, d_nrm, d_out, d_vis, d_rays, d_res, need_bits, need_count, work_list;
     prt_bake_stats stats{};
     bool stats_pending = false, work_pending = false;
+    // grow-only scratch buffers and a phase timer for the other entry points (env.cu, volume.cu): no cudaMalloc / cudaFree per call
+    DevBuf scratch[8];
+    cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr; bool phase_timed = false;
 };
 
 struct prt_scene {
@@ -62,10 +67,51 @@ struct prt_scene {
 };
 
 int prt_set_error(int code, const std::string &msg) { return set_err(code, msg); }
+void *prt_ctx_scratch(prt_ctx *c, int slot, size_t bytes) {
+    if (!c || slot < 0 || slot >= 8) return nullptr;
+    if (c->scratch[slot].reserve(bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return c->scratch[slot].p;
+}
+void prt_ctx_timer_begin(prt_ctx *c, cudaStream_t st) { cudaEventRecord(c->ev_p0, st); c->phase_timed = false; }
+void prt_ctx_timer_end(prt_ctx *c, cudaStream_t st) { cudaEventRecord(c->ev_p1, st); c->phase_timed = true; }
 cudaStream_t prt_ctx_stream(prt_ctx *c) { return c->stream; }
 int prt_ctx_sms(const prt_ctx *c) { return c->n_sms; }
 int prt_ctx_refill_thresh(const prt_ctx *c) { return c->refill_thresh; }
 prt_scene_view prt_scene_get_view(prt_scene *s) { return prt_scene_view{s->d_nodes, s->d_tris, s->ctx}; }
+
+// host BVH build shared by prt_scene_create and prt_group_scene_create (one build, one upload per GPU)
+int prt_build_host_bvh(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx, uint32_t nt, HostBVH8 *h) {
+    if (!pos || !idx || nv == 0 || nt == 0) return set_err(PRT_ERR_INVALID, "prt_scene_create: empty mesh");
+    if (stride == 0) stride = 12;
+    if (stride % 4) return set_err(PRT_ERR_INVALID, "prt_scene_create: stride must be a multiple of 4");
+    char err[256] = {0};
+    if (build_bvh8(pos, stride, nv, idx, nt, h, err, sizeof err) != 0) return set_err(PRT_ERR_BUILD, err);
+    return PRT_OK;
+}
+
+int prt_scene_from_host_bvh(prt_ctx *c, const HostBVH8 *hp, prt_scene **out) {
+    const HostBVH8 &h = *hp;
+    CU_TRY(cudaSetDevice(c->device));
+    prt_scene *s = new prt_scene();
+    s->ctx = c;
+    auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaMalloc(&s->d_nodes, sizeof(Node8) * (size_t)h.n_nodes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, sizeof(Tri48) * (size_t)h.n_tris);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_nodes, h.nodes, sizeof(Node8) * (size_t)h.n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_tris, h.tris, sizeof(Tri48) * (size_t)h.n_tris, cudaMemcpyHostToDevice);
+    s->info.n_tris = h.n_tris; s->info.n_nodes = h.n_nodes; s->info.max_depth = h.max_depth;
+    s->info.node_bytes = sizeof(Node8) * (uint64_t)h.n_nodes; s->info.tri_bytes = sizeof(Tri48) * (uint64_t)h.n_tris;
+    s->info.build_seconds = h.build_seconds; s->info.sah_cost = h.sah_cost;
+    s->info.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (e != cudaSuccess) {
+        if (s->d_nodes) cudaFree(s->d_nodes);
+        if (s->d_tris) cudaFree(s->d_tris);
+        delete s;
+        return set_err(e == cudaErrorMemoryAllocation ? PRT_ERR_NOMEM : PRT_ERR_CUDA, std::string("prt_scene_create: ") + cudaGetErrorString(e));
+    }
+    *out = s;
+    return PRT_OK;
+}
 
 extern "C" {
 
@@ -90,6 +136,8 @@ int prt_ctx_create(int device_id, prt_ctx **out) {
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0)); CU_TRY(cudaEventCreate(&c->ev1));
     CU_TRY(cudaEventCreate(&c->ev2)); CU_TRY(cudaEventCreate(&c->ev3)); CU_TRY(cudaEventCreate(&c->evh));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreate(&c->ev_p0)); CU_TRY(cudaEventCreate(&c->ev_p1));
     *out = c;
     return PRT_OK;
 }
@@ -104,11 +152,27 @@ void prt_ctx_destroy(prt_ctx *c) {
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->evh) cudaEventDestroy(c->evh);
+    if (c->ev_tab) cudaEventDestroy(c->ev_tab);
+    if (c->ev_p0) cudaEventDestroy(c->ev_p0);
+    if (c->ev_p1) cudaEventDestroy(c->ev_p1);
+    for (DevBuf &b : c->scratch) b.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int prt_ctx_device(const prt_ctx *c) { return c ? c->device : -1; }
+
+int prt_ctx_last_kernel_ms(const prt_ctx *c, double *ms) {
+    if (!c || !ms) return set_err(PRT_ERR_INVALID, "prt_ctx_last_kernel_ms: null argument");
+    *ms = 0.0;
+    if (!c->phase_timed) return PRT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventSynchronize(c->ev_p1));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, c->ev_p0, c->ev_p1));
+    *ms = f;
+    return PRT_OK;
+}
 
 int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     if (!c || !name) return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: null argument");
@@ -122,7 +186,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "work_list") c->work_list_on = value < 0 ? -1 : value ? 1 : 0;
     else if (n == "horizon_near") { if (value < 5 || value > 95) return set_err(PRT_ERR_INVALID, "horizon_near (angular radius x100, rad) must be in [5,95]"); c->horizon_near = value; }
     else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
-    else if (n == "pair_queue") { if (value < 0 || value > 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks), 1 (pair queues) or 2 (wavefront)"); c->pair_queue = value; }
+    else if (n == "pair_queue") { if (value != 0 && value != 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks) or 2 (wavefront)"); c->pair_queue = value; }
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
     return PRT_OK;
 }
@@ -130,33 +194,12 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
 int prt_scene_create(prt_ctx *c, const float *pos, size_t stride, uint32_t nv, const uint32_t *idx, uint32_t nt, prt_scene **out) {
     if (!c || !out) return set_err(PRT_ERR_INVALID, "prt_scene_create: null argument");
     *out = nullptr;
-    if (!pos || !idx || nv == 0 || nt == 0) return set_err(PRT_ERR_INVALID, "prt_scene_create: empty mesh");
-    if (stride == 0) stride = 12;
-    if (stride % 4) return set_err(PRT_ERR_INVALID, "prt_scene_create: stride must be a multiple of 4");
     HostBVH8 h;
-    char err[256] = {0};
-    if (build_bvh8(pos, stride, nv, idx, nt, &h, err, sizeof err) != 0) return set_err(PRT_ERR_BUILD, err);
-    CU_TRY(cudaSetDevice(c->device));
-    prt_scene *s = new prt_scene();
-    s->ctx = c;
-    auto t0 = std::chrono::steady_clock::now();
-    cudaError_t e = cudaMalloc(&s->d_nodes, sizeof(Node8) * (size_t)h.n_nodes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, sizeof(Tri48) * (size_t)h.n_tris);
-    if (e == cudaSuccess) e = cudaMemcpy(s->d_nodes, h.nodes, sizeof(Node8) * (size_t)h.n_nodes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->d_tris, h.tris, sizeof(Tri48) * (size_t)h.n_tris, cudaMemcpyHostToDevice);
-    s->info.n_tris = h.n_tris; s->info.n_nodes = h.n_nodes; s->info.max_depth = h.max_depth;
-    s->info.node_bytes = sizeof(Node8) * (uint64_t)h.n_nodes; s->info.tri_bytes = sizeof(Tri48) * (uint64_t)h.n_tris;
-    s->info.build_seconds = h.build_seconds; s->info.sah_cost = h.sah_cost;
-    s->info.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    int rc = prt_build_host_bvh(pos, stride, nv, idx, nt, &h);
+    if (rc) return rc;
+    rc = prt_scene_from_host_bvh(c, &h, out);
     free_bvh8(&h);
-    if (e != cudaSuccess) {
-        if (s->d_nodes) cudaFree(s->d_nodes);
-        if (s->d_tris) cudaFree(s->d_tris);
-        delete s;
-        return set_err(e == cudaErrorMemoryAllocation ? PRT_ERR_NOMEM : PRT_ERR_CUDA, std::string("prt_scene_create: ") + cudaGetErrorString(e));
-    }
-    *out = s;
-    return PRT_OK;
+    return rc;
 }
 
 void prt_scene_destroy(prt_scene *s) {
@@ -208,7 +251,7 @@ void prt_bake_params_default(prt_bake_params *p) {
     if (!p) return;
     p->order = 3; p->samples_u = 32; p->samples_v = 32; p->seed = 0x50525400u; p->bounces = 0;
     p->albedo[0] = p->albedo[1] = p->albedo[2] = 1.0f;
-    p->origin_eps = 1e-4f; p->bounce_eps = 1e-5f; p->mode = PRT_SHADOWED; p->cs_phase = 0; p->jitter = 1;
+    p->origin_eps = 1e-4f; p->bounce_eps = 1e-5f; p->mode = PRT_SHADOWED; p->cs_phase = 1; p->jitter = 1;
 }
 
 }  // extern "C"
@@ -247,7 +290,7 @@ uint32_t morton2(uint32_t i, uint32_t j) {
 
 // Device sample table in *processing* order: strata sorted along a Morton curve over (i,j) so that any run of 32
 // consecutive samples is a compact bundle of directions (coherent warps); w carries the reference index s.
-int ensure_samples(prt_ctx *c, const prt_bake_params *p) {
+int ensure_samples(prt_ctx *c, const prt_bake_params *p, cudaStream_t st) {
     if (c->samples.p && c->s_ru == p->samples_u && c->s_rv == p->samples_v && c->s_jit == p->jitter && c->s_seed == p->seed) return PRT_OK;
     const int S = p->samples_u * p->samples_v;
     std::vector<float> dirs(3 * (size_t)S);
@@ -270,14 +313,23 @@ int ensure_samples(prt_ctx *c, const prt_bake_params *p) {
         const uint32_t w = s | ((uint32_t)bin << 24);
         std::memcpy(&tab[4 * k + 3], &w, 4);
     }
+    // the previous bake (possibly on another stream) may still be reading the old table: wait for it, then upload in stream order
+    // from a host copy that stays alive in the context
+    if (c->tab_in_use) CU_TRY(cudaEventSynchronize(c->ev_tab));
     CU_TRY(c->samples.reserve(sizeof(float) * 4 * (size_t)S));
-    CU_TRY(cudaMemcpy(c->samples.p, tab.data(), sizeof(float) * 4 * (size_t)S, cudaMemcpyHostToDevice));
+    c->h_samples.swap(tab);
+    CU_TRY(cudaMemcpyAsync(c->samples.p, c->h_samples.data(), sizeof(float) * 4 * (size_t)S, cudaMemcpyHostToDevice, st));
     c->s_ru = p->samples_u; c->s_rv = p->samples_v; c->s_jit = p->jitter; c->s_seed = p->seed;
     return PRT_OK;
 }
 
-int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n, uint32_t vid_base,
-                const prt_bake_params *p, float *d_out, uint32_t *d_vis, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+}  // namespace
+
+// The bake on device-resident vertices.  e0 / e1 (optional) bracket the kernels for prt_ctx_last_bake_stats; `place` (optional) says
+// where rows go (row stride, shard of a multi-GPU bake, peer buffers of the fused gather): abi_internal.h.
+int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n, uint32_t vid_base,
+                    const prt_bake_params *p, float *d_out, uint32_t *d_vis, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                    const prt_row_placement *place) {
     int rc = check_params(p);
     if (rc) return rc;
     const bool needs_scene = p->mode == PRT_SHADOWED || p->mode == PRT_INTERREFLECT;
@@ -289,7 +341,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     if (n == 0) return PRT_OK;
     if (!d_pos || !d_nrm || !d_out) return set_err(PRT_ERR_INVALID, "bake: null buffer");
     CU_TRY(cudaSetDevice(c->device));
-    rc = ensure_samples(c, p);
+    rc = ensure_samples(c, p, st);
     if (rc) return rc;
     const int S = p->samples_u * p->samples_v;
     BakeArgs A{};
@@ -304,6 +356,14 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     A.albedo[0] = p->albedo[0]; A.albedo[1] = p->albedo[1]; A.albedo[2] = p->albedo[2];
     A.origin_eps = p->origin_eps; A.bounce_eps = p->bounce_eps; A.cs_phase = p->cs_phase;
     A.refill_thresh = c->refill_thresh;
+    if (place) {
+        const uint32_t n2 = (uint32_t)(p->order * p->order);
+        if (place->out_stride_floats && place->out_stride_floats < n2) return set_err(PRT_ERR_INVALID, "bake: output row stride is shorter than a row");
+        if (place->n_peer < 0 || place->n_peer > 7) return set_err(PRT_ERR_INVALID, "bake: at most 7 peer buffers");
+        A.out_stride = place->out_stride_floats; A.shard_world = place->shard_world; A.shard_rank = place->shard_rank;
+        A.out_global = place->out_global; A.n_peer = place->n_peer;
+        for (int i = 0; i < place->n_peer; i++) A.out_peer[i] = place->out_peer[i];
+    }
     A.entry_list = c->entry_list;
     A.horizon = c->horizon;
     A.horizon_budget = c->horizon_budget;
@@ -338,8 +398,6 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
         CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
         c->stats.block = (uint32_t)bake_wave_block();
     }
-    else if (fast_ok && c->pair_queue == 1 && c->block == 256)
-        CU_TRY(launch_bake_shadow(A, p->order, mode == 0, &used_grid, c->block, c->n_sms, st));
     else {
         A.need_bits = nullptr; A.need_count = nullptr;
         if (mode == 1 && c->horizon && c->entry_list) {
@@ -359,6 +417,7 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
             CU_TRY(launch_bake(A, p->order, mode, &used_grid, c->block, c->n_sms, st));
     }
     if (e1) CU_TRY(cudaEventRecord(e1, st));
+    CU_TRY(cudaEventRecord(c->ev_tab, st)); c->tab_in_use = true;
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;
     c->stats.launches = launches; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
     c->stats_pending = e0 && e1;
@@ -366,14 +425,21 @@ int bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nr
     return PRT_OK;
 }
 
-}  // namespace
-
 extern "C" {
 
 int prt_bake_transfer_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,
                              uint32_t vid_base, const prt_bake_params *p, float *d_out, uint32_t *d_vis, void *stream) {
     if (!c) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device: ctx is null");
-    return bake_device(c, sc, d_pos, d_nrm, stride, n, vid_base, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2);
+    return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, vid_base, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2, nullptr);
+}
+
+int prt_bake_transfer_device_strided(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,
+                                     uint32_t vid_base, const prt_bake_params *p, float *d_out, size_t out_stride_bytes, uint32_t *d_vis, void *stream) {
+    if (!c) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_strided: ctx is null");
+    if (out_stride_bytes % 4) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_strided: out_stride_bytes must be a multiple of 4");
+    prt_row_placement pl{};
+    pl.out_stride_floats = (uint32_t)(out_stride_bytes / 4);
+    return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, vid_base, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2, &pl);
 }
 
 int prt_bake_transfer(prt_ctx *c, prt_scene *sc, const float *pos, const float *nrm, size_t stride, uint32_t n, uint32_t vid_base,
@@ -387,17 +453,22 @@ int prt_bake_transfer(prt_ctx *c, prt_scene *sc, const float *pos, const float *
     if (stride % 4) return set_err(PRT_ERR_INVALID, "prt_bake_transfer: stride must be a multiple of 4");
     CU_TRY(cudaSetDevice(c->device));
     const int n2 = p->order * p->order, S = p->samples_u * p->samples_v, words = (S + 31) / 32;
-    // gather strided host vertices into tight staging copies (what RTScene/bake_SH read from Mesh::verts())
+    // the vertices keep the caller's layout on the device.  Interleaved Mesh::Vert arrays (nrm inside the stride of pos, gl.h:76-80)
+    // are uploaded ONCE; separate position / normal arrays are two uploads
     const size_t span = (size_t)(n - 1) * stride + 12;
-    CU_TRY(c->d_pos.reserve(span)); CU_TRY(c->d_nrm.reserve(span));
+    const ptrdiff_t delta = reinterpret_cast<const char *>(nrm) - reinterpret_cast<const char *>(pos);
+    const bool interleaved = delta >= 12 && (size_t)delta + 12 <= stride;
+    CU_TRY(c->d_pos.reserve(interleaved ? span + (size_t)delta : span));
+    if (!interleaved) CU_TRY(c->d_nrm.reserve(span));
     CU_TRY(c->d_out.reserve((size_t)n * n2 * 4));
     if (out_vis) CU_TRY(c->d_vis.reserve((size_t)n * words * 4));
     cudaStream_t st = c->stream;
     CU_TRY(cudaEventRecord(c->ev0, st));
-    CU_TRY(cudaMemcpyAsync(c->d_pos.p, pos, span, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->d_nrm.p, nrm, span, cudaMemcpyHostToDevice, st));
-    rc = bake_device(c, sc, (const float *)c->d_pos.p, (const float *)c->d_nrm.p, stride, n, vid_base, p, (float *)c->d_out.p,
-                     out_vis ? (uint32_t *)c->d_vis.p : nullptr, st, c->ev1, c->ev2);
+    CU_TRY(cudaMemcpyAsync(c->d_pos.p, pos, interleaved ? span + (size_t)delta : span, cudaMemcpyHostToDevice, st));
+    if (!interleaved) CU_TRY(cudaMemcpyAsync(c->d_nrm.p, nrm, span, cudaMemcpyHostToDevice, st));
+    const float *dp = (const float *)c->d_pos.p;
+    const float *dn = interleaved ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(c->d_pos.p) + delta) : (const float *)c->d_nrm.p;
+    rc = prt_bake_device(c, sc, dp, dn, stride, n, vid_base, p, (float *)c->d_out.p, out_vis ? (uint32_t *)c->d_vis.p : nullptr, st, c->ev1, c->ev2, nullptr);
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * n2 * 4, cudaMemcpyDeviceToHost, st));
     if (out_vis) CU_TRY(cudaMemcpyAsync(out_vis, c->d_vis.p, (size_t)n * words * 4, cudaMemcpyDeviceToHost, st));
@@ -408,7 +479,7 @@ int prt_bake_transfer(prt_ctx *c, prt_scene *sc, const float *pos, const float *
     CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->ev2)); c->stats.kernel_ms = ms;
     if (c->stats.launches >= 2) { CU_TRY(cudaEventElapsedTime(&ms, c->ev1, c->evh)); c->stats.horizon_ms = ms; }
     CU_TRY(cudaEventElapsedTime(&ms, c->ev2, c->ev3)); c->stats.d2h_ms = ms;
-    c->stats.h2d_bytes = 2 * (uint64_t)span;
+    c->stats.h2d_bytes = interleaved ? (uint64_t)span + (uint64_t)delta : 2 * (uint64_t)span;
     c->stats.d2h_bytes = (uint64_t)n * n2 * 4 + (out_vis ? (uint64_t)n * words * 4 : 0);
     c->stats_pending = false;
     return PRT_OK;

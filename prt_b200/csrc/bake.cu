@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
                 if (dot3(tr.d, n) >= -1e-4f) { active = false; continue; }          // :265
                 pos = madd3(pos, tr.best_t, tr.d);                                  // :266
                 float u, w;
-                rand2(A.seed, A.vid_base + v, sidx, (uint32_t)seg, 1u, u, w);        // :267
+                rand2(A.seed, A.vid_base + global_row(A, v), sidx, (uint32_t)seg, 1u, u, w);        // :267
                 const f3 l = cosine_local(u, w);
                 const float pdf = PRT_DIV(l.z, kPiF);
                 const Frame fb = make_frame(n);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) bake_kernel(const BakeArgs A) {
             const float s = warp_sum(acc[k]);
             if (lane == k) mine = s;
         }
-        if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
+        if (lane < N2) store_row(A, v, N2, lane, mine * A.inv_S);
         node_visits += tr.n_node_visits; tri_tests += tr.n_tri_tests;
     }
     if (A.work) {
@@ -222,7 +222,7 @@ __global__ void unshadowed_analytic_kernel(const BakeArgs A) {
     int k = 0;
 #pragma unroll
     for (int l = 0; l < ORDER; l++)
-        for (int m = -l; m <= l; m++, k++) A.out[(size_t)v * N2 + k] = lobe[l] * y[k];
+        for (int m = -l; m <= l; m++, k++) store_row(A, v, N2, k, lobe[l] * y[k]);
 }
 
 __global__ void __launch_bounds__(128) trace_any_kernel(const Node8 *nodes, const Tri48 *tris, const float4 *rays, uint32_t n, uint8_t *out) {

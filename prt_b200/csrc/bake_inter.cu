@@ -53,11 +53,10 @@ template <int ORDER, bool COUNT>
 cudaError_t launch_inter_tc(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
     const int block = 128;
     const size_t smem = sizeof(InterShared) * (size_t)(block / 32);
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_inter_kernel<ORDER, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<unsigned long long> configured{0};   // per instantiation, one bit per device
+    {
+        cudaError_t e = ensure_dynamic_smem(bake_inter_kernel<ORDER, COUNT>, (int)smem, configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (*grid <= 0) {
         int per_sm = 0;

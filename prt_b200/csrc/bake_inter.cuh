@@ -221,7 +221,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
                         if (!(dot3(d, n) >= -1e-4f)) {                                      // :265
                             f3 pos = madd3(mk3(a.x, a.y, a.z), __uint_as_float((uint32_t)(key >> 32)), d);   // :266
                             float u, w;
-                            rand2(A.seed, A.vid_base + v, sidx, (uint32_t)seg, 1u, u, w);    // :267
+                            rand2(A.seed, A.vid_base + global_row(A, v), sidx, (uint32_t)seg, 1u, u, w);    // :267
                             const f3 l = cosine_local(u, w);
                             const float pdf = PRT_DIV(l.z, kPiF);
                             const Frame fb = make_frame(n);
@@ -405,7 +405,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         const float s = warp_sum(acc[k]);
         if (lane == k) mine = s;
     }
-    if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
+    if (lane < N2) store_row(A, v, N2, lane, mine * A.inv_S);
     __syncwarp();
 }
 

@@ -75,11 +75,10 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
 template <int ORDER, bool TRACE, bool COUNT>
 cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
     const size_t smem = (sizeof(WaveShared) + 4 * (size_t)((A.vis_words + 3) & ~3)) * (size_t)(block / 32);
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bake_wave_kernel<ORDER, TRACE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)));
+    static std::atomic<unsigned long long> configured{0};   // per instantiation, one bit per device
+    {
+        cudaError_t e = ensure_dynamic_smem(bake_wave_kernel<ORDER, TRACE, COUNT>, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)), configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (*grid <= 0) {
         int per_sm = 0;

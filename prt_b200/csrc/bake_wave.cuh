@@ -47,6 +47,24 @@ struct WaveShared {
 };
 
 // Tests the 8 quantised child boxes of one node against a ray (interval [0, inf)); bit s of the result = slot s hit.
+// The traversal pass is bound by instruction issue with the XU pipe (I2F, MUFU.RCP; quarter rate) its busiest unit, so the byte ->
+// float conversions of the quantised planes can be moved to the ALU pipe (PRT_NODE_PRMT: 1 = the far planes, 2 = all planes): byte q
+// placed in mantissa bits 8..15 of 2^15 is the float 32768 + q, and the constant is folded into the plane offset,
+// t = (32768 + q) * s + (a - 32768 * s) -- still one FFMA per plane; the offset is rounded once more, at 2^-9 of a quantisation
+// step (covered by the builder's box padding like the other slack of the slab arithmetic).  PRT_NODE_FFMA2 pairs the two planes of
+// an axis in one packed fma.rn.f32x2 (sm_100a); measured: no gain, the FMA pipe is not what binds (profiles/r2_node_test_ab.jsonl).
+#ifndef PRT_NODE_FFMA2
+#define PRT_NODE_FFMA2 0
+#endif
+#ifndef PRT_NODE_PRMT
+#define PRT_NODE_PRMT 0
+#endif
+#define PRT_Q2F_I2F(w, j) ((float)(((w) >> (8 * (j))) & 0xFFu))
+#if defined(__CUDA_ARCH__)
+#define PRT_Q2F_PRMT(w, j) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7604u | ((j) << 4)))
+#else
+#define PRT_Q2F_PRMT(w, j) (32768.0f + PRT_Q2F_I2F(w, j))
+#endif
 __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o,
                                                    const float idx, const float idy, const float idz) {
     const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
@@ -55,6 +73,22 @@ __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, con
     const float ax = (__uint_as_float(n0.x) - o.x) * idx;
     const float ay = (__uint_as_float(n0.y) - o.y) * idy;
     const float az = (__uint_as_float(n0.z) - o.z) * idz;
+#if PRT_NODE_PRMT
+    const float bx = fmaf(-32768.0f, sx, ax), by = fmaf(-32768.0f, sy, ay), bz = fmaf(-32768.0f, sz, az);
+#endif
+#if PRT_NODE_PRMT >= 2
+#define PRT_NEAR(w, j, s, a, b) fmaf(PRT_Q2F_PRMT(w, j), s, b)
+#else
+#define PRT_NEAR(w, j, s, a, b) fmaf(PRT_Q2F_I2F(w, j), s, a)
+#endif
+#if PRT_NODE_PRMT >= 1
+#define PRT_FAR(w, j, s, a, b) fmaf(PRT_Q2F_PRMT(w, j), s, b)
+#else
+#define PRT_FAR(w, j, s, a, b) fmaf(PRT_Q2F_I2F(w, j), s, a)
+#define bx ax
+#define by ay
+#define bz az
+#endif
     const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
     uint32_t hits = 0u;
 #pragma unroll
@@ -66,18 +100,34 @@ __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, con
         const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int sh = 8 * j;
-            const float t0x = (float)((nearx >> sh) & 0xFFu) * sx + ax;
-            const float t0y = (float)((neary >> sh) & 0xFFu) * sy + ay;
-            const float t0z = (float)((nearz >> sh) & 0xFFu) * sz + az;
-            const float t1x = (float)((farx >> sh) & 0xFFu) * sx + ax;
-            const float t1y = (float)((fary >> sh) & 0xFFu) * sy + ay;
-            const float t1z = (float)((farz >> sh) & 0xFFu) * sz + az;
+#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT != 1
+#if PRT_NODE_PRMT
+#define PRT_Q2F PRT_Q2F_PRMT
+#else
+#define PRT_Q2F PRT_Q2F_I2F
+#endif
+            const float2 tx = __ffma2_rn(make_float2(PRT_Q2F(nearx, j), PRT_Q2F(farx, j)), make_float2(sx, sx), make_float2(bx, bx));
+            const float2 ty = __ffma2_rn(make_float2(PRT_Q2F(neary, j), PRT_Q2F(fary, j)), make_float2(sy, sy), make_float2(by, by));
+            const float2 tz = __ffma2_rn(make_float2(PRT_Q2F(nearz, j), PRT_Q2F(farz, j)), make_float2(sz, sz), make_float2(bz, bz));
+            const float t0x = tx.x, t1x = tx.y, t0y = ty.x, t1y = ty.y, t0z = tz.x, t1z = tz.y;
+#undef PRT_Q2F
+#else
+            const float t0x = PRT_NEAR(nearx, j, sx, ax, bx), t1x = PRT_FAR(farx, j, sx, ax, bx);
+            const float t0y = PRT_NEAR(neary, j, sy, ay, by), t1y = PRT_FAR(fary, j, sy, ay, by);
+            const float t0z = PRT_NEAR(nearz, j, sz, az, bz), t1z = PRT_FAR(farz, j, sz, az, bz);
+#endif
             const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
             const float tmax = fminf(fminf(t1x, t1y), t1z);
             if (tmin <= tmax) hits |= 1u << (4 * h + j);
         }
     }
+#if PRT_NODE_PRMT < 1
+#undef bx
+#undef by
+#undef bz
+#endif
+#undef PRT_NEAR
+#undef PRT_FAR
     return hits;
 }
 
@@ -353,7 +403,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
         const float s = warp_sum(acc[k]);
         if (lane == k) mine = s;
     }
-    if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;       // raytracing.cpp:350
+    if (lane < N2) store_row(A, v, N2, lane, mine * A.inv_S);            // raytracing.cpp:350
     if (A.vis) {
         if (TRACE) write_vis_permuted(A.samples, occl, reinterpret_cast<uint32_t *>(W.nq), A.vis + (size_t)v * words, S, words, lane);
         else

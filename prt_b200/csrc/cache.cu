@@ -15,7 +15,7 @@
 namespace {
 
 constexpr char kMagic[8] = {'P', 'R', 'T', 'B', '2', '0', '0', '\0'};
-constexpr uint32_t kVersion = 1u, kKindTransfer = 1u, kKindCsr = 2u;
+constexpr uint32_t kVersion = 2u, kKindTransfer = 1u, kKindCsr = 2u;
 
 struct Header {
     char magic[8];
@@ -89,12 +89,19 @@ extern "C" {
 
 uint64_t prt_hash_bytes(const void *data, size_t n_bytes, uint64_t seed) { return fnv1a(data, n_bytes, seed ? seed : 0xcbf29ce484222325ull); }
 
-uint64_t prt_mesh_hash(const float *pos_xyz, size_t pos_stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris) {
+// The baked rows are a function of positions, NORMALS (ray origin P + eps N, cosine frame) and triangles: all three are hashed.
+// nrm_xyz may be NULL for results that do not depend on normals (a probe capture keys on positions + triangles only).
+uint64_t prt_mesh_hash(const float *pos_xyz, const float *nrm_xyz, size_t stride_bytes, uint32_t n_verts, const uint32_t *tri_idx, uint32_t n_tris) {
     if (!pos_xyz || (!tri_idx && n_tris)) return 0;
-    if (pos_stride_bytes == 0) pos_stride_bytes = 12;
+    if (stride_bytes == 0) stride_bytes = 12;
     uint64_t h = fnv1a(&n_verts, 4);
     h = fnv1a(&n_tris, 4, h);
-    for (uint32_t i = 0; i < n_verts; i++) h = fnv1a(reinterpret_cast<const char *>(pos_xyz) + (size_t)i * pos_stride_bytes, 12, h);
+    for (uint32_t i = 0; i < n_verts; i++) h = fnv1a(reinterpret_cast<const char *>(pos_xyz) + (size_t)i * stride_bytes, 12, h);
+    if (nrm_xyz) {
+        const uint32_t tag = 0x4E524D31u;   // "NRM1"
+        h = fnv1a(&tag, 4, h);
+        for (uint32_t i = 0; i < n_verts; i++) h = fnv1a(reinterpret_cast<const char *>(nrm_xyz) + (size_t)i * stride_bytes, 12, h);
+    }
     return fnv1a(tri_idx, 12 * (size_t)n_tris, h);
 }
 

@@ -343,12 +343,13 @@ int prt_env_create(prt_ctx *c, const float *eq, int w, int h, int cube_size, prt
     int levels = 0;
     while ((cube_size >> levels) >= 1) levels++;
     const size_t texels = level_off(cube_size, levels);
-    float *d_eq = nullptr;
     float4 *cube = nullptr;
-    ENV_TRY(cudaMalloc(&d_eq, sizeof(float) * 3 * (size_t)w * h));
+    float *d_eq = (float *)prt_ctx_scratch(c, 2, sizeof(float) * 3 * (size_t)w * h);       // staging of the equirect image, reused by later calls
+    if (!d_eq) return prt_set_error(PRT_ERR_NOMEM, "prt_env_create: out of device memory");
     cudaError_t e = cudaMalloc(&cube, sizeof(float4) * texels);
-    if (e != cudaSuccess) { cudaFree(d_eq); return prt_set_error(PRT_ERR_NOMEM, "prt_env_create: cudaMalloc failed"); }
+    if (e != cudaSuccess) return prt_set_error(PRT_ERR_NOMEM, "prt_env_create: cudaMalloc failed");
     cudaMemcpyAsync(d_eq, eq, sizeof(float) * 3 * (size_t)w * h, cudaMemcpyHostToDevice, st);
+    prt_ctx_timer_begin(c, st);
     const size_t n = (size_t)6 * cube_size * cube_size;
     equirect_to_cube_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_eq, w, h, cube_size, cube);
     for (int l = 1; l < levels; l++) {
@@ -356,8 +357,8 @@ int prt_env_create(prt_ctx *c, const float *eq, int w, int h, int cube_size, prt
         const size_t m = (size_t)6 * (np >> 1) * (np >> 1);
         cube_downsample_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cube + level_off(cube_size, l - 1), np, cube + level_off(cube_size, l));
     }
+    prt_ctx_timer_end(c, st);
     e = cudaStreamSynchronize(st);
-    cudaFree(d_eq);
     if (e != cudaSuccess) { cudaFree(cube); return prt_set_error(PRT_ERR_CUDA, std::string("prt_env_create: ") + cudaGetErrorString(e)); }
     prt_env *env = new prt_env();
     env->ctx = c; env->cube = cube; env->n0 = cube_size; env->levels = levels;
@@ -385,12 +386,10 @@ int prt_env_get_cube(prt_env *e, int level, float *out_rgb) {
     ENV_TRY(cudaSetDevice(prt_ctx_device(e->ctx)));
     const int n = e->n0 >> level;
     const size_t tex = (size_t)6 * n * n;
-    float *tmp = nullptr;
-    ENV_TRY(cudaMalloc(&tmp, sizeof(float) * 3 * tex));
+    float *tmp = (float *)prt_ctx_scratch(e->ctx, 0, sizeof(float) * 3 * tex);
+    if (!tmp) return prt_set_error(PRT_ERR_NOMEM, "prt_env_get_cube: out of device memory");
     cube_to_rgb_kernel<<<(unsigned)((tex + 255) / 256), 256, 0, prt_ctx_stream(e->ctx)>>>(e->cube + level_off(e->n0, level), tex, tmp);
-    const int rc = download_rgb(e, tmp, 3 * tex, out_rgb);
-    cudaFree(tmp);
-    return rc;
+    return download_rgb(e, tmp, 3 * tex, out_rgb);
 }
 
 // float-accumulated loop variables of the shaders (for (x = 0; x < limit; x += step)), reproduced on the host
@@ -401,53 +400,56 @@ static std::vector<float> loop_values(float limit, float step) {
 }
 
 int prt_env_irradiance(prt_env *e, int n_out, float *out_rgb) {
-    if (!e || !out_rgb || n_out < 1) return prt_set_error(PRT_ERR_INVALID, "prt_env_irradiance: bad argument");
+    if (!e || n_out < 1) return prt_set_error(PRT_ERR_INVALID, "prt_env_irradiance: bad argument");
     ENV_TRY(cudaSetDevice(prt_ctx_device(e->ctx)));
     cudaStream_t st = prt_ctx_stream(e->ctx);
     const std::vector<float> phis = loop_values(2.0f * kPi, 0.025f), thetas = loop_values(0.5f * kPi, 0.025f);   // irradiance.frag:25-29
-    float *d_tab = nullptr, *d_out = nullptr;
     const size_t tex = (size_t)6 * n_out * n_out;
-    ENV_TRY(cudaMalloc(&d_tab, sizeof(float) * (phis.size() + thetas.size())));
-    ENV_TRY(cudaMalloc(&d_out, sizeof(float) * 3 * tex));
+    float *d_tab = (float *)prt_ctx_scratch(e->ctx, 1, sizeof(float) * (phis.size() + thetas.size()));
+    float *d_out = (float *)prt_ctx_scratch(e->ctx, 0, sizeof(float) * 3 * tex);
+    if (!d_tab || !d_out) return prt_set_error(PRT_ERR_NOMEM, "prt_env_irradiance: out of device memory");
     cudaMemcpyAsync(d_tab, phis.data(), sizeof(float) * phis.size(), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_tab + phis.size(), thetas.data(), sizeof(float) * thetas.size(), cudaMemcpyHostToDevice, st);
     CubeView cv{e->cube, e->n0, e->levels};
+    prt_ctx_timer_begin(e->ctx, st);
     irradiance_kernel<<<(unsigned)tex, 128, 0, st>>>(cv, n_out, d_tab, (int)phis.size(), d_tab + phis.size(), (int)thetas.size(), d_out);
-    const int rc = download_rgb(e, d_out, 3 * tex, out_rgb);
-    cudaFree(d_tab); cudaFree(d_out);
-    return rc;
+    prt_ctx_timer_end(e->ctx, st);
+    if (!out_rgb) { ENV_TRY(cudaStreamSynchronize(st)); return PRT_OK; }          // result stays on the device (timing runs)
+    return download_rgb(e, d_out, 3 * tex, out_rgb);
 }
 
 int prt_env_prefilter(prt_env *e, int n_out, int mips, int n_samples, float *out_rgb) {
-    if (!e || !out_rgb || n_out < 1 || mips < 2 || n_samples < 1 || (n_out >> (mips - 1)) < 1) return prt_set_error(PRT_ERR_INVALID, "prt_env_prefilter: bad argument");
+    if (!e || n_out < 1 || mips < 2 || n_samples < 1 || (n_out >> (mips - 1)) < 1) return prt_set_error(PRT_ERR_INVALID, "prt_env_prefilter: bad argument");
     ENV_TRY(cudaSetDevice(prt_ctx_device(e->ctx)));
     cudaStream_t st = prt_ctx_stream(e->ctx);
     const size_t total = level_off(n_out, mips);
-    float *d_out = nullptr;
-    ENV_TRY(cudaMalloc(&d_out, sizeof(float) * 3 * total));
+    float *d_out = (float *)prt_ctx_scratch(e->ctx, 0, sizeof(float) * 3 * total);
+    if (!d_out) return prt_set_error(PRT_ERR_NOMEM, "prt_env_prefilter: out of device memory");
     CubeView cv{e->cube, e->n0, e->levels};
+    prt_ctx_timer_begin(e->ctx, st);
     for (int mip = 0; mip < mips; mip++) {
         const int n = n_out >> mip;
         const float roughness = (float)mip / (float)(mips - 1);                       // gl.cpp:561
         const size_t warps = (size_t)6 * n * n;
         prefilter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(cv, n, roughness, n_samples, d_out + 3 * level_off(n_out, mip));
     }
-    const int rc = download_rgb(e, d_out, 3 * total, out_rgb);
-    cudaFree(d_out);
-    return rc;
+    prt_ctx_timer_end(e->ctx, st);
+    if (!out_rgb) { ENV_TRY(cudaStreamSynchronize(st)); return PRT_OK; }
+    return download_rgb(e, d_out, 3 * total, out_rgb);
 }
 
 int prt_brdf_lut(prt_ctx *c, int w, int h, int n_samples, float *out_rg) {
-    if (!c || !out_rg || w < 1 || h < 1 || n_samples < 1) return prt_set_error(PRT_ERR_INVALID, "prt_brdf_lut: bad argument");
+    if (!c || w < 1 || h < 1 || n_samples < 1) return prt_set_error(PRT_ERR_INVALID, "prt_brdf_lut: bad argument");
     ENV_TRY(cudaSetDevice(prt_ctx_device(c)));
     cudaStream_t st = prt_ctx_stream(c);
-    float *d_out = nullptr;
     const size_t tex = (size_t)w * h;
-    ENV_TRY(cudaMalloc(&d_out, sizeof(float) * 2 * tex));
+    float *d_out = (float *)prt_ctx_scratch(c, 0, sizeof(float) * 2 * tex);
+    if (!d_out) return prt_set_error(PRT_ERR_NOMEM, "prt_brdf_lut: out of device memory");
+    prt_ctx_timer_begin(c, st);
     brdf_lut_kernel<<<(unsigned)((tex * 32 + 255) / 256), 256, 0, st>>>(w, h, n_samples, d_out);
-    cudaError_t e = cudaMemcpyAsync(out_rg, d_out, sizeof(float) * 2 * tex, cudaMemcpyDeviceToHost, st);
+    prt_ctx_timer_end(c, st);
+    cudaError_t e = out_rg ? cudaMemcpyAsync(out_rg, d_out, sizeof(float) * 2 * tex, cudaMemcpyDeviceToHost, st) : cudaSuccess;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_out);
     if (e != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string("prt_brdf_lut: ") + cudaGetErrorString(e));
     return PRT_OK;
 }
@@ -460,9 +462,9 @@ int prt_env_project_sh(prt_env *e, int order, int method, int size, float *out_r
     const int n2 = order * order;
     const float delta = 2.0f * kPi / (float)size;
     const std::vector<float> thetas = loop_values(kPi, delta);                          // projectSH.comp:74
-    double *d_acc = nullptr; float *d_th = nullptr;
-    ENV_TRY(cudaMalloc(&d_acc, sizeof(double) * 3 * n2));
-    ENV_TRY(cudaMalloc(&d_th, sizeof(float) * thetas.size()));
+    double *d_acc = (double *)prt_ctx_scratch(e->ctx, 0, sizeof(double) * 3 * n2);
+    float *d_th = (float *)prt_ctx_scratch(e->ctx, 1, sizeof(float) * thetas.size());
+    if (!d_acc || !d_th) return prt_set_error(PRT_ERR_NOMEM, "prt_env_project_sh: out of device memory");
     cudaMemsetAsync(d_acc, 0, sizeof(double) * 3 * n2, st);
     cudaMemcpyAsync(d_th, thetas.data(), sizeof(float) * thetas.size(), cudaMemcpyHostToDevice, st);
     CubeView cv{e->cube, e->n0, e->levels};
@@ -477,7 +479,6 @@ int prt_env_project_sh(prt_env *e, int order, int method, int size, float *out_r
     std::vector<double> acc(3 * (size_t)n2);
     cudaError_t er = cudaMemcpyAsync(acc.data(), d_acc, sizeof(double) * 3 * n2, cudaMemcpyDeviceToHost, st);
     if (er == cudaSuccess) er = cudaStreamSynchronize(st);
-    cudaFree(d_acc); cudaFree(d_th);
     if (er != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string("prt_env_project_sh: ") + cudaGetErrorString(er));
     const double scale = method == 0 ? (double)delta * (double)delta : 4.0 / (double)size / (double)size;
     for (int k = 0; k < 3 * n2; k++) out_rgb_coeffs[k] = (float)(acc[k] * scale);

@@ -29,8 +29,16 @@ __device__ __forceinline__ void horizon_vertex(const BakeArgs &A, HorizonShared 
     const Frame fr = make_frame(N);
     const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
 
-    const int n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-    build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane);
+    // The map is built in the tangent frame and compared with the LOCAL z and azimuth bin of the samples, which is only valid when
+    // the frame is orthonormal, i.e. |N| = 1: frame(N) (raytracing.cpp:101-107) has |up| = |N|, so a non-unit normal (the reference
+    // passes assimp's normals through un-normalised, model.cpp:27) shears the ray directions against the sample table.  |N|^2 within
+    // 2e-5 of 1 moves a direction by < 1e-5 in sin(elevation), a twentieth of the map's margin; any other normal (also NaN) gets no
+    // map: every sample is traced by the traversal pass, whose arithmetic does not depend on |N|.
+    const bool unit = fabsf(dot3(N, N) - 1.0f) <= 2e-5f;
+    if (unit) {
+        const int n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
+        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane);
+    }
 
     uint32_t *row = A.need_bits + (size_t)v * words;
     uint32_t total = 0u;
@@ -39,7 +47,7 @@ __device__ __forceinline__ void horizon_vertex(const BakeArgs &A, HorizonShared 
         bool need = false;
         if (i < S) {
             const float4 smp = __ldg(&A.samples[i]);
-            need = !(smp.z > __uint_as_float(W.hz[__float_as_uint(smp.w) >> 24]));
+            need = !unit || !(smp.z > __uint_as_float(W.hz[__float_as_uint(smp.w) >> 24]));
         }
         const unsigned nb = __ballot_sync(kFull, need);
         if (lane == 0) row[base >> 5] = nb;
@@ -64,7 +72,7 @@ __device__ __forceinline__ void horizon_vertex(const BakeArgs &A, HorizonShared 
             const float s = warp_sum(acc[k]);
             if (lane == k) mine = s;
         }
-        if (lane < N2) A.out[(size_t)v * N2 + lane] = mine * A.inv_S;
+        if (lane < N2) store_row(A, v, N2, lane, mine * A.inv_S);
         if (A.vis) {
             for (int w = lane; w < words; w += 32) {
                 const int rem = S - 32 * w;

@@ -4,8 +4,24 @@
 #include "horizon_math.cuh"     // kHzBins
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace prt {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: `done` (one static per kernel instantiation) remembers the
+// devices it has been set on, so a second GPU in the same process (multi-GPU driver, a second context) gets it too
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<unsigned long long> &done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 
 struct BakeArgs {
     const Node8 *nodes;
@@ -37,14 +53,34 @@ struct BakeArgs {
     float origin_eps, bounce_eps;
     int cs_phase;
     int refill_thresh;          // refill idle lanes when fewer than this many lanes are traversing (0: static rounds)
+    // ---- output placement / sharding (all zero: rows packed [n_verts][order^2] in launch order) ------------------------------
+    uint32_t out_stride;        // floats between the rows of consecutive vertices; 0 = order^2 (60 B / 4 = 15 writes straight into
+                                // a Mesh::Vert array at sh_coeff, gl.h:76-80)
+    uint32_t shard_world, shard_rank;   // this launch bakes shard `rank` of `world` interleaved kShardChunk-vertex chunks of a longer
+                                // vertex list: local vertex v is global vertex global_row(v); the bounce RNG is keyed by the GLOBAL id
+    int out_global;             // rows are stored at the global index (a full-size buffer per GPU) instead of the local one
+    int n_peer;                 // fused gather: every finished row is also stored into these peer-GPU buffers (P2P over NVLink),
+    float *out_peer[7];         // so that no collective has to follow the kernel
 };
+
+constexpr uint32_t kShardChunk = 64;   // vertices per interleaved chunk of a sharded bake (prt_group_bake_transfer, prt_b200/dist.py)
+
+#if defined(__CUDACC__) || defined(PRT_HOSTCHECK)
+// global index of local vertex v of a sharded launch
+__host__ __device__ __forceinline__ uint32_t global_row(const BakeArgs &A, const uint32_t v) {
+    return A.shard_world > 1u ? ((v / kShardChunk) * A.shard_world + A.shard_rank) * kShardChunk + (v % kShardChunk) : v;
+}
+// coefficient k of vertex v (the lanes k < order^2 of the warp that baked v call this)
+__device__ __forceinline__ void store_row(const BakeArgs &A, const uint32_t v, const int n2, const int k, const float val) {
+    const size_t at = (size_t)(A.out_global ? global_row(A, v) : v) * (A.out_stride ? A.out_stride : (uint32_t)n2) + (size_t)k;
+    A.out[at] = val;
+    for (int p = 0; p < A.n_peer; p++) A.out_peer[p][at] = val;
+}
+#endif
 
 // mode: 0 shadowed, 1 interreflect, 2 unshadowed Monte-Carlo, 3 unshadowed analytic
 // *grid <= 0: one persistent wave, grid = n_sms x occupancy(kernel, block); the grid used is written back
 cudaError_t launch_bake(const BakeArgs &, int order, int mode, int *grid, int block, int n_sms, cudaStream_t);
-// pair-queue kernel for the shadowed (trace = true) and unshadowed Monte-Carlo (trace = false) modes, S <= bake_shadow_max_samples()
-cudaError_t launch_bake_shadow(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
-int bake_shadow_max_samples();
 // horizon pass (horizon.cu): per-vertex horizon map, classification of every sample, rows of fully visible vertices
 cudaError_t launch_bake_inter(const BakeArgs &, int order, int *grid, int n_sms, cudaStream_t);
 int bake_inter_max_samples();

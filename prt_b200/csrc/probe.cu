@@ -18,6 +18,7 @@
 #include "abi_internal.h"
 #include "bvh8.h"
 #include "traverse.cuh"
+#include "kernels.h"
 
 #include <algorithm>
 #include <cuda_runtime.h>
@@ -620,8 +621,8 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order; A.refill_thresh = prt_ctx_refill_thresh(sv.ctx);
     A.ticket = ticket; A.counts = counts; A.ekeys = skeys; A.etransfer = stransfer; A.eacc = sacc_stage;
     const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + std::max((size_t)kThreads * 16 * 4, sizeof(TraceShared) * (size_t)(kThreads / 32));
-    static bool configured = false;
-    if (!configured) { PB_TRY(cudaFuncSetAttribute(probe_capture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    static std::atomic<unsigned long long> configured{0};      // one bit per device
+    PB_TRY(prt::ensure_dynamic_smem(probe_capture_kernel, (int)smem, configured));
     int per_sm = 1;
     PB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_capture_kernel, kThreads, smem));
     const int grid = (int)std::min<unsigned long long>((unsigned long long)prt_ctx_sms(sv.ctx) * (unsigned long long)std::max(per_sm, 1), n_probes);

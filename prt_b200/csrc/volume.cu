@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) volume_weight_kernel(const Node8 *nodes, 
 
 extern "C" int prt_volume_weights(prt_scene *scene, const int32_t probe_res[3], const int32_t volume_res[3], const float scene_size[3],
                                   float *w0123, float *w4567, float *inside_score) {
-    if (!scene || !probe_res || !volume_res || !scene_size || !w0123 || !w4567) return prt_set_error(PRT_ERR_INVALID, "prt_volume_weights: null argument");
+    if (!scene || !probe_res || !volume_res || !scene_size || (!w0123) != (!w4567)) return prt_set_error(PRT_ERR_INVALID, "prt_volume_weights: null argument");
     for (int a = 0; a < 3; a++)
         if (probe_res[a] < 1 || volume_res[a] < 1 || !(scene_size[a] > 0.f)) return prt_set_error(PRT_ERR_INVALID, "prt_volume_weights: bad grid");
     const prt_scene_view sv = prt_scene_get_view(scene);
@@ -124,21 +124,21 @@ extern "C" int prt_volume_weights(prt_scene *scene, const int32_t probe_res[3], 
     const size_t nvox = (size_t)vol.rx * vol.ry * vol.rz;
     float dirs[300];
     prt_fibonacci_dirs(100, dirs);                                                     // static out_dirs = get_dirs(), light_probe.cpp:187
-    float *d_dirs = nullptr, *d_score = nullptr; float4 *d_w0 = nullptr, *d_w1 = nullptr;
-    e = cudaMalloc(&d_dirs, sizeof dirs);
-    if (e == cudaSuccess) e = cudaMalloc(&d_score, 4 * nvox);
-    if (e == cudaSuccess) e = cudaMalloc(&d_w0, 16 * nvox);
-    if (e == cudaSuccess) e = cudaMalloc(&d_w1, 16 * nvox);
-    if (e == cudaSuccess) {
-        cudaMemcpyAsync(d_dirs, dirs, sizeof dirs, cudaMemcpyHostToDevice, st);
-        volume_score_kernel<<<(unsigned)((nvox * 32 + 255) / 256), 256, 0, st>>>(sv.nodes, sv.tris, vol, d_dirs, 100, d_score);
-        volume_weight_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, st>>>(sv.nodes, sv.tris, vol, prb, d_score, d_w0, d_w1);
+    // scratch owned by the context (no cudaMalloc / cudaFree per call); w0123 == w4567 == NULL keeps the weights on the device
+    float *d_dirs = (float *)prt_ctx_scratch(sv.ctx, 3, sizeof dirs), *d_score = (float *)prt_ctx_scratch(sv.ctx, 4, 4 * nvox);
+    float4 *d_w0 = (float4 *)prt_ctx_scratch(sv.ctx, 5, 16 * nvox), *d_w1 = (float4 *)prt_ctx_scratch(sv.ctx, 6, 16 * nvox);
+    if (!d_dirs || !d_score || !d_w0 || !d_w1) return prt_set_error(PRT_ERR_NOMEM, "prt_volume_weights: out of device memory");
+    cudaMemcpyAsync(d_dirs, dirs, sizeof dirs, cudaMemcpyHostToDevice, st);
+    prt_ctx_timer_begin(sv.ctx, st);
+    volume_score_kernel<<<(unsigned)((nvox * 32 + 255) / 256), 256, 0, st>>>(sv.nodes, sv.tris, vol, d_dirs, 100, d_score);
+    volume_weight_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, st>>>(sv.nodes, sv.tris, vol, prb, d_score, d_w0, d_w1);
+    prt_ctx_timer_end(sv.ctx, st);
+    if (w0123) {
         cudaMemcpyAsync(w0123, d_w0, 16 * nvox, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(w4567, d_w1, 16 * nvox, cudaMemcpyDeviceToHost, st);
         if (inside_score) cudaMemcpyAsync(inside_score, d_score, 4 * nvox, cudaMemcpyDeviceToHost, st);
-        e = cudaStreamSynchronize(st);
     }
-    cudaFree(d_dirs); cudaFree(d_score); cudaFree(d_w0); cudaFree(d_w1);
+    e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string("prt_volume_weights: ") + cudaGetErrorString(e));
     return PRT_OK;
 }

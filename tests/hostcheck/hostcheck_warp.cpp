@@ -3,7 +3,9 @@
 // of horizon_kernel (horizon.cu) up to the classification -- UNMODIFIED on the CPU: the header is compiled as plain C++ against the
 // warp emulator (warp_emu.h: one thread per lane, collectives are rendezvous).  The CPU test-suite checks the maps against the
 // oracle's per-ray visibility (tests/test_horizon_math.py): a sample the map frees must be visible.
+#define PRT_HOSTCHECK 1
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __noinline__
 #include "warp_emu.h"

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(prt):
         assert hasattr(L, n), f"{n} declared in include/prt_b200.h but not exported"
     from prt_b200 import api
     assert set(api.ABI_SYMBOLS) <= set(names)
-    assert L.prt_abi_version() == 1
+    assert L.prt_abi_version() == 2
 
 
 def test_library_is_sm100a_only():
@@ -59,6 +59,20 @@ def test_param_struct_layout_matches(prt, oracle):
     prt.load_library().prt_bake_params_default(C.byref(p))
     assert (p.order, p.samples_u, p.samples_v, p.bounces, p.mode, p.jitter) == (3, 32, 32, 0, 1, 1)   # reference defaults
     assert abs(p.origin_eps - 1e-4) < 1e-10 and abs(p.bounce_eps - 1e-5) < 1e-11 and tuple(p.albedo) == (1.0, 1.0, 1.0)
+    assert p.cs_phase == 1                  # bake_SH evaluates the basis with sh::EvalSH (raytracing.cpp:226): Condon-Shortley sign
+    from prt_b200 import api
+    assert C.sizeof(api.GroupStats) == 8 + 8 * 3 + 8 * 8 * 3 + 4 * 8 + 8 * 3
+
+
+def test_group_api_fails_loudly_without_gpu(prt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(prt.PRTError, match="no CUDA device|CUDA"):
+        prt.Group([0, 1])
+    L = prt.load_library()
+    h = C.c_void_p()
+    assert L.prt_group_create(None, 2, C.byref(h)) == -1 and L.prt_group_create((C.c_int * 9)(*range(9)), 9, C.byref(h)) == -1
 
 
 def test_scatter_sh9_mesh_vert_layout(prt):

@@ -12,6 +12,12 @@ def test_transfer_cache_roundtrip_miss_and_corruption(tmp_path):
     assert mh == prt_b200.mesh_hash(pos.copy(), tri.copy()) and mh != 0
     pos2 = pos.copy(); pos2[5, 1] += 1e-3
     assert prt_b200.mesh_hash(pos2, tri) != mh and prt_b200.mesh_hash(pos, tri[::-1].copy()) != mh
+    # the transfer rows depend on the vertex normals (ray origin P + eps N, cosine frame): same geometry with other normals is
+    # another key -- a re-smoothed or flipped mesh must MISS, never load stale rows
+    mhn = prt_b200.mesh_hash(pos, tri, nrm)
+    assert mhn != mh and mhn == prt_b200.mesh_hash(pos, tri, nrm.copy())
+    nrm2 = nrm.copy(); nrm2[7] = -nrm2[7]
+    assert prt_b200.mesh_hash(pos, tri, nrm2) != mhn and prt_b200.mesh_hash(pos, tri, -nrm) != mhn
     p = prt_b200.BakeParams.make(order=4, samples_u=16, samples_v=8)
     rows = np.random.RandomState(0).randn(len(pos), 16).astype(np.float32)
     path = str(tmp_path / "torus.prt")
@@ -20,6 +26,7 @@ def test_transfer_cache_roundtrip_miss_and_corruption(tmp_path):
     assert np.array_equal(prt_b200.cache_load_transfer(path, mh, len(pos), p), rows)
     # any change of the key is a miss, never stale data
     assert prt_b200.cache_load_transfer(path, mh + 1, len(pos), p) is None
+    assert prt_b200.cache_load_transfer(path, mhn, len(pos), p) is None                    # keyed without normals != with normals
     for kw in (dict(order=3), dict(samples_u=32), dict(seed=7), dict(mode=prt_b200.INTERREFLECT, bounces=2), dict(albedo=(0.5, 1, 1)), dict(cs_phase=1)):
         q = prt_b200.BakeParams.make(**{**dict(order=4, samples_u=16, samples_v=8), **kw})
         assert prt_b200.cache_load_transfer(path, mh, len(pos), q) is None, kw

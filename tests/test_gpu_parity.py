@@ -97,7 +97,7 @@ def test_bake_reference_defaults(torus, torus_scenes, prt, oracle):
     assert 0.3 < frac < 0.98  # the torus really is self-occluding
 
 
-@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4), dict(work_list=0), dict(work_list=1), dict(pair_queue=0), dict(pair_queue=1), dict(pair_queue=1, refill_thresh=0),
+@pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4), dict(work_list=0), dict(work_list=1), dict(pair_queue=0),
                                    dict(pair_queue=0, refill_thresh=0), dict(entry_list=0), dict(entry_list=0, refill_thresh=16)])
 def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     """ray compaction, per-origin entry lists and the pair queues only reorganise work: results must not change."""
@@ -252,8 +252,11 @@ def test_bake_SH_mesh_vert_layout(prt, oracle):
     verts[:, 0:3], verts[:, 3:6] = pos, nrm
     out = prt.bake_SH(verts, tri)
     assert np.array_equal(out, verts[:, 6:15])
-    ref, _, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos, nrm, oracle.make_params())
+    ref, _, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos, nrm, oracle.make_params(cs_phase=1))   # sh::EvalSH's sign
     assert rel_l2(verts[:, 6:15], ref).max() <= REL_L2_TOL
+    # the sign-free convention of SH_function.h / SH.glsl differs exactly by (-1)^m
+    out0 = prt.bake_SH(verts.copy(), tri, prt.BakeParams.make(cs_phase=0))
+    assert np.array_equal(out0 * np.array([1, -1, 1, -1, 1, -1, 1, -1, 1], np.float32), out)
 
 
 def test_full_size_properties(prt):

@@ -226,3 +226,33 @@ def test_both_passes_as_the_kernels_run_them(hostcheck, oracle, order, su, sv):
     ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
     assert np.array_equal(vis, ovis)
     assert rel_l2(out, ref).max() <= REL_L2_TOL
+
+
+@pytest.mark.parametrize("scale", [0.5, 1.00008])
+def test_non_unit_normals_through_both_passes(hostcheck, oracle, scale):
+    """The reference hands assimp's normals to frame(N) un-normalised (model.cpp:27, raytracing.cpp:340): with |N| != 1 the frame is
+    sheared against the sample table, so horizon_vertex must not build a map (all samples flagged) -- visibility bits stay exact.
+    (Advisor finding of round 1: 1657 of 24576 bits differed with normals scaled by 0.5.)"""
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    sel = np.arange(7, len(pos), 251)[:24]
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    op = oracle.make_params(order=3, samples_u=32, samples_v=32)
+    tab, _ = processing_table(oracle, op)
+    S, n, words = len(tab), len(sel), (len(tab) + 31) // 32
+    out, vis = np.zeros((n, 9), np.float32), np.zeros((n, words), np.uint32)
+    need_bits, need_count = np.zeros((n, words), np.uint32), np.zeros(n, np.uint32)
+    p32 = np.ascontiguousarray(pos[sel])
+    n32 = np.ascontiguousarray(nrm[sel] * np.float32(scale))
+    n32[::5] = nrm[sel][::5]                                         # unit and non-unit normals mixed
+    try:
+        assert hostcheck.hc_horizon_pass(h, p32.ctypes.data, n32.ctypes.data, n, tab.ctypes.data, S, 3, 64, 30, 1e-4, 0, out.ctypes.data,
+                                         vis.ctypes.data, need_bits.ctypes.data, need_count.ctypes.data) == 0
+        unit = np.zeros(n, bool); unit[::5] = True
+        assert (need_count[~unit] == S).all() and (need_count[unit] < S).any()
+        out, vis = run_wave(hostcheck, h, p32, n32, tab, 3, need=need_bits)
+    finally:
+        hostcheck.hc_free(h)
+    ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), p32, n32, op, want_vis=True)
+    assert np.array_equal(vis, ovis)
+    assert rel_l2(out, ref).max() <= REL_L2_TOL
