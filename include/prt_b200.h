@@ -124,6 +124,14 @@ int prt_bake_transfer_device(prt_ctx *, prt_scene *, const float *d_pos, const f
                              uint32_t n_verts, uint32_t vertex_id_base, const prt_bake_params *,
                              float *d_out_coeffs, uint32_t *d_out_vis, void *stream);
 
+/* One shard of a multi-process bake (one process per GPU, e.g. under torchrun; prt_group_* is the single-process driver): the n_verts
+ * device-resident vertices are shard `shard_rank` of `shard_world` interleaved 64-vertex chunks of a longer list -- local vertex v is
+ * list position ((v / 64) * shard_world + shard_rank) * 64 + v % 64, which keys the bounce RNG, so an interreflection bake does
+ * not depend on the number of ranks.  Rows are written packed in local order (the layout an in-place all-gather wants). */
+int prt_bake_transfer_device_shard(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes, uint32_t n_verts,
+                                   uint32_t shard_world, uint32_t shard_rank, const prt_bake_params *,
+                                   float *d_out_coeffs, uint32_t *d_out_vis, void *stream);
+
 /* Same, with the rows written out_stride_bytes apart instead of packed: d_out_coeffs + 24 bytes into a device-resident Mesh::Vert
  * array with out_stride_bytes = 60 and order 3 fills sh_coeff[9] of every vertex in place (gl.h:76-80) -- the device-side half of
  * Mesh::update (gl.cpp:255-268) for a VBO mapped with cudaGraphicsGLRegisterBuffer: no host hop, no scatter pass. */

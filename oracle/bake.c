@@ -186,3 +186,71 @@ int prt_o_bake_transfer(const prt_o_scene *sc, const float *pos, const float *nr
     free(th); free(jobs); free(dirs);
     return 0;
 }
+
+/* ---- bake_SH in the reference's own order, fed with the reference's own random sequence ---------------------------------------
+ * raytracing.cpp:320-360 + renderSH :228-278 literally: vertices in order, one pass per coefficient (l, m), every pass re-jittered
+ * (x = (i + random()) / res, y = (j + random()) / res), a closest-hit query per path segment, two more random() per front-face
+ * hit -- also on the last segment, whose bounce direction is sampled before the loop ends --, float accumulation, division by
+ * res * res.  `rnd` is the sequence of random() values (the test replays std::mt19937 + uniform_real_distribution<float>, the
+ * generator of raytracing.cpp:14-18; single-threaded, so the consumption order is the program order); u_first: which of the two
+ * random() calls in `cosineSampleHemisphere(random(), random(), normal)` (raytracing.cpp:267; unspecified by C++) lands in u.
+ * Used only to pin this oracle against the reference's bake_SH compiled here with Embree replaced by this oracle's tracer
+ * (oracle/ref_bake.cpp); shares frame / sampling / SH / tracer with prt_o_bake_transfer.  Returns random() values consumed.
+ * rnd == NULL: the same literal loop, but drawing what prt_o_bake_transfer draws (Philox: one jitter pair per stratum shared by all
+ * passes, bounce pairs keyed (vertex, sample, segment), seed / vertex base as given) -- the link between this literal restatement
+ * and the production oracle, which must then agree up to the float accumulation. */
+uint64_t prt_o_bake_transfer_ref_order(const prt_o_scene *sc, const float *pos, const float *nrm, size_t stride, uint32_t n, int order, int res,
+                                       int max_path_length, const float albedo[3], int cs_phase, const float *rnd, uint64_t n_rnd, int u_first,
+                                       uint32_t seed, uint32_t vid_base, float *out) {
+    if (stride == 0) stride = 12;
+    const int n2 = order * order, depth = max_path_length - 1;
+    uint64_t at = 0;
+#define NEXT_RND() (at < n_rnd ? rnd[at++] : (at++, 0.5f))
+    for (uint32_t vi = 0; vi < n; vi++) {
+        const float *P = (const float *)((const char *)pos + (size_t)vi * stride), *Nn = (const float *)((const char *)nrm + (size_t)vi * stride);
+        const v3 N = v3_make(Nn[0], Nn[1], Nn[2]);
+        const frame3 f = prt_frame(N);
+        const v3 org = v3_madd(v3_make(P[0], P[1], P[2]), 1e-4f, N);                                   /* :343 */
+        for (int k = 0; k < n2; k++) {
+            float acc = 0.0f;
+            for (int i = 0; i < res; i++)
+                for (int j = 0; j < res; j++) {
+                    float j1, j2;
+                    if (rnd) { j1 = NEXT_RND(); j2 = NEXT_RND(); }
+                    else prt_rand2(seed, (uint32_t)(i * res + j), 0u, 0u, 0u, &j1, &j2);
+                    const float x = ((float)i + j1) / (float)res, y = ((float)j + j2) / (float)res;                /* :338-339 */
+                    v3 dir = prt_to_world(&f, prt_cosine_local(x, y));
+                    v3 p = org;
+                    float Lw[3] = { 1.f, 1.f, 1.f }, tnear = 0.0f, L = 0.0f;
+                    for (int s = 0; s < depth; s++) {
+                        if (fmaxf(Lw[0], fmaxf(Lw[1], Lw[2])) < 0.01f) break;                          /* :249 */
+                        float o[3] = { p.x, p.y, p.z }, d[3] = { dir.x, dir.y, dir.z }, t, ng[3]; uint32_t prim;
+                        if (!prt_o_closest_hit(sc, o, d, tnear, INFINITY, 1, &t, &prim, ng)) {         /* :257-261 */
+                            float yv[25];
+                            prt_sh_eval(order, cs_phase, dir.z, dir.x, dir.y, yv);
+                            L = Lw[0] * yv[k];
+                            break;
+                        }
+                        const v3 nn = v3_normalize(v3_make(ng[0], ng[1], ng[2]));
+                        if (v3_dot(dir, nn) >= -1e-4f) break;                                          /* :265 */
+                        p = v3_madd(p, t, dir);                                                        /* :266 */
+                        float r0, r1;                                                                  /* :267 */
+                        if (rnd) { r0 = NEXT_RND(); r1 = NEXT_RND(); }
+                        else { prt_rand2(seed, vid_base + vi, (uint32_t)(i * res + j), (uint32_t)s, 1u, &r0, &r1); u_first = 1; }
+                        const v3 l = prt_cosine_local(u_first ? r0 : r1, u_first ? r1 : r0);
+                        const frame3 fb = prt_frame(nn);
+                        dir = prt_to_world(&fb, l);
+                        if (l.z / PRT_PI_F <= 1e-4f) break;                                            /* :269 */
+                        Lw[0] *= albedo[0]; Lw[1] *= albedo[1]; Lw[2] *= albedo[2];
+                        const float sign = v3_dot(dir, nn) < 0.0f ? -1.0f : 1.0f;
+                        p = v3_madd(p, sign * 1e-5f, dir);                                             /* :273-274 */
+                        tnear = 1e-5f;
+                    }
+                    acc += L;                                                                          /* :348 */
+                }
+            out[(size_t)vi * n2 + k] = acc / (float)(res * res);                                       /* :350 */
+        }
+    }
+#undef NEXT_RND
+    return at;
+}

@@ -65,6 +65,11 @@ int prt_o_bake_transfer(const prt_o_scene *, const float *pos, const float *nrm,
                         uint32_t n_verts, uint32_t vertex_id_base, const prt_o_bake_params *,
                         float *out_coeffs, uint32_t *out_vis, int n_threads, int faithful, uint64_t *counters);
 
+/* bake_SH in the reference's own loop order, consuming a given random() sequence (see bake.c); returns the values consumed */
+uint64_t prt_o_bake_transfer_ref_order(const prt_o_scene *, const float *pos, const float *nrm, size_t stride_bytes, uint32_t n_verts, int order, int res,
+                                       int max_path_length, const float albedo[3], int cs_phase, const float *rnd, uint64_t n_rnd, int u_first,
+                                       uint32_t seed, uint32_t vertex_id_base, float *out_coeffs);
+
 /* ---- image-based lighting (oracle/env.c); cube buffers: levels concatenated, [6][n][n][3] floats per level ---- */
 size_t prt_o_cube_floats(int n0, int levels);
 int prt_o_cube_levels(int n0);

@@ -55,6 +55,9 @@ def lib():
         L.prt_o_bake_transfer.restype = C.c_int
         L.prt_o_bake_transfer.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(BakeParams),
                                           vp, vp, C.c_int, C.c_int, vp]
+        L.prt_o_bake_transfer_ref_order.restype = C.c_uint64
+        L.prt_o_bake_transfer_ref_order.argtypes = [vp, vp, vp, C.c_size_t, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_uint64, C.c_int,
+                                                    C.c_uint32, C.c_uint32, vp]
         L.prt_o_sh_eval.argtypes = [C.c_int, C.c_int, f32p, f32p]
         L.prt_o_philox.argtypes = [u32p, u32p, u32p]
         L.prt_o_sincos2pi.argtypes = [C.c_float, f32p, f32p]
@@ -163,6 +166,30 @@ def bake_transfer(scene: Scene | None, pos, nrm, params: BakeParams, want_vis=Fa
     if rc != 0:
         raise RuntimeError(f"oracle bake_transfer failed rc={rc}")
     return out, vis, counters
+
+
+def mt19937_floats(n: int) -> np.ndarray:
+    """The first n values of the reference's ``random()`` (raytracing.cpp:14-18): a default-seeded std::mt19937 (seed 5489; numpy's
+    legacy RandomState(5489) is the same init_genrand + genrand_int32) through libstdc++'s uniform_real_distribution<float>(0, 1) =
+    generate_canonical<float, 24>: float(u32) / 2^32, a value that rounds up to 1 replaced by the float below 1."""
+    u = np.random.RandomState(5489).randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    f = u.astype(np.float32) / np.float32(4294967296.0)
+    f[f >= 1] = np.nextafter(np.float32(1), np.float32(0))
+    return f
+
+
+def bake_transfer_ref_order(scene: Scene, pos, nrm, order=3, res=32, max_path_length=2, albedo=(1.0, 1.0, 1.0), cs_phase=1, rnd=None, u_first=0,
+                            seed=0x50525400, vertex_id_base=0):
+    """bake_SH exactly in the reference's loop order (oracle/bake.c prt_o_bake_transfer_ref_order).  rnd: the random() sequence to
+    consume (``mt19937_floats``), or None for the production oracle's Philox draws.  u_first = 0 is what g++ makes of
+    ``cosineSampleHemisphere(random(), random(), normal)`` (arguments evaluated right to left).  -> (rows, values consumed)"""
+    pos = np.ascontiguousarray(pos, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
+    out = np.zeros((len(pos), order * order), np.float32)
+    a = np.asarray(albedo, np.float32)
+    r = None if rnd is None else np.ascontiguousarray(rnd, np.float32)
+    used = lib().prt_o_bake_transfer_ref_order(scene.h, _ptr(pos), _ptr(nrm), 12, len(pos), order, res, max_path_length, _ptr(a), cs_phase,
+                                               _ptr(r), 0 if r is None else len(r), u_first, seed & 0xFFFFFFFF, vertex_id_base, _ptr(out))
+    return out, int(used)
 
 
 def sh_eval(order: int, d_sh, cs_phase=0) -> np.ndarray:

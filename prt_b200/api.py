@@ -15,7 +15,7 @@ UNSHADOWED, SHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "prt_last_error", "prt_abi_version", "prt_ctx_create", "prt_ctx_destroy", "prt_ctx_device", "prt_ctx_last_kernel_ms", "prt_ctx_set_tuning",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_get_info", "prt_trace_any_hit", "prt_trace_closest_hit",
-    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_bake_transfer_device_strided", "prt_scatter_sh9",
+    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_bake_transfer_device_strided", "prt_bake_transfer_device_shard", "prt_scatter_sh9",
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
@@ -154,6 +154,7 @@ def load_library():
     L.prt_bake_params_default.restype = None
     L.prt_bake_transfer.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp]
     L.prt_bake_transfer_device.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
+    L.prt_bake_transfer_device_shard.argtypes = [vp, vp, vp, vp, sz, u32, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
     L.prt_bake_transfer_device_strided.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, sz, vp, vp]
     L.prt_scatter_sh9.argtypes = [vp, C.c_int32, u32, vp, sz, sz]
     L.prt_bake_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]

@@ -433,6 +433,15 @@ int prt_bake_transfer_device(prt_ctx *c, prt_scene *sc, const float *d_pos, cons
     return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, vid_base, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2, nullptr);
 }
 
+int prt_bake_transfer_device_shard(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,
+                                   uint32_t shard_world, uint32_t shard_rank, const prt_bake_params *p, float *d_out, uint32_t *d_vis, void *stream) {
+    if (!c) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard: ctx is null");
+    if (shard_world < 1 || shard_rank >= shard_world) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard: bad world / rank");
+    prt_row_placement pl{};
+    pl.shard_world = shard_world; pl.shard_rank = shard_rank;
+    return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, 0u, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2, &pl);
+}
+
 int prt_bake_transfer_device_strided(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,
                                      uint32_t vid_base, const prt_bake_params *p, float *d_out, size_t out_stride_bytes, uint32_t *d_vis, void *stream) {
     if (!c) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_strided: ctx is null");

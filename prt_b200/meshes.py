@@ -57,11 +57,12 @@ def icosphere(k: int):
     return pos, nrm.astype(np.float32), f.astype(np.uint32)
 
 
-def bumpy_torus(nu: int, nv: int, seed: int = 7, R: float = 2.0, r: float = 0.8, amp: float = 0.15):
+def bumpy_torus(nu: int, nv: int, seed: int = 7, R: float = 2.0, r: float = 0.8, amp: float = 0.15, fscale: int = 1):
     """Torus (major R, minor r) with a radial displacement amp*sum_j a_j sin(f_j u+phi_j) sin(g_j v+psi_j).
 
     Vertex (i, j) -> index i*nv + j, u = 2 pi i/nu (around the axis), v = 2 pi j/nv (around the tube).
-    Parameters come from numpy's MT19937 (RandomState(seed)); outward-facing CCW triangles.
+    Parameters come from numpy's MT19937 (RandomState(seed)); outward-facing CCW triangles.  ``fscale`` multiplies the bump
+    frequencies: deeper, narrower folds at the same amplitude (the "heavily self-occluding" bench workload uses amp 0.25, fscale 3: 45 % of the rays occluded).
     """
     rs = np.random.RandomState(seed)
     a = rs.uniform(0.3, 1.0, 4)
@@ -73,7 +74,7 @@ def bumpy_torus(nu: int, nv: int, seed: int = 7, R: float = 2.0, r: float = 0.8,
     v = (np.arange(nv, dtype=np.float64) * (2 * np.pi / nv))[None, :]
     d = np.zeros((nu, nv))
     for j in range(4):
-        d += a[j] * np.sin(fu[j] * u + phi[j]) * np.sin(gv[j] * v + psi[j])
+        d += a[j] * np.sin(fscale * fu[j] * u + phi[j]) * np.sin(fscale * gv[j] * v + psi[j])
     rr = r + amp * d
     x = (R + rr * np.cos(v)) * np.cos(u)
     y = rr * np.sin(v) + 0.0 * u

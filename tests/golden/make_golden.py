@@ -9,6 +9,13 @@ Run in the build container (needs /root/reference); the fixtures are committed, 
   ref_prefilter.txt   prefilter.frag main() at texel centres of a 16^2 cube, 5 mips (roughness mip/4), environment = ENV_CUBE below
   ref_irradiance.txt  irradiance.frag main() at texel centres of an 8^2 cube, same environment
   ref_rect2cube.txt   SampleSphericalMap at 64 directions          (src/shaders/rectangle2cube.frag:7-15)
+and, from the reference's WHOLE files compiled unmodified with Embree replaced by the oracle's tracer (oracle/ref_bake.cpp,
+oracle/ref_weight.cpp, stand-in headers under oracle/ref_stub/):
+  ref_bake_SH_*.txt       bake_SH(Mesh&) (src/raytracing/raytracing.cpp:320-360 + renderSH :228-278) on bumpy_torus meshes: sh_coeff[9] of
+                          every vertex; cases: shadow (32x24 mesh, sh_resolution 16, max_path_length 2), bounce (same mesh, 8, 4, albedo 0.5),
+                          default (16x12 mesh, the reference's defaults 32 / 2 / 1.0)
+  ref_volume_weight.txt   calculate_weight(Model&, 4^3 probes, 12^3 voxels, scene_size 6.18) (src/raytracing/light_probe.cpp:156-367) on
+                          data/cube.obj + a torus: weight0123 | weight4567 of every voxel
 """
 import os
 import subprocess
@@ -51,6 +58,48 @@ def main():
         cube.data.tofile(tf.name)
         emit("ref_prefilter.txt", "ref_slices", "prefilter", tf.name, ENV_CUBE, PREF_OUT)
         emit("ref_irradiance.txt", "ref_slices", "irradiance", tf.name, ENV_CUBE, IRR_OUT)
+
+
+    ref_bake_and_weight(ref)
+
+
+BAKE_CASES = {"shadow": (32, 24, 16, 2, 1.0), "bounce": (32, 24, 8, 4, 0.5), "default": (16, 12, 32, 2, 1.0)}   # nu, nv, sh_resolution, max_path_length, albedo
+WEIGHT_CASE = (4, 12, 6.18)                                                                                      # probe_res, volume_res, scene_size
+
+
+def weight_scene():
+    import numpy as np
+    from prt_b200 import meshes
+    pos, _, tri = meshes.load_obj_assimp(os.path.join(here, "cube.obj"))
+    tp, _, tt = meshes.bumpy_torus(40, 28)
+    return (np.concatenate([pos, tp * np.float32(1.3)]).astype(np.float32),
+            np.concatenate([tri, tt + np.uint32(len(pos))]).astype(np.uint32))
+
+
+def write_mesh(path, pos, nrm, tri):
+    import numpy as np
+    with open(path, "wb") as f:
+        f.write(np.array([len(pos), len(tri)], np.uint32).tobytes())
+        f.write(np.ascontiguousarray(pos, np.float32).tobytes())
+        f.write(np.ascontiguousarray(nrm, np.float32).tobytes())
+        f.write(np.ascontiguousarray(tri, np.uint32).tobytes())
+
+
+def ref_bake_and_weight(ref):
+    import numpy as np
+    from prt_b200 import meshes
+    with tempfile.TemporaryDirectory() as td:
+        for name, (nu, nv, res, mpl, alb) in BAKE_CASES.items():
+            pos, nrm, tri = meshes.bumpy_torus(nu, nv)
+            write_mesh(os.path.join(td, "m.bin"), pos, nrm, tri)
+            out = os.path.join(here, f"ref_bake_SH_{name}.txt")
+            subprocess.check_call([os.path.join(ref, "ref_bake"), os.path.join(td, "m.bin"), out, str(res), str(mpl), str(alb)], stdout=subprocess.DEVNULL)
+            print(f"ref_bake_SH_{name}.txt: {len(open(out).readlines())} lines")
+        pos, tri = weight_scene()
+        write_mesh(os.path.join(td, "s.bin"), pos, np.zeros_like(pos), tri)
+        out = os.path.join(here, "ref_volume_weight.txt")
+        subprocess.check_call([os.path.join(ref, "ref_weight"), os.path.join(td, "s.bin"), out] + [str(x) for x in WEIGHT_CASE])
+        print(f"ref_volume_weight.txt: {len(open(out).readlines())} lines")
 
 
 if __name__ == "__main__":

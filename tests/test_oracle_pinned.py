@@ -104,3 +104,63 @@ def test_equirect_uv_matches_reference_source(oracle):
     ref = rows("ref_rect2cube.txt", "uv")
     worst = max(np.abs(oracle.equirect_uv(h) - v).max() for h, v in ref)
     assert len(ref) == 64 and worst <= 2e-7, worst
+
+
+# ---- the reference's WHOLE files, compiled unmodified with Embree replaced by the oracle's tracer (oracle/ref_bake.cpp, ref_weight.cpp) ----
+BAKE_CASES = {"shadow": (32, 24, 16, 2, 1.0), "bounce": (32, 24, 8, 4, 0.5), "default": (16, 12, 32, 2, 1.0)}   # = tests/golden/make_golden.py
+
+
+@pytest.mark.parametrize("case", ["shadow", "bounce", "default"])
+def test_bake_SH_matches_the_reference_binary(oracle, case):
+    """bake_SH(Mesh&) of raytracing.cpp (RTScene set-up, frame, cosine sampling, renderSH path logic with its cut-offs and offsets,
+    estimator) executed from the reference's own source -> sh_coeff[9] of every vertex; the oracle's literal restatement, fed with the
+    same std::mt19937 random() sequence, must reproduce it.  Tolerance 5e-6 relative L2 per vertex (libm sin/cos vs the pinned polynomial
+    at 1e-7 in the directions; measured <= 9e-7) -- a single flipped visibility decision would show as >= 4e-4."""
+    from prt_b200 import meshes
+    nu, nv, res, mpl, alb = BAKE_CASES[case]
+    pos, nrm, tri = meshes.bumpy_torus(nu, nv)
+    ref = np.loadtxt(os.path.join(G, f"ref_bake_SH_{case}.txt"), dtype=np.float32)
+    assert ref.shape == (nu * nv, 9)
+    rnd = oracle.mt19937_floats(len(pos) * 9 * res * res * 2 + len(pos) * 9 * res * res)          # jitter pairs + room for the bounce draws
+    got, used = oracle.bake_transfer_ref_order(oracle.Scene(pos, tri), pos, nrm, res=res, max_path_length=mpl, albedo=(alb,) * 3, rnd=rnd, u_first=0)
+    assert len(pos) * 9 * res * res * 2 < used <= len(rnd)                                           # hits consumed random() pairs as in renderSH
+    rel = np.linalg.norm(got - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-20)
+    assert rel.max() <= 5e-6, rel.max()
+    assert 0.05 < (np.abs(ref[:, 0]) < 0.28).mean()                                                  # the mesh really shadows itself
+
+
+@pytest.mark.parametrize("case", ["shadow", "bounce"])
+def test_production_oracle_equals_the_literal_restatement(oracle, case):
+    """The oracle the GPU is tested against (one trace per sample shared by all coefficients, any-hit on the last segment, double
+    accumulation, Philox draws) against the literal reference-order loop drawing the same Philox numbers: <= 5e-6 (float vs double
+    accumulation; measured 2e-6)."""
+    from prt_b200 import meshes
+    nu, nv, res, mpl, alb = BAKE_CASES[case]
+    pos, nrm, tri = meshes.bumpy_torus(nu, nv)
+    sc = oracle.Scene(pos, tri)
+    kw = dict(order=3, samples_u=res, samples_v=res, cs_phase=1, albedo=(alb,) * 3)
+    if mpl > 2:
+        kw.update(mode=oracle.INTERREFLECT, bounces=mpl - 2)
+    prod, _, _ = oracle.bake_transfer(sc, pos, nrm, oracle.make_params(**kw), vertex_id_base=11)
+    lit, _ = oracle.bake_transfer_ref_order(sc, pos, nrm, res=res, max_path_length=mpl, albedo=(alb,) * 3, rnd=None, vertex_id_base=11)
+    rel = np.linalg.norm(prod - lit, axis=1) / np.maximum(np.linalg.norm(lit, axis=1), 1e-20)
+    assert rel.max() <= 5e-6, rel.max()
+
+
+def weight_scene():
+    from prt_b200 import meshes
+    pos, _, tri = meshes.load_obj_assimp(os.path.join(G, "cube.obj"))
+    tp, _, tt = meshes.bumpy_torus(40, 28)
+    return (np.concatenate([pos, tp * np.float32(1.3)]).astype(np.float32), np.concatenate([tri, tt + np.uint32(len(pos))]).astype(np.uint32))
+
+
+def test_calculate_weight_matches_the_reference_binary(oracle):
+    """calculate_weight of light_probe.cpp executed from the reference's own source (inside scores from 100 get_dirs rays, relocation to
+    the least-inside neighbour, 8 segment rays, masking, renormalisation) on data/cube.obj + a torus: bit-identical weights."""
+    pos, tri = weight_scene()
+    ref = np.loadtxt(os.path.join(G, "ref_volume_weight.txt"), dtype=np.float32)
+    w0, w1, _ = oracle.volume_weights(oracle.Scene(pos, tri), [4] * 3, [12] * 3, [6.18] * 3)
+    got = np.concatenate([w0, w1], 1)
+    assert ref.shape == got.shape == (1728, 8)
+    assert 0.1 < (ref == 0).mean() < 0.9                       # occluded probes are masked, others are not
+    assert np.array_equal(got, ref, equal_nan=True) and np.isnan(ref).mean() < 0.05
