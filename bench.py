@@ -310,7 +310,7 @@ def default_cpu_sample(a):
     if a.cpu_sample:
         return a.cpu_sample
     # ~10-20 s of oracle work on 16 cores
-    return {"1": 196608, "4": 2048, "5": 12288}[a.config]
+    return {"1": 196608, "4": 16384, "5": 12288}[a.config]
 
 
 def run_reference_bake(a):

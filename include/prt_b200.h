@@ -209,6 +209,13 @@ int prt_group_bake_transfer(prt_group *, prt_group_scene *, const float *pos, co
 const float *prt_group_rows_device(prt_group *, int member);
 int prt_group_download_rows(prt_group *, int member, float *out_coeffs);
 
+/* SH_volume::precompute (volume.cpp:149-316) over the group: contiguous probe ranges per GPU, the per-GPU CSR slices merged on the device
+ * of member `target` (GPU-to-GPU copies + an id remap kernel; only the few thousand cluster keys and surfel accumulators pass through
+ * the host).  The resulting prt_csr lives on prt_group_ctx(group, target) and equals a single-GPU prt_probe_capture of all probes. */
+typedef struct prt_csr prt_csr;
+int prt_group_probe_capture(prt_group *, prt_group_scene *, const float *probe_pos_xyz, uint32_t n_probes, const float *dirs_xyz,
+                            const float *solid_angles, uint32_t n_dirs, int target, prt_csr **out, double *capture_kernel_ms_max, double *merge_ms);
+
 /* ---- image-based lighting (BASELINE config 2) ---------------------------------------------------------------------
  * Texture semantics the GL driver leaves open are pinned: FP32 storage, GL cube (sc,tc) table ==
  * cubeCoordToWorld (SH_function.h:104-109), bilinear centres at (i+0.5)/N, seamless re-projection of off-face taps,
@@ -247,7 +254,6 @@ int prt_sh_pack_rh(const float *L9_rgb, float *out28);
  * (probe_range / ID_buffer / transfer_buffer, :265-295) plus the surfel table (primitive_buffer, :301-312), kept on the GPU.
  * Surfel ids are the rank of the cluster key in (x,y,z,direction) lexicographic order (the reference numbers clusters
  * first-seen, which depends on probe order; parity is defined up to that permutation).  n_dirs <= 4096. */
-typedef struct prt_csr prt_csr;
 int prt_probe_capture(prt_scene *, const float *probe_pos_xyz, uint32_t n_probes, const float *dirs_xyz, const float *solid_angles,
                       uint32_t n_dirs, prt_csr **out);
 void prt_csr_destroy(prt_csr *);

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "prt_cache_load_csr",
     "prt_group_create", "prt_group_destroy", "prt_group_size", "prt_group_ctx", "prt_group_capabilities", "prt_group_set_tuning",
     "prt_group_scene_create", "prt_group_scene_destroy", "prt_group_scene_get_info", "prt_group_scene_member", "prt_group_bake_transfer",
-    "prt_group_rows_device", "prt_group_download_rows",
+    "prt_group_rows_device", "prt_group_download_rows", "prt_group_probe_capture",
 ]
 
 
@@ -220,6 +220,7 @@ def load_library():
     L.prt_group_rows_device.argtypes = [vp, i32]
     L.prt_group_rows_device.restype = vp
     L.prt_group_download_rows.argtypes = [vp, i32, vp]
+    L.prt_group_probe_capture.argtypes = [vp, vp, vp, u32, vp, vp, u32, i32, C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.prt_cache_save_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
     L.prt_cache_load_transfer.argtypes = [C.c_char_p, u64, u32, C.POINTER(BakeParams), vp]
     L.prt_cache_save_csr.argtypes = [C.c_char_p, u64, u64, u32, u64, u32, vp, vp, vp, vp, vp]
@@ -429,6 +430,17 @@ class Group:
         _check(self.L.prt_group_bake_transfer(self.h, self.scene_h, _ptr(pos), _ptr(nrm), 12, n, C.byref(params),
                                               _ptr(out) if want_host else None, gather, C.byref(st)), "prt_group_bake_transfer")
         return (out if want_host else None), st
+
+    def probe_capture(self, probe_pos, dirs, weights, target: int = 0):
+        """SH_volume::precompute over the group -> (ProbeTransfer on member ``target``, capture kernel ms (slowest GPU), merge ms)."""
+        pp = np.ascontiguousarray(probe_pos, np.float32); d = np.ascontiguousarray(dirs, np.float32); w = np.ascontiguousarray(weights, np.float32)
+        h, cap, mrg = C.c_void_p(), C.c_double(), C.c_double()
+        _check(self.L.prt_group_probe_capture(self.h, self.scene_h, _ptr(pp), len(pp), _ptr(d), _ptr(w), len(d), target, C.byref(h), C.byref(cap),
+                                              C.byref(mrg)), "prt_group_probe_capture")
+        pt = ProbeTransfer.__new__(ProbeTransfer)
+        pt.scene, pt.L, pt.h = self, self.L, h              # keeps the group alive; `.h` doubles as the liveness check
+        pt._sizes()
+        return pt, cap.value, mrg.value
 
     def download_rows(self, member: int, n: int, n2: int) -> np.ndarray:
         out = np.zeros((n, n2), np.float32)

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -91,6 +92,16 @@ __global__ void unshard_rows_kernel(const float *__restrict__ src, float *__rest
     const uint32_t rank = (uint32_t)(lv / per_rank), v = (uint32_t)(lv % per_rank);
     const unsigned long long g = ((unsigned long long)(v / kShardChunk) * world + rank) * kShardChunk + (v % kShardChunk);
     dst[g * n2 + k] = src[i];
+}
+
+// merged CSR: surfel ids of one member's segment -> global ids, probe ranges shifted by the segment's offset
+__global__ void remap_ids_kernel(uint32_t *ids, const uint32_t *__restrict__ remap, const unsigned long long n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = remap[ids[i]];
+}
+__global__ void shift_range_kernel(uint32_t *range2, const uint32_t n2, const uint32_t base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) range2[i] += base;
 }
 
 }  // namespace
@@ -409,6 +420,120 @@ int prt_group_bake_transfer(prt_group *g, prt_group_scene *gs, const float *pos,
         stats->h2d_bytes = (uint64_t)n * (interleaved ? stride : 24);
         stats->d2h_bytes = out ? (uint64_t)n * row_bytes : 0ull;
     }
+    return PRT_OK;
+}
+
+// SH_volume::precompute (volume.cpp:149-316) over the group: contiguous probe ranges per GPU (probes keep the x-fastest order of
+// volume.cpp:83-90, so the concatenation of the members' CSR slices IS the whole CSR), every member captures its slice, and the
+// slices are merged ON THE DEVICE of `target`: the (few thousand) cluster keys and surfel accumulators go through the host to fix
+// the global surfel ids (rank in the union of the key sets) and the surfel table; the heavy arrays -- ids, 36-byte transfer rows,
+// ranges -- move GPU to GPU (cudaMemcpyPeerAsync over NVLink) straight into their place in the merged arrays, followed by one id
+// remap kernel per segment.  The result is identical to a single-GPU capture of all probes (tests/test_gpu_group.py).
+int prt_group_probe_capture(prt_group *g, prt_group_scene *gs, const float *probe_pos, uint32_t n_probes, const float *dirs, const float *weights,
+                            uint32_t n_dirs, int target, prt_csr **out, double *capture_ms_max, double *merge_ms) {
+    if (!g || !gs || gs->g != g || !probe_pos || !dirs || !weights || !out || n_probes == 0 || target < 0 || target >= g->n)
+        return prt_set_error(PRT_ERR_INVALID, "prt_group_probe_capture: bad argument");
+    *out = nullptr;
+    const int W = g->n;
+    const uint32_t per = (n_probes + (uint32_t)W - 1) / (uint32_t)W;
+    std::vector<prt_csr *> part(W, nullptr);
+    std::vector<int> rcs(W, 0);
+    std::vector<std::string> errs(W);
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < W; r++)
+            th.emplace_back([&, r]() {
+                const uint32_t lo = std::min((uint32_t)r * per, n_probes), hi = std::min((uint32_t)(r + 1) * per, n_probes);
+                if (hi <= lo) return;
+                rcs[r] = prt_probe_capture(gs->sc[r], probe_pos + 3 * (size_t)lo, hi - lo, dirs, weights, n_dirs, &part[r]);
+                if (rcs[r]) errs[r] = prt_last_error();
+            });
+        for (auto &t : th) t.join();
+    }
+    auto cleanup = [&]() { for (prt_csr *c : part) prt_csr_destroy(c); };
+    for (int r = 0; r < W; r++) if (rcs[r]) { const int rc = rcs[r]; const std::string e = errs[r]; cleanup(); return prt_set_error(rc, e); }
+    const auto t0 = std::chrono::steady_clock::now();
+    // ---- global surfel ids: union of the members' (sorted) key sets; accumulators summed per key ------------------------------------
+    std::vector<std::vector<unsigned long long>> keys(W);
+    std::vector<std::vector<double>> sums(W);
+    std::vector<unsigned long long> all;
+    double cap_ms = 0.0;
+    unsigned long long nnz = 0;
+    for (int r = 0; r < W; r++) {
+        if (!part[r]) continue;
+        cap_ms = std::max(cap_ms, part[r]->capture_ms);
+        nnz += part[r]->nnz;
+        keys[r].resize(part[r]->n_prim); sums[r].resize((size_t)part[r]->n_prim * 7);
+        cudaSetDevice(g->m[r].device);
+        if (part[r]->n_prim) {
+            cudaMemcpy(keys[r].data(), part[r]->keys, 8 * (size_t)part[r]->n_prim, cudaMemcpyDeviceToHost);
+            cudaMemcpy(sums[r].data(), part[r]->sums, 56 * (size_t)part[r]->n_prim, cudaMemcpyDeviceToHost);
+        }
+        all.insert(all.end(), keys[r].begin(), keys[r].end());
+    }
+    if (nnz >= 0xFFFFFFFFull) { cleanup(); return prt_set_error(PRT_ERR_UNSUPPORTED, "prt_group_probe_capture: merged CSR exceeds 2^32 entries"); }
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    const uint32_t n_prim = (uint32_t)all.size();
+    std::vector<double> gsum((size_t)n_prim * 7, 0.0);
+    std::vector<std::vector<uint32_t>> remap(W);
+    for (int r = 0; r < W; r++) {
+        remap[r].resize(keys[r].size());
+        for (size_t k = 0; k < keys[r].size(); k++) {
+            const uint32_t gidx = (uint32_t)(std::lower_bound(all.begin(), all.end(), keys[r][k]) - all.begin());
+            remap[r][k] = gidx;
+            for (int q = 0; q < 7; q++) gsum[(size_t)gidx * 7 + q] += sums[r][k * 7 + q];
+        }
+    }
+    std::vector<float> surfels((size_t)n_prim * 6);
+    for (uint32_t k = 0; k < n_prim; k++) {                                       // volume.cpp:301-312: mean position, normalised mean normal
+        const double cnt = gsum[(size_t)k * 7 + 6];
+        double nm[3] = { gsum[(size_t)k * 7 + 3] / cnt, gsum[(size_t)k * 7 + 4] / cnt, gsum[(size_t)k * 7 + 5] / cnt };
+        const double ln = std::sqrt(nm[0] * nm[0] + nm[1] * nm[1] + nm[2] * nm[2]);
+        for (int q = 0; q < 3; q++) { surfels[(size_t)k * 6 + q] = (float)(gsum[(size_t)k * 7 + q] / cnt); surfels[(size_t)k * 6 + 3 + q] = (float)(nm[q] / ln); }
+    }
+    // ---- merged arrays on the target GPU --------------------------------------------------------------------------------------------
+    Member &T = g->m[target];
+    if (cudaSetDevice(T.device) != cudaSuccess) { cleanup(); return prt_set_error(PRT_ERR_CUDA, "prt_group_probe_capture: cudaSetDevice"); }
+    prt_csr *c = new prt_csr();
+    c->ctx = T.ctx; c->n_probes = n_probes; c->nnz = nnz; c->n_prim = n_prim; c->capture_ms = cap_ms;
+    const size_t np = std::max<size_t>(1, n_prim), nz = std::max<size_t>(1, (size_t)nnz);
+    cudaError_t e = cudaMalloc(&c->range, 8 * (size_t)n_probes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * nz);
+    if (e == cudaSuccess) e = cudaMalloc(&c->transfer, 36 * nz);
+    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
+    if (e == cudaSuccess) e = cudaMalloc(&c->keys, 8 * np);
+    if (e == cudaSuccess) e = cudaMalloc(&c->sums, 56 * np);
+    uint32_t *d_remap = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&d_remap, 4 * np * (size_t)W);
+    unsigned long long base = 0;
+    for (int r = 0; r < W && e == cudaSuccess; r++) {
+        if (!part[r]) continue;
+        const uint32_t lo = (uint32_t)r * per;
+        const unsigned long long nr = part[r]->nnz;
+        if (nr) {
+            e = cudaMemcpyPeerAsync(c->ids + base, T.device, part[r]->ids, g->m[r].device, 4 * (size_t)nr, T.st);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(c->transfer + 9 * base, T.device, part[r]->transfer, g->m[r].device, 36 * (size_t)nr, T.st);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(c->range + 2 * (size_t)lo, T.device, part[r]->range, g->m[r].device, 8 * (size_t)part[r]->n_probes, T.st);
+        if (e == cudaSuccess && !remap[r].empty()) e = cudaMemcpyAsync(d_remap + (size_t)r * np, remap[r].data(), 4 * remap[r].size(), cudaMemcpyHostToDevice, T.st);
+        if (e == cudaSuccess && nr) remap_ids_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, T.st>>>(c->ids + base, d_remap + (size_t)r * np, nr);
+        if (e == cudaSuccess && base) shift_range_kernel<<<(2 * part[r]->n_probes + 255) / 256, 256, 0, T.st>>>(c->range + 2 * (size_t)lo, 2 * part[r]->n_probes, (uint32_t)base);
+        base += nr;
+    }
+    if (e == cudaSuccess && n_prim) {
+        e = cudaMemcpyAsync(c->surfels, surfels.data(), 24 * (size_t)n_prim, cudaMemcpyHostToDevice, T.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->keys, all.data(), 8 * (size_t)n_prim, cudaMemcpyHostToDevice, T.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->sums, gsum.data(), 56 * (size_t)n_prim, cudaMemcpyHostToDevice, T.st);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(T.st);
+    cudaFree(d_remap);
+    cleanup();
+    if (e != cudaSuccess) { prt_csr_destroy(c); return prt_set_error(PRT_ERR_CUDA, std::string("prt_group_probe_capture: ") + cudaGetErrorString(e)); }
+    if (capture_ms_max) *capture_ms_max = cap_ms;
+    if (merge_ms) *merge_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = c;
     return PRT_OK;
 }
 

@@ -14,6 +14,9 @@ oracle/ref_weight.cpp, stand-in headers under oracle/ref_stub/):
   ref_bake_SH_*.txt       bake_SH(Mesh&) (src/raytracing/raytracing.cpp:320-360 + renderSH :228-278) on bumpy_torus meshes: sh_coeff[9] of
                           every vertex; cases: shadow (32x24 mesh, sh_resolution 16, max_path_length 2), bounce (same mesh, 8, 4, albedo 0.5),
                           default (16x12 mesh, the reference's defaults 32 / 2 / 1.0)
+  ref_probe_capture.txt   the CPU half of SH_volume::precompute (src/sh/volume.cpp:185-315: clustering, per-texel accumulation, CSR emission,
+                          surfel averaging; oracle/ref_probe.cpp) for the first 3 probes of a 4^3 grid over data/cube.obj + a torus, 64^2 x 6
+                          texels per probe, G-buffer = one oracle closest-hit ray per texel centre
   ref_volume_weight.txt   calculate_weight(Model&, 4^3 probes, 12^3 voxels, scene_size 6.18) (src/raytracing/light_probe.cpp:156-367) on
                           data/cube.obj + a torus: weight0123 | weight4567 of every voxel
 """
@@ -100,6 +103,9 @@ def ref_bake_and_weight(ref):
         out = os.path.join(here, "ref_volume_weight.txt")
         subprocess.check_call([os.path.join(ref, "ref_weight"), os.path.join(td, "s.bin"), out] + [str(x) for x in WEIGHT_CASE])
         print(f"ref_volume_weight.txt: {len(open(out).readlines())} lines")
+        out = os.path.join(here, "ref_probe_capture.txt")
+        subprocess.check_call([os.path.join(ref, "ref_probe"), os.path.join(td, "s.bin"), out, "4", "6.18", "3"], stdout=subprocess.DEVNULL)
+        print(f"ref_probe_capture.txt: {len(open(out).readlines())} lines")
 
 
 if __name__ == "__main__":

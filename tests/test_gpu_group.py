@@ -146,3 +146,27 @@ def test_two_contexts_on_one_device_large_smem_kernels(prt, mesh):
         d, w = prt.fibonacci_dirs(512)
         pt = prt.ProbeTransfer(sc, prt.probe_positions([2, 2, 2], [3, 3, 3]), d, w)
         assert pt.n_probes == 8
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_group_probe_capture_equals_single_gpu_capture(prt, world):
+    """SH_volume::precompute sharded over the group and merged on the device == one capture of all probes: ranges, ids, keys and
+    36-byte transfer rows bit-identical, surfel table to 1e-6 (its means are re-derived from the summed accumulators)."""
+    from test_gpu_probe import scene_with_occluder
+    pos, tri = scene_with_occluder()
+    devs = [i % max(n_gpus(), 1) for i in range(world)]
+    grp = prt.Group(devs)
+    grp.set_scene(pos, tri)
+    probes = prt.probe_positions([5, 3, 3], [6, 6, 6])                 # 45 probes: uneven split
+    d, w = prt.fibonacci_dirs(2048)
+    pt, cap_ms, merge_ms = grp.probe_capture(probes, d, w, target=world - 1)
+    whole = prt.ProbeTransfer(prt.RTScene(pos, tri), probes, d, w)
+    assert (pt.n_probes, pt.nnz, pt.n_surfels) == (whole.n_probes, whole.nnz, whole.n_surfels) and pt.nnz > 1000
+    a, b = pt.download(), whole.download()
+    for k in (0, 1, 2, 4):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.abs(a[3] - b[3]).max() <= 1e-6
+    rad = np.random.RandomState(1).rand(pt.n_surfels, 4).astype(np.float32)
+    assert np.array_equal(pt.project(rad), whole.project(rad))
+    assert cap_ms > 0 and merge_ms >= 0
+    pt.close(); grp.close()

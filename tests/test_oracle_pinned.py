@@ -164,3 +164,35 @@ def test_calculate_weight_matches_the_reference_binary(oracle):
     assert ref.shape == got.shape == (1728, 8)
     assert 0.1 < (ref == 0).mean() < 0.9                       # occluded probes are masked, others are not
     assert np.array_equal(got, ref, equal_nan=True) and np.isnan(ref).mean() < 0.05
+
+
+def test_probe_capture_matches_the_reference_loop(oracle):
+    """The CPU half of SH_volume::precompute executed from the reference's own source (volume.cpp:185-315; G-buffer = one oracle ray per
+    texel centre of its 64^2 x 6 cubemap): same CSR structure (ranges, number of entries and surfels, id sets per probe up to the
+    reference's first-seen numbering), transfer rows <= 1e-6, surfel table <= 5e-4 (the reference averages in float)."""
+    L = open(os.path.join(G, "ref_probe_capture.txt")).read().splitlines()
+    npb, nnz, nprim = (int(x) for x in L[0].split()[1:])
+    probes = np.array([[float(x) for x in ln.split()[1:4]] for ln in L[1:1 + npb]], np.float32)
+    rng = np.array([[int(x) for x in ln.split()[5:7]] for ln in L[1:1 + npb]], np.uint32)
+    ent = L[1 + npb:1 + npb + nnz]
+    ids = np.array([int(ln.split()[1]) for ln in ent], np.int64)
+    tr = np.array([[float(x) for x in ln.split()[3:12]] for ln in ent], np.float32)
+    sf = np.array([[float(x) for x in ln.split()[3:9]] for ln in L[1 + npb + nnz:]], np.float32)
+    assert len(sf) == nprim and npb == 3 and nnz > 500
+    pos, tri = weight_scene()
+    op = oracle.probe_positions([4] * 3, [6.18] * 3)[:npb]
+    assert np.array_equal(op, probes)                                            # volume.cpp:83-90
+    d, w = oracle.cube_dirs(64)
+    o = oracle.ProbeTransfer(oracle.Scene(pos, tri), op, d, w)
+    orng, oids, otr, osf, _ = o.download()
+    assert (o.nnz, o.n_surfels) == (nnz, nprim) and np.array_equal(orng, rng)
+    # reference id (first seen) -> oracle id (rank of the cluster key): match the surfel tables
+    dist = np.abs(sf[:, None, :] - osf[None, :, :]).max(-1)
+    perm = dist.argmin(1)
+    assert dist.min(1).max() <= 5e-4 and len(set(perm.tolist())) == nprim
+    for p in range(npb):
+        a = slice(rng[p, 0], rng[p, 1])
+        rid = perm[ids[a]]
+        order = np.argsort(rid)
+        assert np.array_equal(rid[order], oids[a].astype(np.int64))
+        assert np.abs(tr[a][order] - otr[a]).max() <= 1e-6

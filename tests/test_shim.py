@@ -1,16 +1,21 @@
-"""CPU test: the header-only C++ shim with the reference's signatures compiles against a Mesh stand-in that has the
-reference's members (gl.h:76-80) and links against libprt_b200.so; running it without a GPU must fail loudly (no CPU path)."""
+"""The header-only C++ shim with the reference's signatures (include/prt_b200_shim.hpp) compiles against stand-ins that have the
+reference's members (Mesh: gl.h:76-110; Model: scene/model.h; glm-shaped vectors) and links against libprt_b200.so.
+CPU: running it without a GPU must fail loudly (no CPU path).  GPU (`-m gpu`): every wrapper runs and agrees with the ctypes binding."""
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SRC = r'''
 #include <prt_b200_shim.hpp>
+#include <cmath>
 #include <cstdio>
 struct vec3 { float x, y, z; };
+struct ivec3 { int x, y, z; };
+struct vec4 { float x, y, z, w; };
 struct Mesh {                                   // members of the reference's Mesh used by bake_SH / RTScene
     struct Vert { vec3 pos; vec3 norm; float sh_coeff[9]; };
     std::vector<Vert> v; std::vector<uint32_t> i; bool dirty = false;
@@ -18,29 +23,87 @@ struct Mesh {                                   // members of the reference's Me
     std::vector<Vert>& edit_verts() { dirty = true; return v; }
     const std::vector<uint32_t>& indices() const { return i; }
 };
+struct Model { std::vector<Mesh> meshes; };
 static_assert(sizeof(Mesh::Vert) == 60, "Mesh::Vert is 60 bytes in the reference");
-int main() {
+
+static Mesh room(float h) {                     // closed box, inward facing (the reference's data/cube.obj room)
+    Mesh m;
+    const float c[8][3] = {{-1,-1,-1},{1,-1,-1},{1,1,-1},{-1,1,-1},{-1,-1,1},{1,-1,1},{1,1,1},{-1,1,1}};
+    for (auto &p : c) m.v.push_back({{p[0]*h, p[1]*h, p[2]*h}, {0,0,1}, {}});
+    m.i = {0,1,2, 0,2,3, 4,6,5, 4,7,6, 0,4,5, 0,5,1, 3,2,6, 3,6,7, 0,3,7, 0,7,4, 1,5,6, 1,6,2};
+    return m;
+}
+
+int main(int argc, char **argv) {
     Mesh m;
     m.v = { {{0,0,0},{0,0,1},{}}, {{1,0,0},{0,0,1},{}}, {{0,1,0},{0,0,1},{}} };
     m.i = {0, 1, 2};
-    try { prt_shim::bake_SH(m); }
+    try {
+        prt_shim::bake_SH(m);
+        std::printf("OK %g dirty=%d\n", m.v[0].sh_coeff[0], (int)m.dirty);
+        if (argc > 1) {
+            // multi-GPU entry (the same device twice on a one-GPU box): same rows
+            Mesh m2 = m; for (auto &v : m2.v) for (float &c : v.sh_coeff) c = -1.f;
+            prt_shim::Settings s; s.devices = {0, 0};
+            prt_shim::bake_SH(m2, s);
+            std::printf("MULTI %d\n", (int)(m2.v[1].sh_coeff[2] == m.v[1].sh_coeff[2] && m2.v[2].sh_coeff[0] == m.v[2].sh_coeff[0]));
+            // calculate_weight -> Volume_weight
+            Model model; model.meshes.push_back(room(6.f));
+            auto w = prt_shim::calculate_weight<vec4>(model, ivec3{2,2,2}, ivec3{4,4,4}, vec3{6.f,6.f,6.f});
+            double sum = 0; for (size_t k = 0; k < w.weight0123.size(); k++) sum += w.weight0123[k].x + w.weight0123[k].y + w.weight0123[k].z + w.weight0123[k].w
+                                                                              + w.weight4567[k].x + w.weight4567[k].y + w.weight4567[k].z + w.weight4567[k].w;
+            std::printf("WEIGHT %zu %.6f\n", w.weight0123.size(), sum);
+            // SH_volume::precompute + project_sh
+            auto sc = prt_shim::RTScene::from_model(model);
+            const int32_t pr[3] = {2,2,2}; const float sz[3] = {6.f,6.f,6.f};
+            prt_shim::ProbeBake b = prt_shim::precompute(sc, pr, sz);
+            std::vector<float> rad((size_t)b.num_primitive * 4, 1.f);
+            auto vol = b.project_sh(rad);
+            std::printf("PROBE %u %zu %u %.5f\n", b.n_probes, b.ids.size(), b.num_primitive, vol[3]);       // Ar.w = c4 L00 = pi for constant radiance 1
+            // LightProbe passes + LUT on a constant environment
+            std::vector<float> eq(64 * 32 * 3, 0.5f);
+            prt_shim::LightProbe lp(eq.data(), 64, 32, 16);
+            auto irr = lp.irradiance(4); auto pre = lp.prefilter(8, 2, 64); auto lut = prt_shim::brdf_lut(16, 16, 64); auto sh = lp.project_sh(3, 1, 64);
+            std::printf("ENV %.5f %.5f %.5f %.5f\n", irr[0], pre[0], lut[2 * (15 * 16 + 15)], sh[0]);
+        }
+    }
     catch (const std::exception& e) { std::printf("EXC %s\n", e.what()); return 3; }
-    std::printf("OK %g dirty=%d\n", m.v[0].sh_coeff[0], (int)m.dirty);
     return 0;
 }
 '''
 
 
-def test_shim_compiles_and_links(tmp_path, prt):
+def build(tmp_path):
     src = tmp_path / "shim_test.cpp"
     src.write_text(SRC)
     exe = tmp_path / "shim_test"
     libdir = os.path.join(ROOT, "prt_b200", "csrc")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                            "-L", libdir, "-lprt_b200", f"-Wl,-rpath,{libdir}"])
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    return exe
+
+
+def test_shim_compiles_links_and_fails_loudly_without_gpu(tmp_path, prt):
+    exe = build(tmp_path)
     import torch
     if torch.cuda.is_available():
-        assert r.returncode == 0 and r.stdout.startswith("OK 0.28"), r.stdout + r.stderr   # flat triangle: fully visible
-    else:
-        assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+        pytest.skip("GPU present: see test_shim_wrappers_on_gpu")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_shim_wrappers_on_gpu(tmp_path, prt):
+    exe = build(tmp_path)
+    r = subprocess.run([str(exe), "all"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = dict((ln.split()[0], ln.split()[1:]) for ln in r.stdout.splitlines())
+    assert out["OK"][0].startswith("0.28") and out["OK"][1] == "dirty=1"                   # flat triangle: fully visible, DC = 0.282095
+    assert out["MULTI"] == ["1"]
+    # calculate_weight: empty room -> pure trilinear weights, each voxel's 8 weights sum to 1 (light_probe.cpp:315-316)
+    assert out["WEIGHT"][0] == "64" and abs(float(out["WEIGHT"][1]) - 64.0) < 1e-3
+    # precompute + project_sh in a closed room with constant radiance 1: SH_Irad = c4 * L00 = pi (SURVEY 8c KAT 4)
+    assert out["PROBE"][0] == "8" and int(out["PROBE"][1]) > 100 and abs(float(out["PROBE"][3]) - np.pi) < 2e-2
+    # constant environment 0.5: irradiance = 0.5 * pi (Riemann sum of irradiance.frag: ~ +-1 %), prefilter = 0.5, LUT corner A+B <= 1, L00 = 0.5 * 3.54491
+    irr, pre, lut, sh = (float(x) for x in out["ENV"])
+    assert abs(irr - 0.5 * np.pi) < 0.03 and abs(pre - 0.5) < 1e-4 and 0.0 < lut <= 1.0 and abs(sh - 0.5 * 3.54491) < 0.02
