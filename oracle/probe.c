@@ -191,19 +191,22 @@ void prt_o_csr_destroy(prt_o_csr *c) {
 }
 
 /* precomp_projectSH.comp:51-139: L_k = sum_i transfer[9i+k] * radiance[ID[i]].rgb; window; R-H pack -> out[n_probes][7][4] */
-void prt_o_probe_project(const prt_o_csr *c, const float *radiance_rgba, float *out) {
+void prt_o_project_arrays(const uint32_t *range, uint32_t n_probes, const uint32_t *ids, const float *transfer, const float *radiance_rgba, float *out) {
     const float PI = 3.14159265359f;
     const float w1 = 3.f / PI * sinf(PI / 3), w2 = 3.f / 2 / PI * sinf(2 * PI / 3);                    /* :104-113 */
-    for (uint32_t p = 0; p < c->n_probes; p++) {
+    for (uint32_t p = 0; p < n_probes; p++) {
         float L[27] = { 0 };
-        for (uint32_t i = c->range[2 * p]; i < c->range[2 * p + 1]; i++) {
-            const float *rad = radiance_rgba + 4 * (size_t)c->ids[i];
-            for (int k = 0; k < 9; k++) for (int ch = 0; ch < 3; ch++) L[3 * k + ch] += c->transfer[9 * (size_t)i + k] * rad[ch];
+        for (uint32_t i = range[2 * p]; i < range[2 * p + 1]; i++) {
+            const float *rad = radiance_rgba + 4 * (size_t)ids[i];
+            for (int k = 0; k < 9; k++) for (int ch = 0; ch < 3; ch++) L[3 * k + ch] += transfer[9 * (size_t)i + k] * rad[ch];
         }
         for (int k = 1; k < 4; k++) for (int ch = 0; ch < 3; ch++) L[3 * k + ch] *= w1;
         for (int k = 4; k < 9; k++) for (int ch = 0; ch < 3; ch++) L[3 * k + ch] *= w2;
         prt_o_sh_pack_rh(L, out + 28 * (size_t)p);
     }
+}
+void prt_o_probe_project(const prt_o_csr *c, const float *radiance_rgba, float *out) {
+    prt_o_project_arrays(c->range, c->n_probes, c->ids, c->transfer, radiance_rgba, out);
 }
 
 /* ---- calculate_weight (src/raytracing/light_probe.cpp:156-367): voxel -> 8-probe trilinear weights masked by visibility ----

@@ -96,6 +96,7 @@ void prt_o_csr_get(const prt_o_csr *, uint32_t *range, uint32_t *ids, float *tra
 void prt_o_csr_get_sums(const prt_o_csr *, double *sums /*[n_prim][7]: sum pos, sum normal, count*/);
 void prt_o_csr_destroy(prt_o_csr *);
 void prt_o_probe_project(const prt_o_csr *, const float *radiance_rgba, float *out);
+void prt_o_project_arrays(const uint32_t *range, uint32_t n_probes, const uint32_t *ids, const float *transfer, const float *radiance_rgba, float *out);
 /* calculate_weight (light_probe.cpp:156-367); w0123/w4567 [n_voxels][4], index (z*ry+y)*rx+x; score_out optional [n_voxels] */
 void prt_o_volume_weights(const prt_o_scene *, const int probe_res[3], const int volume_res[3], const float scene_size[3],
                           float *w0123, float *w4567, float *score_out);

@@ -87,6 +87,7 @@ def lib():
         L.prt_o_csr_get_sums.argtypes = [vp, vp]
         L.prt_o_csr_destroy.argtypes = [vp]
         L.prt_o_probe_project.argtypes = [vp, vp, vp]
+        L.prt_o_project_arrays.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
         L.prt_o_volume_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.prt_o_paral_shadow_matrix.argtypes = [C.c_float, C.c_float, vp, vp]
         L.prt_o_shadow_map.argtypes = [vp, vp, C.c_int, vp]
@@ -357,6 +358,15 @@ class ProbeTransfer:
         out = np.zeros((self.n_probes, 7, 4), np.float32)
         lib().prt_o_probe_project(self.h, _ptr(rad), _ptr(out))
         return out
+
+
+def project_arrays(rng, ids, transfer, radiance_rgba) -> np.ndarray:
+    """SH_volume::project_sh's kernel (precomp_projectSH.comp) on a CSR given as arrays -> [n_probes, 7, 4]."""
+    rng = np.ascontiguousarray(rng, np.uint32); ids = np.ascontiguousarray(ids, np.uint32)
+    tr = np.ascontiguousarray(transfer, np.float32); rad = np.ascontiguousarray(radiance_rgba, np.float32)
+    out = np.zeros((len(rng), 7, 4), np.float32)
+    lib().prt_o_project_arrays(_ptr(rng), len(rng), _ptr(ids), _ptr(tr), _ptr(rad), _ptr(out))
+    return out
 
 
 def volume_weights(scene: Scene, probe_res, volume_res, scene_size):

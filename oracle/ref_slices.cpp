@@ -13,6 +13,8 @@
 //   slice_prefilter.inc      src/shaders/prefilter.frag:8-107          DistributionGGX, ..., main()
 //   slice_irradiance.inc     src/shaders/irradiance.frag:7-43          main()
 //   slice_rect2cube.inc      src/shaders/rectangle2cube.frag:7-15      SampleSphericalMap
+//   slice_project_*.inc      src/shaders/precomp_projectSH.comp:22-23,32-143   the live per-probe projection kernel: CSR SpMV over 128
+//                                                                      invocations, shared-memory tree reduction, window, R-H pack
 //
 // The GLSL is compiled as C++ through the reference's vendored glm (`using namespace glm`) in a translation unit of its own
 // (ref_slices_glsl.cpp) with -fsingle-precision-constant, so that literals are float as in GLSL; the C++ slices are compiled
@@ -49,6 +51,7 @@ void ref_glsl_brdf(float ndotv, float roughness, float out[2]);
 void ref_glsl_prefilter(const float *cube, int n0, int levels, const float P[3], float roughness, float out[3]);
 void ref_glsl_irradiance(const float *cube, int n0, int levels, const float P[3], float out[3]);
 void ref_glsl_rect2cube(const float v[3], float uv[2]);
+void ref_glsl_project(const unsigned *range2, int n_probes, const unsigned *ids, const float *transfer9, const float *radiance_rgba, float *out);
 
 static std::vector<float> read_floats(const char *path) {
     std::vector<float> v;
@@ -139,6 +142,25 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
+    if (argc >= 3 && !strcmp(argv[1], "project")) {
+        // csr.bin: uint32 n_probes, nnz, n_surfels; range[n_probes][2]; ids[nnz]; float transfer[nnz][9]; float radiance[n_surfels][4]
+        FILE *f = fopen(argv[2], "rb");
+        if (!f) { perror(argv[2]); return 2; }
+        unsigned hdr[3];
+        if (fread(hdr, 4, 3, f) != 3) return 2;
+        std::vector<unsigned> range(2 * (size_t)hdr[0]), ids(hdr[1]);
+        std::vector<float> tr(9 * (size_t)hdr[1]), rad(4 * (size_t)hdr[2]), out(28 * (size_t)hdr[0]);
+        if (fread(range.data(), 8, hdr[0], f) != hdr[0] || fread(ids.data(), 4, hdr[1], f) != hdr[1] || fread(tr.data(), 36, hdr[1], f) != hdr[1] ||
+            fread(rad.data(), 16, hdr[2], f) != hdr[2]) return 2;
+        fclose(f);
+        ref_glsl_project(range.data(), (int)hdr[0], ids.data(), tr.data(), rad.data(), out.data());
+        for (unsigned p = 0; p < hdr[0]; p++) {
+            printf("probe %u :", p);
+            for (int k = 0; k < 28; k++) printf(" %.9g", out[28 * (size_t)p + k]);
+            printf("\n");
+        }
+        return 0;
+    }
     if (argc >= 3 && !strcmp(argv[1], "rect2cube")) {
         const int n = atoi(argv[2]);
         for (int i = 0; i < n; i++) {
@@ -150,6 +172,6 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
-    fprintf(stderr, "usage: ref_slices sampling | get_dirs n | brdf w h | prefilter cube.f32 n0 n_out | irradiance cube.f32 n0 n_out | rect2cube n\n");
+    fprintf(stderr, "usage: ref_slices sampling | get_dirs n | brdf w h | prefilter cube.f32 n0 n_out | irradiance cube.f32 n0 n_out | rect2cube n | project csr.bin\n");
     return 2;
 }

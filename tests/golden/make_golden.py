@@ -9,6 +9,8 @@ Run in the build container (needs /root/reference); the fixtures are committed, 
   ref_prefilter.txt   prefilter.frag main() at texel centres of a 16^2 cube, 5 mips (roughness mip/4), environment = ENV_CUBE below
   ref_irradiance.txt  irradiance.frag main() at texel centres of an 8^2 cube, same environment
   ref_rect2cube.txt   SampleSphericalMap at 64 directions          (src/shaders/rectangle2cube.frag:7-15)
+  ref_project.txt     precomp_projectSH.comp main() (the live per-probe projection kernel: 128 invocations as host threads, barrier() =
+                      std::barrier) on the random CSR of project_case() below: 7 probes with 0 .. 700 entries
 and, from the reference's WHOLE files compiled unmodified with Embree replaced by the oracle's tracer (oracle/ref_bake.cpp,
 oracle/ref_weight.cpp, stand-in headers under oracle/ref_stub/):
   ref_bake_SH_*.txt       bake_SH(Mesh&) (src/raytracing/raytracing.cpp:320-360 + renderSH :228-278) on bumpy_torus meshes: sh_coeff[9] of
@@ -63,7 +65,31 @@ def main():
         emit("ref_irradiance.txt", "ref_slices", "irradiance", tf.name, ENV_CUBE, IRR_OUT)
 
 
+    import numpy as np
+    rng, ids, tr, rad = project_case()
+    with tempfile.NamedTemporaryFile(suffix=".bin") as tf:
+        with open(tf.name, "wb") as f:
+            f.write(np.array([len(rng), len(ids), len(rad)], np.uint32).tobytes() + rng.tobytes() + ids.tobytes() + tr.tobytes() + rad.tobytes())
+        emit("ref_project.txt", "ref_slices", "project", tf.name)
     ref_bake_and_weight(ref)
+
+
+def project_case():
+    """CSR + surfel radiance fed to the reference's projection kernel; ranges of 0, 1, 127, 128, 129, 700 and 33 entries straddle its
+    128-invocation work group"""
+    import numpy as np
+    rs = np.random.RandomState(4)
+    lens = [0, 1, 127, 128, 129, 700, 33]
+    n_prim = 57
+    rng = np.zeros((len(lens), 2), np.uint32)
+    o = 0
+    for i, n in enumerate(lens):
+        rng[i] = (o, o + n)
+        o += n
+    ids = rs.randint(0, n_prim, o).astype(np.uint32)
+    tr = (rs.randn(o, 9) * 0.01).astype(np.float32)
+    rad = (rs.rand(n_prim, 4) * 3).astype(np.float32)
+    return rng, ids, tr, rad
 
 
 BAKE_CASES = {"shadow": (32, 24, 16, 2, 1.0), "bounce": (32, 24, 8, 4, 0.5), "default": (16, 12, 32, 2, 1.0)}   # nu, nv, sh_resolution, max_path_length, albedo

@@ -196,3 +196,17 @@ def test_probe_capture_matches_the_reference_loop(oracle):
         order = np.argsort(rid)
         assert np.array_equal(rid[order], oids[a].astype(np.int64))
         assert np.abs(tr[a][order] - otr[a]).max() <= 1e-6
+
+
+def test_project_sh_matches_the_reference_kernel(oracle):
+    """precomp_projectSH.comp main() (CSR SpMV over 128 invocations, shared-memory tree reduction, sinc window, Ramamoorthi-Hanrahan
+    pack) compiled from the reference and run on host threads: <= 2e-6 (summation order)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    rng, ids, tr, rad = mg.project_case()
+    ref = np.array([[float(x) for x in ln.split()[3:]] for ln in open(os.path.join(G, "ref_project.txt"))], np.float32).reshape(len(rng), 7, 4)
+    got = oracle.project_arrays(rng, ids, tr, rad)
+    assert np.abs(got - ref).max() <= 2e-6, np.abs(got - ref).max()
+    assert np.array_equal(ref[0, :6], np.zeros((6, 4), np.float32)) and ref[0, 6, 3] == 1.0        # empty range: zeros, C.w = 1
