@@ -645,8 +645,7 @@ def run_bake_group(a, prt, pos, tri, pos_m, nrm_m, params, mesh_name, t_mesh):
     # parity: the sharded rows (host) and the rows gathered on the LAST member GPU against an unsharded single-GPU bake of a sample
     n_chk = min(V, 65536 if a.config == "1" else 4096)
     sel = np.arange(0, V, max(1, V // n_chk))[:n_chk]
-    ctx0 = prt.Context(0)
-    sc0 = prt.RTScene(pos, tri, ctx0)
+    _, sc0 = grp.member(0)                       # the group's own scene copy on GPU 0: no second BVH build
     inter = BAKE_CONFIGS[a.config]["mode"] == "interreflect"
     if inter:
         sel = sel[:256]

@@ -57,6 +57,7 @@ int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
  *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
  *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
  *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first; -1 = only for small vertex counts
+ *   l2_prefetch -1/0/1 (-1)    stream the BVH into L2 before the first pass; -1 = only for small bakes (<= 2^28 rays) of L2-sized scenes
  *   entry_list, pair_queue (0 per-ray stacks / 2 wavefront), refill_thresh, block, ctas_per_sm   the per-ray fallback kernel (S > 8192, horizon off)
  *   count_work 0/1 (0)         instrumented launch filling the work counters of prt_bake_stats */
 int prt_ctx_set_tuning(prt_ctx *, const char *name, int value);

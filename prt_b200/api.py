@@ -431,6 +431,16 @@ class Group:
                                               _ptr(out) if want_host else None, gather, C.byref(st)), "prt_group_bake_transfer")
         return (out if want_host else None), st
 
+    def member(self, i: int):
+        """(context, scene) of member ``i`` as non-owning views: the group's own BVH copy on that GPU, usable with ``bake_transfer`` etc."""
+        class _View:
+            pass
+        ctx, sc = _View(), _View()
+        ctx.L, ctx.h = self.L, C.c_void_p(self.L.prt_group_ctx(self.h, i))
+        sc.L, sc.ctx, sc.h = self.L, ctx, C.c_void_p(self.L.prt_group_scene_member(self.scene_h, i))
+        sc._group = self                                   # keeps the group alive
+        return ctx, sc
+
     def probe_capture(self, probe_pos, dirs, weights, target: int = 0):
         """SH_volume::precompute over the group -> (ProbeTransfer on member ``target``, capture kernel ms (slowest GPU), merge ms)."""
         pp = np.ascontiguousarray(probe_pos, np.float32); d = np.ascontiguousarray(dirs, np.float32); w = np.ascontiguousarray(weights, np.float32)

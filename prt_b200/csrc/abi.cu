@@ -46,7 +46,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 30, work_list_on = -1 /* -1 = auto */;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 30, work_list_on = -1 /* -1 = auto */, l2_prefetch = -1 /* -1 = auto */;
     // cached sample table (the device copy is only replaced after the bake that last read it has finished: ev_tab)
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     std::vector<float> h_samples;
@@ -184,6 +184,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
     else if (n == "horizon") c->horizon = value ? 1 : 0;
     else if (n == "work_list") c->work_list_on = value < 0 ? -1 : value ? 1 : 0;
+    else if (n == "l2_prefetch") c->l2_prefetch = value < 0 ? -1 : value ? 1 : 0;
     else if (n == "horizon_near") { if (value < 5 || value > 95) return set_err(PRT_ERR_INVALID, "horizon_near (angular radius x100, rad) must be in [5,95]"); c->horizon_near = value; }
     else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
     else if (n == "pair_queue") { if (value != 0 && value != 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks) or 2 (wavefront)"); c->pair_queue = value; }
@@ -370,10 +371,17 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
     { const float sn = sinf(0.01f * (float)c->horizon_near); A.horizon_near2 = 1.0f / (sn * sn); }
     CU_TRY(cudaMemsetAsync(A.counter, 0, 128, st));
     if (d_vis) CU_TRY(cudaMemsetAsync(d_vis, 0, (size_t)n * A.vis_words * 4, st));
+    uint32_t prefetched = 0;
     int mode = p->mode == PRT_SHADOWED ? 0 : p->mode == PRT_INTERREFLECT ? 1 : p->mode == PRT_UNSHADOWED ? 2 : 3;
     if (mode == 1 && p->bounces == 0) mode = 0;
     const int grid = c->ctas_per_sm > 0 ? c->n_sms * c->ctas_per_sm : 0;
     if (e0) CU_TRY(cudaEventRecord(e0, st));
+    // small bakes against an L2-sized scene (a shard of a multi-GPU bake): stream the BVH into L2 first instead of demand-missing it
+    if (sc && needs_scene) {
+        const uint64_t bvh = sc->info.node_bytes + sc->info.tri_bytes;
+        const bool on = c->l2_prefetch > 0 || (c->l2_prefetch < 0 && bvh <= (96ull << 20) && (uint64_t)n * (uint64_t)S <= (1ull << 28));
+        if (on) { CU_TRY(launch_l2_prefetch(sc->d_nodes, sc->info.node_bytes, sc->d_tris, sc->info.tri_bytes, c->n_sms, st)); prefetched = 1; }
+    }
     int used_grid = grid;
     const bool fast_ok = (mode == 0 || mode == 2) && c->entry_list && S <= bake_wave_max_samples();
     uint32_t launches = 1;
@@ -419,7 +427,7 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
     if (e1) CU_TRY(cudaEventRecord(e1, st));
     CU_TRY(cudaEventRecord(c->ev_tab, st)); c->tab_in_use = true;
     c->stats.rays = (mode == 0 || mode == 1) ? (uint64_t)n * (uint64_t)S : 0;
-    c->stats.launches = launches; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
+    c->stats.launches = launches + prefetched; c->stats.grid = (uint32_t)used_grid; if (!c->stats.block) c->stats.block = (uint32_t)c->block;
     c->stats_pending = e0 && e1;
     c->work_pending = c->count_work != 0;
     return PRT_OK;

@@ -254,6 +254,15 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(const Node8 *nodes, 
     if (out_ng) { out_ng[3 * (size_t)i] = g.x; out_ng[3 * (size_t)i + 1] = g.y; out_ng[3 * (size_t)i + 2] = g.z; }
 }
 
+// Pulls the BVH into L2 ahead of the first pass with streaming prefetches (one 128-byte line per thread and iteration): a bake that
+// starts on a cold L2 otherwise pays one demand miss per line, serialised behind the traversal's dependent loads -- negligible for a
+// 50 ms bake, a few per cent of the 6 ms shard of an 8-GPU bake.  Only for scenes that fit the L2 (abi.cu decides).
+__global__ void __launch_bounds__(256) l2_prefetch_kernel(const char *a, const size_t na, const char *b, const size_t nb) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 128, first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;
+    for (size_t o = first; o < na; o += stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+    for (size_t o = first; o < nb; o += stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+}
+
 template <int ORDER, int MODE>
 cudaError_t launch_persistent(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
     const size_t smem = sizeof(EntryList) * (size_t)(block / 32);
@@ -295,6 +304,11 @@ cudaError_t launch_bake(const BakeArgs &A, int order, int mode, int *grid, int b
     case 5: return launch_order<5>(A, mode, grid, block, n_sms, st);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_l2_prefetch(const void *a, size_t na, const void *b, size_t nb, int n_sms, cudaStream_t st) {
+    l2_prefetch_kernel<<<n_sms * 8, 256, 0, st>>>((const char *)a, na, (const char *)b, nb);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_trace_any(const Node8 *nodes, const Tri48 *tris, const float *rays, uint32_t n, uint8_t *out, cudaStream_t st) {

@@ -89,6 +89,8 @@ cudaError_t launch_horizon(const BakeArgs &, int order, int *grid, int n_sms, cu
 cudaError_t launch_bake_wave(const BakeArgs &, int order, bool trace, int *grid, int block, int n_sms, cudaStream_t);
 int bake_wave_max_samples();
 int bake_wave_block();   // threads per CTA the wavefront kernel is compiled for
+// streaming L2 prefetch of two arrays (the BVH) ahead of a bake on a cold L2
+cudaError_t launch_l2_prefetch(const void *a, size_t bytes_a, const void *b, size_t bytes_b, int n_sms, cudaStream_t);
 cudaError_t launch_trace_any(const Node8 *, const Tri48 *, const float *rays, uint32_t n, uint8_t *out, cudaStream_t);
 cudaError_t launch_trace_closest(const Node8 *, const Tri48 *, const float *rays, uint32_t n, float *out_t,
                                  uint32_t *out_prim, float *out_ng, cudaStream_t);

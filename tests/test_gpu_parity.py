@@ -121,7 +121,7 @@ def test_work_list_order_independent(torus, torus_scenes, prt):
     gs, _ = torus_scenes
     gp = prt.BakeParams.make(order=3, samples_u=32, samples_v=32)
     try:
-        gs.ctx.set_tuning(work_list=0)
+        gs.ctx.set_tuning(work_list=0, l2_prefetch=0)
         off, voff = prt.bake_transfer(gs, pos, nrm, gp, want_vis=True)
         assert gs.ctx.last_bake_stats().launches == 2
         gs.ctx.set_tuning(work_list=1)
@@ -129,7 +129,7 @@ def test_work_list_order_independent(torus, torus_scenes, prt):
         assert gs.ctx.last_bake_stats().launches == 3
         on_novis = prt.bake_transfer(gs, pos, nrm, gp)[0]
     finally:
-        gs.ctx.set_tuning(work_list=-1)         # auto: on for small vertex counts (a shard of a multi-GPU bake)
+        gs.ctx.set_tuning(work_list=-1, l2_prefetch=-1)         # auto: on for small vertex counts (a shard of a multi-GPU bake)
     assert np.array_equal(von, voff)
     assert np.array_equal(on.view(np.uint32), off.view(np.uint32))
     assert np.array_equal(on.view(np.uint32), on_novis.view(np.uint32))
@@ -149,11 +149,11 @@ def test_bake_interreflect(torus, torus_scenes, prt, oracle, bounces, albedo):
     sh, _ = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(order=4, samples_u=16, samples_v=16))
     assert (got[:, 0] >= sh[:, 0] - 1e-6).all()
     # the horizon pre-pass only skips primary rays that provably escape: same visibility bits, same rows up to summation order
-    gs.ctx.set_tuning(horizon=0)
+    gs.ctx.set_tuning(horizon=0, l2_prefetch=0)
     try:
         got0, gvis0 = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(mode=prt.INTERREFLECT, **kw), want_vis=True, vertex_id_base=1000)
     finally:
-        gs.ctx.set_tuning(horizon=1)
+        gs.ctx.set_tuning(horizon=1, l2_prefetch=-1)
     assert np.array_equal(gvis0, gvis) and rel_l2(got0, got).max() <= 1e-5
     assert gs.ctx.last_bake_stats().launches == 1
 
