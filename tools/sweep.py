@@ -25,16 +25,18 @@ ap.add_argument("--sv", type=int, default=32)
 ap.add_argument("--mode", type=int, default=1)
 ap.add_argument("--bounces", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--mesh", default="torus")
+ap.add_argument("--mesh", default="torus", help="torus | folds (the heavily self-occluding twin of bench.py --workload folds) | icoK")
 ap.add_argument("--world", type=int, default=1, help="time the shard rank --rank of a --world-way split (bench.py's interleaved chunks)")
 ap.add_argument("--rank", type=int, default=0)
-ap.add_argument("--chunk", type=int, default=2048)
+ap.add_argument("--chunk", type=int, default=64)
 ap.add_argument("--flush", action="store_true", help="flush L2 between repetitions, as bench.py does")
 ap.add_argument("knobs", nargs="*")
 a = ap.parse_args()
 
 if a.mesh == "torus":
     pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv)
+elif a.mesh == "folds":
+    pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv, amp=0.25, fscale=3)
 else:
     pos, nrm, tri = meshes.icosphere(int(a.mesh.replace("ico", "")))
 order = meshes.morton_order(pos)
