@@ -134,6 +134,14 @@ int prt_ctx_create(int device_id, prt_ctx **out) {
     prt_ctx *c = new prt_ctx();
     c->device = device_id; c->n_sms = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // stream-ordered allocations (probe capture) keep up to 16 GB cached in the device's default pool instead of returning it
+        // to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess && pool) {
+            uint64_t keep = 16ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else cudaGetLastError();
+    }
     CU_TRY(cudaEventCreate(&c->ev0)); CU_TRY(cudaEventCreate(&c->ev1));
     CU_TRY(cudaEventCreate(&c->ev2)); CU_TRY(cudaEventCreate(&c->ev3)); CU_TRY(cudaEventCreate(&c->evh));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming));

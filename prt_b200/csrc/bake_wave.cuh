@@ -31,6 +31,14 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif
+#ifndef PRT_WAVE_PREFETCH
+#define PRT_WAVE_PREFETCH 0         // 1: an item pushed on a stack prefetches its node / first triangle into L1, one step ahead of the pop
+#endif
+#if defined(__CUDA_ARCH__) && PRT_WAVE_PREFETCH
+#define PRT_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define PRT_PREFETCH_L1(p)
+#endif
 constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP;
 static_assert(kNodeCap * 64 >= kMaxS, "the node stack doubles as the visibility permutation buffer");
 
@@ -210,8 +218,8 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 const uint32_t gx = __float_as_uint(g.z), gy = __float_as_uint(g.w);
                 const bool leaf = has && gy <= 0x00FFFFFFu;
                 const unsigned hb = __ballot_sync(kFull, has), lb = __ballot_sync(kFull, leaf), ib = hb & ~lb;
-                if (leaf) W.lq[ln + __popc(lb & lt_mask)] = make_uint2(sproc | (gy << 16), gx);
-                else if (has) W.nq[nn + __popc(ib & lt_mask)] = make_uint2(sproc, gx);
+                if (leaf) { W.lq[ln + __popc(lb & lt_mask)] = make_uint2(sproc | (gy << 16), gx); PRT_PREFETCH_L1(A.tris + gx); }
+                else if (has) { W.nq[nn + __popc(ib & lt_mask)] = make_uint2(sproc, gx); PRT_PREFETCH_L1(A.nodes + gx); }
                 ln += __popc(lb); nn += __popc(ib);
                 pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
             }
@@ -330,12 +338,15 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
                     while (inner8) {
                         const uint32_t s = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u;
-                        W.nq[pi++] = make_uint2(it.x, child_base + __popc(imask & ((1u << s) - 1u)));
+                        const uint32_t child = child_base + __popc(imask & ((1u << s) - 1u));
+                        W.nq[pi++] = make_uint2(it.x, child);
+                        PRT_PREFETCH_L1(A.nodes + child);
                     }
                     while (leaf8) {
                         const uint32_t s = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
                         const uint32_t meta = ((s < 4u ? meta_lo : meta_hi) >> (8u * (s & 3u))) & 0xFFu;
                         W.lq[pl++] = make_uint2(it.x | ((meta >> 5) << 16), tri_base + (meta & 31u));
+                        PRT_PREFETCH_L1(A.tris + tri_base + (meta & 31u));
                     }
                     nn += (int)(tot & 0xFFFFu); ln += (int)(tot >> 16);
                 } else

@@ -498,14 +498,14 @@ int prt_group_probe_capture(prt_group *g, prt_group_scene *gs, const float *prob
     prt_csr *c = new prt_csr();
     c->ctx = T.ctx; c->n_probes = n_probes; c->nnz = nnz; c->n_prim = n_prim; c->capture_ms = cap_ms;
     const size_t np = std::max<size_t>(1, n_prim), nz = std::max<size_t>(1, (size_t)nnz);
-    cudaError_t e = cudaMalloc(&c->range, 8 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * nz);
-    if (e == cudaSuccess) e = cudaMalloc(&c->transfer, 36 * nz);
-    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&c->keys, 8 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&c->sums, 56 * np);
+    cudaError_t e = cudaMallocAsync((void **)&c->range, 8 * (size_t)n_probes, T.st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c->ids, 4 * nz, T.st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c->transfer, 36 * nz, T.st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c->surfels, 24 * np, T.st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c->keys, 8 * np, T.st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&c->sums, 56 * np, T.st);
     uint32_t *d_remap = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&d_remap, 4 * np * (size_t)W);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_remap, 4 * np * (size_t)W, T.st);
     unsigned long long base = 0;
     for (int r = 0; r < W && e == cudaSuccess; r++) {
         if (!part[r]) continue;
@@ -528,7 +528,7 @@ int prt_group_probe_capture(prt_group *g, prt_group_scene *gs, const float *prob
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(T.st);
-    cudaFree(d_remap);
+    if (d_remap) cudaFreeAsync(d_remap, T.st);
     cleanup();
     if (e != cudaSuccess) { prt_csr_destroy(c); return prt_set_error(PRT_ERR_CUDA, std::string("prt_group_probe_capture: ") + cudaGetErrorString(e)); }
     if (capture_ms_max) *capture_ms_max = cap_ms;

@@ -558,10 +558,16 @@ extern "C" {
 void prt_csr_destroy(prt_csr *c) {
     if (!c) return;
     cudaSetDevice(prt_ctx_device(c->ctx));
-    cudaFree(c->range); cudaFree(c->ids); cudaFree(c->transfer); cudaFree(c->surfels); cudaFree(c->keys); cudaFree(c->sums);
+    cudaStream_t st = prt_ctx_stream(c->ctx);
+    void *arrays[6] = { c->range, c->ids, c->transfer, c->surfels, c->keys, c->sums };
+    for (void *a : arrays) if (a) cudaFreeAsync(a, st);          // stream-ordered: no device-wide synchronisation per array
     delete c;
 }
 
+// temporaries and results come from the device's stream-ordered memory pool (cudaMallocAsync on the context's stream): no
+// device-wide synchronisation per free and no allocator lock shared by the host threads of a multi-GPU capture (group.cu)
+#define PB_MALLOC(pp, n) cudaMallocAsync((void **)(pp), (n), st)
+#define PB_FREE(p) do { if (p) cudaFreeAsync((p), st); } while (0)
 int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probes, const float *dirs, const float *weights,
                       uint32_t n_dirs, prt_csr **out) {
     if (!scene || !probe_pos || !dirs || !weights || !out || n_probes == 0 || n_dirs == 0) return prt_set_error(PRT_ERR_INVALID, "prt_probe_capture: bad argument");
@@ -597,20 +603,20 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     uint32_t *ticket = nullptr, *range = nullptr, *counts = nullptr;
     unsigned long long *offsets = nullptr, *skeys = nullptr, *ekeys = nullptr;
     int *overflow = nullptr;
-    auto free_stage = [&]() { cudaFree(skeys); cudaFree(stransfer); cudaFree(sacc_stage); skeys = nullptr; stransfer = nullptr; sacc_stage = nullptr; };
-    auto cleanup = [&]() { free_stage(); cudaFree(d_order); cudaFree(d_pos); cudaFree(d_dirs); cudaFree(ticket); cudaFree(counts); cudaFree(offsets); cudaFree(ekeys); cudaFree(eacc); cudaFree(overflow); };
-    cudaError_t e = cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&d_dirs, sizeof(float) * 4 * (size_t)n_dirs);
-    if (e == cudaSuccess) e = cudaMalloc(&d_order, 4 * (size_t)n_dirs);
-    if (e == cudaSuccess) e = cudaMalloc(&ticket, 8);
-    if (e == cudaSuccess) e = cudaMalloc(&overflow, 4);
-    if (e == cudaSuccess) e = cudaMalloc(&counts, 4 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&offsets, 8 * ((size_t)n_probes + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&range, 8 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&skeys, 8 * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&stransfer, 36 * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&sacc_stage, 28 * capacity);
-    if (e != cudaSuccess) { cleanup(); cudaFree(range); return prt_set_error(PRT_ERR_NOMEM, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    auto free_stage = [&]() { PB_FREE(skeys); PB_FREE(stransfer); PB_FREE(sacc_stage); skeys = nullptr; stransfer = nullptr; sacc_stage = nullptr; };
+    auto cleanup = [&]() { free_stage(); PB_FREE(d_order); PB_FREE(d_pos); PB_FREE(d_dirs); PB_FREE(ticket); PB_FREE(counts); PB_FREE(offsets); PB_FREE(ekeys); PB_FREE(eacc); PB_FREE(overflow); };
+    cudaError_t e = PB_MALLOC(&d_pos, sizeof(float) * 3 * (size_t)n_probes);
+    if (e == cudaSuccess) e = PB_MALLOC(&d_dirs, sizeof(float) * 4 * (size_t)n_dirs);
+    if (e == cudaSuccess) e = PB_MALLOC(&d_order, 4 * (size_t)n_dirs);
+    if (e == cudaSuccess) e = PB_MALLOC(&ticket, 8);
+    if (e == cudaSuccess) e = PB_MALLOC(&overflow, 4);
+    if (e == cudaSuccess) e = PB_MALLOC(&counts, 4 * (size_t)n_probes);
+    if (e == cudaSuccess) e = PB_MALLOC(&offsets, 8 * ((size_t)n_probes + 1));
+    if (e == cudaSuccess) e = PB_MALLOC(&range, 8 * (size_t)n_probes);
+    if (e == cudaSuccess) e = PB_MALLOC(&skeys, 8 * capacity);
+    if (e == cudaSuccess) e = PB_MALLOC(&stransfer, 36 * capacity);
+    if (e == cudaSuccess) e = PB_MALLOC(&sacc_stage, 28 * capacity);
+    if (e != cudaSuccess) { cleanup(); PB_FREE(range); return prt_set_error(PRT_ERR_NOMEM, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
     cudaMemcpyAsync(d_pos, probe_pos, sizeof(float) * 3 * (size_t)n_probes, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_dirs, dw.data(), sizeof(float) * 4 * (size_t)n_dirs, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_order, order.data(), 4 * (size_t)n_dirs, cudaMemcpyHostToDevice, st);
@@ -626,30 +632,33 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     int per_sm = 1;
     PB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_capture_kernel, kThreads, smem));
     const int grid = (int)std::min<unsigned long long>((unsigned long long)prt_ctx_sms(sv.ctx) * (unsigned long long)std::max(per_sm, 1), n_probes);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // capture_ms = the kernels only (capture + scan, then the compaction); the exact-size allocations between them are host work
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     cudaEventRecord(e0, st);
     probe_capture_kernel<<<grid, kThreads, smem, st>>>(A);
     scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n_probes, offsets);
+    cudaEventRecord(e1, st);
     unsigned long long nnz = 0; int ovf = 0;
     cudaMemcpyAsync(&nnz, offsets + n_probes, 8, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) {
         const unsigned long long nz = std::max<unsigned long long>(1, nnz);
-        e = cudaMalloc(&ekeys, 8 * nz);
-        if (e == cudaSuccess) e = cudaMalloc(&etransfer, 36 * nz);
-        if (e == cudaSuccess) e = cudaMalloc(&eacc, 28 * nz);
+        e = PB_MALLOC(&ekeys, 8 * nz);
+        if (e == cudaSuccess) e = PB_MALLOC(&etransfer, 36 * nz);
+        if (e == cudaSuccess) e = PB_MALLOC(&eacc, 28 * nz);
         if (e == cudaSuccess) {
+            cudaEventRecord(e2, st);
             compact_csr_kernel<<<(unsigned)(((size_t)n_probes * 32 + 255) / 256), 256, 0, st>>>(counts, offsets, n_probes, n_dirs, skeys, stransfer, sacc_stage,
                                                                                           ekeys, etransfer, eacc, range);
-            cudaEventRecord(e1, st);
+            cudaEventRecord(e3, st);
             e = cudaStreamSynchronize(st);
         }
     }
-    float ms = 0.f;
-    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (e != cudaSuccess) { cleanup(); cudaFree(range); cudaFree(etransfer); return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
+    float ms = 0.f, ms2 = 0.f;
+    if (e == cudaSuccess) { cudaEventElapsedTime(&ms, e0, e1); cudaEventElapsedTime(&ms2, e2, e3); ms += ms2; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    if (e != cudaSuccess) { cleanup(); PB_FREE(range); PB_FREE(etransfer); return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_capture: ") + cudaGetErrorString(e)); }
     free_stage();
 
     // ---- global ids ----------------------------------------------------------------------------------------------------------
@@ -660,7 +669,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     for (;;) {
         const uint32_t size = 1u << tbl_bits;
         unsigned long long *table = nullptr, *dlist = nullptr; uint32_t *dcount = nullptr;
-        cudaMalloc(&table, 8 * (size_t)size); cudaMalloc(&dlist, 8 * (size_t)size); cudaMalloc(&dcount, 4);
+        PB_MALLOC(&table, 8 * (size_t)size); PB_MALLOC(&dlist, 8 * (size_t)size); PB_MALLOC(&dcount, 4);
         cudaMemsetAsync(table, 0xFF, 8 * (size_t)size, st); cudaMemsetAsync(dcount, 0, 4, st); cudaMemsetAsync(overflow, 0, 4, st);
         if (nnz) hash_insert_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ekeys, nnz, table, size - 1, overflow);
         hash_compact_kernel<<<(size + 255) / 256, 256, 0, st>>>(table, size, dlist, dcount);
@@ -669,7 +678,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
         cudaStreamSynchronize(st);
         const bool too_full = ovf || cnt > size / 2;
         if (!too_full) { distinct.resize(cnt); if (cnt) cudaMemcpy(distinct.data(), dlist, 8 * (size_t)cnt, cudaMemcpyDeviceToHost); }
-        cudaFree(table); cudaFree(dlist); cudaFree(dcount);
+        PB_FREE(table); PB_FREE(dlist); PB_FREE(dcount);
         if (!too_full) break;
         if (++tbl_bits > 28) { cleanup(); prt_csr_destroy(c); return prt_set_error(PRT_ERR_NOMEM, "prt_probe_capture: too many distinct surfel clusters"); }
     }
@@ -677,11 +686,11 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     c->n_prim = (uint32_t)distinct.size();
     double *sacc = nullptr;
     const size_t np = std::max<size_t>(1, distinct.size());
-    e = cudaMalloc(&c->keys, 8 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * std::max<unsigned long long>(1, nnz));
-    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&sacc, 56 * np);
-    if (e != cudaSuccess) { cleanup(); cudaFree(sacc); prt_csr_destroy(c); return prt_set_error(PRT_ERR_NOMEM, "prt_probe_capture: cudaMalloc failed"); }
+    e = PB_MALLOC(&c->keys, 8 * np);
+    if (e == cudaSuccess) e = PB_MALLOC(&c->ids, 4 * std::max<unsigned long long>(1, nnz));
+    if (e == cudaSuccess) e = PB_MALLOC(&c->surfels, 24 * np);
+    if (e == cudaSuccess) e = PB_MALLOC(&sacc, 56 * np);
+    if (e != cudaSuccess) { cleanup(); PB_FREE(sacc); prt_csr_destroy(c); return prt_set_error(PRT_ERR_NOMEM, "prt_probe_capture: cudaMalloc failed"); }
     if (!distinct.empty()) cudaMemcpyAsync(c->keys, distinct.data(), 8 * distinct.size(), cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(sacc, 0, 56 * np, st);
     if (nnz) assign_ids_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(ekeys, nnz, c->keys, c->n_prim, eacc, c->ids, sacc);
@@ -745,14 +754,16 @@ int prt_csr_upload(prt_ctx *ctx, uint32_t n_probes, uint64_t nnz, uint32_t n_sur
     for (uint64_t i = 0; i < nnz; i++)
         if (ids[i] >= n_surfels) return prt_set_error(PRT_ERR_INVALID, "prt_csr_upload: surfel id out of range");
     PB_TRY(cudaSetDevice(prt_ctx_device(ctx)));
+    cudaStream_t st = prt_ctx_stream(ctx);
     prt_csr *c = new prt_csr();
     c->ctx = ctx; c->n_probes = n_probes; c->nnz = nnz; c->n_prim = n_surfels;
     const size_t np = std::max<size_t>(1, n_surfels), nz = std::max<size_t>(1, (size_t)nnz);
-    cudaError_t e = cudaMalloc(&c->range, 8 * (size_t)n_probes);
-    if (e == cudaSuccess) e = cudaMalloc(&c->ids, 4 * nz);
-    if (e == cudaSuccess) e = cudaMalloc(&c->transfer, 36 * nz);
-    if (e == cudaSuccess) e = cudaMalloc(&c->surfels, 24 * np);
-    if (e == cudaSuccess) e = cudaMalloc(&c->keys, 8 * np);
+    cudaError_t e = PB_MALLOC(&c->range, 8 * (size_t)n_probes);
+    if (e == cudaSuccess) e = PB_MALLOC(&c->ids, 4 * nz);
+    if (e == cudaSuccess) e = PB_MALLOC(&c->transfer, 36 * nz);
+    if (e == cudaSuccess) e = PB_MALLOC(&c->surfels, 24 * np);
+    if (e == cudaSuccess) e = PB_MALLOC(&c->keys, 8 * np);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaMemcpy(c->range, range, 8 * (size_t)n_probes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && nnz) e = cudaMemcpy(c->ids, ids, 4 * (size_t)nnz, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && nnz) e = cudaMemcpy(c->transfer, transfer, 36 * (size_t)nnz, cudaMemcpyHostToDevice);
@@ -769,13 +780,13 @@ int prt_probe_project(const prt_csr *c, const float *radiance_rgba, float *out_s
     PB_TRY(cudaSetDevice(prt_ctx_device(c->ctx)));
     cudaStream_t st = prt_ctx_stream(c->ctx);
     float4 *d_rad = nullptr, *d_out = nullptr;
-    PB_TRY(cudaMalloc(&d_rad, 16 * std::max<size_t>(1, c->n_prim)));
-    PB_TRY(cudaMalloc(&d_out, 112 * (size_t)c->n_probes));
+    PB_TRY(PB_MALLOC(&d_rad, 16 * std::max<size_t>(1, c->n_prim)));
+    PB_TRY(PB_MALLOC(&d_out, 112 * (size_t)c->n_probes));
     if (c->n_prim) cudaMemcpyAsync(d_rad, radiance_rgba, 16 * (size_t)c->n_prim, cudaMemcpyHostToDevice, st);
     probe_project_kernel<<<(unsigned)(((size_t)c->n_probes * 32 + 255) / 256), 256, 0, st>>>(c->range, c->ids, c->transfer, d_rad, c->n_probes, d_out);
     cudaError_t e = cudaMemcpyAsync(out_sh_volumes, d_out, 112 * (size_t)c->n_probes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_rad); cudaFree(d_out);
+    PB_FREE(d_rad); PB_FREE(d_out);
     if (e != cudaSuccess) return prt_set_error(PRT_ERR_CUDA, std::string("prt_probe_project: ") + cudaGetErrorString(e));
     return PRT_OK;
 }

@@ -48,9 +48,12 @@ def unshard_rows(gathered: np.ndarray, n_verts: int, world: int, chunk: int = CH
 
 def sharded_bake(bake_fn, pos: np.ndarray, nrm: np.ndarray, n2: int, group=None, chunk: int = CHUNK) -> np.ndarray:
     """Bakes ``pos/nrm`` (already in the order to be sharded) across the ranks of ``group`` and returns all rows on
-    every rank.  ``bake_fn(pos_shard, nrm_shard, vertex_ids) -> [n, n2] float32`` is the per-rank compute (the CUDA
-    bake on a GPU rank).  Host-side reference implementation of the collective plumbing; bench.py keeps the rows on
-    the device and calls ``all_gather_into_tensor`` directly."""
+    every rank.  ``bake_fn(pos_shard, nrm_shard, vertex_ids) -> [n, n2] float32`` is the per-rank compute; ``vertex_ids``
+    are the positions of the shard's vertices in the whole list, which key the bounce RNG of an interreflection bake -- on a
+    GPU rank the compute is ``prt_bake_transfer_device_shard(..., world, rank, ...)``, which derives exactly these ids from
+    (world, rank) itself (``global_row`` in kernels.h), so a sharded bake does not depend on the number of ranks.
+    Host-side reference implementation of the collective plumbing; bench.py keeps the rows on the device and calls
+    ``all_gather_into_tensor`` directly."""
     import torch
     import torch.distributed as dist
 
