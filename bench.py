@@ -399,6 +399,25 @@ def run_bake(a):
     d_all = torch.zeros((world, n_mine, n2), dtype=torch.float32, device=dev)
     d_out = d_all[rank]
     h_out = torch.zeros((n_mine, n2), dtype=torch.float32).pin_memory()
+    # N > 1: the gather is fused into the kernels (rows stored straight into every rank's full-size buffer through CUDA-IPC-mapped
+    # peer pointers) unless --gather nccl asks for the all-gather baseline or IPC is unavailable
+    fused, peers, peer_arr, d_full, full_buf = False, [], None, None, None
+    if use_dist and a.gather in ("auto", "p2p"):
+        try:
+            full_buf = prt_b200.DeviceBuffer(ctx, v_pad * n2)
+            handles = [None] * world
+            dist.all_gather_object(handles, full_buf.export())
+            peers = [prt_b200.DeviceBuffer.open(ctx, handles[r], v_pad * n2) for r in range(world) if r != rank]
+            peer_arr = (C.c_void_p * len(peers))(*[p_.ptr for p_ in peers])
+            d_full = torch.as_tensor(full_buf, device=dev).view(v_pad, n2)
+            fused = True
+        except Exception as e:                          # noqa: BLE001 -- any failure means: use the NCCL baseline
+            log(f"rank {rank}: fused IPC gather unavailable ({e}); using NCCL all-gather")
+        ok_all = torch.tensor([1.0 if fused else 0.0], device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        fused = bool(ok_all.item() > 0.5)
+    if fused:
+        d_own = d_full.view(v_pad // (world * 64), world, 64, n2)[:, rank]          # this rank's rows inside the full buffer (strided view)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     L = ctx.L
     stream = torch.cuda.current_stream()
@@ -409,7 +428,16 @@ def run_bake(a):
         if rc != 0:
             raise RuntimeError(L.prt_last_error().decode())
 
+    def bake_fused():
+        rc = L.prt_bake_transfer_device_shard_fused(ctx.h, scene.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, n_mine, world, rank,
+                                                    C.byref(params), C.c_void_p(full_buf.ptr), peer_arr, len(peers), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(L.prt_last_error().decode())
+
     def step_device():
+        if fused:
+            bake_fused()                    # rows land in every rank's buffer from the kernels' epilogue: nothing follows
+            return
         bake_shard()
         if use_dist:
             dist.all_gather_into_tensor(d_all.view(-1), d_out.reshape(-1))
@@ -451,9 +479,12 @@ def run_bake(a):
         if use_dist:
             dist.barrier()
         s0.record()
-        bake_shard()
+        if fused:
+            bake_fused()
+        else:
+            bake_shard()
         s1.record()
-        if use_dist:
+        if use_dist and not fused:
             dist.all_gather_into_tensor(d_all.view(-1), d_out.reshape(-1))
         s2.record()
     barrier()
@@ -482,7 +513,7 @@ def run_bake(a):
         else:
             d_pos.copy_(h_pos, non_blocking=True); d_nrm.copy_(h_nrm, non_blocking=True)
             step_device()
-            h_out.copy_(d_out, non_blocking=True)
+            h_out.view(-1, 64, n2).copy_(d_own if fused else d_out.view(-1, 64, n2), non_blocking=True)
             torch.cuda.synchronize()
 
     step_e2e()
@@ -500,21 +531,28 @@ def run_bake(a):
     d2h = world * n_mine * n2 * 4
 
     # --- results: sanity + parity -------------------------------------------------------------------------------
-    step_device(); torch.cuda.synchronize()                       # rows of a device step (the e2e loop left the same rows)
-    rows_all = d_all.view(-1, n2)
+    step_device(); barrier()                                      # rows of a device step (the e2e loop left the same rows)
+    rows_all = d_full[:V] if fused else d_all.view(-1, n2)       # fused: vertex order; all-gather: [rank][local]
     res = rows_all[:, 0]
     hi = 0.2821 if not inter else 0.2821 * 1.0001
-    ok = bool(torch.isfinite(d_all).all().item()) and float(res.min().item()) >= -1e-6 and float(res.max().item()) <= hi
+    ok = bool(torch.isfinite(rows_all).all().item()) and float(res.min().item()) >= -1e-6 and float(res.max().item()) <= hi
     parity = None
     if world > 1:
         # every rank: its own rows of the gathered array are what it baked (bitwise); rank 0: a Morton-strided sample of the whole
         # list re-baked by ONE GPU as an unsharded bake must equal the sharded rows bit for bit
-        same = bool(torch.equal(d_all[rank], d_out))
+        # (fused: every rank compares its full buffer with rank 0's after the barrier -- the peers' stores all arrived)
+        if fused:
+            chk = d_full[:V].clone()
+            dist.broadcast(chk, src=0)
+            same = bool(torch.equal(chk, d_full[:V]))
+            del chk
+        else:
+            same = bool(torch.equal(d_all[rank], d_out))
         n_chk = min(V, 65536 if a.config == "1" else 4096)
         stride = max(1, V // n_chk)
         sel = np.arange(0, V, stride)[:n_chk]
         if rank == 0:
-            full = pdist.unshard_rows(d_all.cpu().numpy(), V, world)
+            full = d_full[:V].cpu().numpy() if fused else pdist.unshard_rows(d_all.cpu().numpy(), V, world)
             if inter:
                 # the bounce RNG is keyed by the list position: bake the sample as singleton "lists" via vertex_id_base
                 sp = np.ascontiguousarray(pos_m[sel]); sn = np.ascontiguousarray(nrm_m[sel])
@@ -523,7 +561,8 @@ def run_bake(a):
             else:
                 one, _ = prt_b200.bake_transfer(scene, pos_m[sel], nrm_m[sel], params)
             bit_equal = bool(np.array_equal(one.view(np.uint32), full[sel].view(np.uint32)))
-            parity = {"vs": "unsharded single-GPU bake of a Morton-strided sample", "rows_bit_equal": bit_equal, "own_rows_bit_equal": same,
+            parity = {"vs": "unsharded single-GPU bake of a Morton-strided sample", "rows_bit_equal": bit_equal,
+                      "all_ranks_hold_rank0s_rows" if fused else "own_rows_bit_equal": same,
                       "n_vertices": int(len(sel))}
             ok = ok and bit_equal and same
         flag = torch.tensor([1.0 if (same and ok) else 0.0], dtype=torch.float64, device=dev)
@@ -576,8 +615,10 @@ def run_bake(a):
                           "max_depth": int(info.max_depth), "build_s": info.build_seconds, "upload_s": info.upload_seconds, "mesh_s": t_mesh},
                 "launch": {"grid": int(st.grid), "block": int(st.block)}}
         if world > 1:
-            line["all_gather"] = {"ms": gather_ms_max, "bytes_received_per_gpu": (world - 1) * n_mine * n2 * 4,
-                                  "gbs": (world - 1) * n_mine * n2 * 4 / (gather_ms_max * 1e-3) / 1e9 if gather_ms_max > 0 else None}
+            line["all_gather"] = {"mode": "fused into the kernels: P2P row stores into every rank's buffer through CUDA IPC (no collective)" if fused
+                                  else "NCCL all_gather_into_tensor after the kernels",
+                                  "ms": gather_ms_max, "bytes_received_per_gpu": (world - 1) * n_mine * n2 * 4,
+                                  "gbs": (world - 1) * n_mine * n2 * 4 / (gather_ms_max * 1e-3) / 1e9 if (gather_ms_max > 0 and not fused) else None}
             line["parity"] = parity
         if world == 1 and not a.no_cpu_baseline:
             # the oracle's rows are kept: parity of the benchmarked launch at the benchmarked size, not just a CPU timing
@@ -603,6 +644,12 @@ def run_bake(a):
         emit_line(line)
     if use_dist:
         dist.barrier()
+        for p_ in peers:
+            p_.close()
+        dist.barrier()
+        if full_buf is not None:
+            d_full = None
+            full_buf.close()
         dist.destroy_process_group()
 
 

@@ -57,7 +57,7 @@ int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
  *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
  *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
  *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first; -1 = only for small vertex counts
- *   l2_prefetch -1/0/1 (-1)    stream the BVH into L2 before the first pass; -1 = only for small bakes (<= 2^28 rays) of L2-sized scenes
+ *   l2_prefetch 0/1 (0)        stream the BVH into L2 before the first pass (measured: no effect, the cold-start misses are hidden)
  *   entry_list, pair_queue (0 per-ray stacks / 2 wavefront), refill_thresh, block, ctas_per_sm   the per-ray fallback kernel (S > 8192, horizon off)
  *   count_work 0/1 (0)         instrumented launch filling the work counters of prt_bake_stats */
 int prt_ctx_set_tuning(prt_ctx *, const char *name, int value);
@@ -132,6 +132,21 @@ int prt_bake_transfer_device(prt_ctx *, prt_scene *, const float *d_pos, const f
 int prt_bake_transfer_device_shard(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes, uint32_t n_verts,
                                    uint32_t shard_world, uint32_t shard_rank, const prt_bake_params *,
                                    float *d_out_coeffs, uint32_t *d_out_vis, void *stream);
+
+/* The same shard with the gather FUSED into the kernels, for one process per GPU: rows are stored at their list position in this
+ * rank's full-size buffer d_rows_full [padded list][order^2] AND in the full-size buffers of the peer ranks (device pointers valid
+ * in this process: opened with prt_ipc_open from handles the peers exported with prt_ipc_export) -- P2P stores over NVLink from the
+ * projection epilogue, so no collective follows the kernel; the ranks only need a barrier before anybody READS the gathered rows.
+ * The padded list has ceil(ceil(n_list / 64) / world) * world * 64 rows. */
+int prt_bake_transfer_device_shard_fused(prt_ctx *, prt_scene *, const float *d_pos, const float *d_nrm, size_t stride_bytes, uint32_t n_verts,
+                                         uint32_t shard_world, uint32_t shard_rank, const prt_bake_params *, float *d_rows_full,
+                                         float *const *peer_rows_full, int32_t n_peers, void *stream);
+/* plain device allocations (cudaMalloc, zeroed) that can be exported to other processes, and CUDA IPC export / open / close */
+int prt_device_alloc(prt_ctx *, size_t bytes, void **out_d_ptr);
+int prt_device_free(prt_ctx *, void *d_ptr);
+int prt_ipc_export(prt_ctx *, const void *d_ptr, uint8_t handle[64]);
+int prt_ipc_open(prt_ctx *, const uint8_t handle[64], void **out_d_ptr);
+int prt_ipc_close(prt_ctx *, void *d_ptr);
 
 /* Same, with the rows written out_stride_bytes apart instead of packed: d_out_coeffs + 24 bytes into a device-resident Mesh::Vert
  * array with out_stride_bytes = 60 and order 3 fills sh_coeff[9] of every vertex in place (gl.h:76-80) -- the device-side half of

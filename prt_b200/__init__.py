@@ -13,8 +13,8 @@ the thin Python binding used by the tests and by ``bench.py``.  It mirrors the r
 There is no CPU fallback: importing works anywhere, but creating a context without the built CUDA library or
 without a B200-class GPU raises.
 """
-from .api import (Group, GroupStats, GATHER_NONE, GATHER_NCCL, GATHER_P2P, GATHER_AUTO, mesh_hash, hash_arrays, cache_save_transfer, cache_load_transfer, cache_save_csr, cache_load_csr, Film, Camera, raytrace, AO, NORMAL, SHVolume, RelightParams, paral_shadow_matrix, shadow_map, calculate_weight, ProbeTransfer, probe_positions, fibonacci_dirs, cube_dirs, LightProbe, brdf_lut, sh_pack_rh, BakeParams, Context, PRTError, RTScene, bake_SH, bake_transfer, lib_path, load_library,  # noqa: F401
+from .api import (DeviceBuffer, Group, GroupStats, GATHER_NONE, GATHER_NCCL, GATHER_P2P, GATHER_AUTO, mesh_hash, hash_arrays, cache_save_transfer, cache_load_transfer, cache_save_csr, cache_load_csr, Film, Camera, raytrace, AO, NORMAL, SHVolume, RelightParams, paral_shadow_matrix, shadow_map, calculate_weight, ProbeTransfer, probe_positions, fibonacci_dirs, cube_dirs, LightProbe, brdf_lut, sh_pack_rh, BakeParams, Context, PRTError, RTScene, bake_SH, bake_transfer, lib_path, load_library,  # noqa: F401
                   SHADOWED, UNSHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC)
 
-__all__ = ["Group", "GroupStats", "GATHER_NONE", "GATHER_NCCL", "GATHER_P2P", "GATHER_AUTO", "mesh_hash", "hash_arrays", "cache_save_transfer", "cache_load_transfer", "cache_save_csr", "cache_load_csr", "Film", "Camera", "raytrace", "AO", "NORMAL", "SHVolume", "RelightParams", "paral_shadow_matrix", "shadow_map", "calculate_weight", "ProbeTransfer", "probe_positions", "fibonacci_dirs", "cube_dirs", "LightProbe", "brdf_lut", "sh_pack_rh", "BakeParams", "Context", "PRTError", "RTScene", "bake_SH", "bake_transfer", "lib_path", "load_library",
+__all__ = ["DeviceBuffer", "Group", "GroupStats", "GATHER_NONE", "GATHER_NCCL", "GATHER_P2P", "GATHER_AUTO", "mesh_hash", "hash_arrays", "cache_save_transfer", "cache_load_transfer", "cache_save_csr", "cache_load_csr", "Film", "Camera", "raytrace", "AO", "NORMAL", "SHVolume", "RelightParams", "paral_shadow_matrix", "shadow_map", "calculate_weight", "ProbeTransfer", "probe_positions", "fibonacci_dirs", "cube_dirs", "LightProbe", "brdf_lut", "sh_pack_rh", "BakeParams", "Context", "PRTError", "RTScene", "bake_SH", "bake_transfer", "lib_path", "load_library",
            "SHADOWED", "UNSHADOWED", "INTERREFLECT", "UNSHADOWED_ANALYTIC"]

@@ -15,7 +15,8 @@ UNSHADOWED, SHADOWED, INTERREFLECT, UNSHADOWED_ANALYTIC = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "prt_last_error", "prt_abi_version", "prt_ctx_create", "prt_ctx_destroy", "prt_ctx_device", "prt_ctx_last_kernel_ms", "prt_ctx_set_tuning",
     "prt_scene_create", "prt_scene_destroy", "prt_scene_get_info", "prt_trace_any_hit", "prt_trace_closest_hit",
-    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_bake_transfer_device_strided", "prt_bake_transfer_device_shard", "prt_scatter_sh9",
+    "prt_bake_params_default", "prt_bake_transfer", "prt_bake_transfer_device", "prt_bake_transfer_device_strided", "prt_bake_transfer_device_shard", "prt_bake_transfer_device_shard_fused",
+    "prt_device_alloc", "prt_device_free", "prt_ipc_export", "prt_ipc_open", "prt_ipc_close", "prt_scatter_sh9",
     "prt_bake_sample_table", "prt_ctx_last_bake_stats",
     "prt_env_create", "prt_env_destroy", "prt_env_levels", "prt_env_get_cube", "prt_env_irradiance", "prt_env_prefilter",
     "prt_brdf_lut", "prt_env_project_sh", "prt_sh_pack_rh",
@@ -155,6 +156,12 @@ def load_library():
     L.prt_bake_transfer.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp]
     L.prt_bake_transfer_device.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
     L.prt_bake_transfer_device_shard.argtypes = [vp, vp, vp, vp, sz, u32, u32, u32, C.POINTER(BakeParams), vp, vp, vp]
+    L.prt_bake_transfer_device_shard_fused.argtypes = [vp, vp, vp, vp, sz, u32, u32, u32, C.POINTER(BakeParams), vp, C.POINTER(vp), C.c_int32, vp]
+    L.prt_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.prt_device_free.argtypes = [vp, vp]
+    L.prt_ipc_export.argtypes = [vp, vp, vp]
+    L.prt_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.prt_ipc_close.argtypes = [vp, vp]
     L.prt_bake_transfer_device_strided.argtypes = [vp, vp, vp, vp, sz, u32, u32, C.POINTER(BakeParams), vp, sz, vp, vp]
     L.prt_scatter_sh9.argtypes = [vp, C.c_int32, u32, vp, sz, sz]
     L.prt_bake_sample_table.argtypes = [C.POINTER(BakeParams), vp, vp]
@@ -374,6 +381,43 @@ def bake_SH(verts: np.ndarray, indices: np.ndarray, params: BakeParams | None = 
         _check(L.prt_scatter_sh9(_ptr(out), params.order, n, C.c_void_p(base), 60, 24), "prt_scatter_sh9")
     scene.close()
     return out
+
+
+class DeviceBuffer:
+    """A plain device allocation of the library (``prt_device_alloc``: cudaMalloc, zeroed) that other processes can map through CUDA
+    IPC (``export`` -> 64-byte handle, ``DeviceBuffer.open(ctx, handle)`` in the peer).  ``__cuda_array_interface__`` lets
+    ``torch.as_tensor(buf, device=...)`` view it as float32 [n_floats] without a copy."""
+
+    def __init__(self, ctx: Context, n_floats: int, _ptr_=None):
+        self.ctx, self.L, self.n_floats, self.opened = ctx, ctx.L, int(n_floats), _ptr_ is not None
+        if _ptr_ is None:
+            p = C.c_void_p()
+            _check(self.L.prt_device_alloc(ctx.h, self.n_floats * 4, C.byref(p)), "prt_device_alloc")
+            _ptr_ = p.value
+        self.ptr = _ptr_
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n_floats,), "typestr": "<f4", "data": (self.ptr, False), "version": 2}
+
+    def export(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        _check(self.L.prt_ipc_export(self.ctx.h, C.c_void_p(self.ptr), h), "prt_ipc_export")
+        return bytes(h)
+
+    @classmethod
+    def open(cls, ctx: Context, handle: bytes, n_floats: int) -> "DeviceBuffer":
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(ctx.L.prt_ipc_open(ctx.h, h, C.byref(p)), "prt_ipc_open")
+        return cls(ctx, n_floats, _ptr_=p.value)
+
+    def close(self):
+        if getattr(self, "ptr", None) and getattr(self.ctx, "h", None):
+            (self.L.prt_ipc_close if self.opened else self.L.prt_device_free)(self.ctx.h, C.c_void_p(self.ptr))
+        self.ptr = None
+
+    __del__ = close
 
 
 class Group:

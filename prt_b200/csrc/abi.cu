@@ -46,7 +46,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 30, work_list_on = -1 /* -1 = auto */, l2_prefetch = -1 /* -1 = auto */;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 30, work_list_on = -1 /* -1 = auto */, l2_prefetch = 0;
     // cached sample table (the device copy is only replaced after the bake that last read it has finished: ev_tab)
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     std::vector<float> h_samples;
@@ -192,7 +192,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "entry_list") c->entry_list = value ? 1 : 0;
     else if (n == "horizon") c->horizon = value ? 1 : 0;
     else if (n == "work_list") c->work_list_on = value < 0 ? -1 : value ? 1 : 0;
-    else if (n == "l2_prefetch") c->l2_prefetch = value < 0 ? -1 : value ? 1 : 0;
+    else if (n == "l2_prefetch") c->l2_prefetch = value > 0 ? 1 : 0;
     else if (n == "horizon_near") { if (value < 5 || value > 95) return set_err(PRT_ERR_INVALID, "horizon_near (angular radius x100, rad) must be in [5,95]"); c->horizon_near = value; }
     else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
     else if (n == "pair_queue") { if (value != 0 && value != 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks) or 2 (wavefront)"); c->pair_queue = value; }
@@ -384,10 +384,10 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
     if (mode == 1 && p->bounces == 0) mode = 0;
     const int grid = c->ctas_per_sm > 0 ? c->n_sms * c->ctas_per_sm : 0;
     if (e0) CU_TRY(cudaEventRecord(e0, st));
-    // small bakes against an L2-sized scene (a shard of a multi-GPU bake): stream the BVH into L2 first instead of demand-missing it
+    // optional (knob l2_prefetch, default off): stream the BVH into L2 before the first pass.  Measured on the 68 k-vertex shard of an
+    // 8-GPU bake with a flushed L2: 6.647 ms with and without -- the demand misses of a cold start are already hidden by the other warps
     if (sc && needs_scene) {
-        const uint64_t bvh = sc->info.node_bytes + sc->info.tri_bytes;
-        const bool on = c->l2_prefetch > 0 || (c->l2_prefetch < 0 && bvh <= (96ull << 20) && (uint64_t)n * (uint64_t)S <= (1ull << 28));
+        const bool on = c->l2_prefetch > 0;
         if (on) { CU_TRY(launch_l2_prefetch(sc->d_nodes, sc->info.node_bytes, sc->d_tris, sc->info.tri_bytes, c->n_sms, st)); prefetched = 1; }
     }
     int used_grid = grid;
@@ -403,13 +403,14 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
             // heaviest-first work list: pays only when a warp gets few vertices (a shard of a multi-GPU bake: -1.5 % at 16
             // vertices per warp, nothing at 130), so "auto" turns it on below 32 vertices per resident warp (7 CTAs x 4 warps per SM)
             if (c->work_list_on > 0 || (c->work_list_on < 0 && (uint64_t)n < 32ull * 28ull * (uint64_t)c->n_sms)) {
-                CU_TRY(c->work_list.reserve((size_t)n * 16));
+                CU_TRY(c->work_list.reserve(((size_t)n + 512) * 4));
                 A.work_list = (uint32_t *)c->work_list.p;
+                CU_TRY(cudaMemsetAsync(A.work_list + n, 0, 512 * 4, st));        // histogram + offsets of the counting sort
             }
             int hgrid = 0;
             CU_TRY(launch_horizon(A, p->order, &hgrid, c->n_sms, st));
             if (e0) CU_TRY(cudaEventRecord(c->evh, st));
-            launches = A.work_list ? 3 : 2;        // horizon_kernel (+ work_list_kernel) + bake_wave_kernel
+            launches = A.work_list ? 5 : 2;        // horizon_kernel (+ the three kernels of the work-list sort) + bake_wave_kernel
         }
         CU_TRY(launch_bake_wave(A, p->order, mode == 0, &used_grid, bake_wave_block(), c->n_sms, st));
         c->stats.block = (uint32_t)bake_wave_block();
@@ -456,6 +457,65 @@ int prt_bake_transfer_device_shard(prt_ctx *c, prt_scene *sc, const float *d_pos
     prt_row_placement pl{};
     pl.shard_world = shard_world; pl.shard_rank = shard_rank;
     return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, 0u, p, d_out, d_vis, (cudaStream_t)stream, c->ev1, c->ev2, &pl);
+}
+
+int prt_bake_transfer_device_shard_fused(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,
+                                         uint32_t shard_world, uint32_t shard_rank, const prt_bake_params *p, float *d_rows_full,
+                                         float *const *peer_rows_full, int32_t n_peers, void *stream) {
+    if (!c) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard_fused: ctx is null");
+    if (shard_world < 1 || shard_rank >= shard_world) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard_fused: bad world / rank");
+    if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_rows_full)) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard_fused: 0..7 peer buffers");
+    prt_row_placement pl{};
+    pl.shard_world = shard_world; pl.shard_rank = shard_rank; pl.out_global = 1; pl.n_peer = n_peers;
+    for (int i = 0; i < n_peers; i++) {
+        if (!peer_rows_full[i]) return set_err(PRT_ERR_INVALID, "prt_bake_transfer_device_shard_fused: null peer buffer");
+        pl.out_peer[i] = peer_rows_full[i];
+    }
+    return prt_bake_device(c, sc, d_pos, d_nrm, stride, n, 0u, p, d_rows_full, nullptr, (cudaStream_t)stream, c->ev1, c->ev2, &pl);
+}
+
+int prt_device_alloc(prt_ctx *c, size_t bytes, void **out) {
+    if (!c || !out || !bytes) return set_err(PRT_ERR_INVALID, "prt_device_alloc: bad argument");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(c->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(PRT_ERR_NOMEM, std::string("prt_device_alloc: ") + cudaGetErrorString(e)); }
+    CU_TRY(cudaMemset(p, 0, bytes));
+    *out = p;
+    return PRT_OK;
+}
+int prt_device_free(prt_ctx *c, void *p) {
+    if (!c) return set_err(PRT_ERR_INVALID, "prt_device_free: ctx is null");
+    if (!p) return PRT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaFree(p));
+    return PRT_OK;
+}
+int prt_ipc_export(prt_ctx *c, const void *d_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!c || !d_ptr || !handle) return set_err(PRT_ERR_INVALID, "prt_ipc_export: null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    std::memcpy(handle, &h, 64);
+    return PRT_OK;
+}
+int prt_ipc_open(prt_ctx *c, const uint8_t handle[64], void **out) {
+    if (!c || !handle || !out) return set_err(PRT_ERR_INVALID, "prt_ipc_open: null argument");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PRT_OK;
+}
+int prt_ipc_close(prt_ctx *c, void *d_ptr) {
+    if (!c) return set_err(PRT_ERR_INVALID, "prt_ipc_close: ctx is null");
+    if (!d_ptr) return PRT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return PRT_OK;
 }
 
 int prt_bake_transfer_device_strided(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *d_nrm, size_t stride, uint32_t n,

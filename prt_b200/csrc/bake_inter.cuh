@@ -43,36 +43,7 @@ struct InterShared {
 
 __device__ __forceinline__ uint32_t node_slots_hit_range(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx,
                                                          const float idy, const float idz, const float tnear, const float tfar) {
-    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
-    const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
-    const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
-    const float ax = (__uint_as_float(n0.x) - o.x) * idx;
-    const float ay = (__uint_as_float(n0.y) - o.y) * idy;
-    const float az = (__uint_as_float(n0.z) - o.z) * idz;
-    const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
-    uint32_t hits = 0u;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
-        const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
-        const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
-        const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
-        const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sh = 8 * j;
-            const float t0x = (float)((nearx >> sh) & 0xFFu) * sx + ax;
-            const float t0y = (float)((neary >> sh) & 0xFFu) * sy + ay;
-            const float t0z = (float)((nearz >> sh) & 0xFFu) * sz + az;
-            const float t1x = (float)((farx >> sh) & 0xFFu) * sx + ax;
-            const float t1y = (float)((fary >> sh) & 0xFFu) * sy + ay;
-            const float t1z = (float)((farz >> sh) & 0xFFu) * sz + az;
-            const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear));
-            const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, tfar));
-            if (tmin <= tmax) hits |= 1u << (4 * h + j);
-        }
-    }
-    return hits;
+    return node_slots_hit_t<true>(n0, n2, n3, n4, o, idx, idy, idz, tnear, tfar);          // traverse.cuh
 }
 
 // rare overflow path: ordinary closest-hit stack traversal of one subtree

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
     unsigned long long cand_tests = 0ull, rays_scanned = 0ull;
     uint32_t node_visits = 0u, tri_tests = 0u;
 
-    // cost-class work list of the horizon pass (work_list_kernel, horizon.cu), walked heaviest class first
+    // work list of the horizon pass (horizon.cu): the unfinished vertices, heaviest first
     const bool listed = TRACE && A.work_list != nullptr;
 
     for (;;) {
@@ -50,15 +50,9 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         if (lane == 0) {
             v = atomicAdd(A.counter, 1u);
             if (listed) {
-                // class sizes are re-read per vertex (L2 hits on lane 0 only) rather than kept in registers
-                const uint4 cc = __ldcg(reinterpret_cast<const uint4 *>(A.counter + 4));
-                const uint32_t wl1 = cc.x, wl2 = wl1 + cc.y, wl3 = wl2 + cc.z, wl4 = wl3 + cc.w;
-                if (v >= wl4) v = 0xFFFFFFFFu;
-                else {
-                    const uint32_t cls = v < wl1 ? 0u : v < wl2 ? 1u : v < wl3 ? 2u : 3u;
-                    const uint32_t first = cls == 0u ? 0u : cls == 1u ? wl1 : cls == 2u ? wl2 : wl3;
-                    v = __ldcg(A.work_list + (size_t)cls * A.n_verts + (v - first));
-                }
+                // the list's length is re-read per vertex (an L2 hit on lane 0 only) rather than kept in a register
+                const uint32_t total = __ldcg(A.counter + 4);
+                v = v < total ? __ldcg(A.work_list + v) : 0xFFFFFFFFu;
             }
         }
         v = __shfl_sync(kFull, v, 0);

@@ -31,14 +31,6 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif
-#ifndef PRT_WAVE_PREFETCH
-#define PRT_WAVE_PREFETCH 0         // 1: an item pushed on a stack prefetches its node / first triangle into L1, one step ahead of the pop
-#endif
-#if defined(__CUDA_ARCH__) && PRT_WAVE_PREFETCH
-#define PRT_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
-#else
-#define PRT_PREFETCH_L1(p)
-#endif
 constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP;
 static_assert(kNodeCap * 64 >= kMaxS, "the node stack doubles as the visibility permutation buffer");
 
@@ -54,89 +46,10 @@ struct WaveShared {
     uint32_t pend[64];                  // processing indices of rays that are not above the horizon, waiting for a scan round
 };
 
-// Tests the 8 quantised child boxes of one node against a ray (interval [0, inf)); bit s of the result = slot s hit.
-// The traversal pass is bound by instruction issue with the XU pipe (I2F, MUFU.RCP; quarter rate) its busiest unit, so the byte ->
-// float conversions of the quantised planes can be moved to the ALU pipe (PRT_NODE_PRMT: 1 = the far planes, 2 = all planes): byte q
-// placed in mantissa bits 8..15 of 2^15 is the float 32768 + q, and the constant is folded into the plane offset,
-// t = (32768 + q) * s + (a - 32768 * s) -- still one FFMA per plane; the offset is rounded once more, at 2^-9 of a quantisation
-// step (covered by the builder's box padding like the other slack of the slab arithmetic).  PRT_NODE_FFMA2 pairs the two planes of
-// an axis in one packed fma.rn.f32x2 (sm_100a); measured: no gain, the FMA pipe is not what binds (profiles/r2_node_test_ab.jsonl).
-#ifndef PRT_NODE_FFMA2
-#define PRT_NODE_FFMA2 0
-#endif
-#ifndef PRT_NODE_PRMT
-#define PRT_NODE_PRMT 0
-#endif
-#define PRT_Q2F_I2F(w, j) ((float)(((w) >> (8 * (j))) & 0xFFu))
-#if defined(__CUDA_ARCH__)
-#define PRT_Q2F_PRMT(w, j) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7604u | ((j) << 4)))
-#else
-#define PRT_Q2F_PRMT(w, j) (32768.0f + PRT_Q2F_I2F(w, j))
-#endif
+// 8 quantised child boxes of one node against a ray from the vertex (interval [0, inf)): traverse.cuh
 __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o,
                                                    const float idx, const float idy, const float idz) {
-    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
-    const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
-    const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
-    const float ax = (__uint_as_float(n0.x) - o.x) * idx;
-    const float ay = (__uint_as_float(n0.y) - o.y) * idy;
-    const float az = (__uint_as_float(n0.z) - o.z) * idz;
-#if PRT_NODE_PRMT
-    const float bx = fmaf(-32768.0f, sx, ax), by = fmaf(-32768.0f, sy, ay), bz = fmaf(-32768.0f, sz, az);
-#endif
-#if PRT_NODE_PRMT >= 2
-#define PRT_NEAR(w, j, s, a, b) fmaf(PRT_Q2F_PRMT(w, j), s, b)
-#else
-#define PRT_NEAR(w, j, s, a, b) fmaf(PRT_Q2F_I2F(w, j), s, a)
-#endif
-#if PRT_NODE_PRMT >= 1
-#define PRT_FAR(w, j, s, a, b) fmaf(PRT_Q2F_PRMT(w, j), s, b)
-#else
-#define PRT_FAR(w, j, s, a, b) fmaf(PRT_Q2F_I2F(w, j), s, a)
-#define bx ax
-#define by ay
-#define bz az
-#endif
-    const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
-    uint32_t hits = 0u;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
-        const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
-        const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
-        const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
-        const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT != 1
-#if PRT_NODE_PRMT
-#define PRT_Q2F PRT_Q2F_PRMT
-#else
-#define PRT_Q2F PRT_Q2F_I2F
-#endif
-            const float2 tx = __ffma2_rn(make_float2(PRT_Q2F(nearx, j), PRT_Q2F(farx, j)), make_float2(sx, sx), make_float2(bx, bx));
-            const float2 ty = __ffma2_rn(make_float2(PRT_Q2F(neary, j), PRT_Q2F(fary, j)), make_float2(sy, sy), make_float2(by, by));
-            const float2 tz = __ffma2_rn(make_float2(PRT_Q2F(nearz, j), PRT_Q2F(farz, j)), make_float2(sz, sz), make_float2(bz, bz));
-            const float t0x = tx.x, t1x = tx.y, t0y = ty.x, t1y = ty.y, t0z = tz.x, t1z = tz.y;
-#undef PRT_Q2F
-#else
-            const float t0x = PRT_NEAR(nearx, j, sx, ax, bx), t1x = PRT_FAR(farx, j, sx, ax, bx);
-            const float t0y = PRT_NEAR(neary, j, sy, ay, by), t1y = PRT_FAR(fary, j, sy, ay, by);
-            const float t0z = PRT_NEAR(nearz, j, sz, az, bz), t1z = PRT_FAR(farz, j, sz, az, bz);
-#endif
-            const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-            const float tmax = fminf(fminf(t1x, t1y), t1z);
-            if (tmin <= tmax) hits |= 1u << (4 * h + j);
-        }
-    }
-#if PRT_NODE_PRMT < 1
-#undef bx
-#undef by
-#undef bz
-#endif
-#undef PRT_NEAR
-#undef PRT_FAR
-    return hits;
+    return node_slots_hit_t<false>(n0, n2, n3, n4, o, idx, idy, idz, 0.0f, 0.0f);
 }
 
 // rare overflow paths, kept out of line so that they do not occupy the instruction cache of the hot loop
@@ -218,8 +131,8 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 const uint32_t gx = __float_as_uint(g.z), gy = __float_as_uint(g.w);
                 const bool leaf = has && gy <= 0x00FFFFFFu;
                 const unsigned hb = __ballot_sync(kFull, has), lb = __ballot_sync(kFull, leaf), ib = hb & ~lb;
-                if (leaf) { W.lq[ln + __popc(lb & lt_mask)] = make_uint2(sproc | (gy << 16), gx); PRT_PREFETCH_L1(A.tris + gx); }
-                else if (has) { W.nq[nn + __popc(ib & lt_mask)] = make_uint2(sproc, gx); PRT_PREFETCH_L1(A.nodes + gx); }
+                if (leaf) W.lq[ln + __popc(lb & lt_mask)] = make_uint2(sproc | (gy << 16), gx);
+                else if (has) W.nq[nn + __popc(ib & lt_mask)] = make_uint2(sproc, gx);
                 ln += __popc(lb); nn += __popc(ib);
                 pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
             }
@@ -338,15 +251,12 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
                     while (inner8) {
                         const uint32_t s = (uint32_t)__ffs(inner8) - 1u; inner8 &= inner8 - 1u;
-                        const uint32_t child = child_base + __popc(imask & ((1u << s) - 1u));
-                        W.nq[pi++] = make_uint2(it.x, child);
-                        PRT_PREFETCH_L1(A.nodes + child);
+                        W.nq[pi++] = make_uint2(it.x, child_base + __popc(imask & ((1u << s) - 1u)));
                     }
                     while (leaf8) {
                         const uint32_t s = (uint32_t)__ffs(leaf8) - 1u; leaf8 &= leaf8 - 1u;
                         const uint32_t meta = ((s < 4u ? meta_lo : meta_hi) >> (8u * (s & 3u))) & 0xFFu;
                         W.lq[pl++] = make_uint2(it.x | ((meta >> 5) << 16), tri_base + (meta & 31u));
-                        PRT_PREFETCH_L1(A.tris + tri_base + (meta & 31u));
                     }
                     nn += (int)(tot & 0xFFFFu); ln += (int)(tot >> 16);
                 } else

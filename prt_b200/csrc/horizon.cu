@@ -38,27 +38,49 @@ __global__ void __launch_bounds__(128, PRT_HZ_MINB) horizon_kernel(const BakeArg
     }
 }
 
-// Files every unfinished vertex under one of four cost classes (the quartile of S its need count falls in).  The traversal pass
-// walks the classes heaviest first, so that the warps still busy when the work runs out hold cheap vertices (shorter tail).
-// Thread per vertex, one atomic per warp and class; the order inside a class stays close to the (Morton) vertex order.
-__global__ void __launch_bounds__(256) work_list_kernel(const uint32_t *need_count, const uint32_t n, const uint32_t S, uint32_t *list, uint32_t *class_count) {
+// Work list of the traversal pass: the unfinished vertices in DESCENDING order of their need count (a counting sort over kWorkBuckets
+// buckets of need / S), so that the persistent warps take the heaviest vertices first and the warps still busy when the work runs out
+// hold cheap ones (longest-processing-time-first: the makespan of a small shard is bounded by the mean load plus one LIGHT vertex).
+// list[0 .. total): vertex indices; aux = [hist kWorkBuckets][offsets kWorkBuckets] (hist pre-zeroed); total -> class_count[0].
+#ifndef PRT_WORK_BUCKETS
+#define PRT_WORK_BUCKETS 32          // <= 256; inside a bucket the vertices keep (roughly) their Morton order, which the L1 likes
+#endif
+constexpr uint32_t kWorkBuckets = 256;                 // size of the histogram arrays
+constexpr uint32_t kWorkUsed = PRT_WORK_BUCKETS;
+static_assert(kWorkUsed >= 1 && kWorkUsed <= kWorkBuckets, "PRT_WORK_BUCKETS out of range");
+__device__ __forceinline__ uint32_t work_bucket(const uint32_t need, const uint32_t S) {
+    return (kWorkUsed - 1u) - min(kWorkUsed - 1u, (uint32_t)(((unsigned long long)need * kWorkUsed) / (S + 1u)));   // heavy -> bucket 0
+}
+__global__ void __launch_bounds__(256) work_hist_kernel(const uint32_t *need_count, const uint32_t n, const uint32_t S, uint32_t *hist) {
+    __shared__ uint32_t h[kWorkBuckets];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const uint32_t need = need_count[v];
+        if (need) atomicAdd(&h[work_bucket(need, S)], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) work_scan_kernel(const uint32_t *hist, uint32_t *offsets, uint32_t *total) {
+    __shared__ uint32_t s[kWorkBuckets];
+    const uint32_t mine = hist[threadIdx.x];
+    s[threadIdx.x] = mine;
+    __syncthreads();
+    for (uint32_t o = 1; o < kWorkBuckets; o <<= 1) {
+        const uint32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    offsets[threadIdx.x] = s[threadIdx.x] - mine;
+    if (threadIdx.x == kWorkBuckets - 1u) *total = s[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) work_scatter_kernel(const uint32_t *need_count, const uint32_t n, const uint32_t S, uint32_t *offsets, uint32_t *list) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t cls = 4u;
-    if (v < n) {
-        const uint32_t q = 4u * need_count[v];
-        if (q) cls = q > 3u * S ? 0u : q > 2u * S ? 1u : q > S ? 2u : 3u;
-    }
-#pragma unroll
-    for (uint32_t c = 0; c < 4u; c++) {
-        const unsigned m = __ballot_sync(kFull, cls == c);
-        if (!m) continue;
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0u;
-        if (lane == leader) base = atomicAdd(class_count + c, (uint32_t)__popc(m));
-        base = __shfl_sync(kFull, base, leader);
-        if (cls == c) list[(size_t)c * n + base + __popc(m & ((1u << lane) - 1u))] = v;
-    }
+    if (v >= n) return;
+    const uint32_t need = need_count[v];
+    if (need) list[atomicAdd(&offsets[work_bucket(need, S)], 1u)] = v;
 }
 
 template <int ORDER>
@@ -74,7 +96,13 @@ cudaError_t launch_horizon_t(const BakeArgs &A, int *grid, int n_sms, cudaStream
     const long long need = ((long long)A.n_verts + 3) / 4;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
     horizon_kernel<ORDER><<<*grid, block, smem, st>>>(A);
-    if (A.work_list) work_list_kernel<<<(A.n_verts + 255u) / 256u, 256, 0, st>>>(A.need_count, A.n_verts, (uint32_t)A.S, A.work_list, A.counter + 4);
+    if (A.work_list) {
+        uint32_t *hist = A.work_list + A.n_verts, *offsets = hist + kWorkBuckets;          // zeroed by the caller (abi.cu)
+        const unsigned g = (unsigned)min((A.n_verts + 255u) / 256u, 1024u);
+        work_hist_kernel<<<g, 256, 0, st>>>(A.need_count, A.n_verts, (uint32_t)A.S, hist);
+        work_scan_kernel<<<1, 256, 0, st>>>(hist, offsets, A.counter + 4);
+        work_scatter_kernel<<<(A.n_verts + 255u) / 256u, 256, 0, st>>>(A.need_count, A.n_verts, (uint32_t)A.S, offsets, A.work_list);
+    }
     return cudaGetLastError();
 }
 

@@ -44,9 +44,9 @@ struct BakeArgs {
     uint32_t *need_bits;        // horizon pass output / traversal pass input: [n_verts][vis_words], bit i of a row = sample with
                                 // processing index i is NOT above the horizon and must be traced
     uint32_t *need_count;       // [n_verts] number of such samples; 0 = the horizon pass already wrote the vertex's row
-    uint32_t *work_list;        // optional [4][n_verts]: the horizon pass files every unfinished vertex under one of four cost
-                                // classes (quartile of S its need count falls in; class sizes in counter[4..7]) and the traversal
-                                // pass walks the classes heaviest first, so the warps that finish last hold cheap vertices
+    uint32_t *work_list;        // optional [n_verts + 512]: the unfinished vertices in descending order of their need count (counting
+                                // sort after the horizon pass, horizon.cu; length in counter[4]; the tail holds the sort's histogram) --
+                                // the traversal pass takes the heaviest vertices first, so the warps that finish last hold cheap ones
     uint32_t seed;
     int depth;                  // path segments = bounces + 1
     float albedo[3];

@@ -39,6 +39,73 @@ PRT_HD float safe_rcp(float d) {
     return 1.0f / d;
 }
 
+// ---- quantised child boxes of one node against one ray (the wavefront kernels: one lane = one (ray, node) item) -----------------------
+// Bit s of the result = slot s hit in (RANGE ? [tnear, tfar] : [0, inf)).
+// These kernels are bound by instruction issue with the XU pipe (I2F, MUFU.RCP; quarter rate) their busiest unit (62 % in the traversal
+// pass) and the ALU pipe at 49 %.  PRT_NODE_PRMT = n moves the byte -> float conversion of n of the six plane groups (far x, far y, far z,
+// near x, near y, near z) from I2F to a byte permute on the ALU pipe: byte q placed in mantissa bits 8..15 of 2^15 is the float
+// 32768 + q, and the constant is folded into the plane offset, t = (32768 + q) * s + (a - 32768 * s) -- still one FFMA per plane.  The
+// offset is rounded once more, at 2^-9 of a quantisation step; it is pushed OUTWARD by 2^-8 of a step (one more FFMA per axis and
+// node), so the test stays conservative whatever the node's size -- box tests only ever have to be conservative.
+// Measured on the headline bake (profiles/r2_node_test_ab.jsonl, step ms): n = 0: 51.1, 3: 49.8, 6: 50.4 -- balancing the two pipes is
+// what pays: far planes through the ALU, near planes on the XU.  PRT_NODE_FFMA2 pairs the two planes of an axis in one packed
+// fma.rn.f32x2 (sm_100a): no gain, the FMA pipe (25 %) is not what binds.
+#ifndef PRT_NODE_FFMA2
+#define PRT_NODE_FFMA2 0
+#endif
+#ifndef PRT_NODE_PRMT
+#define PRT_NODE_PRMT 3
+#endif
+#define PRT_Q2F_I2F(w, j) ((float)(((w) >> (8 * (j))) & 0xFFu))
+#if defined(__CUDA_ARCH__)
+#define PRT_Q2F_PRMT(w, j) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7604u | ((j) << 4)))
+#else
+#define PRT_Q2F_PRMT(w, j) (32768.0f + PRT_Q2F_I2F(w, j))
+#endif
+// plane group g (0..5 = far x, far y, far z, near x, near y, near z): conversion by byte permute (offset b) or by I2F (offset a)
+#define PRT_PLANE(g, w, j, s, a, b) ((g) < PRT_NODE_PRMT ? fmaf(PRT_Q2F_PRMT(w, j), s, b) : fmaf(PRT_Q2F_I2F(w, j), s, a))
+template <bool RANGE>
+PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx, const float idy,
+                                 const float idz, const float tnear, const float tfar) {
+    const float sx = PRT_U2F((n0.w & 0xFFu) << 23) * idx;
+    const float sy = PRT_U2F(((n0.w >> 8) & 0xFFu) << 23) * idy;
+    const float sz = PRT_U2F(((n0.w >> 16) & 0xFFu) << 23) * idz;
+    const float ax = (PRT_U2F(n0.x) - o.x) * idx;
+    const float ay = (PRT_U2F(n0.y) - o.y) * idy;
+    const float az = (PRT_U2F(n0.z) - o.z) * idz;
+    // offsets of the permuted planes: far planes pushed out (+), near planes pushed out (-) by 2^-8 of a quantisation step (dead code
+    // for the groups that stay on I2F)
+    const float gx = fabsf(sx) * 0.00390625f, gy = fabsf(sy) * 0.00390625f, gz = fabsf(sz) * 0.00390625f;
+    const float fx = fmaf(-32768.0f, sx, ax) + gx, fy = fmaf(-32768.0f, sy, ay) + gy, fz = fmaf(-32768.0f, sz, az) + gz;
+    const float mx = fmaf(-32768.0f, sx, ax) - gx, my = fmaf(-32768.0f, sy, ay) - gy, mz = fmaf(-32768.0f, sz, az) - gz;
+    const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+        const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+        const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
+        const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
+        const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 0
+            const float2 tx = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearx, j), PRT_Q2F_I2F(farx, j)), make_float2(sx, sx), make_float2(ax, ax));
+            const float2 ty = __ffma2_rn(make_float2(PRT_Q2F_I2F(neary, j), PRT_Q2F_I2F(fary, j)), make_float2(sy, sy), make_float2(ay, ay));
+            const float2 tz = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearz, j), PRT_Q2F_I2F(farz, j)), make_float2(sz, sz), make_float2(az, az));
+            const float t0x = tx.x, t1x = tx.y, t0y = ty.x, t1y = ty.y, t0z = tz.x, t1z = tz.y;
+#else
+            const float t1x = PRT_PLANE(0, farx, j, sx, ax, fx), t1y = PRT_PLANE(1, fary, j, sy, ay, fy), t1z = PRT_PLANE(2, farz, j, sz, az, fz);
+            const float t0x = PRT_PLANE(3, nearx, j, sx, ax, mx), t0y = PRT_PLANE(4, neary, j, sy, ay, my), t0z = PRT_PLANE(5, nearz, j, sz, az, mz);
+#endif
+            const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, RANGE ? tnear : 0.0f));
+            const float tmax = RANGE ? fminf(fminf(t1x, t1y), fminf(t1z, tfar)) : fminf(fminf(t1x, t1y), t1z);
+            if (tmin <= tmax) hits |= 1u << (4 * h + j);
+        }
+    }
+    return hits;
+}
+
 // run() results: RUNNING = interrupted for a refill (state kept); HIT = any-hit found (ANY only);
 // EMPTY = stack and current groups exhausted (closest-hit result, if any, is in best_*)
 enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_EMPTY = 2 };

@@ -170,3 +170,69 @@ def test_group_probe_capture_equals_single_gpu_capture(prt, world):
     assert np.array_equal(pt.project(rad), whole.project(rad))
     assert cap_ms > 0 and merge_ms >= 0
     pt.close(); grp.close()
+
+
+IPC_WORKER = r'''
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.environ["PRT_ROOT"])
+import torch, torch.distributed as dist
+import prt_b200
+from prt_b200 import meshes, dist as pdist
+dist.init_process_group("gloo")                      # handles travel through gloo: both ranks may sit on ONE GPU (NCCL would refuse that)
+world, rank = dist.get_world_size(), dist.get_rank()
+dev = rank % torch.cuda.device_count()
+torch.cuda.set_device(dev)
+pos, nrm, tri = meshes.bumpy_torus(96, 64)
+order = meshes.morton_order(pos)
+pm, nm = pos[order][:6100], nrm[order][:6100]        # ragged: the last chunk is partial
+V, n2 = len(pm), 16
+ctx = prt_b200.Context(dev)
+scene = prt_b200.RTScene(pos, tri, ctx)
+params = prt_b200.BakeParams.make(order=4, samples_u=16, samples_v=16, mode=prt_b200.INTERREFLECT, bounces=1, albedo=(0.5, 0.5, 0.5))
+mine, valid, v_pad = pdist.shard_indices(V, world, rank)
+d_pos = torch.from_numpy(np.ascontiguousarray(pm[mine])).cuda(); d_nrm = torch.from_numpy(np.ascontiguousarray(nm[mine])).cuda()
+full = prt_b200.DeviceBuffer(ctx, v_pad * n2)
+handles = [None] * world
+dist.all_gather_object(handles, full.export())
+peers = [prt_b200.DeviceBuffer.open(ctx, handles[r], v_pad * n2) for r in range(world) if r != rank]
+arr = (C.c_void_p * len(peers))(*[p.ptr for p in peers])
+st = torch.cuda.current_stream()
+rc = ctx.L.prt_bake_transfer_device_shard_fused(ctx.h, scene.h, C.c_void_p(d_pos.data_ptr()), C.c_void_p(d_nrm.data_ptr()), 12, int(valid.sum()), world, rank,
+                                                C.byref(params), C.c_void_p(full.ptr), arr, len(peers), C.c_void_p(st.cuda_stream))
+assert rc == 0, ctx.L.prt_last_error()
+torch.cuda.synchronize()
+dist.barrier()                                       # every rank's stores have landed
+rows = torch.as_tensor(full, device="cuda").view(v_pad, n2)[:V].cpu().numpy()
+np.save(os.environ["PRT_OUT"] + f".{rank}.npy", rows)
+dist.barrier()
+for p in peers: p.close()
+dist.barrier()
+full.close()
+dist.destroy_process_group()
+'''
+
+
+def test_fused_gather_between_processes_over_cuda_ipc(prt, tmp_path):
+    """One process per GPU (torchrun): every rank stores its finished rows straight into the full-size buffer of every peer through
+    CUDA-IPC-mapped pointers (prt_ipc_export / prt_ipc_open, prt_bake_transfer_device_shard_fused).  After a barrier EVERY rank
+    holds all rows, bit-identical to an unsharded bake (the bounce RNG is keyed by the list position).  Two ranks; on a one-GPU box
+    both sit on GPU 0."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ipc_worker.py"
+    script.write_text(IPC_WORKER)
+    out = str(tmp_path / "rows")
+    env = dict(os.environ, PRT_ROOT=root, PRT_OUT=out)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29631", str(script)], check=True, env=env, timeout=600)
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    order = meshes.morton_order(pos)
+    pm, nm = pos[order][:6100], nrm[order][:6100]
+    params = prt.BakeParams.make(order=4, samples_u=16, samples_v=16, mode=prt.INTERREFLECT, bounces=1, albedo=(0.5, 0.5, 0.5))
+    ref, _ = prt.bake_transfer(prt.RTScene(pos, tri), pm, nm, params)
+    for r in range(2):
+        rows = np.load(out + f".{r}.npy")
+        assert np.array_equal(rows.view(np.uint32), ref.view(np.uint32)), f"rank {r}"
