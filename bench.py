@@ -729,9 +729,9 @@ def run_bake_group(a, prt, pos, tri, pos_m, nrm_m, params, mesh_name, t_mesh):
 # ----------------------------------------------------------------------------------------------------------------
 def env_image():
     from prt_b200 import hdr
-    for p in (os.path.join(ROOT, "tests", "golden", "newport_loft.hdr"), "/root/reference/data/hdr/newport_loft.hdr"):
-        if os.path.exists(p):
-            return hdr.load_hdr(p), "data/hdr/newport_loft.hdr (1600x800)"
+    p = os.path.join(ROOT, "tests", "golden", "newport_loft.hdr")            # the reference's data/hdr/newport_loft.hdr, a committed fixture
+    if os.path.exists(p):
+        return hdr.load_hdr(p), "data/hdr/newport_loft.hdr (1600x800)"
     return hdr.synthetic_env(1600, 800), "synthetic 1600x800 HDR (range of newport_loft)"
 
 

@@ -79,3 +79,18 @@ def test_full_size_properties(prt):
     assert np.abs(e_sh - centre).max() / centre.max() < 0.08
     lut = prt.brdf_lut(512, 512, 1024)
     assert lut.shape == (512, 512, 2) and (lut.sum(-1) <= 1.0 + 1e-4).all()
+
+
+def test_reference_hdr_asset_against_oracle(prt, oracle):
+    """BASELINE configs[1] on the reference's own data/hdr/newport_loft.hdr (1600 x 800 RGBE, values up to 15.25): the 512^2 cube, the SH9
+    projection (both quadratures) and a 32^2 x 5 prefilter chain against the oracle (gate 1e-3 abs on the maps, relative on SH)."""
+    import os
+    eq = hdr.load_hdr(os.path.join(os.path.dirname(__file__), "golden", "newport_loft.hdr"))
+    g, o = prt.LightProbe(eq, 512), oracle.EnvCube(eq, 512)
+    assert np.abs(g.cube(0) - o.cube(0)).max() <= 1e-3 and np.abs(g.cube(4) - o.cube(4)).max() <= 1e-3
+    for method in (0, 1):
+        a, b = g.project_sh(3, method), o.project_sh(3, method)
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
+    gp, op = g.prefilter(32, 5, 1024), o.prefilter(32, 5, 1024)
+    for x, y in zip(gp, op):
+        assert np.abs(x - y).max() <= 1e-3

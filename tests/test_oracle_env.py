@@ -1,5 +1,5 @@
-"""CPU tests: known answers for the oracle's image-based-lighting restatement (SURVEY 8c KATs 6, 7) and, when the reference
-asset is present (build container only), the RGBE reader against the statistics SURVEY section 0.5 records for stb_image."""
+"""CPU tests: known answers for the oracle's image-based-lighting restatement (SURVEY 8c KATs 6, 7) and the RGBE reader on the
+reference's own data/hdr/newport_loft.hdr (tests/golden/) against the statistics SURVEY section 0.5 records for stb_image."""
 import os
 
 import numpy as np
@@ -9,9 +9,7 @@ from prt_b200 import hdr
 
 
 def test_hdr_reader_matches_reference_asset_stats():
-    path = "/root/reference/data/hdr/newport_loft.hdr"
-    if not os.path.exists(path):
-        pytest.skip("reference asset not present on this machine")
+    path = os.path.join(os.path.dirname(__file__), "golden", "newport_loft.hdr")
     img = hdr.load_hdr(path)
     assert img.shape == (800, 1600, 3)
     assert abs(img.mean() - 0.2516) < 1e-3 and abs(img.max() - 15.25) < 1e-6
