@@ -56,7 +56,7 @@ int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
  *   horizon 0/1 (1)            per-origin horizon pass before the shadowed / interreflected bake
  *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
  *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
- *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first; -1 = only for small vertex counts
+ *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first (counting sort of the need counts); -1 = below ~1 M vertices
  *   l2_prefetch 0/1 (0)        stream the BVH into L2 before the first pass (measured: no effect, the cold-start misses are hidden)
  *   entry_list, pair_queue (0 per-ray stacks / 2 wavefront), refill_thresh, block, ctas_per_sm   the per-ray fallback kernel (S > 8192, horizon off)
  *   count_work 0/1 (0)         instrumented launch filling the work counters of prt_bake_stats */

@@ -400,9 +400,10 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
             CU_TRY(c->need_bits.reserve((size_t)n * A.vis_words * 4));
             CU_TRY(c->need_count.reserve((size_t)n * 4));
             A.need_bits = (uint32_t *)c->need_bits.p; A.need_count = (uint32_t *)c->need_count.p;
-            // heaviest-first work list: pays only when a warp gets few vertices (a shard of a multi-GPU bake: -1.5 % at 16
-            // vertices per warp, nothing at 130), so "auto" turns it on below 32 vertices per resident warp (7 CTAs x 4 warps per SM)
-            if (c->work_list_on > 0 || (c->work_list_on < 0 && (uint64_t)n < 32ull * 28ull * (uint64_t)c->n_sms)) {
+            // heaviest-first work list (a counting sort of the need counts, horizon.cu): shortens the tail of the persistent grid.  Measured
+            // on the bench mesh, list on vs off: 543 k vertices 0.0 %, 272 k -0.1 %, 136 k -0.7 %, 68 k (the shard of an 8-GPU bake) -3.2 %;
+            // "auto" sorts below 256 vertices per resident warp (7 CTAs x 4 warps per SM), where the tail is a visible share of the launch
+            if (c->work_list_on > 0 || (c->work_list_on < 0 && (uint64_t)n < 256ull * 28ull * (uint64_t)c->n_sms)) {
                 CU_TRY(c->work_list.reserve(((size_t)n + 512) * 4));
                 A.work_list = (uint32_t *)c->work_list.p;
                 CU_TRY(cudaMemsetAsync(A.work_list + n, 0, 512 * 4, st));        // histogram + offsets of the counting sort
