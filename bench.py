@@ -679,7 +679,8 @@ def run_bake_group(a, prt, pos, tri, pos_m, nrm_m, params, mesh_name, t_mesh):
     for _ in range(a.steps):
         for f in flush:
             f.zero_()
-        torch.cuda.synchronize()
+        for i in range(a.gpus):
+            torch.cuda.synchronize(i)
         t0 = time.perf_counter()
         _, st = grp.bake_transfer(hp, hn, params, gather=mode, out=ho)
         wall_ms.append(1e3 * (time.perf_counter() - t0))

@@ -33,4 +33,15 @@ prt_b200.raytrace(sc, film, prt_b200.Camera.look_at((5, 3, 4), (0, 0, 0)), n_fra
 lp = prt_b200.LightProbe(hdr.synthetic_env(64, 32), 16, sc.ctx)
 lp.irradiance(4); lp.prefilter(8, 2, 32); lp.project_sh(3, 0); lp.project_sh(3, 1)
 prt_b200.brdf_lut(16, 16, 32, sc.ctx)
+# multi-GPU driver (the same device twice on a one-GPU box): sharded bake with fused P2P row stores, sorted work list, device-side CSR merge
+grp = prt_b200.Group([0, 0])
+grp.set_scene(pos, tri)
+order = meshes.morton_order(pos)
+rows, st = grp.bake_transfer(pos[order], nrm[order], prt_b200.BakeParams.make(samples_u=16, samples_v=16))
+assert np.isfinite(rows).all() and st.n_devices == 2
+sc.ctx.set_tuning(work_list=1)
+prt_b200.bake_transfer(sc, pos[sel], nrm[sel], prt_b200.BakeParams.make(samples_u=16, samples_v=16))
+sc.ctx.set_tuning(work_list=-1)
+gpt, _, _ = grp.probe_capture(prt_b200.probe_positions([3, 2, 2], [3, 3, 3]), d, w)
+gpt.close(); grp.close()
 print("sanitize_small: all kernels ran")
