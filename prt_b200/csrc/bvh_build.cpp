@@ -252,6 +252,15 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
     double sah = 0.0;
     const double root_area = std::max(1e-30f, bn[0].box.area());
 
+    // triangle range ids[first, first + count) of every binary node (children are allocated after their parent)
+    std::vector<uint32_t> bfirst(n_bin), bcount(n_bin);
+    for (uint32_t n = n_bin; n-- > 0;) {
+        if (bn[n].count) { bfirst[n] = bn[n].left; bcount[n] = bn[n].count; }
+        else { bfirst[n] = bfirst[bn[n].left]; bcount[n] = bcount[bn[n].left] + bcount[bn[n].left + 1]; }
+    }
+    std::vector<uint32_t> wide_bnode; wide_bnode.reserve(n_bin / 4 + 16);      // binary node behind every 8-wide node
+    wide_bnode.push_back(0);
+
     struct WJob { uint32_t bnode, wnode, depth; };
     std::vector<WJob> stack;
     wn.emplace_back(); std::memset(&wn[0], 0, sizeof(Node8));
@@ -308,7 +317,7 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
         for (int s = 0; s < 8; s++) if (slot_child[s] >= 0 && !bn[ch[slot_child[s]]].count) n_internal++;
         nd.child_base = (uint32_t)wn.size();
         nd.tri_base = n_tri_out;
-        if (n_internal) wn.resize(wn.size() + n_internal);
+        if (n_internal) { wn.resize(wn.size() + n_internal); wide_bnode.resize(wn.size()); }
         uint32_t rank = 0, toff = 0;
         uint8_t *qlo[3] = { nd.qlox, nd.qloy, nd.qloz }, *qhi[3] = { nd.qhix, nd.qhiy, nd.qhiz };
         for (int s = 0; s < 8; s++) {
@@ -326,6 +335,7 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
                 nd.imask |= (uint8_t)(1u << s);
                 nd.meta[s] = (uint8_t)(0x20 | (24 + s));
                 stack.push_back({ch[slot_child[s]], nd.child_base + rank, j.depth + 1});
+                wide_bnode[nd.child_base + rank] = ch[slot_child[s]];
                 rank++;
             } else {
                 uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
@@ -350,6 +360,56 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
     out->nodes = (Node8 *)std::malloc(sizeof(Node8) * wn.size());
     if (!out->nodes) { std::free(tris); return fail("build_bvh8: out of memory"); }
     std::memcpy(out->nodes, wn.data(), sizeof(Node8) * wn.size());
+    // ---- oriented slabs (bvh8.h): mean normal of the triangles below every 8-wide node and their extent along it -----------------
+    out->slabs = (Slab32 *)std::malloc(sizeof(Slab32) * wn.size());
+    if (!out->slabs) { std::free(tris); std::free(out->nodes); out->nodes = nullptr; return fail("build_bvh8: out of memory"); }
+    {
+        const uint32_t n_wide = (uint32_t)wn.size();
+        std::atomic<uint32_t> next{0};
+        auto slab_worker = [&]() {
+            for (;;) {
+                const uint32_t w0 = next.fetch_add(64);
+                if (w0 >= n_wide) return;
+                for (uint32_t w = w0; w < std::min(n_wide, w0 + 64); w++) {
+                    const uint32_t b = wide_bnode[w], first = bfirst[b], count = bcount[b];
+                    Slab32 sl; std::memset(&sl, 0, sizeof(sl));
+                    sl.d0 = -3.0e38f; sl.d1 = 3.0e38f;
+                    double sx = 0, sy = 0, sz = 0;
+                    for (uint32_t i = first; i < first + count; i++) {
+                        const uint32_t t = ids[i];
+                        const float *a = P(idx[3 * (size_t)t]), *bb = P(idx[3 * (size_t)t + 1]), *c = P(idx[3 * (size_t)t + 2]);
+                        const double e1[3] = {(double)bb[0] - a[0], (double)bb[1] - a[1], (double)bb[2] - a[2]};
+                        const double e2[3] = {(double)c[0] - a[0], (double)c[1] - a[1], (double)c[2] - a[2]};
+                        sx += e1[1] * e2[2] - e1[2] * e2[1]; sy += e1[2] * e2[0] - e1[0] * e2[2]; sz += e1[0] * e2[1] - e1[1] * e2[0];
+                    }
+                    const double len = std::sqrt(sx * sx + sy * sy + sz * sz);
+                    if (len > 0.0 && std::isfinite(len)) {
+                        // the slab is stated for the float vector the kernels will use
+                        const float mx = (float)(sx / len), my = (float)(sy / len), mz = (float)(sz / len);
+                        double lo = 3.0e38, hi = -3.0e38;
+                        for (uint32_t i = first; i < first + count; i++) {
+                            const uint32_t t = ids[i];
+                            for (int k = 0; k < 3; k++) {
+                                const float *q = P(idx[3 * (size_t)t + k]);
+                                const double d = (double)mx * q[0] + (double)my * q[1] + (double)mz * q[2];
+                                lo = std::min(lo, d); hi = std::max(hi, d);
+                            }
+                        }
+                        // same padding as the triangle boxes: absorbs the float evaluation of m . x on the device
+                        sl.mx = mx; sl.my = my; sl.mz = mz;
+                        sl.d0 = std::nextafter((float)(lo - (double)pad), -3.0e38f); sl.d1 = std::nextafter((float)(hi + (double)pad), 3.0e38f);
+                    }
+                    out->slabs[w] = sl;
+                }
+            }
+        };
+        if (nth == 1) slab_worker();
+        else {
+            std::vector<std::thread> th;
+            for (unsigned i = 0; i < nth; i++) th.emplace_back(slab_worker);
+            for (auto &t : th) t.join();
+        }
+    }
     out->tris = tris; out->n_tris = nt; out->max_depth = max_depth; out->sah_cost = sah; out->pad = pad;
     out->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
@@ -357,8 +417,8 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
 
 void free_bvh8(HostBVH8 *b) {
     if (!b) return;
-    std::free(b->nodes); std::free(b->tris);
-    b->nodes = nullptr; b->tris = nullptr;
+    std::free(b->nodes); std::free(b->tris); std::free(b->slabs);
+    b->nodes = nullptr; b->tris = nullptr; b->slabs = nullptr;
 }
 
 }  // namespace prt

@@ -181,6 +181,16 @@ __device__ __forceinline__ bool hz_useful(const HzItem it, const uint32_t *hz) {
                           __uint_as_float(hz[kHzBins * k + ((it.b1 - (1 << k) + 1) & (kHzBins - 1))]));
     return it.v > m;
 }
+// estimate of what merging the item would cost: the share of a bin's cosine-weighted samples between the published map (its minimum m
+// over the item's bins) and the item's value, (v^2 - m^2), times the bins it spans -- x S / kHzBins = samples that would have to be traced
+// (> 0 <=> hz_useful).  The range minimum overestimates the cost of a wide item; it is only used to decide which boxes are worth opening.
+__device__ __forceinline__ float hz_gain(const HzItem it, const uint32_t *hz) {
+    if (!(it.v > 0.f)) return 0.f;
+    const int k = min(31 - __clz(it.b1 - it.b0 + 1), kHzLevels - 1);
+    const float m = fminf(__uint_as_float(hz[kHzBins * k + (it.b0 & (kHzBins - 1))]),
+                          __uint_as_float(hz[kHzBins * k + ((it.b1 - (1 << k) + 1) & (kHzBins - 1))]));
+    return (it.v - m) * (it.v + m) * (float)(it.b1 - it.b0 + 1);
+}
 // warp-collective: every lane contributes one item (if `useful`); lane = bin keeps the running maximum.  Only the useful items
 // go through the serial broadcast loop; the map is re-published when it may have changed.
 __device__ __forceinline__ float hz_merge(float my, const HzItem it, const bool useful, const int lane, uint32_t *hz) {
@@ -218,10 +228,13 @@ __device__ __forceinline__ HzItem hz_tri_item(const Tri48 *tris, const uint32_t 
 #endif
 constexpr int kHzQueue = 64;
 constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp round: < 32 left over + at most 3 x 32 new per iteration
-// `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2)).
+// `near2`: a box is "near" (gets refined) when d^2 < near2 * r^2, i.e. its angular radius exceeds asin(1/sqrt(near2)); `mid2`, `gain_min`: a
+// smaller box (d^2 < mid2 * r^2) is refined too when merging its bound would leave more than gain_min x S / kHzBins samples to trace (hz_gain).
 // hz: kHzWords words of shared memory; on return hz[0..kHzBins) is the map.
+// slabs (optional): the oriented slab of every node (bvh8.h); tightens the bound of subtree boxes before they are merged or opened.
 __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
-                                              const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane) {
+                                              const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane,
+                                              const Slab32 *slabs = nullptr, const float mid2 = 0.f, const float gain_min = 0.f) {
     const unsigned lt_mask = (1u << lane) - 1u;
     float my = 0.f;                                          // lane b owns bin b
     int rn = 0, tn = 0;
@@ -285,15 +298,32 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         // ---- classify the lane's box ------------------------------------------------------------------------------------
         HzItem it = hz_item(0.f, 0.f, false, 0.f);
         bool merge = false, push = false, leaf = false, nearb = false;
+        float slab_v = 2.0f;
         if (valid) PRT_HZ_STAT(boxes_bounded, 1);
         if (valid && !(e.x < 1e30f)) { it = hz_item(0.f, 0.f, true, 1.0f); merge = true; }      // overflow candidate: unbounded
         else if (valid) {
             const float r2 = e.x * e.x + e.y * e.y + e.z * e.z, d2 = c.x * c.x + c.y * c.y + c.z * c.z;
-            const HzItem cb = hz_cheap_box(c, e, r2, d2, fr);
+            HzItem cb = hz_cheap_box(c, e, r2, d2, fr);
             if (hz_useful(cb, hz)) {
                 if (!inner) leaf = true;
-                else if (!(d2 < near2 * r2)) { it = cb; merge = true; PRT_HZ_TRACE_FAR(c, e, cb); }
-                else { nearb = true; push = budget > 0; }
+                else {
+                    bool useful = true;
+                    if (slabs) {
+                        // the subtree is a sheet inside its box: bound the sheet (horizon_math.cuh)
+                        const char *sp = reinterpret_cast<const char *>(slabs + gx);
+                        const u4 s0 = ld16(sp), s1 = ld16(sp + 16);
+                        const f3 m = mk3(PRT_U2F(s0.x), PRT_U2F(s0.y), PRT_U2F(s0.z));
+                        const float mo = m.x * O.x + m.y * O.y + m.z * O.z;
+                        slab_v = hz_slab_value(c, e, fr.n, m, PRT_U2F(s0.w) - mo, PRT_U2F(s1.x) - mo);
+                        if (slab_v < cb.v) { cb.v = slab_v; useful = hz_useful(cb, hz); }
+                    }
+                    if (useful) {
+                        // a mid-sized box whose bound would cost many samples is opened as well (mid2 = 0: rule off)
+                        const bool mid = d2 < mid2 * r2 && hz_gain(cb, hz) > gain_min;
+                        if (!(d2 < near2 * r2) && !mid) { it = cb; merge = true; PRT_HZ_TRACE_FAR(c, e, cb); }
+                        else { nearb = true; push = budget > 0; }
+                    }
+                }
             }
         }
         const unsigned pb = __ballot_sync(kFull, push);
@@ -301,7 +331,7 @@ __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_ca
         if (push && pos < kHzQueue) rq[pos] = gx;
         // near, but no budget / queue space left: exact bound of the box itself
         const bool boxed = nearb && !(push && pos < kHzQueue);
-        if (__any_sync(kFull, boxed)) { if (boxed) { it = hz_box(c, e, fr); merge = hz_useful(it, hz); } }
+        if (__any_sync(kFull, boxed)) { if (boxed) { it = hz_box(c, e, fr); it.v = fminf(it.v, slab_v); merge = hz_useful(it, hz); } }
         rn = min(rn + __popc(pb), kHzQueue);
         my = hz_merge(my, it, merge, lane, hz);
         // leaves: their triangles are queued and bounded 32 at a time, so the (long) triangle bound always runs on a full warp;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void horizon_vertex(const BakeArgs &A, HorizonShared 
     const bool unit = fabsf(dot3(N, N) - 1.0f) <= 2e-5f;
     if (unit) {
         const int n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
-        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane);
+        build_horizon(W.el, n_cand, A.nodes, A.tris, org, N, fr, W.hz, W.rq, W.tq, A.horizon_budget, A.horizon_near2, lane, A.slabs, A.horizon_mid2, A.horizon_gain);
     }
 
     uint32_t *row = A.need_bits + (size_t)v * words;

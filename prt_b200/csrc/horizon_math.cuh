@@ -172,4 +172,34 @@ PRT_HD HzItem hz_cheap_box(const f3 c, const f3 e, const float r2, const float d
     return cb;
 }
 
+// Bound of a box CUT BY THE ORIENTED SLAB of its node (bvh8.h, Slab32): the geometry lies in {x : |x - c| <= e} and between the planes
+// L0 <= m . x <= U0 (x relative to the origin: L0 = d0 - m . O, U0 = d1 - m . O).  The height above the tangent plane n . x = n . c + n . y,
+// |y| <= e, L <= m . y <= U (L = L0 - m . c, U = U0 - m . c), is a linear programme with one two-sided constraint; by weak duality
+//     n . y = (n - lambda m) . y + lambda (m . y) <= sum_i |n_i - lambda m_i| e_i + (lambda >= 0 ? lambda U : lambda L)      for EVERY lambda,
+// so any choice of lambda gives a valid bound (lambda = 0 is the plain box).  The dual function is convex and piecewise linear with
+// breakpoints n_i / m_i, hence its minimum -- the exact optimum of the programme -- is attained at one of them or at 0; n . m (the
+// projection) is tried as well: it is the minimiser for a cube.  The distance bound uses the slab too (the origin may lie outside it).
+// Returns the sin(elevation) bound in the form of hz_cheap_box (same margins); the caller keeps the azimuth range of the box.
+PRT_HD float hz_slab_value(const f3 c, const f3 e, const f3 n, const f3 m, const float L0, const float U0) {
+    const float mc = m.x * c.x + m.y * c.y + m.z * c.z;
+    // rounding of L0, U0 (a difference of two dot products of scene-scale numbers) and of mc is covered by the padding of d0 / d1
+    const float L = L0 - mc, U = U0 - mc;
+    float best = fabsf(n.x) * e.x + fabsf(n.y) * e.y + fabsf(n.z) * e.z;
+    const float nm = n.x * m.x + n.y * m.y + n.z * m.z;
+    const float lam[4] = {nm, fabsf(m.x) > 1e-6f ? PRT_FDIVIDEF(n.x, m.x) : nm, fabsf(m.y) > 1e-6f ? PRT_FDIVIDEF(n.y, m.y) : nm,
+                          fabsf(m.z) > 1e-6f ? PRT_FDIVIDEF(n.z, m.z) : nm};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float l = lam[k];
+        const float f = fabsf(n.x - l * m.x) * e.x + fabsf(n.y - l * m.y) * e.y + fabsf(n.z - l * m.z) * e.z + l * (l >= 0.f ? U : L);
+        best = fminf(best, f);
+    }
+    const float zt = n.x * c.x + n.y * c.y + n.z * c.z + best;
+    const float mx = fmaxf(fabsf(c.x) - e.x, 0.f), my_ = fmaxf(fabsf(c.y) - e.y, 0.f), mz = fmaxf(fabsf(c.z) - e.z, 0.f);
+    const float gap = fmaxf(fmaxf(L0, -U0), 0.f);                  // distance from the origin to the slab (|m| = 1 up to rounding)
+    const float dm2 = fmaxf(mx * mx + my_ * my_ + mz * mz, gap * gap * 0.999f);
+    if (!(dm2 > 0.f)) return 2.0f;
+    return fmaxf(zt, 0.f) * PRT_RSQRTF(dm2) * 1.0001f + (1e-6f + 2e-4f);
+}
+
 }  // namespace prt

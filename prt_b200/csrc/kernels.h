@@ -26,6 +26,7 @@ inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<unsigned
 struct BakeArgs {
     const Node8 *nodes;
     const Tri48 *tris;
+    const Slab32 *slabs;        // optional [n_nodes]: oriented slab of every node (horizon pass)
     const float *pos, *nrm;     // device; consecutive vertices `stride` bytes apart
     size_t stride;
     uint32_t n_verts, vid_base;
@@ -41,6 +42,8 @@ struct BakeArgs {
     int horizon;                // 1: per-origin horizon map (bake_wave.cu): rays above it skip traversal
     int horizon_budget;         // refinement iterations (4 nodes each) the horizon builder may spend per vertex
     float horizon_near2;        // refine boxes with d^2 < near2 * r^2 (angular radius above asin(1/sqrt(near2)))
+    float horizon_mid2;         // ... and boxes with d^2 < mid2 * r^2 whose bound would leave more than horizon_gain (in units of
+    float horizon_gain;         //     S / kHzBins samples) to trace; mid2 = 0: rule off
     uint32_t *need_bits;        // horizon pass output / traversal pass input: [n_verts][vis_words], bit i of a row = sample with
                                 // processing index i is NOT above the horizon and must be traced
     uint32_t *need_count;       // [n_verts] number of such samples; 0 = the horizon pass already wrote the vertex's row

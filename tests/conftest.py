@@ -57,6 +57,13 @@ def load_hostcheck(extra_flags=None):
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hc_entry_list.restype = C.c_int
     L.hc_entry_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.hc_use_slabs.argtypes = [C.c_int]
+    L.hc_hz_slab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.hc_slabs.restype = C.c_uint32
+    L.hc_slabs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.hc_node_tri_ranges.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_tris.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_horizon_mid.argtypes = [C.c_int, C.c_float]
     L.hc_horizon_trace_far.restype = C.c_uint32
     L.hc_horizon_trace_far.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     return L

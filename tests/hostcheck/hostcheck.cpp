@@ -6,6 +6,7 @@
 #include "../../prt_b200/csrc/traverse.cuh"
 #include "../../prt_b200/csrc/horizon_math.cuh"
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
@@ -334,5 +335,51 @@ extern "C" void hc_hz_box(const float *c, const float *e, const float *nrm, uint
         else if (which == 1) it = hz_box(cc, ee, fr);
         else it = d2 > 1.05f * r2 ? hz_sphere(cc, r2, d2, fr) : hz_item(0.f, 0.f, true, 1.0f);
         bins[2 * i] = it.b0; bins[2 * i + 1] = it.b1; val[i] = it.v;
+    }
+}
+
+// box cut by an oriented slab (hz_slab_value, horizon_math.cuh): boxes as in hc_hz_box; slab[5i..] = m (3), L0, U0 relative to the origin
+extern "C" void hc_hz_slab(const float *c, const float *e, const float *nrm, const float *slab, uint32_t n, float *val) {
+    for (uint32_t i = 0; i < n; i++) {
+        const f3 cc = mk3(c[3 * i], c[3 * i + 1], c[3 * i + 2]), ee = mk3(e[3 * i], e[3 * i + 1], e[3 * i + 2]);
+        const Frame fr = make_frame(mk3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+        const float *s = slab + 5 * (size_t)i;
+        val[i] = hz_slab_value(cc, ee, fr.n, mk3(s[0], s[1], s[2]), s[3], s[4]);
+    }
+}
+// the builder's slabs: out[8 * node ..] = m (3), d0, d1, 0, 0, 0
+extern "C" uint32_t hc_slabs(void *h, float *out, uint32_t cap) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    const uint32_t n = std::min(cap, b->n_nodes);
+    if (out && b->slabs) std::memcpy(out, b->slabs, (size_t)n * sizeof(Slab32));
+    return b->slabs ? b->n_nodes : 0u;
+}
+// triangle range below every node: out[2 * node] = first triangle (index into the emitted Tri48 array), out[2 * node + 1] = count
+extern "C" void hc_node_tri_ranges(void *h, uint32_t *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    // depth-first emission: children are emitted after their parent; a reverse sweep accumulates the ranges
+    std::vector<uint32_t> lo(b->n_nodes, 0xFFFFFFFFu), hi(b->n_nodes, 0u);
+    for (uint32_t x = b->n_nodes; x-- > 0;) {
+        const Node8 &nd = b->nodes[x];
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            if ((nd.imask >> s) & 1) { const uint32_t ch = nd.child_base + rank++; lo[x] = std::min(lo[x], lo[ch]); hi[x] = std::max(hi[x], hi[ch]); }
+            else {
+                const uint32_t t0 = nd.tri_base + (nd.meta[s] & 31u), cnt = (uint32_t)__builtin_popcount(nd.meta[s] >> 5);
+                lo[x] = std::min(lo[x], t0); hi[x] = std::max(hi[x], t0 + cnt);
+            }
+        }
+    }
+    for (uint32_t x = 0; x < b->n_nodes; x++) { out[2 * x] = lo[x]; out[2 * x + 1] = hi[x] > lo[x] ? hi[x] - lo[x] : 0u; }
+}
+// emitted triangles: out[9 * t ..] = v0, v0 + e1, v0 + e2
+extern "C" void hc_tris(void *h, float *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    for (uint32_t t = 0; t < b->n_tris; t++) {
+        const Tri48 &T = b->tris[t];
+        float *o = out + 9 * (size_t)t;
+        o[0] = T.v0x; o[1] = T.v0y; o[2] = T.v0z; o[3] = T.v0x + T.e1x; o[4] = T.v0y + T.e1y; o[5] = T.v0z + T.e1z;
+        o[6] = T.v0x + T.e2x; o[7] = T.v0y + T.e2y; o[8] = T.v0z + T.e2z;
     }
 }

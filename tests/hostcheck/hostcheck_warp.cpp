@@ -29,6 +29,13 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
 
 using namespace prt;
 
+// oriented slabs of the nodes (bvh8.h) in the horizon builder: on by default, as in the product; the studies switch them off to compare
+namespace { bool g_use_slabs = true; int g_mid100 = 12; float g_gain = 0.2f; }
+extern "C" void hc_use_slabs(int on) { g_use_slabs = on != 0; }
+// refinement rule for mid-sized boxes (build_horizon: mid2, gain_min): angular radius x 100 (0 = rule off), gain in units of S / 32 samples
+extern "C" void hc_horizon_mid(int mid100, float gain) { g_mid100 = mid100; g_gain = gain; }
+namespace { float mid2_of(int mid100) { if (mid100 <= 0) return 0.f; const float s = sinf(0.01f * (float)mid100); return 1.0f / (s * s); } }
+
 // h: HostBVH8* from hc_build.  pos / nrm: n x 3 floats.  near100: horizon_near (angular radius x 100, rad); budget: horizon_budget.
 // out_hz: n x kHzBins floats (the map), out_ncand: n (entry-list candidates).
 // stats (optional, 4 x uint64): refinement iterations, nodes expanded, boxes bounded, triangle rounds -- summed over the n vertices.
@@ -50,7 +57,7 @@ extern "C" void hc_horizon_maps(void *h, const float *pos, const float *nrm, uin
                 const Frame fr = make_frame(N);
                 const f3 org = madd3(P, origin_eps, N);
                 const int n_cand = build_entry_list(b->nodes, org, N, W.el, lane);
-                build_horizon(W.el, n_cand, b->nodes, b->tris, org, N, fr, W.hz, W.rq, W.tq, budget, near2, lane);
+                build_horizon(W.el, n_cand, b->nodes, b->tris, org, N, fr, W.hz, W.rq, W.tq, budget, near2, lane, g_use_slabs ? b->slabs : nullptr, mid2_of(g_mid100), g_gain);
                 out_hz[(size_t)v * kHzBins + lane] = __uint_as_float(W.hz[lane]);
                 if (lane == 0) out_ncand[v] = n_cand;
                 __syncwarp();
@@ -236,6 +243,7 @@ extern "C" int hc_horizon_pass(void *h, const float *pos, const float *nrm, uint
     A.origin_eps = origin_eps; A.cs_phase = cs_phase;
     A.horizon_budget = budget;
     { const float sn = sinf(0.01f * (float)near100); A.horizon_near2 = 1.0f / (sn * sn); }
+    A.slabs = g_use_slabs ? b->slabs : nullptr; A.horizon_mid2 = mid2_of(g_mid100); A.horizon_gain = g_gain;
     switch (order) {
     case 1: run_horizon<1>(A); break;
     case 2: run_horizon<2>(A); break;

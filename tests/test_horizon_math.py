@@ -165,9 +165,124 @@ def test_slab_clamp_tightens_flat_boxes(hostcheck):
     assert np.median(out[2] / out[0]) > 10          # cone: ~0.2, slab: ~0.005
 
 
+# ---- oriented slabs (bvh8.h Slab32, hz_slab_value) ---------------------------------------------------------------------------------
+def _slab_cases(rng, n, kind):
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    c = rng.normal(size=(n, 3))
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    c *= rng.uniform(1.5, 12.0, size=(n, 1))
+    e = rng.uniform(0.05, 1.0, size=(n, 3))
+    m = rng.normal(size=(n, 3))
+    if kind == "sheet_near_tangent":          # a sheet almost parallel to the tangent plane: the case the slab is made for
+        m = nrm + rng.normal(size=(n, 3)) * 0.15
+    elif kind == "axis":                      # slab normal along a coordinate axis (zero components: no breakpoint there)
+        m[:] = 0.0
+        m[np.arange(n), rng.randint(0, 3, n)] = rng.choice([-1.0, 1.0], n)
+    m /= np.linalg.norm(m, axis=1, keepdims=True)
+    # slab through the box: centre offset within the box's extent along m, random thickness
+    ext = (np.abs(m) * e).sum(axis=1)
+    mid = (m * c).sum(axis=1) + rng.uniform(-0.8, 0.8, n) * ext
+    half = rng.uniform(0.01, 0.5, n) * ext
+    if kind == "wide":                        # slab wider than the box: must reduce to the plain box bound
+        half = 3.0 * ext
+    return nrm, c, e, m, mid - half, mid + half
+
+
+@pytest.mark.parametrize("kind", ["generic", "sheet_near_tangent", "axis", "wide"])
+def test_slab_bound_is_conservative_and_solves_the_lp(hostcheck, kind):
+    """hz_slab_value bounds sin(elevation) of everything inside box AND slab: never below brute-force samples of that set, and its
+    height term equals the optimum of the linear programme (scipy) -- the dual breakpoints it tries include the minimiser."""
+    from scipy.optimize import linprog
+    rng = np.random.RandomState({"generic": 21, "sheet_near_tangent": 22, "axis": 23, "wide": 24}[kind])
+    n = 300
+    nrm, c, e, m, L0, U0 = _slab_cases(rng, n, kind)
+    c32, e32, n32 = (np.ascontiguousarray(a, np.float32) for a in (c, e, nrm))
+    slab = np.ascontiguousarray(np.concatenate([m, L0[:, None], U0[:, None]], axis=1), np.float32)
+    val = np.zeros(n, np.float32)
+    hostcheck.hc_hz_slab(c32.ctypes.data, e32.ctypes.data, n32.ctypes.data, slab.ctypes.data, n, val.ctypes.data)
+    box = np.zeros(n, np.float32)
+    bins = np.zeros((n, 2), np.int32)
+    hostcheck.hc_hz_box(c32.ctypes.data, e32.ctypes.data, n32.ctypes.data, n, 0, bins.ctypes.data, box.ctypes.data)
+    fr = np.zeros(9, np.float32)
+    tight = eligible = 0
+    for i in range(n):
+        cc, ee, mm = c32[i].astype(np.float64), e32[i].astype(np.float64), slab[i, :3].astype(np.float64)
+        lo, hi = float(slab[i, 3]), float(slab[i, 4])
+        pts = _box_points(cc, ee, rng, k=3000)
+        # project a share of the samples onto the two slab planes (clipped to the box afterwards), where the extrema lie
+        d = pts @ mm
+        k3 = len(pts) // 3
+        pts[:k3] += np.outer(hi - d[:k3], mm) / (mm @ mm)
+        pts[k3:2 * k3] += np.outer(lo - d[k3:2 * k3], mm) / (mm @ mm)
+        d = pts @ mm
+        keep = (d >= lo - 1e-9) & (d <= hi + 1e-9) & (np.abs(pts - cc) <= ee + 1e-9).all(axis=1)
+        pts = pts[keep]
+        hostcheck.hc_frame(n32[i].ctypes.data, fr.ctypes.data)
+        nn = fr.reshape(3, 3).astype(np.float64)[2]
+        if len(pts):
+            z = pts @ nn
+            r = np.linalg.norm(pts, axis=1)
+            up = (z > 0) & (r > 0)
+            if up.any():
+                assert (z[up] / r[up]).max() <= val[i] + 1e-6, f"{kind} {i}: a point of box and slab lies above the bound"
+        # exactness of the height term: max n . x over the polytope
+        res = linprog(-nn, A_ub=np.stack([mm, -mm]), b_ub=[hi, -lo], bounds=list(zip(cc - ee, cc + ee)), method="highs")
+        if res.status == 0:
+            zmax = -res.fun
+            mxyz = np.maximum(np.abs(cc) - ee, 0.0)
+            gap = max(lo, -hi, 0.0)
+            dm = max(np.linalg.norm(mxyz), gap * np.sqrt(0.999))
+            if dm > 0 and zmax > 1e-3:
+                want = zmax / dm * 1.0001 + (1e-6 + 2e-4)
+                eligible += 1
+                assert val[i] >= want - 2e-5 * max(1.0, want), f"{kind} {i}: bound {val[i]} below the programme's optimum {want}"
+                if abs(val[i] - want) <= 1e-4 * max(1.0, want):
+                    tight += 1
+        if kind == "wide":
+            assert val[i] >= min(box[i], 2.0) - 1e-5 or box[i] >= 1.0       # a slab that does not cut cannot beat the box's z_max / d_min
+    assert eligible > n // 4
+    assert tight >= 0.98 * eligible, f"only {tight} of {eligible} bounds equal the optimum of the linear programme"
+
+
+def test_builder_slabs_contain_their_triangles(hostcheck):
+    """Slab32 of every 8-wide node (bvh_build.cpp): all triangles below the node lie between its two planes; on a surface mesh the
+    slabs of the lower levels are thin compared with their boxes."""
+    from prt_b200 import meshes
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    info = np.zeros(3, np.uint32)
+    hostcheck.hc_info(h, info.ctypes.data)
+    n_nodes, n_tris = int(info[0]), int(info[1])
+    slabs = np.zeros((n_nodes, 8), np.float32)
+    assert hostcheck.hc_slabs(h, slabs.ctypes.data, n_nodes) == n_nodes
+    rng_ = np.zeros((n_nodes, 2), np.uint32)
+    hostcheck.hc_node_tri_ranges(h, rng_.ctypes.data)
+    tv = np.zeros((n_tris, 9), np.float32)
+    hostcheck.hc_tris(h, tv.ctypes.data)
+    hostcheck.hc_free(h)
+    assert rng_[0, 0] == 0 and rng_[0, 1] == n_tris
+    thin = []
+    for x in range(n_nodes):
+        m, d0, d1 = slabs[x, :3].astype(np.float64), float(slabs[x, 3]), float(slabs[x, 4])
+        v = tv[rng_[x, 0]: rng_[x, 0] + rng_[x, 1]].reshape(-1, 3).astype(np.float64)
+        assert len(v)
+        if not m.any():
+            continue
+        assert abs(np.linalg.norm(m) - 1.0) < 1e-5
+        d = v @ m
+        assert d.min() >= d0 and d.max() <= d1, f"node {x}: triangles outside the slab"
+        if rng_[x, 1] <= 64:
+            thin.append((d1 - d0) / max(np.linalg.norm(v.max(axis=0) - v.min(axis=0)), 1e-30))
+    assert np.median(thin) < 0.25
+
+
 # ---- the warp-cooperative builder itself, run on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) --------------------
-def _maps(hostcheck, h, pos, nrm, budget=64, near=30, eps=1e-4, stats=None):
+def _maps(hostcheck, h, pos, nrm, budget=64, near=157, eps=1e-4, stats=None, slabs=1, mid=12, gain=0.2):
+    """defaults = the product's (abi.cu: horizon_near 157, horizon_mid 12, horizon_gain 6.4 samples = 0.2 x 1024 / 32, slabs on)"""
     n = len(pos)
+    hostcheck.hc_use_slabs(slabs)
+    hostcheck.hc_horizon_mid(mid, gain)
     hz = np.zeros((n, BINS), np.float32)
     ncand = np.zeros(n, np.int32)
     p32, n32 = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32)
@@ -185,7 +300,8 @@ def _free_mask(dirs, hz):
     return dirs[None, :, 2] > hz[:, bins]
 
 
-@pytest.mark.parametrize("knobs", [dict(), dict(budget=0), dict(near=60, budget=4), dict(near=12, budget=256)])
+@pytest.mark.parametrize("knobs", [dict(), dict(budget=0), dict(near=60, budget=4), dict(near=12, budget=256), dict(near=30, slabs=0, mid=0),
+                                   dict(near=30, mid=0), dict(slabs=0), dict(mid=40, gain=0.01, budget=200), dict(near=157, mid=5, gain=1.5)])
 def test_horizon_map_never_frees_an_occluded_ray(hostcheck, oracle, knobs):
     """build_entry_list + build_horizon (the product's device code, unmodified, on the warp emulator) against the oracle's
     per-ray visibility on a self-occluding mesh: every freed sample must be visible -- and the map must be worth having."""
@@ -244,7 +360,7 @@ def test_horizon_map_adversarial_geometry(hostcheck, oracle):
     _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), p, n, op, want_vis=True)
     visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
     try:
-        for knobs in (dict(), dict(budget=0), dict(near=90, budget=1), dict(near=10, budget=256)):
+        for knobs in (dict(), dict(budget=0), dict(near=90, budget=1), dict(near=10, budget=256), dict(near=30, slabs=0, mid=0), dict(mid=40, gain=0.0, budget=256)):
             hz, _ = _maps(hostcheck, h, p, n, **knobs)
             free = _free_mask(dirs, hz)
             assert not (free & ~visible).any(), knobs
@@ -282,7 +398,7 @@ def test_horizon_map_other_scenes(hostcheck, oracle, scene_kind):
     _, vis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel], nrm[sel], op, want_vis=True)
     visible = np.unpackbits(vis.view(np.uint8), axis=1, bitorder="little")[:, :1024].astype(bool)
     try:
-        for knobs in (dict(), dict(near=15, budget=200), dict(budget=1)):
+        for knobs in (dict(), dict(near=15, budget=200), dict(budget=1), dict(near=30, slabs=0, mid=0), dict(mid=40, gain=0.0, budget=256)):
             hz, _ = _maps(hostcheck, h, pos[sel], nrm[sel], **knobs)
             free = _free_mask(dirs, hz)
             assert not (free & ~visible).any(), (scene_kind, knobs)

@@ -24,12 +24,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--nu", type=int, default=737)
 ap.add_argument("--nv", type=int, default=737)
 ap.add_argument("--n", type=int, default=200)
-ap.add_argument("--near", default="30")
+ap.add_argument("--near", default="157")
 ap.add_argument("--budget", type=int, default=64)
+ap.add_argument("--folds", action="store_true", help="the heavily self-occluding twin of the bench mesh (amp 0.25, fscale 3)")
+ap.add_argument("--mid", default="12", help="mid-size refinement rule: angular radius x 100 (0 = off), comma list")
+ap.add_argument("--gain", default="0.2", help="... its threshold in units of S / 32 samples, comma list")
+ap.add_argument("--slabs", default="1", help="oriented slabs of the nodes in the builder: 1, 0 or 0,1 to compare")
 a = ap.parse_args()
 
 hc = conftest.load_hostcheck()
-pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv)
+pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv, amp=0.25, fscale=3) if a.folds else meshes.bumpy_torus(a.nu, a.nv)
 order = meshes.morton_order(pos)
 sel = order[:: max(1, len(order) // a.n)][: a.n]
 h = hc.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
@@ -49,12 +53,16 @@ ideal_traversed = (dirs[None, :, 2] <= ideal[:, bins]).mean()
 out = {"vertices": len(sel), "occluded": float(1.0 - visible.mean()), "best_32_bin_map_traversed": float(ideal_traversed)}
 print(json.dumps(out))
 for near in [int(x) for x in a.near.split(",")]:
-    if True:
+  for mid in [int(x) for x in a.mid.split(",")]:
+   for gain in [float(x) for x in a.gain.split(",")]:
+    for slabs in [int(x) for x in a.slabs.split(",")]:
+        hc.hc_use_slabs(slabs)
+        hc.hc_horizon_mid(mid, gain)
         st = np.zeros(4, np.uint64)
-        hz, ncand = _maps(hc, h, pos[sel], nrm[sel], budget=a.budget, near=near, stats=st)
+        hz, ncand = _maps(hc, h, pos[sel], nrm[sel], budget=a.budget, near=near, stats=st, slabs=slabs, mid=mid, gain=gain)
         free = _free_mask(dirs, hz)
         assert not (free & ~visible).any()
-        print(json.dumps({"near": near, "budget": a.budget, "traversed": round(float(1.0 - free.mean()), 4),
+        print(json.dumps({"near": near, "budget": a.budget, "slabs": slabs, "mid": mid, "gain": gain, "traversed": round(float(1.0 - free.mean()), 4),
                           "map_minus_ideal": round(float(np.mean(hz - ideal)), 4),
                           "per_vertex": {"iterations": round(float(st[0]) / len(sel), 2), "nodes_expanded": round(float(st[1]) / len(sel), 1),
                                          "boxes_bounded": round(float(st[2]) / len(sel), 1), "triangle_rounds": round(float(st[3]) / len(sel), 2)}}), flush=True)
