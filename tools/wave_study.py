@@ -3,7 +3,7 @@
 the warp emulator (tests/hostcheck) for a Morton-strided sample of the bench mesh and prints the work counters bench.py reports
 from an instrumented GPU launch (node visits, triangle tests, entry-list box tests per ray, share of rays traversed), so that
 algorithmic changes can be scored before any GPU time is spent.
-Usage: python tools/wave_study.py [--nu 737 --nv 737] [--n 96] [--near 30] [--budget 64]"""
+Usage: python tools/wave_study.py [--nu 737 --nv 737] [--n 96] [--near 157 --mid 12 --gain 0.2 --slabs 1] [--budget 64]  (old builder: --near 30 --mid 0 --slabs 0)"""
 import argparse
 import json
 import os
@@ -24,7 +24,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--nu", type=int, default=737)
 ap.add_argument("--nv", type=int, default=737)
 ap.add_argument("--n", type=int, default=96)
-ap.add_argument("--near", type=int, default=30)
+ap.add_argument("--near", type=int, default=157)
+ap.add_argument("--mid", type=int, default=12)
+ap.add_argument("--gain", type=float, default=0.2)
+ap.add_argument("--slabs", type=int, default=1)
+ap.add_argument("--wave-slabs", type=int, default=1, help="ray / slab culling of node visits in the traversal pass")
 ap.add_argument("--budget", type=int, default=64)
 a = ap.parse_args()
 
@@ -35,12 +39,22 @@ sel = order[:: max(1, len(order) // a.n)][: a.n]
 h = hc.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
 op = oracle.make_params(order=3, samples_u=32, samples_v=32)
 tab, bins = processing_table(oracle, op)
-hz, _ = _maps(hc, h, pos[sel], nrm[sel], budget=a.budget, near=a.near)
+hz, _ = _maps(hc, h, pos[sel], nrm[sel], budget=a.budget, near=a.near, slabs=a.slabs, mid=a.mid, gain=a.gain)
 need = ~(tab[None, :, 2] > hz[:, bins])
 need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
 keep = need.any(axis=1)                         # vertices the horizon pass finishes are never seen by the traversal pass
-work = np.zeros(4, np.uint64)
+work = np.zeros(5, np.uint64)
+hc.hc_wave_use_slabs(a.wave_slabs)
+hc.hc_wave_slab_culls.restype = __import__("ctypes").c_uint64
+hc.hc_wave_slab_culls(1)
 got, vis = run_wave(hc, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(need_words[keep]), work=work)
+import ctypes
+ns = np.zeros(4, np.uint64)
+hc.hc_node_slab_study.argtypes = [ctypes.c_void_p, ctypes.c_int]
+hc.hc_node_slab_study(ns.ctypes.data, 1)
+print(json.dumps({"node_slab_study": {"node_visits": int(ns[0]), "culled_by_slab_in_frame_interval": float(ns[1]) / max(1.0, float(ns[0])),
+                                      "culled_by_slab_whole_ray": float(ns[2]) / max(1.0, float(ns[0])), "culled_by_slab_in_true_box_interval": float(ns[3]) / max(1.0, float(ns[0]))}}))
+print(json.dumps({"slab_filter_tests_per_ray": float(work[4]) / float(len(sel) * len(tab)), "culled_share": float(hc.hc_wave_slab_culls(0)) / max(1.0, float(work[4]))}))
 rays = float(len(sel) * len(tab))
 trav = float(work[3])
 print(json.dumps({"vertices": len(sel), "finished_by_horizon_pass": int((~keep).sum()), "rays_traversed_frac": trav / rays,
