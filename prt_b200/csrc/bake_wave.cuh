@@ -215,6 +215,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     __syncwarp();
                     const int cnt = min(npend, 32);
                     npend -= cnt;
+                    if (lane == 0) { PRT_WAVE_STAT(scan_steps, 1); PRT_WAVE_STAT(scan_lanes, cnt); }
 #if PRT_WAVE_CULL
                     // candidates whose elevation bound lies below the lowest ray of the round are skipped by the whole warp
                     uint32_t ci = 0u;
@@ -254,6 +255,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 // ---- filter step ----------------------------------------------------------------------------------
                 const int cnt = min(nn, 32);
                 nn -= cnt;
+                if (lane == 0) { PRT_WAVE_STAT(filter_steps, 1); PRT_WAVE_STAT(filter_lanes, cnt); }
                 uint2 it = make_uint2(0u, 0u);
                 bool keep = false;
                 if (lane < cnt) {
@@ -273,6 +275,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 // ---- leaf step ------------------------------------------------------------------------------------
                 const int cnt = min(ln, 32);
                 ln -= cnt;
+                if (lane == 0) { PRT_WAVE_STAT(leaf_steps, 1); PRT_WAVE_STAT(leaf_lanes, cnt); }
                 if (lane < cnt) {
                     const uint2 it = W.lq[ln + lane];
                     const uint32_t oi = it.x & 0xFFFFu;
@@ -308,6 +311,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 bool has;
                 if (filt) { cnt = min(rn, 32); rn -= cnt; has = lane < cnt; if (has) it = W.rq[rn + lane]; }
                 else { cnt = min(nn, 32); nn -= cnt; has = lane < cnt; if (has) it = W.nq[nn + lane]; }
+                if (lane == 0) { PRT_WAVE_STAT(node_steps, 1); PRT_WAVE_STAT(node_lanes, cnt); }
                 __syncwarp();                   // all pops are done before anybody pushes
                 uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
                 f3 d = mk3(0.f, 0.f, 1.f);

@@ -64,7 +64,12 @@ inline void node_slab_study(const BakeArgs &A, uint32_t node, const u4 n0, const
 }
 } }
 #define PRT_WAVE_NODE_STUDY(A, node, n0, org, d) node_slab_study(A, node, n0, org, d)
-namespace { struct WaveStats { std::atomic<uint64_t> slab_culls{0}; } g_wave_stats; bool g_wave_slabs = true; }
+namespace { struct WaveStats { std::atomic<uint64_t> slab_culls{0}, filter_steps{0}, filter_lanes{0}, leaf_steps{0}, leaf_lanes{0}, node_steps{0}, node_lanes{0}, scan_steps{0}, scan_lanes{0}; } g_wave_stats; bool g_wave_slabs = true; }
+extern "C" void hc_wave_step_stats(uint64_t *out, int reset) {
+    std::atomic<uint64_t> *a[8] = {&g_wave_stats.filter_steps, &g_wave_stats.filter_lanes, &g_wave_stats.leaf_steps, &g_wave_stats.leaf_lanes, &g_wave_stats.node_steps,
+                                   &g_wave_stats.node_lanes, &g_wave_stats.scan_steps, &g_wave_stats.scan_lanes};
+    for (int i = 0; i < 8; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
+}
 #define PRT_WAVE_STAT(counter, n) (g_wave_stats.counter.fetch_add((n), std::memory_order_relaxed))
 extern "C" uint64_t hc_wave_slab_culls(int reset) { const uint64_t v = g_wave_stats.slab_culls; if (reset) g_wave_stats.slab_culls = 0; return v; }
 // ray / slab culling in the traversal pass: on by default, as in the product
@@ -211,7 +216,8 @@ void run_inter(const BakeArgs &A) {
             for (uint32_t v = 0; v < A.n_verts; v++) {
                 const int n_need = (int)A.need_count[v];
                 if (n_need == 0) continue;                      // the kernel skips the vertices the horizon pass finished
-                bake_inter_vertex<ORDER, false>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                if (A.filter_slabs) bake_inter_vertex<ORDER, false, true>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                else bake_inter_vertex<ORDER, false, false>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
             }
         });
     }
@@ -233,6 +239,7 @@ extern "C" int hc_bake_inter(void *h, const float *pos, const float *nrm, uint32
     A.seed = seed; A.depth = bounces + 1;
     A.albedo[0] = albedo[0]; A.albedo[1] = albedo[1]; A.albedo[2] = albedo[2];
     A.origin_eps = origin_eps; A.bounce_eps = bounce_eps;
+    A.filter_slabs = g_wave_slabs ? b->slabs : nullptr;
     switch (order) {
     case 1: run_inter<1>(A); break;
     case 2: run_inter<2>(A); break;
