@@ -29,9 +29,10 @@ namespace {
 #endif
 constexpr int kSlots = 64;
 constexpr int kCap = PRT_INTER_CAP;
-constexpr int kNCap = PRT_INTER_CAP - PRT_INTER_RCAP;       // node stack (unfiltered items)
+constexpr int kNCap = PRT_INTER_CAP;                        // node stack (unfiltered items): never shrunk, its overflow path is a per-ray traversal
+constexpr int kLCap = PRT_INTER_CAP - PRT_INTER_RCAP;       // leaf stack: leaf steps have priority, it stays short (the ready queue's space comes from here)
 constexpr int kRCap = PRT_INTER_RCAP;
-static_assert(kRCap >= 64 && kNCap >= 64, "stack split");
+static_assert(kRCap >= 64 && kLCap >= 96, "stack split");
 constexpr uint32_t kFree = 0xFFFFFFFFu;
 constexpr unsigned long long kNoHit = 0x7F800000FFFFFFFFull;        // (+inf, invalid prim)
 
@@ -45,7 +46,7 @@ struct InterShared {
     uint32_t info[kSlots];              // processing index of the sample | segment << 24; kFree = empty
     uint2 nq[kNCap];                    // (slot, node index)
     uint2 rq[kRCap];                    // the same, after the slab filter: the items a node step opens
-    uint2 lq[kCap];                     // (slot | triangle bits << 16, first triangle)
+    uint2 lq[kLCap];                    // (slot | triangle bits << 16, first triangle)
 };
 
 __device__ __forceinline__ uint32_t node_slots_hit_range(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx,
@@ -140,7 +141,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         if (++guard > (1u << 24)) { if (lane == 0 && A.work) atomicAdd(&A.work[3], 1ull << 60); break; }     // never expected: bail out instead of hanging
         // ---- emit pending (slot, candidate) items while one more warp-wide append fits ------------------------------------
         bool pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
-        while (pending && nn <= kNCap - 32 && ln <= kCap - 32) {
+        while (pending && nn <= kNCap - 32 && ln <= kLCap - 32) {
             int k = -1;
             if (m0) { k = __ffs(m0) - 1; m0 &= m0 - 1u; }
             else if (m1) { k = 32 + __ffs(m1) - 1; m1 &= m1 - 1u; }
@@ -232,7 +233,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         }
 
         // ---- refill: the next flagged samples take free slots, 32 at a time (lockstep entry-list scan) ------------------------
-        if (!pending && fetched < n_need && nn <= kNCap * PRT_INTER_ROOM8 / 8 && ln <= kCap * PRT_INTER_ROOM8 / 8 && (nfree >= 32 || (nn == 0 && ln == 0 && rn == 0 && nfree > 0))) {
+        if (!pending && fetched < n_need && nn + rn <= kNCap * PRT_INTER_ROOM8 / 8 && ln <= kLCap * PRT_INTER_ROOM8 / 8 && (nfree >= 32 || (nn == 0 && ln == 0 && rn == 0 && nfree > 0))) {
             const int cnt = min(min(32, nfree), n_need - fetched);
             // the cnt next flagged samples, in processing order
             int taken = 0, my_k = -1;
@@ -344,7 +345,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
             __syncwarp();
             uint32_t tot;
             const uint32_t ex = warp_excl_scan_packed((uint32_t)__popc(inner8) | ((uint32_t)__popc(leaf8) << 16), lane, tot);
-            if (nn + (int)(tot & 0xFFFFu) <= kNCap && ln + (int)(tot >> 16) <= kCap) {
+            if (nn + (int)(tot & 0xFFFFu) <= kNCap && ln + (int)(tot >> 16) <= kLCap) {
                 // everything fits (the common case): one packed warp scan gave every lane its write positions on both stacks
                 int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
                 while (inner8) {
@@ -384,13 +385,13 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
                 const unsigned pb = __ballot_sync(kFull, p);
                 const int pos = ln + __popc(pb & lt_mask);
                 if (p) {
-                    if (pos < kCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
+                    if (pos < kLCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                     else {
                         fallback_leaf_closest(A.tris, W, it.x, tri0, bits, tri_tests);
                         atomicSub(&W.refc[it.x], 1);
                     }
                 }
-                ln = min(ln + __popc(pb), kCap);
+                ln = min(ln + __popc(pb), kLCap);
             }
         }
         __syncwarp();

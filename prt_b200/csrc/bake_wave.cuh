@@ -25,11 +25,16 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_RCAP
 #define PRT_WAVE_RCAP 64            // ready queue: (ray, node) items that passed the slab filter, at most 31 + 32
 #endif
+// The ready queue's space comes out of the LEAF stack: leaf steps have priority once 32 items wait, so that stack stays short, and
+// its overflow path is three triangle tests.  The NODE stack must not shrink: an overflowing push runs a whole per-ray stack traversal
+// on a handful of lanes (measured with 192 entries: 37 % of the kernel's instructions at 3 of 32 lanes, step 47 -> 66 ms).
+// CPU work model (tools/wave_study.py, stack overflows per vertex of the bench mesh): 256 / 256 without the filter 0.39; with the filter
+// 256 / 192: 1.3, 320 / 128: 0.27 -- the leaf stack never comes near 128 entries.
 #ifndef PRT_WAVE_NCAP
-#define PRT_WAVE_NCAP (PRT_WAVE_CAP - PRT_WAVE_RCAP)
+#define PRT_WAVE_NCAP (PRT_WAVE_CAP + 64)
 #endif
 #ifndef PRT_WAVE_LCAP
-#define PRT_WAVE_LCAP PRT_WAVE_CAP
+#define PRT_WAVE_LCAP (PRT_WAVE_CAP - 64 - PRT_WAVE_RCAP)
 #endif
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
@@ -198,7 +203,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
             }
             // ---- classify samples: a ray above the horizon of its azimuth bin is visible without any test ---------------
-            const bool room = nn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;
+            const bool room = nn + rn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;     // ready items count as node items
             if (!pending && room) {
                 while (base < S && npend < 32) {
                     const int i = base + lane;
@@ -362,6 +367,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         else {
                             // stack full: ordinary traversal of this subtree (rare)
                             PRT_WAVE_FRAME();
+                            PRT_WAVE_STAT(overflow_subtrees, 1);
                             if (fallback_subtree(A.nodes, A.tris, org, d, child, node_visits, tri_tests)) {
                                 atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
                                 inner8 = 0u; leaf8 = 0u;
@@ -384,6 +390,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                         else {
                             PRT_WAVE_FRAME();
+                            PRT_WAVE_STAT(overflow_leaves, 1);
                             if (fallback_leaf(A.tris, org, d, tri0, bits, tri_tests)) {
                                 atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
                                 leaf8 = 0u;

@@ -64,11 +64,11 @@ inline void node_slab_study(const BakeArgs &A, uint32_t node, const u4 n0, const
 }
 } }
 #define PRT_WAVE_NODE_STUDY(A, node, n0, org, d) node_slab_study(A, node, n0, org, d)
-namespace { struct WaveStats { std::atomic<uint64_t> slab_culls{0}, filter_steps{0}, filter_lanes{0}, leaf_steps{0}, leaf_lanes{0}, node_steps{0}, node_lanes{0}, scan_steps{0}, scan_lanes{0}; } g_wave_stats; bool g_wave_slabs = true; }
+namespace { struct WaveStats { std::atomic<uint64_t> slab_culls{0}, filter_steps{0}, filter_lanes{0}, leaf_steps{0}, leaf_lanes{0}, node_steps{0}, node_lanes{0}, scan_steps{0}, scan_lanes{0}, overflow_subtrees{0}, overflow_leaves{0}; } g_wave_stats; bool g_wave_slabs = true; }
 extern "C" void hc_wave_step_stats(uint64_t *out, int reset) {
-    std::atomic<uint64_t> *a[8] = {&g_wave_stats.filter_steps, &g_wave_stats.filter_lanes, &g_wave_stats.leaf_steps, &g_wave_stats.leaf_lanes, &g_wave_stats.node_steps,
-                                   &g_wave_stats.node_lanes, &g_wave_stats.scan_steps, &g_wave_stats.scan_lanes};
-    for (int i = 0; i < 8; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
+    std::atomic<uint64_t> *a[10] = {&g_wave_stats.filter_steps, &g_wave_stats.filter_lanes, &g_wave_stats.leaf_steps, &g_wave_stats.leaf_lanes, &g_wave_stats.node_steps,
+                                   &g_wave_stats.node_lanes, &g_wave_stats.scan_steps, &g_wave_stats.scan_lanes, &g_wave_stats.overflow_subtrees, &g_wave_stats.overflow_leaves};
+    for (int i = 0; i < 10; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
 }
 #define PRT_WAVE_STAT(counter, n) (g_wave_stats.counter.fetch_add((n), std::memory_order_relaxed))
 extern "C" uint64_t hc_wave_slab_culls(int reset) { const uint64_t v = g_wave_stats.slab_culls; if (reset) g_wave_stats.slab_culls = 0; return v; }

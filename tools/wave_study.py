@@ -48,7 +48,7 @@ hc.hc_wave_use_slabs(a.wave_slabs)
 hc.hc_wave_slab_culls.restype = __import__("ctypes").c_uint64
 hc.hc_wave_slab_culls(1)
 hc.hc_wave_step_stats.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
-_ss = np.zeros(8, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
+_ss = np.zeros(10, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
 got, vis = run_wave(hc, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(need_words[keep]), work=work)
 import ctypes
 ns = np.zeros(4, np.uint64)
@@ -59,6 +59,7 @@ print(json.dumps({"node_slab_study": {"node_visits": int(ns[0]), "culled_by_slab
 print(json.dumps({"slab_filter_tests_per_ray": float(work[4]) / float(len(sel) * len(tab)), "culled_share": float(hc.hc_wave_slab_culls(0)) / max(1.0, float(work[4]))}))
 hc.hc_wave_step_stats(_ss.ctypes.data, 0)
 print(json.dumps({"steps_per_vertex": {k: round(float(_ss[2 * i]) / len(sel), 1) for i, k in enumerate(["filter", "leaf", "node", "scan"])},
+                  "stack_overflows_per_vertex": {"subtrees": round(float(_ss[8]) / len(sel), 3), "leaves": round(float(_ss[9]) / len(sel), 3)},
                   "lanes_per_step": {k: round(float(_ss[2 * i + 1]) / max(1.0, float(_ss[2 * i])), 1) for i, k in enumerate(["filter", "leaf", "node", "scan"])}}))
 rays = float(len(sel) * len(tab))
 trav = float(work[3])
