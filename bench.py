@@ -459,7 +459,6 @@ def run_bake(a):
     step_device(); torch.cuda.synchronize()
     st = ctx.last_bake_stats()
     visits, tests, cands, traversed = int(st.node_visits), int(st.tri_tests), int(st.cand_tests), int(st.rays_traversed)
-    slab_tests = int(st.slab_tests)
     launches_per_step = int(st.launches)
     ctx.set_tuning(count_work=0)
 
@@ -591,16 +590,16 @@ def run_bake(a):
                 ncu["kernel"] = ncu.get("kernel", "") + f" [counts of every {f}-th chunk of the shard x {k:.3f}]"
         rays_launch = float(n_valid) * S
         need_bytes = n_mine * (4.0 * ((S + 31) // 32) + 4.0) if launches_per_step >= 2 else 0.0
-        bvh_bytes = float(info.node_bytes + info.tri_bytes) + 48.0 * info.n_nodes          # + the 48-byte slab record of every node
-        l2_alg = visits * 80.0 + tests * 48.0 + slab_tests * 48.0
+        bvh_bytes = float(info.node_bytes + info.tri_bytes)
+        l2_alg = visits * 80.0 + tests * 48.0
         floor = n_valid * (24.0 + 4.0 * n2) + need_bytes + min(bvh_bytes, l2_alg)
         roofline = issue_roofline(ncu, k_ms_max, n_sms, clk.get("sm_mhz") if clk else None, peaks, floor, l2_alg,
                                   f"{kname}<{a.order}> (traversal + projection of this rank's shard; the horizon pass ran {hz_ms:.2f} ms before it)")
         roofline.update({"rays_per_launch": rays_launch, "node_visits_per_ray": visits / rays_launch, "tri_tests_per_ray": tests / rays_launch,
-                         "entry_list_box_tests_per_ray": cands / rays_launch, "slab_filter_tests_per_ray": slab_tests / rays_launch, "rays_traversed_frac": traversed / rays_launch if traversed else None,
+                         "entry_list_box_tests_per_ray": cands / rays_launch, "rays_traversed_frac": traversed / rays_launch if traversed else None,
                          "horizon_pass_ms": hz_ms,
                          "note": "hbm.floor = vertex I/O + need bits + every BVH byte the launch touches once (capped at the BVH size); l2_algorithmic = node "
-                                 f"fetches x 80 B + triangle fetches x 48 B + slab-filter fetches x 48 B; the BVH is {bvh_bytes / 1e6:.1f} MB ("
+                                 f"fetches x 80 B + triangle fetches x 48 B; the BVH is {bvh_bytes / 1e6:.1f} MB ("
                                  + ("L2-resident" if bvh_bytes < 100e6 else "larger than the 126 MB L2: deep levels stream from HBM") + ")"})
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": W_,
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PRT_B200_ABI_VERSION 3
+#define PRT_B200_ABI_VERSION 2
 
 enum {
     PRT_OK = 0,
@@ -176,7 +176,6 @@ typedef struct {
     uint64_t cand_tests;     /* 32-byte entry-list candidate boxes tested (shared memory) */
     uint64_t rays_traversed; /* rays NOT resolved by the horizon map (0 when the kernel variant has no horizon map) */
     double horizon_ms;       /* part of kernel_ms spent in the horizon pass (0 when it did not run) */
-    uint64_t slab_tests;     /* count_work=1: 48-byte slab records fetched by the filter steps of the traversal pass (ABI version 3) */
 } prt_bake_stats;
 int prt_ctx_last_bake_stats(const prt_ctx *, prt_bake_stats *out);
 

@@ -109,7 +109,7 @@ class SceneInfo(C.Structure):
 class BakeStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("rays", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32), ("grid", C.c_uint32),
-                ("block", C.c_uint32), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("cand_tests", C.c_uint64), ("rays_traversed", C.c_uint64), ("horizon_ms", C.c_double), ("slab_tests", C.c_uint64)]
+                ("block", C.c_uint32), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("cand_tests", C.c_uint64), ("rays_traversed", C.c_uint64), ("horizon_ms", C.c_double)]
 
 
 class GroupStats(C.Structure):

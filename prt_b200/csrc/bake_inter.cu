@@ -23,8 +23,7 @@ namespace prt {
 namespace {
 
 // COUNT: carry the work counters (instrumented launches only; the timed variant keeps those registers free)
-// FILT: (slot, node) items pass the slab filter before their node is opened (scenes with oriented slabs, bake_inter.cuh)
-template <int ORDER, bool COUNT, bool FILT>
+template <int ORDER, bool COUNT>
 __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const BakeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     InterShared &W = reinterpret_cast<InterShared *>(smem_raw)[threadIdx.x >> 5];
@@ -42,7 +41,7 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
         if (v >= A.n_verts) break;
         const int n_need = (int)__ldg(&A.need_count[v]);
         if (n_need == 0) continue;                                           // finished by the horizon pass
-        bake_inter_vertex<ORDER, COUNT, FILT>(A, W, v, n_need, lane, S, depth, lt_mask, sgn, cand_tests, rays_scanned, node_visits, tri_tests);
+        bake_inter_vertex<ORDER, COUNT>(A, W, v, n_need, lane, S, depth, lt_mask, sgn, cand_tests, rays_scanned, node_visits, tri_tests);
     }
     if (COUNT && A.work) {
         const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
@@ -50,31 +49,30 @@ __global__ void __launch_bounds__(128, PRT_INTER_MINB) bake_inter_kernel(const B
     }
 }
 
-template <int ORDER, bool COUNT, bool FILT>
+template <int ORDER, bool COUNT>
 cudaError_t launch_inter_tc(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
     const int block = 128;
     const size_t smem = sizeof(InterShared) * (size_t)(block / 32);
     static std::atomic<unsigned long long> configured{0};   // per instantiation, one bit per device
     {
-        cudaError_t e = ensure_dynamic_smem(bake_inter_kernel<ORDER, COUNT, FILT>, (int)smem, configured);
+        cudaError_t e = ensure_dynamic_smem(bake_inter_kernel<ORDER, COUNT>, (int)smem, configured);
         if (e != cudaSuccess) return e;
     }
     if (*grid <= 0) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_inter_kernel<ORDER, COUNT, FILT>, block, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_inter_kernel<ORDER, COUNT>, block, smem);
         if (e != cudaSuccess) return e;
         *grid = n_sms * (per_sm > 0 ? per_sm : 1);
     }
     const long long need = ((long long)A.n_verts + 3) / 4;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
-    bake_inter_kernel<ORDER, COUNT, FILT><<<*grid, block, smem, st>>>(A);
+    bake_inter_kernel<ORDER, COUNT><<<*grid, block, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 template <int ORDER>
 cudaError_t launch_inter_t(const BakeArgs &A, int *grid, int n_sms, cudaStream_t st) {
-    if (A.filter_slabs) return A.work ? launch_inter_tc<ORDER, true, true>(A, grid, n_sms, st) : launch_inter_tc<ORDER, false, true>(A, grid, n_sms, st);
-    return A.work ? launch_inter_tc<ORDER, true, false>(A, grid, n_sms, st) : launch_inter_tc<ORDER, false, false>(A, grid, n_sms, st);
+    return A.work ? launch_inter_tc<ORDER, true>(A, grid, n_sms, st) : launch_inter_tc<ORDER, false>(A, grid, n_sms, st);
 }
 
 }  // namespace

@@ -24,15 +24,8 @@ namespace {
 #ifndef PRT_INTER_ROOM8
 #define PRT_INTER_ROOM8 4          // new primary rays are scanned while both stacks are at most ROOM8/8 full
 #endif
-#ifndef PRT_INTER_RCAP
-#define PRT_INTER_RCAP 64          // ready queue of the slab filter (bake_wave.cuh): at most 31 waiting + 32 new items
-#endif
 constexpr int kSlots = 64;
 constexpr int kCap = PRT_INTER_CAP;
-constexpr int kNCap = PRT_INTER_CAP;                        // node stack (unfiltered items): never shrunk, its overflow path is a per-ray traversal
-constexpr int kLCap = PRT_INTER_CAP - PRT_INTER_RCAP;       // leaf stack: leaf steps have priority, it stays short (the ready queue's space comes from here)
-constexpr int kRCap = PRT_INTER_RCAP;
-static_assert(kRCap >= 64 && kLCap >= 96, "stack split");
 constexpr uint32_t kFree = 0xFFFFFFFFu;
 constexpr unsigned long long kNoHit = 0x7F800000FFFFFFFFull;        // (+inf, invalid prim)
 
@@ -44,9 +37,8 @@ struct InterShared {
     uint32_t btri[kSlots];              // triangle slot of `best`
     int refc[kSlots];                   // outstanding work items of the slot's current segment
     uint32_t info[kSlots];              // processing index of the sample | segment << 24; kFree = empty
-    uint2 nq[kNCap];                    // (slot, node index)
-    uint2 rq[kRCap];                    // the same, after the slab filter: the items a node step opens
-    uint2 lq[kLCap];                    // (slot | triangle bits << 16, first triangle)
+    uint2 nq[kCap];                     // (slot, node index)
+    uint2 lq[kCap];                     // (slot | triangle bits << 16, first triangle)
 };
 
 __device__ __forceinline__ uint32_t node_slots_hit_range(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx,
@@ -94,9 +86,7 @@ __device__ __noinline__ uint32_t repair_hit_triangle(const Node8 *nodes, const T
 
 // One vertex with n_need > 0 flagged samples (the caller skips the vertices the horizon pass finished).  lt_mask = (1 << lane) - 1,
 // sgn = Condon-Shortley sign; the last four arguments are the work counters of an instrumented launch (COUNT).
-// FILT (scenes with oriented slabs, A.filter_slabs): a (slot, node) item passes the slab filter of bake_wave.cuh -- here with the segment's
-// current closest hit as the far end of the interval -- before its node is opened; an item that fails gives its reference back at once.
-template <int ORDER, bool COUNT, bool FILT>
+template <int ORDER, bool COUNT>
 __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared &W, const uint32_t v, const int n_need, const int lane, const int S,
                                                   const int depth, const unsigned lt_mask, const float sgn, unsigned long long &cand_tests,
                                                   unsigned long long &rays_scanned, uint32_t &node_visits, uint32_t &tri_tests) {
@@ -132,7 +122,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         }
     }
 
-    int nn = 0, ln = 0, rn = 0, nfree = kSlots, fetched = 0;      // warp-uniform
+    int nn = 0, ln = 0, nfree = kSlots, fetched = 0;      // warp-uniform
     int need_word = -1;
     uint32_t need_cur = 0u;
     uint32_t m0 = 0u, m1 = 0u, m2 = 0u, sslot = 0u;       // candidate hits of the lane's scanned primary ray not yet queued
@@ -141,7 +131,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         if (++guard > (1u << 24)) { if (lane == 0 && A.work) atomicAdd(&A.work[3], 1ull << 60); break; }     // never expected: bail out instead of hanging
         // ---- emit pending (slot, candidate) items while one more warp-wide append fits ------------------------------------
         bool pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
-        while (pending && nn <= kNCap - 32 && ln <= kLCap - 32) {
+        while (pending && nn <= kCap - 32 && ln <= kCap - 32) {
             int k = -1;
             if (m0) { k = __ffs(m0) - 1; m0 &= m0 - 1u; }
             else if (m1) { k = 32 + __ffs(m1) - 1; m1 &= m1 - 1u; }
@@ -162,11 +152,11 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         // (batched: shading a couple of slots per iteration would run the long bounce code on a few lanes each time, so it waits
         //  until PRT_INTER_SHADE_MIN slots are finished or the stacks run low)
         bool shade_now = false;
-        if (!pending && nn <= kNCap - 64) {
+        if (!pending && nn <= kCap - 64) {
             const unsigned f0 = __ballot_sync(kFull, W.info[lane] != kFree && W.refc[lane] == 0);
             const unsigned f1 = __ballot_sync(kFull, W.info[lane + 32] != kFree && W.refc[lane + 32] == 0);
             const int nfin = __popc(f0) + __popc(f1);
-            shade_now = nfin > 0 && (nfin >= PRT_INTER_SHADE_MIN || nn + ln + rn < 32);
+            shade_now = nfin > 0 && (nfin >= PRT_INTER_SHADE_MIN || nn + ln < 32);
         }
         if (shade_now) {
 #pragma unroll 1
@@ -233,7 +223,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
         }
 
         // ---- refill: the next flagged samples take free slots, 32 at a time (lockstep entry-list scan) ------------------------
-        if (!pending && fetched < n_need && nn + rn <= kNCap * PRT_INTER_ROOM8 / 8 && ln <= kLCap * PRT_INTER_ROOM8 / 8 && (nfree >= 32 || (nn == 0 && ln == 0 && rn == 0 && nfree > 0))) {
+        if (!pending && fetched < n_need && nn <= kCap * PRT_INTER_ROOM8 / 8 && ln <= kCap * PRT_INTER_ROOM8 / 8 && (nfree >= 32 || (nn == 0 && ln == 0 && nfree > 0))) {
             const int cnt = min(min(32, nfree), n_need - fetched);
             // the cnt next flagged samples, in processing order
             int taken = 0, my_k = -1;
@@ -268,29 +258,11 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
             __syncwarp();
             continue;
         }
-        if (nn == 0 && ln == 0 && rn == 0) {
+        if (nn == 0 && ln == 0) {
             if (!pending && fetched >= n_need && nfree == kSlots) break;
             continue;                                   // slots finished without items (or pending emission) are handled above
         }
-        if (FILT && nn > 0 && rn < 32 && ln < 32) {
-            // ---- filter step ----------------------------------------------------------------------------------------------
-            const int cnt = min(nn, 32);
-            nn -= cnt;
-            uint2 it = make_uint2(0u, 0u);
-            bool keep = false;
-            if (lane < cnt) {
-                it = W.nq[nn + lane];
-                const float4 a = W.od0[it.x], b = W.od1[it.x];
-                const float tfar = __uint_as_float((uint32_t)(W.best[it.x] >> 32));
-                const char *sp = reinterpret_cast<const char *>(A.filter_slabs + it.y);
-                const u4 s0 = ld16(sp), s1 = ld16(sp + 16), s2 = ld16(sp + 32);
-                keep = !ray_misses_slab(s0, s1, s2, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), rcp_box(b.x), rcp_box(b.y), rcp_box(b.z), tfar);
-                if (!keep) atomicSub(&W.refc[it.x], 1);
-            }
-            const unsigned kb = __ballot_sync(kFull, keep);
-            if (keep) W.rq[rn + __popc(kb & lt_mask)] = it;
-            rn += __popc(kb);
-        } else if (ln >= 32 || (nn == 0 && rn == 0)) {
+        if (ln >= 32 || nn == 0) {
             // ---- leaf step ------------------------------------------------------------------------------------------------
             const int cnt = min(ln, 32);
             ln -= cnt;
@@ -322,11 +294,11 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
             }
         } else {
             // ---- node step ------------------------------------------------------------------------------------------------
-            int cnt;
+            const int cnt = min(nn, 32);
+            nn -= cnt;
             uint2 it = make_uint2(0u, 0u);
-            bool has;
-            if (FILT) { cnt = min(rn, 32); rn -= cnt; has = lane < cnt; if (has) it = W.rq[rn + lane]; }
-            else { cnt = min(nn, 32); nn -= cnt; has = lane < cnt; if (has) it = W.nq[nn + lane]; }
+            const bool has = lane < cnt;
+            if (has) it = W.nq[nn + lane];
             __syncwarp();                   // all pops are done before anybody pushes
             uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
             int delta = 0;
@@ -345,7 +317,7 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
             __syncwarp();
             uint32_t tot;
             const uint32_t ex = warp_excl_scan_packed((uint32_t)__popc(inner8) | ((uint32_t)__popc(leaf8) << 16), lane, tot);
-            if (nn + (int)(tot & 0xFFFFu) <= kNCap && ln + (int)(tot >> 16) <= kLCap) {
+            if (nn + (int)(tot & 0xFFFFu) <= kCap && ln + (int)(tot >> 16) <= kCap) {
                 // everything fits (the common case): one packed warp scan gave every lane its write positions on both stacks
                 int pi = nn + (int)(ex & 0xFFFFu), pl = ln + (int)(ex >> 16);
                 while (inner8) {
@@ -366,13 +338,13 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
                 const unsigned pb = __ballot_sync(kFull, p);
                 const int pos = nn + __popc(pb & lt_mask);
                 if (p) {
-                    if (pos < kNCap) W.nq[pos] = make_uint2(it.x, child);
+                    if (pos < kCap) W.nq[pos] = make_uint2(it.x, child);
                     else {
                         fallback_subtree_closest(A.nodes, A.tris, W, it.x, child, node_visits, tri_tests);
                         atomicSub(&W.refc[it.x], 1);
                     }
                 }
-                nn = min(nn + __popc(pb), kNCap);
+                nn = min(nn + __popc(pb), kCap);
             }
             while (__any_sync(kFull, leaf8 != 0u)) {
                 const bool p = leaf8 != 0u;
@@ -385,13 +357,13 @@ __device__ __forceinline__ void bake_inter_vertex(const BakeArgs &A, InterShared
                 const unsigned pb = __ballot_sync(kFull, p);
                 const int pos = ln + __popc(pb & lt_mask);
                 if (p) {
-                    if (pos < kLCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
+                    if (pos < kCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                     else {
                         fallback_leaf_closest(A.tris, W, it.x, tri0, bits, tri_tests);
                         atomicSub(&W.refc[it.x], 1);
                     }
                 }
-                ln = min(ln + __popc(pb), kLCap);
+                ln = min(ln + __popc(pb), kCap);
             }
         }
         __syncwarp();

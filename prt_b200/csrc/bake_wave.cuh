@@ -22,25 +22,16 @@ constexpr int kMaxS = 8192;             // occlusion bitset capacity (samples pe
 #ifndef PRT_WAVE_BLOCK
 #define PRT_WAVE_BLOCK 128
 #endif
-#ifndef PRT_WAVE_RCAP
-#define PRT_WAVE_RCAP 64            // ready queue: (ray, node) items that passed the slab filter, at most 31 + 32
-#endif
-// The ready queue's space comes out of the LEAF stack: leaf steps have priority once 32 items wait, so that stack stays short, and
-// its overflow path is three triangle tests.  The NODE stack must not shrink: an overflowing push runs a whole per-ray stack traversal
-// on a handful of lanes (measured with 192 entries: 37 % of the kernel's instructions at 3 of 32 lanes, step 47 -> 66 ms).
-// CPU work model (tools/wave_study.py, stack overflows per vertex of the bench mesh): 256 / 256 without the filter 0.39; with the filter
-// 256 / 192: 1.3, 320 / 128: 0.27 -- the leaf stack never comes near 128 entries.
 #ifndef PRT_WAVE_NCAP
-#define PRT_WAVE_NCAP (PRT_WAVE_CAP + 64)
+#define PRT_WAVE_NCAP PRT_WAVE_CAP
 #endif
 #ifndef PRT_WAVE_LCAP
-#define PRT_WAVE_LCAP (PRT_WAVE_CAP - 64 - PRT_WAVE_RCAP)
+#define PRT_WAVE_LCAP PRT_WAVE_CAP
 #endif
 #ifndef PRT_WAVE_ROOM8
 #define PRT_WAVE_ROOM8 2            // new rays are scanned while both stacks are at most ROOM8/8 full
 #endif
-constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP, kReadyCap = PRT_WAVE_RCAP;
-static_assert(kReadyCap >= 64, "a filter step appends up to 32 items to at most 31 waiting ones");
+constexpr int kNodeCap = PRT_WAVE_NCAP, kLeafCap = PRT_WAVE_LCAP;
 static_assert(kNodeCap * 64 >= kMaxS, "the node stack doubles as the visibility permutation buffer");
 
 // per-warp shared memory: this struct followed by the occlusion bitset (vis_words words rounded up to 16 bytes; bit i: the
@@ -51,27 +42,14 @@ static_assert(kNodeCap * 64 >= kMaxS, "the node stack doubles as the visibility 
 struct WaveShared {
     EntryList el;
     uint2 nq[kNodeCap];                 // (processing index of the ray, node index)
-    uint2 rq[kReadyCap];                // the same, after the slab filter: what a node step opens (only used when the scene has slabs)
     uint2 lq[kLeafCap];                 // (processing index | triangle bits << 16, first triangle)
     uint32_t pend[64];                  // processing indices of rays that are not above the horizon, waiting for a scan round
-    float4 frame[3];                    // (right, org.x), (up, org.y), (n, org.z): the steps re-read the vertex's frame and ray origin from here
-};                                      // (three broadcast LDS.128) instead of holding twelve registers across the traversal loop
+};
 
-#ifndef PRT_WAVE_FRAME_SMEM
-#define PRT_WAVE_FRAME_SMEM 1
-#endif
-__device__ __forceinline__ void load_frame(const float4 *F, Frame &fr, f3 &org) {
-    const float4 a = F[0], b = F[1], c = F[2];
-    fr.right = mk3(a.x, a.y, a.z); fr.up = mk3(b.x, b.y, b.z); fr.n = mk3(c.x, c.y, c.z);
-    org = mk3(a.w, b.w, c.w);
-}
-
-// study hook of the CPU harness (tests/hostcheck): called for every live (ray, node) item of a node step; nothing in a product build
+// work counters of the CPU harness (tests/hostcheck, tools/wave_study.py): steps by kind, lanes per step, stack overflows; nothing in a
+// product build
 #ifndef PRT_WAVE_STAT
 #define PRT_WAVE_STAT(counter, n)
-#endif
-#ifndef PRT_WAVE_NODE_STUDY
-#define PRT_WAVE_NODE_STUDY(A, node, n0, org, d)
 #endif
 
 // 8 quantised child boxes of one node against a ray from the vertex (interval [0, inf)): traverse.cuh
@@ -99,22 +77,6 @@ __device__ __noinline__ bool fallback_leaf(const Tri48 *tris, const f3 org, cons
     return false;
 }
 
-// slab filter of one (ray, node) item, out of line (PRT_WAVE_FILT_INLINE = 0): its twelve words of slab record and the interval arithmetic
-// stay out of the register allocation of the traversal loop
-#ifndef PRT_WAVE_FILT_INLINE
-#define PRT_WAVE_FILT_INLINE 0
-#endif
-#if PRT_WAVE_FILT_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-bool slab_filter_keeps(const Slab48 *slabs, const uint32_t node, const f3 org, const f3 d) {
-    const char *sp = reinterpret_cast<const char *>(slabs + node);
-    const u4 s0 = ld16(sp), s1 = ld16(sp + 16), s2 = ld16(sp + 32);
-    return !ray_misses_slab(s0, s1, s2, org, d, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), INFINITY);
-}
-
 // The visibility words of the C ABI are in reference order, the occlusion bitset in processing order: permute through `perm`
 // (the node stack, empty by then).  Out of line: only callers that ask for visibility words pay for it, and its registers
 // stay out of the traversal loop's allocation.
@@ -133,15 +95,10 @@ __device__ __noinline__ void write_vis_permuted(const float4 *samples, const uin
 // One vertex: entry list, lockstep scan of the flagged samples, node / leaf steps until both stacks are empty, projection, row
 // and (optional) visibility words.  W / occl: the warp's shared memory; lt_mask = (1 << lane) - 1; sgn = Condon-Shortley sign; the last four
 // arguments are the work counters of an instrumented launch (COUNT).
-//
-// Scenes with oriented slabs (A.filter_slabs, bvh8.h): a (ray, node) item is FILTERED before the node is opened -- a filter step pops 32 items
-// from the node stack, tests each ray against box and slab of its node (three 16-byte words, ray_misses_slab) and appends the survivors
-// to the ready queue; a node step opens 32 ready items.  On the bench mesh 36 % of the popped items fail the filter and 44 % fewer nodes
-// are opened (tools/wave_study.py); done inside the node step instead, the culled lanes would idle through the 8-box test of the others.
-template <int ORDER, bool TRACE, bool COUNT, bool FILT>
+template <int ORDER, bool TRACE, bool COUNT>
 __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &W, uint32_t *const occl, const uint32_t v, const int lane, const int S, const int words,
                                                  const unsigned lt_mask, const float sgn, unsigned long long &cand_tests,
-                                                 unsigned long long &rays_scanned, uint32_t &node_visits, uint32_t &tri_tests, uint32_t &slab_tests) {
+                                                 unsigned long long &rays_scanned, uint32_t &node_visits, uint32_t &tri_tests) {
     constexpr int N2 = ORDER * ORDER;
     const uint32_t *need_row = (TRACE && A.need_bits) ? A.need_bits + (size_t)v * A.vis_words : nullptr;
 
@@ -149,38 +106,21 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
     const float *np = reinterpret_cast<const float *>(reinterpret_cast<const char *>(A.nrm) + (size_t)v * A.stride);
     const f3 N = mk3(__ldg(np), __ldg(np + 1), __ldg(np + 2));
     const f3 P = mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2));
-#if PRT_WAVE_FRAME_SMEM
-    {
-        const Frame fr0 = make_frame(N);
-        const f3 org0 = madd3(P, A.origin_eps, N);                  // raytracing.cpp:343
-        if (lane == 0) {
-            W.frame[0] = make_float4(fr0.right.x, fr0.right.y, fr0.right.z, org0.x);
-            W.frame[1] = make_float4(fr0.up.x, fr0.up.y, fr0.up.z, org0.y);
-            W.frame[2] = make_float4(fr0.n.x, fr0.n.y, fr0.n.z, org0.z);
-        }
-        __syncwarp();
-    }
-#define PRT_WAVE_FRAME() Frame fr; f3 org; load_frame(W.frame, fr, org)
-#else
     const Frame fr = make_frame(N);
     const f3 org = madd3(P, A.origin_eps, N);                       // raytracing.cpp:343
-#define PRT_WAVE_FRAME()
-#endif
 
     for (int w = lane; w < words; w += 32) occl[w] = 0u;
     int n_cand = 0;
     if (TRACE) {
-        { PRT_WAVE_FRAME(); n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
+        n_cand = build_entry_list(A.nodes, org, N, W.el, lane);
 #if PRT_WAVE_CULL
         entry_list_elevation_bounds(W.el, n_cand, fr, lane);
 #endif
-        }
     }
     __syncwarp();
 
     if (TRACE) {
-        int base = 0, nn = 0, ln = 0, rn = 0;     // warp-uniform: next sample, node-stack fill, leaf-stack fill, ready-queue fill
-        constexpr bool filt = FILT;               // the scene has slabs (A.filter_slabs)
+        int base = 0, nn = 0, ln = 0;             // warp-uniform: next sample, node-stack fill, leaf-stack fill
         int npend = 0;                            // warp-uniform: rays waiting in W.pend
         uint32_t m0 = 0u, m1 = 0u, m2 = 0u;       // candidate hits of the lane's scanned ray not yet queued
         uint32_t sproc = 0u;
@@ -203,7 +143,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
             }
             // ---- classify samples: a ray above the horizon of its azimuth bin is visible without any test ---------------
-            const bool room = nn + rn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;     // ready items count as node items
+            const bool room = nn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;
             if (!pending && room) {
                 while (base < S && npend < 32) {
                     const int i = base + lane;
@@ -230,7 +170,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) zmin = fminf(zmin, __shfl_xor_sync(kFull, zmin, o));
                     if (lane < cnt) {
-                        PRT_WAVE_FRAME();
                         const f3 d = to_world(fr, mk3(csmp.x, csmp.y, csmp.z));   // raytracing.cpp:340
                         uint32_t cm[3];
                         scan_entry_list_culled(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), zmin, cm);
@@ -241,7 +180,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     if (lane < cnt) {
                         const uint32_t i = W.pend[npend + lane];
                         const float4 smp = __ldg(&A.samples[i]);
-                        PRT_WAVE_FRAME();
                         const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));   // raytracing.cpp:340
                         uint32_t cm[3];
                         scan_entry_list(W.el, n_cand, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), cm);
@@ -254,29 +192,9 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     continue;
                 }
             }
-            if (nn == 0 && ln == 0 && rn == 0) { if (!pending && base >= S && npend == 0) break; else continue; }
+            if (nn == 0 && ln == 0) { if (!pending && base >= S && npend == 0) break; else continue; }
             __syncwarp();
-            if (filt && nn > 0 && rn < 32 && ln < 32) {
-                // ---- filter step ----------------------------------------------------------------------------------
-                const int cnt = min(nn, 32);
-                nn -= cnt;
-                if (lane == 0) { PRT_WAVE_STAT(filter_steps, 1); PRT_WAVE_STAT(filter_lanes, cnt); }
-                uint2 it = make_uint2(0u, 0u);
-                bool keep = false;
-                if (lane < cnt) {
-                    it = W.nq[nn + lane];
-                    if (!((occl[it.x >> 5] >> (it.x & 31u)) & 1u)) {
-                        const float4 smp = __ldg(&A.samples[it.x]);
-                        PRT_WAVE_FRAME();
-                        keep = slab_filter_keeps(A.filter_slabs, it.y, org, to_world(fr, mk3(smp.x, smp.y, smp.z)));
-                        if (COUNT) slab_tests++;
-                        if (!keep) PRT_WAVE_STAT(slab_culls, 1);
-                    }
-                }
-                const unsigned kb = __ballot_sync(kFull, keep);
-                if (keep) W.rq[rn + __popc(kb & lt_mask)] = it;
-                rn += __popc(kb);
-            } else if (ln >= 32 || (nn == 0 && rn == 0)) {
+            if (ln >= 32 || nn == 0) {
                 // ---- leaf step ------------------------------------------------------------------------------------
                 const int cnt = min(ln, 32);
                 ln -= cnt;
@@ -292,7 +210,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         const char *tp = reinterpret_cast<const char *>(A.tris + it.y + b);
                         u4 ta = ld16(tp), tb = ld16(tp + 16), tc = ld16(tp + 32);
                         const float4 smp = __ldg(&A.samples[oi]);
-                        PRT_WAVE_FRAME();
                         const f3 d = to_world(fr, mk3(smp.x, smp.y, smp.z));
                         for (;;) {
                             float t; uint32_t prim;
@@ -311,12 +228,12 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 }
             } else {
                 // ---- node step ------------------------------------------------------------------------------------
-                int cnt;
-                uint2 it = make_uint2(0u, 0u);
-                bool has;
-                if (filt) { cnt = min(rn, 32); rn -= cnt; has = lane < cnt; if (has) it = W.rq[rn + lane]; }
-                else { cnt = min(nn, 32); nn -= cnt; has = lane < cnt; if (has) it = W.nq[nn + lane]; }
+                const int cnt = min(nn, 32);
+                nn -= cnt;
                 if (lane == 0) { PRT_WAVE_STAT(node_steps, 1); PRT_WAVE_STAT(node_lanes, cnt); }
+                uint2 it = make_uint2(0u, 0u);
+                bool has = lane < cnt;
+                if (has) it = W.nq[nn + lane];
                 __syncwarp();                   // all pops are done before anybody pushes
                 uint32_t inner8 = 0u, leaf8 = 0u, child_base = 0u, tri_base = 0u, imask = 0u, meta_lo = 0u, meta_hi = 0u;
                 f3 d = mk3(0.f, 0.f, 1.f);
@@ -326,9 +243,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         const char *npn = reinterpret_cast<const char *>(A.nodes + it.y);
                         const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
                         const float4 smp = __ldg(&A.samples[it.x]);       // issued together with the node fetch
-                        PRT_WAVE_FRAME();
                         d = to_world(fr, mk3(smp.x, smp.y, smp.z));
-                        PRT_WAVE_NODE_STUDY(A, it.y, n0, org, d);
                         const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                         imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                         inner8 = hits & imask; leaf8 = hits & ~imask;
@@ -366,7 +281,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         if (pos < kNodeCap) W.nq[pos] = make_uint2(it.x, child);
                         else {
                             // stack full: ordinary traversal of this subtree (rare)
-                            PRT_WAVE_FRAME();
                             PRT_WAVE_STAT(overflow_subtrees, 1);
                             if (fallback_subtree(A.nodes, A.tris, org, d, child, node_visits, tri_tests)) {
                                 atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
@@ -389,7 +303,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                     if (p) {
                         if (pos < kLeafCap) W.lq[pos] = make_uint2(it.x | (bits << 16), tri0);
                         else {
-                            PRT_WAVE_FRAME();
                             PRT_WAVE_STAT(overflow_leaves, 1);
                             if (fallback_leaf(A.tris, org, d, tri0, bits, tri_tests)) {
                                 atomicOr(&occl[it.x >> 5], 1u << (it.x & 31u));
@@ -406,7 +319,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
     }
 
     // ---- projection: L = Y_lm(dir) for every unoccluded sample (raytracing.cpp:226,257-261,348) ---------------
-    PRT_WAVE_FRAME();
     float acc[N2];
 #pragma unroll
     for (int k = 0; k < N2; k++) acc[k] = 0.f;
@@ -436,7 +348,6 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
         }
     }
     __syncwarp();
-#undef PRT_WAVE_FRAME
 }
 
 }  // namespace

@@ -37,20 +37,20 @@ constexpr int kStackEntries = 48;   // traversal stack capacity (node groups); b
 // Oriented slab of one 8-wide node (horizon pass only, entry_list.cuh): every triangle below the node lies between the planes
 // m . x = d0 and m . x = d1, m = the (unit) area-weighted mean normal of those triangles.  A surface patch is a thin sheet inside its
 // fat axis-aligned box; the slab lets the horizon builder bound the height of the sheet above a tangent plane instead of the box's.
-// m = 0: no slab (degenerate mean normal): d0 = -3e38, d1 = 3e38.  The record also carries the node's own (padded) box, which the node
-// itself only holds implicitly as the union of its child boxes: the traversal pass tests a ray against slab and box of a node BEFORE it
-// opens it (traverse.cuh, ray_misses_slab) from these three 16-byte words alone.
-struct alignas(16) Slab48 {
+// m = 0: no slab (degenerate mean normal): d0 = -3e38, d1 = 3e38.
+// (A ray / slab test in the TRAVERSAL pass -- filtering (ray, node) items before their node is opened -- removes 40 % of the node tests on
+// the bench mesh but was 20 % slower on the GPU: the extra steps cost as many instructions as they save and one more dependent fetch
+// each; measured and removed, profiles/r2_slab_filter_rejected_ncu_summary.txt.)
+struct alignas(16) Slab32 {
     float mx, my, mz, d0;
-    float d1, lox, loy, loz;
-    float hix, hiy, hiz, pad;
+    float d1, pad0, pad1, pad2;
 };
-static_assert(sizeof(Slab48) == 48, "Slab48 must be 48 bytes");
+static_assert(sizeof(Slab32) == 32, "Slab32 must be 32 bytes");
 
 struct HostBVH8 {
     Node8 *nodes = nullptr;
     Tri48 *tris = nullptr;
-    Slab48 *slabs = nullptr;        // [n_nodes]
+    Slab32 *slabs = nullptr;        // [n_nodes]
     uint32_t n_nodes = 0, n_tris = 0, max_depth = 0;
     double sah_cost = 0.0, build_seconds = 0.0;
     float pad = 0.f;

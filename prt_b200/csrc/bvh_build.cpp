@@ -361,7 +361,7 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
     if (!out->nodes) { std::free(tris); return fail("build_bvh8: out of memory"); }
     std::memcpy(out->nodes, wn.data(), sizeof(Node8) * wn.size());
     // ---- oriented slabs (bvh8.h): mean normal of the triangles below every 8-wide node and their extent along it -----------------
-    out->slabs = (Slab48 *)std::malloc(sizeof(Slab48) * wn.size());
+    out->slabs = (Slab32 *)std::malloc(sizeof(Slab32) * wn.size());
     if (!out->slabs) { std::free(tris); std::free(out->nodes); out->nodes = nullptr; return fail("build_bvh8: out of memory"); }
     {
         const uint32_t n_wide = (uint32_t)wn.size();
@@ -372,7 +372,7 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
                 if (w0 >= n_wide) return;
                 for (uint32_t w = w0; w < std::min(n_wide, w0 + 64); w++) {
                     const uint32_t b = wide_bnode[w], first = bfirst[b], count = bcount[b];
-                    Slab48 sl; std::memset(&sl, 0, sizeof(sl));
+                    Slab32 sl; std::memset(&sl, 0, sizeof(sl));
                     sl.d0 = -3.0e38f; sl.d1 = 3.0e38f;
                     double sx = 0, sy = 0, sz = 0;
                     for (uint32_t i = first; i < first + count; i++) {
@@ -399,8 +399,6 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
                         sl.mx = mx; sl.my = my; sl.mz = mz;
                         sl.d0 = std::nextafter((float)(lo - (double)pad), -3.0e38f); sl.d1 = std::nextafter((float)(hi + (double)pad), 3.0e38f);
                     }
-                    sl.lox = bn[b].box.lo[0]; sl.loy = bn[b].box.lo[1]; sl.loz = bn[b].box.lo[2];
-                    sl.hix = bn[b].box.hi[0]; sl.hiy = bn[b].box.hi[1]; sl.hiz = bn[b].box.hi[2];
                     out->slabs[w] = sl;
                 }
             }

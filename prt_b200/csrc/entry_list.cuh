@@ -234,7 +234,7 @@ constexpr int kHzTriQueue = 128;       // triangles waiting for a full-warp roun
 // slabs (optional): the oriented slab of every node (bvh8.h); tightens the bound of subtree boxes before they are merged or opened.
 __device__ __forceinline__ void build_horizon(const EntryList &W, const int n_cand, const Node8 *nodes, const Tri48 *tris, const f3 O, const f3 N,
                                               const Frame &fr, uint32_t *hz, uint32_t *rq, uint32_t *tq, const int budget_iters, const float near2, const int lane,
-                                              const Slab48 *slabs = nullptr, const float mid2 = 0.f, const float gain_min = 0.f) {
+                                              const Slab32 *slabs = nullptr, const float mid2 = 0.f, const float gain_min = 0.f) {
     const unsigned lt_mask = (1u << lane) - 1u;
     float my = 0.f;                                          // lane b owns bin b
     int rn = 0, tn = 0;

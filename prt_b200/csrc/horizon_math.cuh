@@ -172,7 +172,7 @@ PRT_HD HzItem hz_cheap_box(const f3 c, const f3 e, const float r2, const float d
     return cb;
 }
 
-// Bound of a box CUT BY THE ORIENTED SLAB of its node (bvh8.h, Slab48): the geometry lies in {x : |x - c| <= e} and between the planes
+// Bound of a box CUT BY THE ORIENTED SLAB of its node (bvh8.h, Slab32): the geometry lies in {x : |x - c| <= e} and between the planes
 // L0 <= m . x <= U0 (x relative to the origin: L0 = d0 - m . O, U0 = d1 - m . O).  The height above the tangent plane n . x = n . c + n . y,
 // |y| <= e, L <= m . y <= U (L = L0 - m . c, U = U0 - m . c), is a linear programme with one two-sided constraint; by weak duality
 //     n . y = (n - lambda m) . y + lambda (m . y) <= sum_i |n_i - lambda m_i| e_i + (lambda >= 0 ? lambda U : lambda L)      for EVERY lambda,

@@ -26,8 +26,7 @@ inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<unsigned
 struct BakeArgs {
     const Node8 *nodes;
     const Tri48 *tris;
-    const Slab48 *slabs;        // optional [n_nodes]: oriented slab of every node, for the horizon pass ...
-    const Slab48 *filter_slabs; // ... and for the slab filter of the traversal pass (the same array; each nullable by its tuning knob)
+    const Slab32 *slabs;        // optional [n_nodes]: oriented slab of every node (horizon pass)
     const float *pos, *nrm;     // device; consecutive vertices `stride` bytes apart
     size_t stride;
     uint32_t n_verts, vid_base;

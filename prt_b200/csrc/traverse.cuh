@@ -115,28 +115,6 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
     return hits;
 }
 
-// ---- ray against the oriented slab of a node (bvh8.h Slab48) -------------------------------------------------------------------------
-// Every triangle below the node lies inside the node's box AND between the planes d0 <= m . x <= d1.  m . (o + t d) is linear in t, so
-// over the ray's interval inside the box it ranges between its values at the two ends: if that range misses [d0, d1] the ray passes
-// through the box beside the sheet of triangles in it and the node need not be opened.  Conservative: the interval is widened by 1e-5
-// relative, box and d0 / d1 carry the padding of the triangle boxes (bvh_build.cpp); a ray that misses the box altogether is culled as
-// well (tighter than the quantised copy of the box its parent tested).  idx.. = the clamped reciprocals of d.
-PRT_HD bool ray_misses_slab(const u4 s0, const u4 s1, const u4 s2, const f3 o, const f3 d, const float idx, const float idy, const float idz,
-                            const float tfar) {
-    const f3 m = mk3(PRT_U2F(s0.x), PRT_U2F(s0.y), PRT_U2F(s0.z));
-    const float d0 = PRT_U2F(s0.w), d1 = PRT_U2F(s1.x);
-    const float ax = (PRT_U2F(s1.y) - o.x) * idx, ay = (PRT_U2F(s1.z) - o.y) * idy, az = (PRT_U2F(s1.w) - o.z) * idz;
-    const float bx = (PRT_U2F(s2.x) - o.x) * idx, by = (PRT_U2F(s2.y) - o.y) * idy, bz = (PRT_U2F(s2.z) - o.z) * idz;
-    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tfar));
-    t0 *= 0.99999f; t1 = fmaf(t1, 1.00001f, 1e-30f);
-    if (!(t0 <= t1)) return true;
-    const float mo = m.x * o.x + m.y * o.y + m.z * o.z, md = m.x * d.x + m.y * d.y + m.z * d.z;
-    const float sa = fmaf(t0, md, mo), sb = fmaf(t1, md, mo);
-    // m = 0 (no slab): d0 = -3e38, d1 = 3e38, never culled by the planes
-    return fmaxf(sa, sb) < d0 || fminf(sa, sb) > d1;
-}
-
 // run() results: RUNNING = interrupted for a refill (state kept); HIT = any-hit found (ANY only);
 // EMPTY = stack and current groups exhausted (closest-hit result, if any, is in best_*)
 enum { TRAV_RUNNING = 0, TRAV_HIT = 1, TRAV_EMPTY = 2 };

@@ -347,11 +347,11 @@ extern "C" void hc_hz_slab(const float *c, const float *e, const float *nrm, con
         val[i] = hz_slab_value(cc, ee, fr.n, mk3(s[0], s[1], s[2]), s[3], s[4]);
     }
 }
-// the builder's slabs: out[12 * node ..] = m (3), d0, d1, box lo (3), box hi (3), 0
+// the builder's slabs: out[8 * node ..] = m (3), d0, d1, 0, 0, 0
 extern "C" uint32_t hc_slabs(void *h, float *out, uint32_t cap) {
     HostBVH8 *b = (HostBVH8 *)h;
     const uint32_t n = std::min(cap, b->n_nodes);
-    if (out && b->slabs) std::memcpy(out, b->slabs, (size_t)n * sizeof(Slab48));
+    if (out && b->slabs) std::memcpy(out, b->slabs, (size_t)n * sizeof(Slab32));
     return b->slabs ? b->n_nodes : 0u;
 }
 // triangle range below every node: out[2 * node] = first triangle (index into the emitted Tri48 array), out[2 * node + 1] = count

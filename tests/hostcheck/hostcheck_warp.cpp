@@ -20,64 +20,14 @@ namespace { std::mutex g_trace_mu; std::vector<float> g_trace; bool g_trace_on =
 #define PRT_HZ_TRACE_FAR(c, e, item) do { if (g_trace_on) { std::lock_guard<std::mutex> lk(g_trace_mu); \
     const float rec[9] = {(c).x, (c).y, (c).z, (e).x, (e).y, (e).z, (item).v, (float)(item).b0, (float)(item).b1}; g_trace.insert(g_trace.end(), rec, rec + 9); } } while (0)
 #include "../../prt_b200/csrc/bvh8.h"
-#include "../../prt_b200/csrc/kernels.h"
-#include "../../prt_b200/csrc/traverse.cuh"
-// study: how many node visits of the traversal pass would a ray / oriented-slab test of the visited node remove?  (a) the ray's
-// interval inside the node's quantisation frame, (b) the whole ray [0, inf)
-namespace { std::atomic<uint64_t> g_ns_visits{0}, g_ns_cull_frame{0}, g_ns_cull_ray{0}, g_ns_cull_box{0}; }
-namespace prt { namespace {
-inline void node_slab_study(const BakeArgs &A, uint32_t node, const u4 n0, const f3 o, const f3 d) {
-    g_ns_visits++;
-    if (!A.filter_slabs) return;
-    const Slab48 &s = A.filter_slabs[node];
-    if (s.mx == 0.f && s.my == 0.f && s.mz == 0.f) return;
-    const double mo = (double)s.mx * o.x + (double)s.my * o.y + (double)s.mz * o.z, md = (double)s.mx * d.x + (double)s.my * d.y + (double)s.mz * d.z;
-    auto miss = [&](double t0, double t1) {
-        if (!(t0 <= t1)) return true;
-        const double a = mo + t0 * md, b = std::isfinite(t1) ? mo + t1 * md : (md > 0 ? INFINITY : md < 0 ? -INFINITY : mo);
-        return std::max(a, b) < s.d0 || std::min(a, b) > s.d1;
-    };
-    if (miss(0.0, INFINITY)) g_ns_cull_ray++;
-    const float lo[3] = {PRT_U2F(n0.x), PRT_U2F(n0.y), PRT_U2F(n0.z)};
-    const float sc[3] = {PRT_U2F((n0.w & 0xFFu) << 23), PRT_U2F(((n0.w >> 8) & 0xFFu) << 23), PRT_U2F(((n0.w >> 16) & 0xFFu) << 23)};
-    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-    double t0 = 0.0, t1 = INFINITY;
-    for (int a = 0; a < 3; a++) {
-        const double id = 1.0 / (std::fabs(dd[a]) < 1e-18 ? 1e-18 : dd[a]);
-        const double ta = (lo[a] - oo[a]) * id, tb = (lo[a] + 255.0 * sc[a] - oo[a]) * id;
-        t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb));
-    }
-    if (miss(t0, t1)) g_ns_cull_frame++;
-    // (c) the node's true box = union of its child boxes
-    const Node8 &nd = A.nodes[node];
-    float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
-    const uint8_t *ql[3] = {nd.qlox, nd.qloy, nd.qloz}, *qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
-    for (int sl = 0; sl < 8; sl++) if (nd.meta[sl]) for (int a = 0; a < 3; a++) {
-        blo[a] = std::min(blo[a], lo[a] + ql[a][sl] * sc[a]); bhi[a] = std::max(bhi[a], lo[a] + qh[a][sl] * sc[a]); }
-    t0 = 0.0; t1 = INFINITY;
-    for (int a = 0; a < 3; a++) {
-        const double id = 1.0 / (std::fabs(dd[a]) < 1e-18 ? 1e-18 : dd[a]);
-        const double ta = (blo[a] - oo[a]) * id, tb = (bhi[a] - oo[a]) * id;
-        t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb));
-    }
-    if (miss(t0, t1)) g_ns_cull_box++;
-}
-} }
-#define PRT_WAVE_NODE_STUDY(A, node, n0, org, d) node_slab_study(A, node, n0, org, d)
-namespace { struct WaveStats { std::atomic<uint64_t> slab_culls{0}, filter_steps{0}, filter_lanes{0}, leaf_steps{0}, leaf_lanes{0}, node_steps{0}, node_lanes{0}, scan_steps{0}, scan_lanes{0}, overflow_subtrees{0}, overflow_leaves{0}; } g_wave_stats; bool g_wave_slabs = true; }
+// step / overflow counters of the traversal pass (bake_wave.cuh calls PRT_WAVE_STAT)
+namespace { struct WaveStats { std::atomic<uint64_t> leaf_steps{0}, leaf_lanes{0}, node_steps{0}, node_lanes{0}, scan_steps{0}, scan_lanes{0}, overflow_subtrees{0}, overflow_leaves{0}; } g_wave_stats; }
 extern "C" void hc_wave_step_stats(uint64_t *out, int reset) {
-    std::atomic<uint64_t> *a[10] = {&g_wave_stats.filter_steps, &g_wave_stats.filter_lanes, &g_wave_stats.leaf_steps, &g_wave_stats.leaf_lanes, &g_wave_stats.node_steps,
+    std::atomic<uint64_t> *a[8] = {&g_wave_stats.leaf_steps, &g_wave_stats.leaf_lanes, &g_wave_stats.node_steps,
                                    &g_wave_stats.node_lanes, &g_wave_stats.scan_steps, &g_wave_stats.scan_lanes, &g_wave_stats.overflow_subtrees, &g_wave_stats.overflow_leaves};
-    for (int i = 0; i < 10; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
+    for (int i = 0; i < 8; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
 }
 #define PRT_WAVE_STAT(counter, n) (g_wave_stats.counter.fetch_add((n), std::memory_order_relaxed))
-extern "C" uint64_t hc_wave_slab_culls(int reset) { const uint64_t v = g_wave_stats.slab_culls; if (reset) g_wave_stats.slab_culls = 0; return v; }
-// ray / slab culling in the traversal pass: on by default, as in the product
-extern "C" void hc_wave_use_slabs(int on) { g_wave_slabs = on != 0; }
-extern "C" void hc_node_slab_study(uint64_t *out, int reset) {
-    out[0] = g_ns_visits; out[1] = g_ns_cull_frame; out[2] = g_ns_cull_ray; out[3] = g_ns_cull_box;
-    if (reset) { g_ns_visits = 0; g_ns_cull_frame = 0; g_ns_cull_ray = 0; g_ns_cull_box = 0; }
-}
 #include "../../prt_b200/csrc/entry_list.cuh"
 #include "../../prt_b200/csrc/horizon.cuh"
 #include "../../prt_b200/csrc/bake_wave.cuh"
@@ -149,31 +99,30 @@ extern "C" uint32_t hc_horizon_trace_far(void *h, const float *pos, const float 
 namespace {
 struct WaveSharedHost { WaveShared W; uint32_t occl[kMaxS / 32]; };
 
-// work (optional, 5 x uint64): node visits, triangle tests, entry-list box tests, rays scanned, slab filter tests -- the counters of an instrumented
+// work (optional, 4 x uint64): node visits, triangle tests, entry-list box tests, rays scanned -- the counters of an instrumented
 // launch (COUNT variant of the kernel), summed over lanes as the kernel does
 template <int ORDER, bool COUNT>
 void run_wave(const BakeArgs &A, uint64_t *work) {
     warp_emu::State state;
     warp_emu::g_state = &state;
     static WaveSharedHost sh;
-    std::atomic<uint64_t> w_nv{0}, w_nt{0}, w_cand{0}, w_scanned{0}, w_ns{0};
+    std::atomic<uint64_t> w_nv{0}, w_nt{0}, w_cand{0}, w_scanned{0};
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; lane++) {
         lanes.emplace_back([&, lane]() {
             warp_emu::t_lane = lane;
             unsigned long long cand = 0ull, scanned = 0ull;
-            uint32_t nv = 0u, nt = 0u, ns = 0u;
+            uint32_t nv = 0u, nt = 0u;
             const float sgn = A.cs_phase ? -1.0f : 1.0f;
             for (uint32_t v = 0; v < A.n_verts; v++)
-                if (A.filter_slabs) bake_wave_vertex<ORDER, true, COUNT, true>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt, ns);
-                else bake_wave_vertex<ORDER, true, COUNT, false>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt, ns);
-            w_nv += nv; w_nt += nt; w_ns += ns;
+                bake_wave_vertex<ORDER, true, COUNT>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+            w_nv += nv; w_nt += nt;
             if (lane == 0) { w_cand += cand; w_scanned += scanned; }      // warp-uniform counters
         });
     }
     for (auto &t : lanes) t.join();
     warp_emu::g_state = nullptr;
-    if (work) { work[0] = w_nv; work[1] = w_nt; work[2] = w_cand; work[3] = w_scanned; work[4] = w_ns; }
+    if (work) { work[0] = w_nv; work[1] = w_nt; work[2] = w_cand; work[3] = w_scanned; }
 }
 }
 
@@ -187,7 +136,6 @@ extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_
     A.out = out; A.vis = vis; A.vis_words = (S + 31) / 32;
     A.need_bits = const_cast<uint32_t *>(need_bits);
     A.origin_eps = origin_eps; A.cs_phase = cs_phase;
-    A.filter_slabs = g_wave_slabs ? b->slabs : nullptr;
     switch (order) {
     case 1: run_wave<1, false>(A, nullptr); break;
     case 2: run_wave<2, false>(A, nullptr); break;
@@ -216,8 +164,7 @@ void run_inter(const BakeArgs &A) {
             for (uint32_t v = 0; v < A.n_verts; v++) {
                 const int n_need = (int)A.need_count[v];
                 if (n_need == 0) continue;                      // the kernel skips the vertices the horizon pass finished
-                if (A.filter_slabs) bake_inter_vertex<ORDER, false, true>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
-                else bake_inter_vertex<ORDER, false, false>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                bake_inter_vertex<ORDER, false>(A, W, v, n_need, lane, A.S, A.depth, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
             }
         });
     }
@@ -239,7 +186,6 @@ extern "C" int hc_bake_inter(void *h, const float *pos, const float *nrm, uint32
     A.seed = seed; A.depth = bounces + 1;
     A.albedo[0] = albedo[0]; A.albedo[1] = albedo[1]; A.albedo[2] = albedo[2];
     A.origin_eps = origin_eps; A.bounce_eps = bounce_eps;
-    A.filter_slabs = g_wave_slabs ? b->slabs : nullptr;
     switch (order) {
     case 1: run_inter<1>(A); break;
     case 2: run_inter<2>(A); break;

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(prt):
         assert hasattr(L, n), f"{n} declared in include/prt_b200.h but not exported"
     from prt_b200 import api
     assert set(api.ABI_SYMBOLS) <= set(names)
-    assert L.prt_abi_version() == 3
+    assert L.prt_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

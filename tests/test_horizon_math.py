@@ -165,7 +165,7 @@ def test_slab_clamp_tightens_flat_boxes(hostcheck):
     assert np.median(out[2] / out[0]) > 10          # cone: ~0.2, slab: ~0.005
 
 
-# ---- oriented slabs (bvh8.h Slab48, hz_slab_value) ---------------------------------------------------------------------------------
+# ---- oriented slabs (bvh8.h Slab32, hz_slab_value) ---------------------------------------------------------------------------------
 def _slab_cases(rng, n, kind):
     nrm = rng.normal(size=(n, 3))
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
@@ -246,7 +246,7 @@ def test_slab_bound_is_conservative_and_solves_the_lp(hostcheck, kind):
 
 
 def test_builder_slabs_contain_their_triangles(hostcheck):
-    """Slab48 of every 8-wide node (bvh_build.cpp): all triangles below the node lie between its two planes; on a surface mesh the
+    """Slab32 of every 8-wide node (bvh_build.cpp): all triangles below the node lie between its two planes; on a surface mesh the
     slabs of the lower levels are thin compared with their boxes."""
     from prt_b200 import meshes
     pos, nrm, tri = meshes.bumpy_torus(96, 64)
@@ -254,7 +254,7 @@ def test_builder_slabs_contain_their_triangles(hostcheck):
     info = np.zeros(3, np.uint32)
     hostcheck.hc_info(h, info.ctypes.data)
     n_nodes, n_tris = int(info[0]), int(info[1])
-    slabs = np.zeros((n_nodes, 12), np.float32)
+    slabs = np.zeros((n_nodes, 8), np.float32)
     assert hostcheck.hc_slabs(h, slabs.ctypes.data, n_nodes) == n_nodes
     rng_ = np.zeros((n_nodes, 2), np.uint32)
     hostcheck.hc_node_tri_ranges(h, rng_.ctypes.data)

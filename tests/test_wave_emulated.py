@@ -258,12 +258,11 @@ def test_non_unit_normals_through_both_passes(hostcheck, oracle, scale):
     assert rel_l2(out, ref).max() <= REL_L2_TOL
 
 
-@pytest.mark.parametrize("filt", [1, 0])
-def test_work_model_of_the_traversal_pass(hostcheck, oracle, filt):
+def test_work_model_of_the_traversal_pass(hostcheck, oracle):
     """Regression guard on the WORK the traversal pass does (results are covered above): on a dense mesh with 1024 samples the item
-    stacks must all but never overflow -- an overflowing push runs a whole per-ray stack traversal on a few lanes, which on the GPU
-    turned a 47 ms step into 66 ms when the node stack was 192 entries -- the steps must stay full, and the slab filter must remove
-    a good share of the node visits."""
+    stacks must all but never overflow -- an overflowing push runs a whole per-ray stack traversal on a few lanes; on the GPU a
+    node stack of 192 entries turned a 47 ms step into 66 ms (profiles/r2_slab_filter_rejected_ncu_summary.txt) -- and the steps must
+    stay full."""
     import ctypes
     pos, nrm, tri = meshes.bumpy_torus(320, 320)
     order_ = meshes.morton_order(pos)
@@ -278,25 +277,18 @@ def test_work_model_of_the_traversal_pass(hostcheck, oracle, filt):
         need = ~(tab[None, :, 2] > hz[:, bins])
         keep = need.any(axis=1)
         words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
-        st = np.zeros(10, np.uint64)
-        work = np.zeros(5, np.uint64)
-        hostcheck.hc_wave_use_slabs(filt)
+        st = np.zeros(8, np.uint64)
+        work = np.zeros(4, np.uint64)
         hostcheck.hc_wave_step_stats(st.ctypes.data, 1)
         got, vis = run_wave(hostcheck, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(words[keep]), work=work)
         hostcheck.hc_wave_step_stats(st.ctypes.data, 0)
     finally:
-        hostcheck.hc_wave_use_slabs(1)
         hostcheck.hc_free(h)
     _, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), pos[sel][keep], nrm[sel][keep], op, want_vis=True)
     assert np.array_equal(vis, ovis)
     n = int(keep.sum())
-    filter_steps, filter_lanes, leaf_steps, leaf_lanes, node_steps, node_lanes, scan_steps, scan_lanes, ovf_sub, ovf_leaf = (float(x) for x in st)
+    leaf_steps, leaf_lanes, node_steps, node_lanes, scan_steps, scan_lanes, ovf_sub, ovf_leaf = (float(x) for x in st)
     assert node_steps > 20 * n
     assert ovf_sub <= 1.0 * n and ovf_leaf <= 1.0 * n, (ovf_sub / n, ovf_leaf / n)
     assert node_lanes / node_steps > 28 and leaf_lanes / leaf_steps > 28
-    if filt:
-        assert filter_lanes / filter_steps > 28
-        assert float(work[4]) == filter_lanes or float(work[4]) <= filter_lanes        # items of occluded rays are dropped before the test
-        assert float(work[0]) < 0.8 * float(work[4])                                    # at least a fifth of the items never open their node
-    else:
-        assert filter_steps == 0 and work[4] == 0
+    assert node_lanes == float(work[0]) or node_lanes >= float(work[0])              # items of occluded rays are dropped when popped

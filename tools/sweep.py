@@ -79,5 +79,5 @@ for combo in itertools.product(*values) if values else [()]:
     best = min(ms)
     print(json.dumps({"knobs": kw, "kernel_ms": best, "horizon_ms": round(st.horizon_ms, 2), "grays_per_s": n * S / best / 1e6, "grid": st.grid, "block": st.block,
                       "nodes_per_ray": round(st.node_visits / (n * S), 2), "tris_per_ray": round(st.tri_tests / (n * S), 2),
-                      "cands_per_ray": round(st.cand_tests / (n * S), 2), "traversed_frac": round(st.rays_traversed / (n * S), 3), "slab_tests_per_ray": round(st.slab_tests / (n * S), 2),
+                      "cands_per_ray": round(st.cand_tests / (n * S), 2), "traversed_frac": round(st.rays_traversed / (n * S), 3),
                       "all_ms": [round(m, 2) for m in ms]}), flush=True)

@@ -28,7 +28,6 @@ ap.add_argument("--near", type=int, default=157)
 ap.add_argument("--mid", type=int, default=12)
 ap.add_argument("--gain", type=float, default=0.2)
 ap.add_argument("--slabs", type=int, default=1)
-ap.add_argument("--wave-slabs", type=int, default=1, help="ray / slab culling of node visits in the traversal pass")
 ap.add_argument("--budget", type=int, default=64)
 a = ap.parse_args()
 
@@ -43,24 +42,14 @@ hz, _ = _maps(hc, h, pos[sel], nrm[sel], budget=a.budget, near=a.near, slabs=a.s
 need = ~(tab[None, :, 2] > hz[:, bins])
 need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
 keep = need.any(axis=1)                         # vertices the horizon pass finishes are never seen by the traversal pass
-work = np.zeros(5, np.uint64)
-hc.hc_wave_use_slabs(a.wave_slabs)
-hc.hc_wave_slab_culls.restype = __import__("ctypes").c_uint64
-hc.hc_wave_slab_culls(1)
+work = np.zeros(4, np.uint64)
 hc.hc_wave_step_stats.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
-_ss = np.zeros(10, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
+_ss = np.zeros(8, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
 got, vis = run_wave(hc, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(need_words[keep]), work=work)
-import ctypes
-ns = np.zeros(4, np.uint64)
-hc.hc_node_slab_study.argtypes = [ctypes.c_void_p, ctypes.c_int]
-hc.hc_node_slab_study(ns.ctypes.data, 1)
-print(json.dumps({"node_slab_study": {"node_visits": int(ns[0]), "culled_by_slab_in_frame_interval": float(ns[1]) / max(1.0, float(ns[0])),
-                                      "culled_by_slab_whole_ray": float(ns[2]) / max(1.0, float(ns[0])), "culled_by_slab_in_true_box_interval": float(ns[3]) / max(1.0, float(ns[0]))}}))
-print(json.dumps({"slab_filter_tests_per_ray": float(work[4]) / float(len(sel) * len(tab)), "culled_share": float(hc.hc_wave_slab_culls(0)) / max(1.0, float(work[4]))}))
 hc.hc_wave_step_stats(_ss.ctypes.data, 0)
-print(json.dumps({"steps_per_vertex": {k: round(float(_ss[2 * i]) / len(sel), 1) for i, k in enumerate(["filter", "leaf", "node", "scan"])},
-                  "stack_overflows_per_vertex": {"subtrees": round(float(_ss[8]) / len(sel), 3), "leaves": round(float(_ss[9]) / len(sel), 3)},
-                  "lanes_per_step": {k: round(float(_ss[2 * i + 1]) / max(1.0, float(_ss[2 * i])), 1) for i, k in enumerate(["filter", "leaf", "node", "scan"])}}))
+print(json.dumps({"steps_per_vertex": {k: round(float(_ss[2 * i]) / len(sel), 1) for i, k in enumerate(["leaf", "node", "scan"])},
+                  "stack_overflows_per_vertex": {"subtrees": round(float(_ss[6]) / len(sel), 3), "leaves": round(float(_ss[7]) / len(sel), 3)},
+                  "lanes_per_step": {k: round(float(_ss[2 * i + 1]) / max(1.0, float(_ss[2 * i])), 1) for i, k in enumerate(["leaf", "node", "scan"])}}))
 rays = float(len(sel) * len(tab))
 trav = float(work[3])
 print(json.dumps({"vertices": len(sel), "finished_by_horizon_pass": int((~keep).sum()), "rays_traversed_frac": trav / rays,
