@@ -54,8 +54,11 @@ int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
 /* name/value tuning knobs for experiments; unknown names and out-of-range values fail.  None of them changes a result
  * (tests/test_gpu_parity.py), only how the work is organised:
  *   horizon 0/1 (1)            per-origin horizon pass before the shadowed / interreflected bake
- *   horizon_near 5..95 (30)    subtrees of angular radius above value/100 rad are refined by the horizon builder
- *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex; 128 with horizon_near 20 suits 8192 samples
+ *   horizon_near 5..157 (157)  subtrees of angular radius above value/100 rad are always refined by the horizon builder
+ *   horizon_mid 0..157 (24)    ... and those above this radius when merging their bound would leave more than
+ *   horizon_gain (64)          this many tenths of a sample to trace (estimate; 0 = every such box); horizon_mid 0 = rule off
+ *   horizon_slabs 0/1 (1)      the builder bounds a subtree by its oriented slab (mean normal of its triangles) inside its box
+ *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex
  *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first (counting sort of the need counts); -1 = below ~1 M vertices
  *   l2_prefetch 0/1 (0)        stream the BVH into L2 before the first pass (measured: no effect, the cold-start misses are hidden)
  *   entry_list, pair_queue (0 per-ray stacks / 2 wavefront), refill_thresh, block, ctas_per_sm   the per-ray fallback kernel (S > 8192, horizon off)

@@ -46,7 +46,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 157, horizon_mid = 12, horizon_gain = 64 /* tenths of a sample */, horizon_slabs = 1, work_list_on = -1 /* -1 = auto */, l2_prefetch = 0;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 157, horizon_mid = 24, horizon_gain = 64 /* tenths of a sample */, horizon_slabs = 1, work_list_on = -1 /* -1 = auto */, l2_prefetch = 0;
     // cached sample table (the device copy is only replaced after the bake that last read it has finished: ev_tab)
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     std::vector<float> h_samples;

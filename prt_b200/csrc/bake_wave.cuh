@@ -51,6 +51,10 @@ struct WaveShared {
 #ifndef PRT_WAVE_STAT
 #define PRT_WAVE_STAT(counter, n)
 #endif
+// study hook of the CPU harness: may clear bits of the hit masks of a node step (models a tighter child test); nothing in a product build
+#ifndef PRT_WAVE_NODE_STUDY
+#define PRT_WAVE_NODE_STUDY(A, node, org, d, inner8, leaf8)
+#endif
 
 // 8 quantised child boxes of one node against a ray from the vertex (interval [0, inf)): traverse.cuh
 __device__ __forceinline__ uint32_t node_slots_hit(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o,
@@ -247,6 +251,7 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                         imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                         inner8 = hits & imask; leaf8 = hits & ~imask;
+                        PRT_WAVE_NODE_STUDY(A, it.y, org, d, inner8, leaf8);
                         if (COUNT) node_visits++;
                     }
                 }

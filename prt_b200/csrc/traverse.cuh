@@ -57,7 +57,10 @@ PRT_HD float safe_rcp(float d) {
 #define PRT_NODE_PRMT 3
 #endif
 #define PRT_Q2F_I2F(w, j) ((float)(((w) >> (8 * (j))) & 0xFFu))
-#if defined(__CUDACC__)
+#ifndef PRT_NODE_PRMT_REG
+#define PRT_NODE_PRMT_REG 1         // 0: the exponent word is an immediate again (A/B)
+#endif
+#if defined(__CUDACC__) && PRT_NODE_PRMT_REG
 static __constant__ uint32_t prt_q2f_exp = 0x47000000u;
 #endif
 #if defined(__CUDA_ARCH__)
@@ -85,8 +88,10 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
     const float fx = fmaf(-32768.0f, sx, ax) + gx, fy = fmaf(-32768.0f, sy, ay) + gy, fz = fmaf(-32768.0f, sz, az) + gz;
     const float mx = fmaf(-32768.0f, sx, ax) - gx, my = fmaf(-32768.0f, sy, ay) - gy, mz = fmaf(-32768.0f, sz, az) - gz;
     const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && PRT_NODE_PRMT_REG
     const uint32_t q2f_exp = prt_q2f_exp;
+#elif defined(__CUDA_ARCH__)
+    const uint32_t q2f_exp = 0x47000000u;
 #endif
     uint32_t hits = 0u;
 #pragma unroll

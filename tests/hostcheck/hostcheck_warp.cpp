@@ -28,6 +28,89 @@ extern "C" void hc_wave_step_stats(uint64_t *out, int reset) {
     for (int i = 0; i < 8; i++) { out[i] = *a[i]; if (reset) *a[i] = 0; }
 }
 #define PRT_WAVE_STAT(counter, n) (g_wave_stats.counter.fetch_add((n), std::memory_order_relaxed))
+// ---- study: a fourth slab axis per node (the node's mean normal m, shared by its eight children; every child carries its extent along m,
+// quantised to 8 bits over the node's own extent) tested together with the three box axes -- how many hit children would it remove?
+// mode 0: off, 1: quantised (255 steps, one step of padding either side), 2: exact child extents (upper bound of what the idea can do)
+#include "../../prt_b200/csrc/kernels.h"
+#include "../../prt_b200/csrc/traverse.cuh"
+namespace {
+int g_dop_mode = 0;
+std::vector<float> g_dop;          // [n_nodes][8][2] child extents along the parent's m
+std::atomic<uint64_t> g_dop_tests{0}, g_dop_culled_inner{0}, g_dop_culled_leaf{0};
+}
+namespace prt { namespace {
+inline void dop_study(const BakeArgs &A, uint32_t node, const f3 o, const f3 d, uint32_t &inner8, uint32_t &leaf8) {
+    if (!g_dop_mode || !A.slabs || g_dop.empty()) return;
+    const Slab32 &sl = A.slabs[node];
+    if (sl.mx == 0.f && sl.my == 0.f && sl.mz == 0.f) return;
+    const Node8 &nd = A.nodes[node];
+    const double so = (double)sl.mx * o.x + (double)sl.my * o.y + (double)sl.mz * o.z, sd = (double)sl.mx * d.x + (double)sl.my * d.y + (double)sl.mz * d.z;
+    const float lo3[3] = {nd.px, nd.py, nd.pz};
+    const float sc[3] = {PRT_U2F((uint32_t)nd.ex << 23), PRT_U2F((uint32_t)nd.ey << 23), PRT_U2F((uint32_t)nd.ez << 23)};
+    const uint8_t *ql[3] = {nd.qlox, nd.qloy, nd.qloz}, *qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    const double T = std::max((double)sl.d1 - (double)sl.d0, 1e-30), step = T / 255.0;
+    uint32_t bits = inner8 | leaf8;
+    while (bits) {
+        const int s = __builtin_ctz(bits); bits &= bits - 1u;
+        g_dop_tests++;
+        double t0 = 0.0, t1 = INFINITY;
+        for (int a = 0; a < 3; a++) {
+            const double id = 1.0 / (std::fabs(dd[a]) < 1e-18 ? 1e-18 : dd[a]);
+            const double ta = (lo3[a] + ql[a][s] * sc[a] - oo[a]) * id, tb = (lo3[a] + qh[a][s] * sc[a] - oo[a]) * id;
+            t0 = std::max(t0, std::min(ta, tb)); t1 = std::min(t1, std::max(ta, tb));
+        }
+        double lo = g_dop[((size_t)node * 8 + s) * 2], hi = g_dop[((size_t)node * 8 + s) * 2 + 1];
+        if (g_dop_mode == 1) {
+            lo = sl.d0 + (std::floor((lo - sl.d0) / step) - 1.0) * step; hi = sl.d0 + (std::ceil((hi - sl.d0) / step) + 1.0) * step;
+        }
+        // s(t) = so + t sd must meet [lo, hi] for some t in [t0, t1]
+        const double a = so + t0 * sd, b = so + (std::isfinite(t1) ? t1 * sd : (sd > 0 ? INFINITY : sd < 0 ? -INFINITY : 0.0));
+        if (std::max(a, b) < lo || std::min(a, b) > hi) {
+            if ((inner8 >> s) & 1u) { inner8 &= ~(1u << s); g_dop_culled_inner++; } else { leaf8 &= ~(1u << s); g_dop_culled_leaf++; }
+        }
+    }
+}
+} }
+#define PRT_WAVE_NODE_STUDY(A, node, org, d, inner8, leaf8) dop_study(A, node, org, d, inner8, leaf8)
+extern "C" void hc_dop_study(void *h, int mode, uint64_t *out) {
+    using namespace prt;
+    HostBVH8 *b = (HostBVH8 *)h;
+    if (out) { out[0] = g_dop_tests; out[1] = g_dop_culled_inner; out[2] = g_dop_culled_leaf; }
+    g_dop_tests = 0; g_dop_culled_inner = 0; g_dop_culled_leaf = 0;
+    g_dop_mode = mode;
+    if (!mode || !b || !b->slabs || !g_dop.empty()) return;
+    // triangle range below every node (children are emitted after their parent)
+    std::vector<uint32_t> lo(b->n_nodes, 0xFFFFFFFFu), hi(b->n_nodes, 0u);
+    for (uint32_t x = b->n_nodes; x-- > 0;) {
+        const Node8 &nd = b->nodes[x];
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            if ((nd.imask >> s) & 1) { const uint32_t ch = nd.child_base + rank++; lo[x] = std::min(lo[x], lo[ch]); hi[x] = std::max(hi[x], hi[ch]); }
+            else { const uint32_t t0 = nd.tri_base + (nd.meta[s] & 31u), cnt = (uint32_t)__builtin_popcount(nd.meta[s] >> 5); lo[x] = std::min(lo[x], t0); hi[x] = std::max(hi[x], t0 + cnt); }
+        }
+    }
+    g_dop.assign((size_t)b->n_nodes * 16, 0.f);
+    for (uint32_t x = 0; x < b->n_nodes; x++) {
+        const Node8 &nd = b->nodes[x];
+        const Slab32 &sl = b->slabs[x];
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; s++) {
+            if (!nd.meta[s]) continue;
+            uint32_t t0, t1;
+            if ((nd.imask >> s) & 1) { const uint32_t ch = nd.child_base + rank++; t0 = lo[ch]; t1 = hi[ch]; }
+            else { t0 = nd.tri_base + (nd.meta[s] & 31u); t1 = t0 + (uint32_t)__builtin_popcount(nd.meta[s] >> 5); }
+            double mn = 3e38, mx = -3e38;
+            for (uint32_t t = t0; t < t1; t++) {
+                const Tri48 &T = b->tris[t];
+                const double v[3][3] = {{T.v0x, T.v0y, T.v0z}, {T.v0x + T.e1x, T.v0y + T.e1y, T.v0z + T.e1z}, {T.v0x + T.e2x, T.v0y + T.e2y, T.v0z + T.e2z}};
+                for (int k = 0; k < 3; k++) { const double q = sl.mx * v[k][0] + sl.my * v[k][1] + sl.mz * v[k][2]; mn = std::min(mn, q); mx = std::max(mx, q); }
+            }
+            g_dop[((size_t)x * 8 + s) * 2] = (float)(mn - b->pad); g_dop[((size_t)x * 8 + s) * 2 + 1] = (float)(mx + b->pad);
+        }
+    }
+}
 #include "../../prt_b200/csrc/entry_list.cuh"
 #include "../../prt_b200/csrc/horizon.cuh"
 #include "../../prt_b200/csrc/bake_wave.cuh"
@@ -38,7 +121,7 @@ extern "C" void hc_wave_step_stats(uint64_t *out, int reset) {
 using namespace prt;
 
 // oriented slabs of the nodes (bvh8.h) in the horizon builder: on by default, as in the product; the studies switch them off to compare
-namespace { bool g_use_slabs = true; int g_mid100 = 12; float g_gain = 0.2f; }
+namespace { bool g_use_slabs = true; int g_mid100 = 24; float g_gain = 0.2f; }
 extern "C" void hc_use_slabs(int on) { g_use_slabs = on != 0; }
 // refinement rule for mid-sized boxes (build_horizon: mid2, gain_min): angular radius x 100 (0 = rule off), gain in units of S / 32 samples
 extern "C" void hc_horizon_mid(int mid100, float gain) { g_mid100 = mid100; g_gain = gain; }
@@ -136,6 +219,7 @@ extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_
     A.out = out; A.vis = vis; A.vis_words = (S + 31) / 32;
     A.need_bits = const_cast<uint32_t *>(need_bits);
     A.origin_eps = origin_eps; A.cs_phase = cs_phase;
+    A.slabs = b->slabs;                 // the traversal pass does not read them; the DOP study hook does
     switch (order) {
     case 1: run_wave<1, false>(A, nullptr); break;
     case 2: run_wave<2, false>(A, nullptr); break;

@@ -110,7 +110,7 @@ def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     try:
         got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(samples_u=16, samples_v=16), want_vis=True)
     finally:
-        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, work_list=-1, horizon_near=157, horizon_mid=12, horizon_gain=64, horizon_slabs=1)
+        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, work_list=-1, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1)
     ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(samples_u=16, samples_v=16), want_vis=True)
     assert np.array_equal(gvis, ovis)
     assert rel_l2(got, ref).max() <= REL_L2_TOL
@@ -333,6 +333,6 @@ def test_horizon_map_is_conservative_on_adversarial_scenes(prt, oracle, case):
         try:
             got, gvis = prt.bake_transfer(gs, org, nrm, prt.BakeParams.make(**kw), want_vis=True)
         finally:
-            gs.ctx.set_tuning(horizon=1, horizon_budget=64, horizon_near=157, horizon_mid=12, horizon_gain=64, horizon_slabs=1)
+            gs.ctx.set_tuning(horizon=1, horizon_budget=64, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1)
         assert np.array_equal(gvis, ovis), f"{case} {knobs}: {np.count_nonzero(gvis != ovis)} visibility words differ"
         assert rel_l2(got, ref)[np.linalg.norm(ref, axis=1) > 1e-3].max(initial=0) <= REL_L2_TOL

@@ -278,8 +278,8 @@ def test_builder_slabs_contain_their_triangles(hostcheck):
 
 
 # ---- the warp-cooperative builder itself, run on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) --------------------
-def _maps(hostcheck, h, pos, nrm, budget=64, near=157, eps=1e-4, stats=None, slabs=1, mid=12, gain=0.2):
-    """defaults = the product's (abi.cu: horizon_near 157, horizon_mid 12, horizon_gain 6.4 samples = 0.2 x 1024 / 32, slabs on)"""
+def _maps(hostcheck, h, pos, nrm, budget=64, near=157, eps=1e-4, stats=None, slabs=1, mid=24, gain=0.2):
+    """defaults = the product's (abi.cu: horizon_near 157, horizon_mid 24, horizon_gain 6.4 samples = 0.2 x 1024 / 32, slabs on)"""
     n = len(pos)
     hostcheck.hc_use_slabs(slabs)
     hostcheck.hc_horizon_mid(mid, gain)

@@ -27,7 +27,7 @@ ap.add_argument("--n", type=int, default=200)
 ap.add_argument("--near", default="157")
 ap.add_argument("--budget", type=int, default=64)
 ap.add_argument("--folds", action="store_true", help="the heavily self-occluding twin of the bench mesh (amp 0.25, fscale 3)")
-ap.add_argument("--mid", default="12", help="mid-size refinement rule: angular radius x 100 (0 = off), comma list")
+ap.add_argument("--mid", default="24", help="mid-size refinement rule: angular radius x 100 (0 = off), comma list")
 ap.add_argument("--gain", default="0.2", help="... its threshold in units of S / 32 samples, comma list")
 ap.add_argument("--slabs", default="1", help="oriented slabs of the nodes in the builder: 1, 0 or 0,1 to compare")
 a = ap.parse_args()

@@ -3,7 +3,7 @@
 the warp emulator (tests/hostcheck) for a Morton-strided sample of the bench mesh and prints the work counters bench.py reports
 from an instrumented GPU launch (node visits, triangle tests, entry-list box tests per ray, share of rays traversed), so that
 algorithmic changes can be scored before any GPU time is spent.
-Usage: python tools/wave_study.py [--nu 737 --nv 737] [--n 96] [--near 157 --mid 12 --gain 0.2 --slabs 1] [--budget 64]  (old builder: --near 30 --mid 0 --slabs 0)"""
+Usage: python tools/wave_study.py [--nu 737 --nv 737] [--n 96] [--near 157 --mid 24 --gain 0.2 --slabs 1] [--budget 64]  (old builder: --near 30 --mid 0 --slabs 0)"""
 import argparse
 import json
 import os
@@ -25,9 +25,10 @@ ap.add_argument("--nu", type=int, default=737)
 ap.add_argument("--nv", type=int, default=737)
 ap.add_argument("--n", type=int, default=96)
 ap.add_argument("--near", type=int, default=157)
-ap.add_argument("--mid", type=int, default=12)
+ap.add_argument("--mid", type=int, default=24)
 ap.add_argument("--gain", type=float, default=0.2)
 ap.add_argument("--slabs", type=int, default=1)
+ap.add_argument("--dop", type=int, default=0, help="study: fourth slab axis per node in the child test (1 quantised, 2 exact extents)")
 ap.add_argument("--budget", type=int, default=64)
 a = ap.parse_args()
 
@@ -43,10 +44,16 @@ need = ~(tab[None, :, 2] > hz[:, bins])
 need_words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
 keep = need.any(axis=1)                         # vertices the horizon pass finishes are never seen by the traversal pass
 work = np.zeros(4, np.uint64)
+hc.hc_dop_study.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_void_p]
+hc.hc_dop_study(h, a.dop, None)
 hc.hc_wave_step_stats.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
 _ss = np.zeros(8, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
 got, vis = run_wave(hc, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(need_words[keep]), work=work)
 hc.hc_wave_step_stats(_ss.ctypes.data, 0)
+_ds = np.zeros(3, np.uint64); hc.hc_dop_study(h, 0, _ds.ctypes.data)
+if a.dop:
+    print(json.dumps({"dop_study": {"mode": a.dop, "hit_children_tested": int(_ds[0]), "culled_inner_share": float(_ds[1]) / max(1.0, float(_ds[0])),
+                                    "culled_leaf_share": float(_ds[2]) / max(1.0, float(_ds[0]))}}))
 print(json.dumps({"steps_per_vertex": {k: round(float(_ss[2 * i]) / len(sel), 1) for i, k in enumerate(["leaf", "node", "scan"])},
                   "stack_overflows_per_vertex": {"subtrees": round(float(_ss[6]) / len(sel), 3), "leaves": round(float(_ss[7]) / len(sel), 3)},
                   "lanes_per_step": {k: round(float(_ss[2 * i + 1]) / max(1.0, float(_ss[2 * i])), 1) for i, k in enumerate(["leaf", "node", "scan"])}}))
