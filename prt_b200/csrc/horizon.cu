@@ -18,7 +18,8 @@ namespace prt {
 namespace {
 
 #ifndef PRT_HZ_MINB
-#define PRT_HZ_MINB 9               // CTAs per SM the register allocation aims at (56 registers; 10 CTAs at 48 registers measured 3 % slower)
+#define PRT_HZ_MINB 8               // CTAs per SM the register allocation aims at (64 registers; with the slab bound of round 2: 9 CTAs at 56 registers
+                                    // 5.70 ms, 8 CTAs 5.58 ms on the headline bake; round 1, before it: 9 CTAs best, 10 CTAs at 48 registers 3 % slower)
 #endif
 
 template <int ORDER>
