@@ -103,7 +103,13 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
         const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 0
+#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 3
+            // near plane (I2F, offset a) and far plane (byte permute, offset f) of an axis in one packed FFMA2
+            const float2 tx = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearx, j), PRT_Q2F_PRMT(farx, j)), make_float2(sx, sx), make_float2(ax, fx));
+            const float2 ty = __ffma2_rn(make_float2(PRT_Q2F_I2F(neary, j), PRT_Q2F_PRMT(fary, j)), make_float2(sy, sy), make_float2(ay, fy));
+            const float2 tz = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearz, j), PRT_Q2F_PRMT(farz, j)), make_float2(sz, sz), make_float2(az, fz));
+            const float t0x = tx.x, t1x = tx.y, t0y = ty.x, t1y = ty.y, t0z = tz.x, t1z = tz.y;
+#elif defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 0
             const float2 tx = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearx, j), PRT_Q2F_I2F(farx, j)), make_float2(sx, sx), make_float2(ax, ax));
             const float2 ty = __ffma2_rn(make_float2(PRT_Q2F_I2F(neary, j), PRT_Q2F_I2F(fary, j)), make_float2(sy, sy), make_float2(ay, ay));
             const float2 tz = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearz, j), PRT_Q2F_I2F(farz, j)), make_float2(sz, sz), make_float2(az, az));
