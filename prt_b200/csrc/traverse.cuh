@@ -49,9 +49,12 @@ PRT_HD float safe_rcp(float d) {
 // node), so the test stays conservative whatever the node's size -- box tests only ever have to be conservative.
 // Measured on the headline bake (profiles/r2_node_test_ab.jsonl, step ms): n = 0: 51.1, 3: 49.8, 6: 50.4 -- balancing the two pipes is
 // what pays: far planes through the ALU, near planes on the XU.  PRT_NODE_FFMA2 pairs the two planes of an axis in one packed
-// fma.rn.f32x2 (sm_100a): no gain, the FMA pipe (25 %) is not what binds.
+// fma.rn.f32x2 (sm_100a; near plane from I2F with offset a, far plane from the byte permute with offset f): 24 FFMA2 instead of 48 FFMA per
+// node test, 24 instructions net after the moves that build the operand pairs.  With all six planes on I2F (first half of round 2) it
+// gained nothing -- the XU pipe was what bound; with the 3 / 3 split it is -1.8 % on the headline step (45.66 -> 44.85 ms) and -1.7 % on
+// the folded mesh (profiles/r2_ffma2_ab.jsonl).  The host build (tests/hostcheck) evaluates the same expressions with scalar fmaf.
 #ifndef PRT_NODE_FFMA2
-#define PRT_NODE_FFMA2 0
+#define PRT_NODE_FFMA2 1
 #endif
 #ifndef PRT_NODE_PRMT
 #define PRT_NODE_PRMT 3
