@@ -117,8 +117,15 @@ __device__ __forceinline__ void entry_list_leaf_mask(const EntryList &W, const i
 }
 
 // approximate reciprocal for box tests only (never used by the pinned triangle test)
+#ifndef PRT_RCP_FMNMX
+#define PRT_RCP_FMNMX 1
+#endif
 __device__ __forceinline__ float rcp_box(float d) {
+#if PRT_RCP_FMNMX
+    d = copysignf(fmaxf(fabsf(d), 1e-18f), d);              // one FMNMX + one LOP3 (a NaN direction becomes 1e-18)
+#else
     if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+#endif
 #if defined(__CUDA_ARCH__)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));

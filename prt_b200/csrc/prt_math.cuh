@@ -96,11 +96,35 @@ PRT_HD Frame make_frame(f3 N) {
     f.n = N;
     return f;
 }
+// Packed variants (sm_100a, fma.rn.f32x2 / mul.rn.f32x2): component-wise the SAME IEEE operations in the same order, so the results
+// are bit-identical to the scalar forms -- only the number of issue slots changes.  The host build keeps the scalar forms.
+// Measured on the headline bake (profiles/r2_packed_math_ab.jsonl): 44.87 -> 44.50 ms, with the FMNMX clamp of rcp_box 44.39 ms.
+#ifndef PRT_PACKED_MATH
+#define PRT_PACKED_MATH 1
+#endif
+struct fpair { float x, y; };
+#if defined(__CUDA_ARCH__) && PRT_PACKED_MATH
+__device__ __forceinline__ f3 to_world(const Frame &f, f3 l) {
+    float2 t = __fmul2_rn(make_float2(f.right.x, f.right.y), make_float2(l.x, l.x));
+    t = __ffma2_rn(make_float2(f.up.x, f.up.y), make_float2(l.y, l.y), t);
+    t = __ffma2_rn(make_float2(f.n.x, f.n.y), make_float2(l.z, l.z), t);
+    return mk3(t.x, t.y, PRT_FMA(f.n.z, l.z, PRT_FMA(f.up.z, l.y, PRT_MUL(f.right.z, l.x))));
+}
+// (dot3(a, c), dot3(b, c))
+__device__ __forceinline__ fpair dot3_pair(f3 a, f3 b, f3 c) {
+    float2 t = __fmul2_rn(make_float2(a.x, b.x), make_float2(c.x, c.x));
+    t = __ffma2_rn(make_float2(a.y, b.y), make_float2(c.y, c.y), t);
+    t = __ffma2_rn(make_float2(a.z, b.z), make_float2(c.z, c.z), t);
+    fpair r; r.x = t.x; r.y = t.y; return r;
+}
+#else
 PRT_HD f3 to_world(const Frame &f, f3 l) {
     return mk3(PRT_FMA(f.n.x, l.z, PRT_FMA(f.up.x, l.y, PRT_MUL(f.right.x, l.x))),
                PRT_FMA(f.n.y, l.z, PRT_FMA(f.up.y, l.y, PRT_MUL(f.right.y, l.x))),
                PRT_FMA(f.n.z, l.z, PRT_FMA(f.up.z, l.y, PRT_MUL(f.right.z, l.x))));
 }
+PRT_HD fpair dot3_pair(f3 a, f3 b, f3 c) { fpair r; r.x = dot3(a, c); r.y = dot3(b, c); return r; }
+#endif
 
 // Philox4x32-10 (Random123 constants); integer only.
 PRT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {

@@ -142,11 +142,11 @@ PRT_HD bool tri_hit_regs(const u4 a, const u4 b, const u4 c, f3 o, f3 d, float t
     const f3 e2 = mk3(PRT_U2F(c.x), PRT_U2F(c.y), PRT_U2F(c.z));
     const f3 tv = sub3(o, v0);
     const f3 pv = cross3(d, e2);
-    const float det = dot3(e1, pv);
-    const float U = dot3(tv, pv);
+    const fpair du = dot3_pair(e1, tv, pv);          // the two dot products with pv, and below the two with qv, share their packed ops
+    const float det = du.x, U = du.y;
     const f3 qv = cross3(tv, e1);
-    const float V = dot3(d, qv);
-    const float T = dot3(e2, qv);
+    const fpair vt = dot3_pair(d, e2, qv);
+    const float V = vt.x, T = vt.y;
     const uint32_t sgn = PRT_F2U(det) & 0x80000000u;
     const float ad = fabsf(det);
     const float Us = PRT_U2F(PRT_F2U(U) ^ sgn), Vs = PRT_U2F(PRT_F2U(V) ^ sgn), Ts = PRT_U2F(PRT_F2U(T) ^ sgn);
