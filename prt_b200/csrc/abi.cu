@@ -78,6 +78,7 @@ void prt_ctx_timer_end(prt_ctx *c, cudaStream_t st) { cudaEventRecord(c->ev_p1, 
 cudaStream_t prt_ctx_stream(prt_ctx *c) { return c->stream; }
 int prt_ctx_sms(const prt_ctx *c) { return c->n_sms; }
 int prt_ctx_refill_thresh(const prt_ctx *c) { return c->refill_thresh; }
+int prt_ctx_entry_list(const prt_ctx *c) { return c->entry_list; }
 prt_scene_view prt_scene_get_view(prt_scene *s) { return prt_scene_view{s->d_nodes, s->d_tris, s->ctx}; }
 
 // host BVH build shared by prt_scene_create and prt_group_scene_create (one build, one upload per GPU)

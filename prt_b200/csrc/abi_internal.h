@@ -9,6 +9,7 @@ int prt_set_error(int code, const std::string &msg);   // records the thread-loc
 cudaStream_t prt_ctx_stream(prt_ctx *);                // the context's own stream
 int prt_ctx_sms(const prt_ctx *);
 int prt_ctx_refill_thresh(const prt_ctx *);            // tuning knob: refill idle lanes when fewer than this many are traversing
+int prt_ctx_entry_list(const prt_ctx *);               // tuning knob: per-origin entry lists (vertex bakes, probe capture)
 
 // grow-only device scratch owned by the context (8 slots; nullptr when the allocation fails) and the phase timer behind
 // prt_ctx_last_kernel_ms: entry points outside the bake bracket their kernels with begin / end on the stream they launch on

@@ -19,6 +19,7 @@
 #include "bvh8.h"
 #include "traverse.cuh"
 #include "kernels.h"
+#include "entry_list.cuh"
 
 #include <algorithm>
 #include <cuda_runtime.h>
@@ -39,6 +40,7 @@ struct CaptureArgs {
     const float4 *dirs;          // xyz = direction, w = solid angle
     uint32_t n_dirs;
     int refill_thresh;
+    int entry_list;              // per-probe entry list (tuning knob entry_list)
     const uint32_t *order;       // [n_dirs] trace slot -> ray index (directions sorted along a space-filling curve: coherent warps)
     uint32_t *ticket;            // [1] zeroed
     uint32_t *counts;            // [n_probes] entries (clusters) of each probe
@@ -124,7 +126,13 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
     float *tt = reinterpret_cast<float *>(sk + kMaxRays);                          // [4096] hit distance by ray
     uint32_t *tri = reinterpret_cast<uint32_t *>(tt + kMaxRays);                   // [4096] hit triangle slot by ray
     float *s_lead = reinterpret_cast<float *>(tri + kMaxRays);                      // [kThreads][16] partial sums handed to an earlier chunk
-    __shared__ uint32_t s_probe, s_next, s_counts[kThreads], s_through[kThreads];
+    // s_counts / s_through (reduction phase) share their 4 KB with the probe's entry list (trace phase)
+    __shared__ __align__(16) unsigned char s_aux[2 * kThreads * sizeof(uint32_t)];
+    static_assert(sizeof(EntryList) <= sizeof(s_aux), "the entry list aliases the reduction counters");
+    uint32_t *const s_counts = reinterpret_cast<uint32_t *>(s_aux), *const s_through = s_counts + kThreads;
+    EntryList &EL = *reinterpret_cast<EntryList *>(s_aux);
+    __shared__ uint32_t s_probe, s_next;
+    __shared__ int s_ncand;
     const int tid = threadIdx.x;
 
     for (;;) {
@@ -140,9 +148,17 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
         // [0, closest t], a leaf step runs the pinned triangle tests and lowers the slot's (t, prim) key with a 64-bit atomicMin;
         // a slot whose outstanding-item count reaches zero is finished, stored and refilled.  Per-ray stacks ran this phase at
         // 12.5 of 32 active lanes (profiles/r1_probe_capture_ncu_summary.txt).
+        // Per-origin entry list (entry_list.cuh, as in the vertex bakes): all rays of a probe share its position, so the chain of nodes
+        // containing it is expanded ONCE, by warp 0, into candidate boxes; a ray then starts at the candidates it hits instead of repeating
+        // the descent from the root.  No tangent plane here (normal 0: nothing is culled).
         for (int i = tid; i < kMaxRays; i += kThreads) sk[i] = kInvalid;
         if (tid == 0) s_next = 0u;
+        if (tid < 32) {
+            const int nc = A.entry_list ? build_entry_list(A.nodes, P, mk3(0.f, 0.f, 0.f), EL, tid) : 0;
+            if (tid == 0) s_ncand = nc;
+        }
         __syncthreads();
+        const int n_cand = s_ncand;
         {
             const int lane = tid & 31;
             const unsigned lt_mask = (1u << lane) - 1u;
@@ -151,7 +167,26 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
             __syncwarp();
             int nn = 0, ln = 0;
             bool exhausted = false;
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u;                                  // candidate hits of the lane's new ray not yet queued
             for (uint32_t guard = 0; guard < (1u << 22); guard++) {               // (bounded: a logic error must not hang the device)
+                // emit pending (slot, candidate) items while one more warp-wide append fits
+                bool pending = __any_sync(0xFFFFFFFFu, (m0 | m1 | m2) != 0u);
+                while (pending && nn <= kWaveCap - 32 && ln <= kWaveCap - 32) {
+                    int k = -1;
+                    if (m0) { k = __ffs(m0) - 1; m0 &= m0 - 1u; }
+                    else if (m1) { k = 32 + __ffs(m1) - 1; m1 &= m1 - 1u; }
+                    else if (m2) { k = 64 + __ffs(m2) - 1; m2 &= m2 - 1u; }
+                    const bool hasc = k >= 0;
+                    const float4 g = EL.cb[hasc ? k : 0];
+                    const uint32_t gx = __float_as_uint(g.z), gy = __float_as_uint(g.w);
+                    const bool leafc = hasc && gy <= 0x00FFFFFFu;
+                    const unsigned hb = __ballot_sync(0xFFFFFFFFu, hasc), lb = __ballot_sync(0xFFFFFFFFu, leafc), ib = hb & ~lb;
+                    if (leafc) W.lq[ln + __popc(lb & lt_mask)] = make_uint2((uint32_t)lane | (gy << 16), gx);
+                    else if (hasc) W.nq[nn + __popc(ib & lt_mask)] = make_uint2((uint32_t)lane, gx);
+                    ln += __popc(lb); nn += __popc(ib);
+                    pending = __any_sync(0xFFFFFFFFu, (m0 | m1 | m2) != 0u);
+                }
+                __syncwarp();
                 // finished slots: store the hit, free the slot
                 const uint32_t myray = W.ray[lane];
                 const bool fin = myray != kFreeSlot && W.refc[lane] == 0;
@@ -178,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
                 __syncwarp();
                 // refill free slots while rays remain and one warp-wide push fits
                 const unsigned freeb = __ballot_sync(0xFFFFFFFFu, W.ray[lane] == kFreeSlot);
-                if (freeb && !exhausted && nn <= kWaveCap - 32) {
+                if (freeb && !exhausted && !pending && nn <= kWaveCap - 32) {
                     uint32_t base = 0u;
                     if (lane == 0) base = atomicAdd(&s_next, (uint32_t)__popc(freeb));
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -188,15 +223,24 @@ __global__ void __launch_bounds__(kThreads, 2) probe_capture_kernel(const Captur
                         const uint32_t r = __ldg(&A.order[base + slot_rank]);          // results are stored by ray index, so the
                         const float4 dw = __ldg(&A.dirs[r]);                           // trace order does not change them
                         W.dir[lane] = make_float4(dw.x, dw.y, dw.z, 0.f);
-                        W.best[lane] = kNoHit; W.refc[lane] = 1; W.ray[lane] = r;
+                        W.best[lane] = kNoHit; W.ray[lane] = r;
+                        if (n_cand > 0) {
+                            uint32_t cm[3];
+                            scan_entry_list(EL, n_cand, rcp_dir(dw.x), rcp_dir(dw.y), rcp_dir(dw.z), cm);
+                            m0 = cm[0]; m1 = cm[1]; m2 = cm[2];
+                            W.refc[lane] = __popc(m0) + __popc(m1) + __popc(m2);     // 0: the ray misses everything (sky), finished at once
+                        } else W.refc[lane] = 1;
                     }
-                    const unsigned tb = __ballot_sync(0xFFFFFFFFu, take);
-                    if (take) W.nq[nn + __popc(tb & lt_mask)] = make_uint2((uint32_t)lane, 0u);      // start at the root
-                    nn += __popc(tb);
+                    if (n_cand == 0) {
+                        const unsigned tb = __ballot_sync(0xFFFFFFFFu, take);
+                        if (take) W.nq[nn + __popc(tb & lt_mask)] = make_uint2((uint32_t)lane, 0u);      // no entry list: start at the root
+                        nn += __popc(tb);
+                    }
                     exhausted = base + (uint32_t)__popc(freeb) >= A.n_dirs;
                 }
                 __syncwarp();
                 if (nn == 0 && ln == 0) {
+                    if (__any_sync(0xFFFFFFFFu, (m0 | m1 | m2) != 0u)) continue;            // items of the rays just scanned are emitted first
                     if (exhausted && __all_sync(0xFFFFFFFFu, W.ray[lane] == kFreeSlot)) break;
                     if (exhausted && !__any_sync(0xFFFFFFFFu, W.ray[lane] != kFreeSlot && W.refc[lane] != 0)) continue;   // only finished slots left
                     continue;
@@ -607,7 +651,7 @@ int prt_probe_capture(prt_scene *scene, const float *probe_pos, uint32_t n_probe
     cudaMemsetAsync(overflow, 0, 4, st);
 
     CaptureArgs A{};
-    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order; A.refill_thresh = prt_ctx_refill_thresh(sv.ctx);
+    A.nodes = sv.nodes; A.tris = sv.tris; A.probe_pos = d_pos; A.n_probes = n_probes; A.dirs = (const float4 *)d_dirs; A.n_dirs = n_dirs; A.order = d_order; A.refill_thresh = prt_ctx_refill_thresh(sv.ctx); A.entry_list = prt_ctx_entry_list(sv.ctx);
     A.ticket = ticket; A.counts = counts; A.ekeys = skeys; A.etransfer = stransfer; A.eacc = sacc_stage;
     const size_t smem = (size_t)kMaxRays * (8 + 4 + 4) + std::max((size_t)kThreads * 16 * 4, sizeof(TraceShared) * (size_t)(kThreads / 32));
     static std::atomic<unsigned long long> configured{0};      // one bit per device
