@@ -147,7 +147,11 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                 pending = __any_sync(kFull, (m0 | m1 | m2) != 0u);
             }
             // ---- classify samples: a ray above the horizon of its azimuth bin is visible without any test ---------------
+#ifdef PRT_WAVE_ROOM
+            const bool room = nn <= PRT_WAVE_ROOM && ln <= PRT_WAVE_ROOM;              // absolute admission threshold (A/B builds)
+#else
             const bool room = nn <= kNodeCap * PRT_WAVE_ROOM8 / 8 && ln <= kLeafCap * PRT_WAVE_ROOM8 / 8;
+#endif
             if (!pending && room) {
                 while (base < S && npend < 32) {
                     const int i = base + lane;

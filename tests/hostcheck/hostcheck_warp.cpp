@@ -296,7 +296,7 @@ extern "C" int hc_entry_list(void *h, const float *pos, const float *nrm, float 
     for (auto &t : lanes) t.join();
     warp_emu::g_state = nullptr;
     for (int k = 0; k < n_cand; k++) {
-        const float rec[8] = {el.ca[k].x, el.ca[k].y, el.ca[k].z, el.ca[k].w, el.cb[k].x, el.cb[k].y, el.cb[k].z, el.cb[k].w};
+        const float rec[8] = {el.ca[k].x, el.ca[k].y, el.ca[k].z, el.cb[k].x, el.cb[k].y, el.ca[k].w, el.cb[k].z, el.cb[k].w};     // centre, half extents x y z, group
         std::memcpy(out + 8 * k, rec, sizeof rec);
     }
     return n_cand;
