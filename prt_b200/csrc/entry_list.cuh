@@ -412,6 +412,10 @@ __device__ __forceinline__ void scan_entry_list_culled(const EntryList &W, const
 #ifndef PRT_SCAN_PACKED
 #define PRT_SCAN_PACKED 1
 #endif
+#ifndef PRT_SCAN_UNROLL
+#define PRT_SCAN_UNROLL 2
+#endif
+constexpr int kScanUnroll = PRT_SCAN_UNROLL;
 __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n, const float idx, const float idy, const float idz, uint32_t m[3]) {
     const float aix = fabsf(idx), aiy = fabsf(idy), aiz = fabsf(idz);
 #if defined(__CUDA_ARCH__) && PRT_SCAN_PACKED
@@ -421,10 +425,7 @@ __device__ __forceinline__ void scan_entry_list(const EntryList &W, const int n,
     for (int w = 0; w < 3; w++) {
         uint32_t bits = 0u, bit = 1u;
         const int k1 = min(n, 32 * (w + 1));
-#ifndef PRT_SCAN_UNROLL
-#define PRT_SCAN_UNROLL 2
-#endif
-#pragma unroll PRT_SCAN_UNROLL
+#pragma unroll kScanUnroll
         for (int k = 32 * w; k < k1; k++) {
             const float4 a = W.ca[k], b = W.cb[k];
 #if defined(__CUDA_ARCH__) && PRT_SCAN_PACKED
