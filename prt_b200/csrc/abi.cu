@@ -46,7 +46,7 @@ struct prt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evh = nullptr;
     // tuning
-    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 157, horizon_mid = 24, horizon_gain = 64 /* tenths of a sample */, horizon_slabs = 1, work_list_on = -1 /* -1 = auto */, l2_prefetch = 0;
+    int block = 256, ctas_per_sm = 0 /* 0 = occupancy */, refill_thresh = 8, count_work = 0, entry_list = 1, pair_queue = 2, horizon = 1, horizon_budget = 64, horizon_near = 157, horizon_mid = 24, horizon_gain = 64 /* tenths of a sample */, horizon_slabs = 1, wave_dop = 1, work_list_on = -1 /* -1 = auto */, l2_prefetch = 0;
     // cached sample table (the device copy is only replaced after the bake that last read it has finished: ev_tab)
     DevBuf samples; int s_ru = -1, s_rv = -1, s_jit = -1; uint32_t s_seed = 0;
     std::vector<float> h_samples;
@@ -64,6 +64,7 @@ struct prt_scene {
     Node8 *d_nodes = nullptr;
     Tri48 *d_tris = nullptr;
     Slab32 *d_slabs = nullptr;          // oriented slab of every node (horizon pass)
+    Dop32 *d_dops = nullptr;            // fourth slab axis of every node (traversal pass)
     prt_scene_info info{};
 };
 
@@ -105,6 +106,10 @@ int prt_scene_from_host_bvh(prt_ctx *c, const HostBVH8 *hp, prt_scene **out) {
         e = cudaMalloc(&s->d_slabs, sizeof(Slab32) * (size_t)h.n_nodes);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_slabs, h.slabs, sizeof(Slab32) * (size_t)h.n_nodes, cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && h.dops) {
+        e = cudaMalloc(&s->d_dops, sizeof(Dop32) * (size_t)h.n_nodes);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_dops, h.dops, sizeof(Dop32) * (size_t)h.n_nodes, cudaMemcpyHostToDevice);
+    }
     s->info.n_tris = h.n_tris; s->info.n_nodes = h.n_nodes; s->info.max_depth = h.max_depth;
     s->info.node_bytes = sizeof(Node8) * (uint64_t)h.n_nodes; s->info.tri_bytes = sizeof(Tri48) * (uint64_t)h.n_tris;
     s->info.build_seconds = h.build_seconds; s->info.sah_cost = h.sah_cost;
@@ -113,6 +118,7 @@ int prt_scene_from_host_bvh(prt_ctx *c, const HostBVH8 *hp, prt_scene **out) {
         if (s->d_nodes) cudaFree(s->d_nodes);
         if (s->d_tris) cudaFree(s->d_tris);
         if (s->d_slabs) cudaFree(s->d_slabs);
+        if (s->d_dops) cudaFree(s->d_dops);
         delete s;
         return set_err(e == cudaErrorMemoryAllocation ? PRT_ERR_NOMEM : PRT_ERR_CUDA, std::string("prt_scene_create: ") + cudaGetErrorString(e));
     }
@@ -204,6 +210,7 @@ int prt_ctx_set_tuning(prt_ctx *c, const char *name, int value) {
     else if (n == "horizon_mid") { if (value < 0 || value > 157) return set_err(PRT_ERR_INVALID, "horizon_mid (angular radius x100, rad; 0 = off) must be in [0,157]"); c->horizon_mid = value; }
     else if (n == "horizon_gain") { if (value < 0 || value > 1000000) return set_err(PRT_ERR_INVALID, "horizon_gain (tenths of a sample) must be in [0,1000000]"); c->horizon_gain = value; }
     else if (n == "horizon_slabs") c->horizon_slabs = value ? 1 : 0;
+    else if (n == "wave_dop") c->wave_dop = value ? 1 : 0;
     else if (n == "horizon_budget") { if (value < 0 || value > 4096) return set_err(PRT_ERR_INVALID, "horizon_budget must be in [0,4096]"); c->horizon_budget = value; }
     else if (n == "pair_queue") { if (value != 0 && value != 2) return set_err(PRT_ERR_INVALID, "pair_queue must be 0 (per-ray stacks) or 2 (wavefront)"); c->pair_queue = value; }
     else return set_err(PRT_ERR_INVALID, "prt_ctx_set_tuning: unknown knob " + n);
@@ -227,6 +234,7 @@ void prt_scene_destroy(prt_scene *s) {
     if (s->d_nodes) cudaFree(s->d_nodes);
     if (s->d_tris) cudaFree(s->d_tris);
     if (s->d_slabs) cudaFree(s->d_slabs);
+    if (s->d_dops) cudaFree(s->d_dops);
     delete s;
 }
 
@@ -391,6 +399,7 @@ int prt_bake_device(prt_ctx *c, prt_scene *sc, const float *d_pos, const float *
     if (c->horizon_mid > 0) { const float sn = sinf(0.01f * (float)c->horizon_mid); A.horizon_mid2 = 1.0f / (sn * sn); }
     A.horizon_gain = 0.1f * (float)c->horizon_gain * (float)kHzBins / (float)S;         // samples -> units of S / kHzBins (hz_gain)
     A.slabs = (sc && c->horizon_slabs) ? sc->d_slabs : nullptr;
+    A.dops = (sc && c->wave_dop) ? sc->d_dops : nullptr;
     CU_TRY(cudaMemsetAsync(A.counter, 0, 128, st));
     if (d_vis) CU_TRY(cudaMemsetAsync(d_vis, 0, (size_t)n * A.vis_words * 4, st));
     uint32_t prefetched = 0;

@@ -29,7 +29,8 @@ namespace prt {
 namespace {
 
 // COUNT: carry the work counters (an instrumented, untimed launch of bench.py); the timed variant keeps those registers free
-template <int ORDER, bool TRACE, bool COUNT>
+// DOP: the node test includes the fourth slab axis of the node (A.dops, bvh8.h Dop32)
+template <int ORDER, bool TRACE, bool COUNT, bool DOP>
 __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kernel(const BakeArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = A.S, words = A.vis_words;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
         v = __shfl_sync(kFull, v, 0);
         if (v >= A.n_verts) break;
         if (TRACE && !listed && A.need_count && __ldg(&A.need_count[v]) == 0u) continue;     // finished by the horizon pass
-        bake_wave_vertex<ORDER, TRACE, COUNT>(A, W, occl, v, lane, S, words, lt_mask, sgn, cand_tests, rays_scanned, node_visits, tri_tests);
+        bake_wave_vertex<ORDER, TRACE, COUNT, DOP>(A, W, occl, v, lane, S, words, lt_mask, sgn, cand_tests, rays_scanned, node_visits, tri_tests);
     }
     if (COUNT && A.work) {
         const unsigned long long nv = warp_sum_u64(node_visits), nt = warp_sum_u64(tri_tests);
@@ -66,31 +67,32 @@ __global__ void __launch_bounds__(PRT_WAVE_BLOCK, PRT_WAVE_MINB) bake_wave_kerne
     }
 }
 
-template <int ORDER, bool TRACE, bool COUNT>
+template <int ORDER, bool TRACE, bool COUNT, bool DOP>
 cudaError_t launch_wave_t(const BakeArgs &A, int *grid, int block, int n_sms, cudaStream_t st) {
     const size_t smem = (sizeof(WaveShared) + 4 * (size_t)((A.vis_words + 3) & ~3)) * (size_t)(block / 32);
     static std::atomic<unsigned long long> configured{0};   // per instantiation, one bit per device
     {
-        cudaError_t e = ensure_dynamic_smem(bake_wave_kernel<ORDER, TRACE, COUNT>, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)), configured);
+        cudaError_t e = ensure_dynamic_smem(bake_wave_kernel<ORDER, TRACE, COUNT, DOP>, (int)((sizeof(WaveShared) + kMaxS / 8) * (PRT_WAVE_BLOCK / 32)), configured);
         if (e != cudaSuccess) return e;
     }
     if (*grid <= 0) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_wave_kernel<ORDER, TRACE, COUNT>, block, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bake_wave_kernel<ORDER, TRACE, COUNT, DOP>, block, smem);
         if (e != cudaSuccess) return e;
         *grid = n_sms * (per_sm > 0 ? per_sm : 1);
     }
     const int warps_per_block = block / 32;
     const long long need = ((long long)A.n_verts + warps_per_block - 1) / warps_per_block;
     if (need < *grid) *grid = (int)(need > 0 ? need : 1);
-    bake_wave_kernel<ORDER, TRACE, COUNT><<<*grid, block, smem, st>>>(A);
+    bake_wave_kernel<ORDER, TRACE, COUNT, DOP><<<*grid, block, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 template <int ORDER>
 cudaError_t launch_wave_o(const BakeArgs &A, bool trace, int *grid, int block, int n_sms, cudaStream_t st) {
-    if (A.work) return trace ? launch_wave_t<ORDER, true, true>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false, true>(A, grid, block, n_sms, st);
-    return trace ? launch_wave_t<ORDER, true, false>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false, false>(A, grid, block, n_sms, st);
+    if (!trace) return A.work ? launch_wave_t<ORDER, false, true, false>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, false, false, false>(A, grid, block, n_sms, st);
+    if (A.dops) return A.work ? launch_wave_t<ORDER, true, true, true>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, true, false, true>(A, grid, block, n_sms, st);
+    return A.work ? launch_wave_t<ORDER, true, true, false>(A, grid, block, n_sms, st) : launch_wave_t<ORDER, true, false, false>(A, grid, block, n_sms, st);
 }
 
 }  // namespace

@@ -99,7 +99,7 @@ __device__ __noinline__ void write_vis_permuted(const float4 *samples, const uin
 // One vertex: entry list, lockstep scan of the flagged samples, node / leaf steps until both stacks are empty, projection, row
 // and (optional) visibility words.  W / occl: the warp's shared memory; lt_mask = (1 << lane) - 1; sgn = Condon-Shortley sign; the last four
 // arguments are the work counters of an instrumented launch (COUNT).
-template <int ORDER, bool TRACE, bool COUNT>
+template <int ORDER, bool TRACE, bool COUNT, bool DOP>
 __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &W, uint32_t *const occl, const uint32_t v, const int lane, const int S, const int words,
                                                  const unsigned lt_mask, const float sgn, unsigned long long &cand_tests,
                                                  unsigned long long &rays_scanned, uint32_t &node_visits, uint32_t &tri_tests) {
@@ -252,7 +252,13 @@ __device__ __forceinline__ void bake_wave_vertex(const BakeArgs &A, WaveShared &
                         const u4 n0 = ld16(npn), n1 = ld16(npn + 16), n2 = ld16(npn + 32), n3 = ld16(npn + 48), n4 = ld16(npn + 64);
                         const float4 smp = __ldg(&A.samples[it.x]);       // issued together with the node fetch
                         d = to_world(fr, mk3(smp.x, smp.y, smp.z));
-                        const uint32_t hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
+                        uint32_t hits;
+                        if (DOP) {
+                            // the node's fourth slab axis (32 bytes of a side array, fetched with the node)
+                            const char *dpn = reinterpret_cast<const char *>(A.dops + it.y);
+                            const u4 p0 = ld16(dpn), p1 = ld16(dpn + 16);
+                            hits = node_slots_hit_t<false, true>(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z), 0.0f, 0.0f, p0, p1, d);
+                        } else hits = node_slots_hit(n0, n2, n3, n4, org, rcp_box(d.x), rcp_box(d.y), rcp_box(d.z));
                         imask = n0.w >> 24; child_base = n1.x; tri_base = n1.y; meta_lo = n1.z; meta_hi = n1.w;
                         inner8 = hits & imask; leaf8 = hits & ~imask;
                         PRT_WAVE_NODE_STUDY(A, it.y, org, d, inner8, leaf8);

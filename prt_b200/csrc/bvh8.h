@@ -47,10 +47,22 @@ struct alignas(16) Slab32 {
 };
 static_assert(sizeof(Slab32) == 32, "Slab32 must be 32 bytes");
 
+// Fourth slab axis of the node test (traversal pass, traverse.cuh): the node's mean normal m (the Slab32's), scaled so that
+// s(x) = M . x - D0 runs over [0, 255] across the node's own extent along m, and the extent of every CHILD's triangles along it, quantised
+// outward to those 255 steps plus one step of padding either side (covers the float evaluation of s on the device).  A child is culled
+// when the ray's interval inside its box does not meet its [qlo, qhi] along m: a surface patch is a thin sheet in its box, and a ray that
+// grazes the surface passes through many such boxes beside their sheets.  M = 0: no axis (qlo = 0, qhi = 255: never culls).
+struct alignas(16) Dop32 {
+    float Mx, My, Mz, D0;
+    uint8_t qlo[8], qhi[8];
+};
+static_assert(sizeof(Dop32) == 32, "Dop32 must be 32 bytes");
+
 struct HostBVH8 {
     Node8 *nodes = nullptr;
     Tri48 *tris = nullptr;
     Slab32 *slabs = nullptr;        // [n_nodes]
+    Dop32 *dops = nullptr;          // [n_nodes]
     uint32_t n_nodes = 0, n_tris = 0, max_depth = 0;
     double sah_cost = 0.0, build_seconds = 0.0;
     float pad = 0.f;

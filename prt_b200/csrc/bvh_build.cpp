@@ -260,6 +260,8 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
     }
     std::vector<uint32_t> wide_bnode; wide_bnode.reserve(n_bin / 4 + 16);      // binary node behind every 8-wide node
     wide_bnode.push_back(0);
+    std::vector<uint32_t> wide_child; wide_child.reserve(8 * (n_bin / 4 + 16));  // [8 * node + slot] binary node of the child, 0xFFFFFFFF = empty
+    wide_child.resize(8, 0xFFFFFFFFu);
 
     struct WJob { uint32_t bnode, wnode, depth; };
     std::vector<WJob> stack;
@@ -317,7 +319,8 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
         for (int s = 0; s < 8; s++) if (slot_child[s] >= 0 && !bn[ch[slot_child[s]]].count) n_internal++;
         nd.child_base = (uint32_t)wn.size();
         nd.tri_base = n_tri_out;
-        if (n_internal) { wn.resize(wn.size() + n_internal); wide_bnode.resize(wn.size()); }
+        if (n_internal) { wn.resize(wn.size() + n_internal); wide_bnode.resize(wn.size()); wide_child.resize(8 * wn.size(), 0xFFFFFFFFu); }
+        for (int s = 0; s < 8; s++) wide_child[8 * (size_t)j.wnode + s] = slot_child[s] < 0 ? 0xFFFFFFFFu : ch[slot_child[s]];
         uint32_t rank = 0, toff = 0;
         uint8_t *qlo[3] = { nd.qlox, nd.qloy, nd.qloz }, *qhi[3] = { nd.qhix, nd.qhiy, nd.qhiz };
         for (int s = 0; s < 8; s++) {
@@ -362,7 +365,8 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
     std::memcpy(out->nodes, wn.data(), sizeof(Node8) * wn.size());
     // ---- oriented slabs (bvh8.h): mean normal of the triangles below every 8-wide node and their extent along it -----------------
     out->slabs = (Slab32 *)std::malloc(sizeof(Slab32) * wn.size());
-    if (!out->slabs) { std::free(tris); std::free(out->nodes); out->nodes = nullptr; return fail("build_bvh8: out of memory"); }
+    out->dops = (Dop32 *)std::malloc(sizeof(Dop32) * wn.size());
+    if (!out->slabs || !out->dops) { std::free(tris); std::free(out->nodes); std::free(out->slabs); std::free(out->dops); out->nodes = nullptr; out->slabs = nullptr; out->dops = nullptr; return fail("build_bvh8: out of memory"); }
     {
         const uint32_t n_wide = (uint32_t)wn.size();
         std::atomic<uint32_t> next{0};
@@ -400,6 +404,34 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
                         sl.d0 = std::nextafter((float)(lo - (double)pad), -3.0e38f); sl.d1 = std::nextafter((float)(hi + (double)pad), 3.0e38f);
                     }
                     out->slabs[w] = sl;
+                    // fourth slab axis (Dop32): extents of the children along m on a 255-step grid over the node's own extent, which is
+                    // floored at 2^-9 of the scene size so that the float evaluation of M . o stays far below one step
+                    Dop32 dp; std::memset(&dp, 0, sizeof(dp));
+                    for (int s = 0; s < 8; s++) { dp.qlo[s] = 0; dp.qhi[s] = 255; }
+                    if (sl.mx != 0.f || sl.my != 0.f || sl.mz != 0.f) {
+                        const double T = std::max((double)sl.d1 - (double)sl.d0, (double)amax * (1.0 / 512.0));
+                        const double scale = 255.0 / T, base = 0.5 * ((double)sl.d0 + (double)sl.d1) - 0.5 * T;
+                        dp.Mx = (float)(sl.mx * scale); dp.My = (float)(sl.my * scale); dp.Mz = (float)(sl.mz * scale);
+                        dp.D0 = (float)(base * scale);
+                        for (int s = 0; s < 8; s++) {
+                            const uint32_t cb = wide_child[8 * (size_t)w + s];
+                            if (cb == 0xFFFFFFFFu) continue;
+                            double lo = 3.0e38, hi = -3.0e38;
+                            for (uint32_t i = bfirst[cb]; i < bfirst[cb] + bcount[cb]; i++) {
+                                const uint32_t t = ids[i];
+                                for (int k = 0; k < 3; k++) {
+                                    const float *q = P(idx[3 * (size_t)t + k]);
+                                    // evaluated with the float vector the kernels use
+                                    const double d = (double)dp.Mx * q[0] + (double)dp.My * q[1] + (double)dp.Mz * q[2] - (double)dp.D0;
+                                    lo = std::min(lo, d); hi = std::max(hi, d);
+                                }
+                            }
+                            const double padq = (double)pad * scale + 1.0;            // the triangle-box padding, in steps, + one step
+                            dp.qlo[s] = (uint8_t)std::min(255.0, std::max(0.0, std::floor(lo - padq)));
+                            dp.qhi[s] = (uint8_t)std::min(255.0, std::max(0.0, std::ceil(hi + padq)));
+                        }
+                    }
+                    out->dops[w] = dp;
                 }
             }
         };
@@ -417,8 +449,8 @@ int build_bvh8(const float *pos, size_t stride, uint32_t nv, const uint32_t *idx
 
 void free_bvh8(HostBVH8 *b) {
     if (!b) return;
-    std::free(b->nodes); std::free(b->tris); std::free(b->slabs);
-    b->nodes = nullptr; b->tris = nullptr; b->slabs = nullptr;
+    std::free(b->nodes); std::free(b->tris); std::free(b->slabs); std::free(b->dops);
+    b->nodes = nullptr; b->tris = nullptr; b->slabs = nullptr; b->dops = nullptr;
 }
 
 }  // namespace prt

@@ -27,6 +27,7 @@ struct BakeArgs {
     const Node8 *nodes;
     const Tri48 *tris;
     const Slab32 *slabs;        // optional [n_nodes]: oriented slab of every node (horizon pass)
+    const Dop32 *dops;          // optional [n_nodes]: fourth slab axis of the node test (traversal pass; nullable by the tuning knob wave_dop)
     const float *pos, *nrm;     // device; consecutive vertices `stride` bytes apart
     size_t stride;
     uint32_t n_verts, vid_base;

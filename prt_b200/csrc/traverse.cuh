@@ -76,9 +76,14 @@ static __constant__ uint32_t prt_q2f_exp = 0x47000000u;
 #endif
 // plane group g (0..5 = far x, far y, far z, near x, near y, near z): conversion by byte permute (offset b) or by I2F (offset a)
 #define PRT_PLANE(g, w, j, s, a, b) ((g) < PRT_NODE_PRMT ? fmaf(PRT_Q2F_PRMT(w, j), s, b) : fmaf(PRT_Q2F_I2F(w, j), s, a))
-template <bool RANGE>
+// DOP: a fourth slab axis (bvh8.h Dop32: p0 = scaled mean normal M and offset D0, p1 = the children's quantised extents along it; d = the ray
+// direction): s(t) = M . o - D0 + t (M . d) must meet [qlo, qhi] of a child inside the ray's interval in the child's box -- the same
+// arithmetic as the three box axes with "scale" 1 / (M . d), folded into the interval with one more min (the max comes for free: the
+// clamp at 0 becomes a three-input max).  Box tests only ever have to be conservative; the extents carry a step of padding either side.
+template <bool RANGE, bool DOP = false>
 PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4 n4, const f3 o, const float idx, const float idy,
-                                 const float idz, const float tnear, const float tfar) {
+                                 const float idz, const float tnear, const float tfar, const u4 p0 = u4{0u, 0u, 0u, 0u},
+                                 const u4 p1 = u4{0u, 0u, 0u, 0u}, const f3 d = f3{0.f, 0.f, 0.f}) {
     const float sx = PRT_U2F((n0.w & 0xFFu) << 23) * idx;
     const float sy = PRT_U2F(((n0.w >> 8) & 0xFFu) << 23) * idy;
     const float sz = PRT_U2F(((n0.w >> 16) & 0xFFu) << 23) * idz;
@@ -91,6 +96,22 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
     const float fx = fmaf(-32768.0f, sx, ax) + gx, fy = fmaf(-32768.0f, sy, ay) + gy, fz = fmaf(-32768.0f, sz, az) + gz;
     const float mx = fmaf(-32768.0f, sx, ax) - gx, my = fmaf(-32768.0f, sy, ay) - gy, mz = fmaf(-32768.0f, sz, az) - gz;
     const bool nx = idx < 0.f, ny = idy < 0.f, nz = idz < 0.f;
+    // fourth axis: s = so + t sd; t = (q - so) / sd = q * ss + as
+    float ss = 0.f, as = 0.f, fs = 0.f;
+    bool ns = false;
+    if (DOP) {
+        const float so = fmaf(PRT_U2F(p0.z), o.z, fmaf(PRT_U2F(p0.y), o.y, PRT_U2F(p0.x) * o.x)) - PRT_U2F(p0.w);
+        float sd = fmaf(PRT_U2F(p0.z), d.z, fmaf(PRT_U2F(p0.y), d.y, PRT_U2F(p0.x) * d.x));
+        sd = copysignf(fmaxf(fabsf(sd), 1e-18f), sd);
+#if defined(__CUDA_ARCH__)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ss) : "f"(sd));       // box tests only (2 ulp; the extents carry a step of padding)
+#else
+        ss = 1.0f / sd;
+#endif
+        as = -so * ss;
+        fs = fmaf(-32768.0f, ss, as) + fabsf(ss) * 0.00390625f;
+        ns = ss < 0.f;
+    }
 #if defined(__CUDA_ARCH__) && PRT_NODE_PRMT_REG
     const uint32_t q2f_exp = prt_q2f_exp;
 #elif defined(__CUDA_ARCH__)
@@ -104,8 +125,19 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
         const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
         const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
         const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+        const uint32_t qls = h ? p1.y : p1.x, qhs = h ? p1.w : p1.z;
+        const uint32_t nears = ns ? qhs : qls, fars = ns ? qls : qhs;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            float t0s = 0.0f, t1s = 0.0f;
+            if (DOP) {
+#if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 3
+                const float2 ts = __ffma2_rn(make_float2(PRT_Q2F_I2F(nears, j), PRT_Q2F_PRMT(fars, j)), make_float2(ss, ss), make_float2(as, fs));
+                t0s = ts.x; t1s = ts.y;
+#else
+                t0s = fmaf(PRT_Q2F_I2F(nears, j), ss, as); t1s = fmaf(PRT_Q2F_PRMT(fars, j), ss, fs);     // the same formulas, scalar
+#endif
+            }
 #if defined(__CUDA_ARCH__) && PRT_NODE_FFMA2 && PRT_NODE_PRMT == 3
             // near plane (I2F, offset a) and far plane (byte permute, offset f) of an axis in one packed FFMA2
             const float2 tx = __ffma2_rn(make_float2(PRT_Q2F_I2F(nearx, j), PRT_Q2F_PRMT(farx, j)), make_float2(sx, sx), make_float2(ax, fx));
@@ -121,8 +153,9 @@ PRT_HD uint32_t node_slots_hit_t(const u4 n0, const u4 n2, const u4 n3, const u4
             const float t1x = PRT_PLANE(0, farx, j, sx, ax, fx), t1y = PRT_PLANE(1, fary, j, sy, ay, fy), t1z = PRT_PLANE(2, farz, j, sz, az, fz);
             const float t0x = PRT_PLANE(3, nearx, j, sx, ax, mx), t0y = PRT_PLANE(4, neary, j, sy, ay, my), t0z = PRT_PLANE(5, nearz, j, sz, az, mz);
 #endif
-            const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, RANGE ? tnear : 0.0f));
-            const float tmax = RANGE ? fminf(fminf(t1x, t1y), fminf(t1z, tfar)) : fminf(fminf(t1x, t1y), t1z);
+            float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, RANGE ? tnear : 0.0f));
+            float tmax = RANGE ? fminf(fminf(t1x, t1y), fminf(t1z, tfar)) : fminf(fminf(t1x, t1y), t1z);
+            if (DOP) { tmin = fmaxf(tmin, t0s); tmax = fminf(tmax, t1s); }
             if (tmin <= tmax) hits |= 1u << (4 * h + j);
         }
     }

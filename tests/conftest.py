@@ -63,6 +63,10 @@ def load_hostcheck(extra_flags=None):
     L.hc_slabs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.hc_node_tri_ranges.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_tris.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_dops.restype = C.c_uint32
+    L.hc_dops.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.hc_child_tri_ranges.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_wave_dop.argtypes = [C.c_int]
     L.hc_horizon_mid.argtypes = [C.c_int, C.c_float]
     L.hc_horizon_trace_far.restype = C.c_uint32
     L.hc_horizon_trace_far.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_uint32]

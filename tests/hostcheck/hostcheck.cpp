@@ -383,3 +383,29 @@ extern "C" void hc_tris(void *h, float *out) {
         o[6] = T.v0x + T.e2x; o[7] = T.v0y + T.e2y; o[8] = T.v0z + T.e2z;
     }
 }
+
+// the builder's fourth slab axis: out[12 * node ..] = M (3), D0, then qlo[8], qhi[8] as floats would not fit: raw 32-byte records instead
+extern "C" uint32_t hc_dops(void *h, uint8_t *out, uint32_t cap) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    const uint32_t n = std::min(cap, b->n_nodes);
+    if (out && b->dops) std::memcpy(out, b->dops, (size_t)n * sizeof(Dop32));
+    return b->dops ? b->n_nodes : 0u;
+}
+// per node and slot: the triangle range of the child (first, count; count 0 = empty slot): out[16 * node + 2 * slot ..]
+extern "C" void hc_child_tri_ranges(void *h, uint32_t *out) {
+    HostBVH8 *b = (HostBVH8 *)h;
+    std::vector<uint32_t> lo(b->n_nodes, 0xFFFFFFFFu), hi(b->n_nodes, 0u);
+    for (uint32_t x = b->n_nodes; x-- > 0;) {
+        const Node8 &nd = b->nodes[x];
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; s++) {
+            out[16 * (size_t)x + 2 * s] = 0; out[16 * (size_t)x + 2 * s + 1] = 0;
+            if (!nd.meta[s]) continue;
+            uint32_t t0, t1;
+            if ((nd.imask >> s) & 1) { const uint32_t ch = nd.child_base + rank++; t0 = lo[ch]; t1 = hi[ch]; }
+            else { t0 = nd.tri_base + (nd.meta[s] & 31u); t1 = t0 + (uint32_t)__builtin_popcount(nd.meta[s] >> 5); }
+            out[16 * (size_t)x + 2 * s] = t0; out[16 * (size_t)x + 2 * s + 1] = t1 - t0;
+            lo[x] = std::min(lo[x], t0); hi[x] = std::max(hi[x], t1);
+        }
+    }
+}

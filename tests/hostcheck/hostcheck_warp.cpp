@@ -73,6 +73,9 @@ inline void dop_study(const BakeArgs &A, uint32_t node, const f3 o, const f3 d, 
 }
 } }
 #define PRT_WAVE_NODE_STUDY(A, node, org, d, inner8, leaf8) dop_study(A, node, org, d, inner8, leaf8)
+// fourth slab axis of the node test in the traversal pass (Dop32): on by default, as in the product
+namespace { bool g_wave_dop = true; }
+extern "C" void hc_wave_dop(int on) { g_wave_dop = on != 0; }
 extern "C" void hc_dop_study(void *h, int mode, uint64_t *out) {
     using namespace prt;
     HostBVH8 *b = (HostBVH8 *)h;
@@ -122,6 +125,8 @@ using namespace prt;
 
 // oriented slabs of the nodes (bvh8.h) in the horizon builder: on by default, as in the product; the studies switch them off to compare
 namespace { bool g_use_slabs = true; int g_mid100 = 24; float g_gain = 0.2f; }
+// fourth slab axis of the node test in the traversal pass: on by default, as in the product
+extern "C" void hc_wave_dop(int on);
 extern "C" void hc_use_slabs(int on) { g_use_slabs = on != 0; }
 // refinement rule for mid-sized boxes (build_horizon: mid2, gain_min): angular radius x 100 (0 = rule off), gain in units of S / 32 samples
 extern "C" void hc_horizon_mid(int mid100, float gain) { g_mid100 = mid100; g_gain = gain; }
@@ -198,7 +203,8 @@ void run_wave(const BakeArgs &A, uint64_t *work) {
             uint32_t nv = 0u, nt = 0u;
             const float sgn = A.cs_phase ? -1.0f : 1.0f;
             for (uint32_t v = 0; v < A.n_verts; v++)
-                bake_wave_vertex<ORDER, true, COUNT>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                if (A.dops) bake_wave_vertex<ORDER, true, COUNT, true>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
+                else bake_wave_vertex<ORDER, true, COUNT, false>(A, sh.W, sh.occl, v, lane, A.S, A.vis_words, (1u << lane) - 1u, sgn, cand, scanned, nv, nt);
             w_nv += nv; w_nt += nt;
             if (lane == 0) { w_cand += cand; w_scanned += scanned; }      // warp-uniform counters
         });
@@ -220,6 +226,7 @@ extern "C" int hc_bake_wave(void *h, const float *pos, const float *nrm, uint32_
     A.need_bits = const_cast<uint32_t *>(need_bits);
     A.origin_eps = origin_eps; A.cs_phase = cs_phase;
     A.slabs = b->slabs;                 // the traversal pass does not read them; the DOP study hook does
+    A.dops = g_wave_dop ? b->dops : nullptr;
     switch (order) {
     case 1: run_wave<1, false>(A, nullptr); break;
     case 2: run_wave<2, false>(A, nullptr); break;

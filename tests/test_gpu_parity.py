@@ -98,7 +98,7 @@ def test_bake_reference_defaults(torus, torus_scenes, prt, oracle):
 
 
 @pytest.mark.parametrize("knobs", [dict(refill_thresh=0), dict(refill_thresh=24), dict(refill_thresh=32), dict(horizon=0), dict(horizon=1, horizon_budget=0), dict(horizon=1, horizon_near=60, horizon_budget=4),
-                                   dict(horizon_near=30, horizon_mid=0, horizon_slabs=0), dict(horizon_slabs=0), dict(horizon_mid=40, horizon_gain=0, horizon_budget=256),
+                                   dict(horizon_near=30, horizon_mid=0, horizon_slabs=0), dict(horizon_slabs=0), dict(wave_dop=0), dict(horizon_mid=40, horizon_gain=0, horizon_budget=256),
                                    dict(horizon_mid=5, horizon_gain=500), dict(work_list=0), dict(work_list=1), dict(pair_queue=0),
                                    dict(pair_queue=0, refill_thresh=0), dict(entry_list=0), dict(entry_list=0, refill_thresh=16)])
 def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
@@ -110,7 +110,7 @@ def test_bake_tuning_invariant(torus, torus_scenes, prt, oracle, knobs):
     try:
         got, gvis = prt.bake_transfer(gs, pos[sel], nrm[sel], prt.BakeParams.make(samples_u=16, samples_v=16), want_vis=True)
     finally:
-        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, work_list=-1, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1)
+        gs.ctx.set_tuning(refill_thresh=8, entry_list=1, pair_queue=2, horizon=1, horizon_budget=64, work_list=-1, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1, wave_dop=1)
     ref, ovis, _ = oracle.bake_transfer(os_, pos[sel], nrm[sel], oracle.make_params(samples_u=16, samples_v=16), want_vis=True)
     assert np.array_equal(gvis, ovis)
     assert rel_l2(got, ref).max() <= REL_L2_TOL
@@ -328,11 +328,11 @@ def test_horizon_map_is_conservative_on_adversarial_scenes(prt, oracle, case):
     frac = np.unpackbits(ovis.view(np.uint8)).mean()
     assert 0.02 < frac < 0.99 or case in ("room_inside", "sphere_shell")
     for knobs in (dict(), dict(horizon=0), dict(horizon_budget=0), dict(horizon_budget=3, horizon_near=80), dict(horizon_budget=200, horizon_near=10),
-                  dict(horizon_near=30, horizon_mid=0, horizon_slabs=0), dict(horizon_mid=40, horizon_gain=0, horizon_budget=256), dict(horizon_slabs=0)):
+                  dict(horizon_near=30, horizon_mid=0, horizon_slabs=0), dict(horizon_mid=40, horizon_gain=0, horizon_budget=256), dict(horizon_slabs=0), dict(wave_dop=0)):
         gs.ctx.set_tuning(**knobs)
         try:
             got, gvis = prt.bake_transfer(gs, org, nrm, prt.BakeParams.make(**kw), want_vis=True)
         finally:
-            gs.ctx.set_tuning(horizon=1, horizon_budget=64, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1)
+            gs.ctx.set_tuning(horizon=1, horizon_budget=64, horizon_near=157, horizon_mid=24, horizon_gain=64, horizon_slabs=1, wave_dop=1)
         assert np.array_equal(gvis, ovis), f"{case} {knobs}: {np.count_nonzero(gvis != ovis)} visibility words differ"
         assert rel_l2(got, ref)[np.linalg.norm(ref, axis=1) > 1e-3].max(initial=0) <= REL_L2_TOL

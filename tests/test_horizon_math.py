@@ -277,6 +277,48 @@ def test_builder_slabs_contain_their_triangles(hostcheck):
     assert np.median(thin) < 0.25
 
 
+def test_builder_dops_contain_their_children(hostcheck):
+    """Dop32 of every 8-wide node (bvh_build.cpp): the triangles of every child lie inside the child's quantised extent along the node's
+    scaled mean normal, with at least one step to spare either side (the padding the float evaluation on the device lives on), and the
+    extents are worth having: on a surface mesh the median child spans well under half of the 255 steps."""
+    from prt_b200 import meshes
+    pos, nrm, tri = meshes.bumpy_torus(96, 64)
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    info = np.zeros(3, np.uint32)
+    hostcheck.hc_info(h, info.ctypes.data)
+    n_nodes, n_tris = int(info[0]), int(info[1])
+    raw = np.zeros((n_nodes, 32), np.uint8)
+    assert hostcheck.hc_dops(h, raw.ctypes.data, n_nodes) == n_nodes
+    M = raw[:, :16].copy().view(np.float32).reshape(n_nodes, 4)
+    qlo, qhi = raw[:, 16:24].astype(np.float64), raw[:, 24:32].astype(np.float64)
+    ranges = np.zeros((n_nodes, 8, 2), np.uint32)
+    hostcheck.hc_child_tri_ranges(h, ranges.ctypes.data)
+    tv = np.zeros((n_tris, 9), np.float32)
+    hostcheck.hc_tris(h, tv.ctypes.data)
+    hostcheck.hc_free(h)
+    spans = []
+    checked = 0
+    for x in range(n_nodes):
+        m, d0 = M[x, :3].astype(np.float64), float(M[x, 3])
+        if not m.any():
+            assert (qlo[x] == 0).all() and (qhi[x] == 255).all()
+            continue
+        for s_ in range(8):
+            t0, cnt = int(ranges[x, s_, 0]), int(ranges[x, s_, 1])
+            if cnt == 0:
+                continue
+            v = tv[t0:t0 + cnt].reshape(-1, 3).astype(np.float64)
+            sv = v @ m - d0
+            lo_ok = sv.min() >= qlo[x, s_] + 1.0 or qlo[x, s_] == 0
+            hi_ok = sv.max() <= qhi[x, s_] - 1.0 or qhi[x, s_] == 255
+            assert lo_ok and hi_ok, (x, s_, sv.min(), sv.max(), qlo[x, s_], qhi[x, s_])
+            assert -1e-3 <= sv.min() and sv.max() <= 255.001            # inside the node's own range
+            spans.append(qhi[x, s_] - qlo[x, s_])
+            checked += 1
+    assert checked > n_nodes
+    assert np.median(spans) < 160 and np.percentile(spans, 25) < 110
+
+
 # ---- the warp-cooperative builder itself, run on the CPU through the warp emulator (tests/hostcheck/warp_emu.h) --------------------
 def _maps(hostcheck, h, pos, nrm, budget=64, near=157, eps=1e-4, stats=None, slabs=1, mid=24, gain=0.2):
     """defaults = the product's (abi.cu: horizon_near 157, horizon_mid 24, horizon_gain 6.4 samples = 0.2 x 1024 / 32, slabs on)"""

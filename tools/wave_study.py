@@ -28,6 +28,7 @@ ap.add_argument("--near", type=int, default=157)
 ap.add_argument("--mid", type=int, default=24)
 ap.add_argument("--gain", type=float, default=0.2)
 ap.add_argument("--slabs", type=int, default=1)
+ap.add_argument("--wave-dop", type=int, default=1, help="fourth slab axis in the node test of the traversal pass (product default: on)")
 ap.add_argument("--dop", type=int, default=0, help="study: fourth slab axis per node in the child test (1 quantised, 2 exact extents)")
 ap.add_argument("--budget", type=int, default=64)
 a = ap.parse_args()
@@ -46,6 +47,7 @@ keep = need.any(axis=1)                         # vertices the horizon pass fini
 work = np.zeros(4, np.uint64)
 hc.hc_dop_study.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_void_p]
 hc.hc_dop_study(h, a.dop, None)
+hc.hc_wave_dop(a.wave_dop)
 hc.hc_wave_step_stats.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
 _ss = np.zeros(8, np.uint64); hc.hc_wave_step_stats(_ss.ctypes.data, 1)
 got, vis = run_wave(hc, h, pos[sel][keep], nrm[sel][keep], tab, 3, need=np.ascontiguousarray(need_words[keep]), work=work)
