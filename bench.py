@@ -590,8 +590,10 @@ def run_bake(a):
                 ncu["kernel"] = ncu.get("kernel", "") + f" [counts of every {f}-th chunk of the shard x {k:.3f}]"
         rays_launch = float(n_valid) * S
         need_bytes = n_mine * (4.0 * ((S + 31) // 32) + 4.0) if launches_per_step >= 2 else 0.0
-        bvh_bytes = float(info.node_bytes + info.tri_bytes)
-        l2_alg = visits * 80.0 + tests * 48.0
+        shadowed = kname.startswith("bake_wave")                     # its node test also fetches the 32-byte fourth-axis record of the node
+        node_fetch = 112.0 if shadowed else 80.0
+        bvh_bytes = float(info.node_bytes + info.tri_bytes) + (32.0 * info.n_nodes if shadowed else 0.0)
+        l2_alg = visits * node_fetch + tests * 48.0
         floor = n_valid * (24.0 + 4.0 * n2) + need_bytes + min(bvh_bytes, l2_alg)
         roofline = issue_roofline(ncu, k_ms_max, n_sms, clk.get("sm_mhz") if clk else None, peaks, floor, l2_alg,
                                   f"{kname}<{a.order}> (traversal + projection of this rank's shard; the horizon pass ran {hz_ms:.2f} ms before it)")
@@ -599,7 +601,7 @@ def run_bake(a):
                          "entry_list_box_tests_per_ray": cands / rays_launch, "rays_traversed_frac": traversed / rays_launch if traversed else None,
                          "horizon_pass_ms": hz_ms,
                          "note": "hbm.floor = vertex I/O + need bits + every BVH byte the launch touches once (capped at the BVH size); l2_algorithmic = node "
-                                 f"fetches x 80 B + triangle fetches x 48 B; the BVH is {bvh_bytes / 1e6:.1f} MB ("
+                                 f"fetches x {node_fetch:.0f} B + triangle fetches x 48 B; the BVH is {bvh_bytes / 1e6:.1f} MB ("
                                  + ("L2-resident" if bvh_bytes < 100e6 else "larger than the 126 MB L2: deep levels stream from HBM") + ")"})
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": W_,
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
