@@ -324,3 +324,73 @@ def test_fourth_slab_axis_only_removes_work(hostcheck, oracle):
         assert rel_l2(out[dop][0], ref).max() <= REL_L2_TOL
     assert float(out[1][2][0]) < 0.92 * float(out[0][2][0])          # node visits
     assert float(out[1][2][1]) < 0.92 * float(out[0][2][1])          # triangle tests
+
+
+@pytest.mark.parametrize("scene_kind", ["flat_room", "triangle_soup", "far_from_origin", "degenerate"])
+def test_fourth_slab_axis_on_awkward_geometry(hostcheck, oracle, scene_kind):
+    """The fourth slab axis of the node test and the oriented slabs of the horizon pass on geometry that is NOT a smooth bumpy surface:
+    axis-aligned flat walls (slabs of zero thickness: the extent is floored), an unstructured triangle soup (mean normals mean nothing),
+    a mesh far from the coordinate origin (large |M . o|: the float evaluation of the slab coordinate is what the padding is for) and
+    zero-area / duplicated triangles (degenerate mean normals).  Both passes, emulated, against the oracle, bit for bit."""
+    rng = np.random.RandomState(5)
+    if scene_kind == "flat_room":
+        # a closed box seen from inside with a floating slab in it
+        def quad(a, b, c, d):
+            return [a, b, c, a, c, d]
+        L = 2.0
+        corners = np.array([[x, y, z] for x in (-L, L) for y in (-L, L) for z in (-L, L)], np.float32)
+        faces = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+        verts = []
+        for f in faces:                                        # every wall tessellated 6 x 6
+            p = corners[list(f)]
+            for i in range(6):
+                for j in range(6):
+                    u0, u1, v0, v1 = i / 6, (i + 1) / 6, j / 6, (j + 1) / 6
+                    bil = lambda u, v: (1 - u) * (1 - v) * p[0] + u * (1 - v) * p[1] + u * v * p[2] + (1 - u) * v * p[3]
+                    verts += quad(bil(u0, v0), bil(u1, v0), bil(u1, v1), bil(u0, v1))
+        verts += quad(np.float32([-1, -1, 0.3]), np.float32([1, -1, 0.3]), np.float32([1, 1, 0.3]), np.float32([-1, 1, 0.3]))
+        pos = np.array(verts, np.float32)
+        tri = np.arange(len(pos), dtype=np.uint32).reshape(-1, 3)
+        org = np.float32([[0.1, 0.2, -1.9], [1.5, -0.3, 0.0], [0.0, 0.0, 0.31], [-1.99, 0.5, 0.5]])
+        nrm = np.float32([[0, 0, 1], [-1, 0, 0], [0, 0, 1], [1, 0, 0]])
+    elif scene_kind == "triangle_soup":
+        k = 500
+        c = rng.uniform(-2, 2, size=(k, 1, 3))
+        pos = (c + rng.normal(size=(k, 3, 3)) * 0.3).reshape(-1, 3).astype(np.float32)
+        tri = np.arange(3 * k, dtype=np.uint32).reshape(k, 3)
+        org = rng.uniform(-1.5, 1.5, size=(8, 3)).astype(np.float32)
+        nrm = rng.normal(size=(8, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    elif scene_kind == "far_from_origin":
+        pos, n0, tri = meshes.bumpy_torus(64, 48)
+        pos = (pos * 0.01 + np.float32([250.0, -180.0, 90.0])).astype(np.float32)
+        sel = np.arange(7, len(pos), 211)[:10]
+        org, nrm = pos[sel], n0[sel]
+    else:
+        pos, n0, tri = meshes.bumpy_torus(48, 32)
+        extra = np.concatenate([tri[:50], np.stack([tri[:50, 0], tri[:50, 0], tri[:50, 1]], axis=1)])     # duplicates and zero-area triangles
+        tri = np.concatenate([tri, extra]).astype(np.uint32)
+        sel = np.arange(3, len(pos), 97)[:12]
+        org, nrm = pos[sel], n0[sel]
+    org, nrm = np.ascontiguousarray(org, np.float32), np.ascontiguousarray(nrm, np.float32)
+    eps = 1e-4 if scene_kind != "far_from_origin" else 1e-4
+    h = hostcheck.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
+    assert h
+    op = oracle.make_params(order=3, samples_u=16, samples_v=32)
+    tab, bins = processing_table(oracle, op)
+    try:
+        hz, _ = _maps(hostcheck, h, org, nrm, eps=eps)
+        need = ~(tab[None, :, 2] > hz[:, bins])
+        words = np.ascontiguousarray(np.packbits(need, axis=1, bitorder="little")).view(np.uint32).copy()
+        ref, ovis, _ = oracle.bake_transfer(oracle.Scene(pos, tri), org, nrm, oracle.make_params(order=3, samples_u=16, samples_v=32, origin_eps=eps), want_vis=True)
+        visible = np.unpackbits(ovis.view(np.uint8), axis=1, bitorder="little")[:, :len(tab)].astype(bool)
+        # (1) the horizon pass never frees an occluded ray (need bits are in processing order, the oracle's words in reference order)
+        sref = (tab[:, 3].view(np.uint32) & 0xFFFFFF).astype(np.int64)
+        assert not (~need & ~visible[:, sref]).any()
+        # (2) the traversal pass with the fourth axis on, all rays and the flagged ones only
+        for nb in (None, words):
+            got, gvis = run_wave(hostcheck, h, org, nrm, tab, 3, need=nb)
+            assert np.array_equal(gvis, ovis), scene_kind
+            assert rel_l2(got, ref)[np.linalg.norm(ref, axis=1) > 1e-3].max(initial=0) <= REL_L2_TOL
+    finally:
+        hostcheck.hc_free(h)
