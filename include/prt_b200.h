@@ -58,6 +58,7 @@ int prt_ctx_last_kernel_ms(const prt_ctx *, double *ms);
  *   horizon_mid 0..157 (24)    ... and those above this radius when merging their bound would leave more than
  *   horizon_gain (64)          this many tenths of a sample to trace (estimate; 0 = every such box); horizon_mid 0 = rule off
  *   horizon_slabs 0/1 (1)      the builder bounds a subtree by its oriented slab (mean normal of its triangles) inside its box
+ *   wave_dop 0/1 (1)           node test of the traversal pass with a fourth slab axis (the node's mean normal; children's extents quantised)
  *   horizon_budget 0..4096 (64) refinement iterations (4 nodes each) per vertex
  *   work_list -1/0/1 (-1)      traversal pass walks the vertices heaviest first (counting sort of the need counts); -1 = below ~1 M vertices
  *   l2_prefetch 0/1 (0)        stream the BVH into L2 before the first pass (measured: no effect, the cold-start misses are hidden)
