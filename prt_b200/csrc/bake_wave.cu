@@ -10,8 +10,10 @@
 //     scan                  32 rays x all candidate boxes; every hit becomes an item
 //                             subtree candidate  -> node stack  (ray, node)
 //                             leaf candidate     -> leaf stack  (ray, first triangle, count bits)
-//     node step             pops 32 (ray, node) items: each lane decodes ONE 80-byte node, tests its 8 child boxes and
-//                           pushes (ray, child) / (ray, leaf) items (ballot/popc compaction)
+//     node step             pops 32 (ray, node) items: each lane decodes ONE 80-byte node, tests its 8 child boxes -- three box axes and a
+//                           fourth slab axis along the node's mean normal (Dop32, bvh8.h: a ray grazing the surface passes through many
+//                           boxes beside the sheet of triangles in them; -21 % node visits, -24 % triangle tests) -- and pushes
+//                           (ray, child) / (ray, leaf) items (one packed warp scan)
 //     leaf step             pops 32 (ray, leaf) items: each lane runs <= 3 pinned triangle tests, sets the occlusion bit
 //     project               every unoccluded sample direction -> SH basis in registers, shuffle reduction, row store
 //

@@ -3,7 +3,8 @@
 // One persistent warp per vertex:
 //   1. build_entry_list   candidate boxes for the shared ray origin (entry_list.cuh)
 //   2. build_horizon      conservative bound of sin(elevation) of all geometry per azimuth bin (kHzBins = 32 or 64), refined through near
-//                         subtrees down to exact triangle bounds
+//                         subtrees down to exact triangle bounds; a subtree is bounded by its box CUT BY ITS ORIENTED SLAB (Slab32, bvh8.h:
+//                         hz_slab_value) and opened when merging that bound would leave many samples to trace (hz_gain)
 //   3. classify           sample i needs tracing iff its local z does not exceed the horizon of its bin; the need bits of the
 //                         vertex (processing order) and their count go to global memory for the traversal pass
 //   4. vertices with no sample to trace are finished here: every sample is visible, so the row is the plain cosine-weighted
