@@ -10,7 +10,7 @@ import conftest
 # load the TSan build instead of the regular one
 L = C.CDLL(os.environ.get('PRT_HOSTCHECK_TSAN', '/tmp/libhostcheck_tsan.so'))
 ref = conftest.load_hostcheck()
-for name in ('hc_build','hc_free','hc_horizon_maps','hc_bake_wave','hc_bake_inter'):
+for name in ('hc_build','hc_free','hc_horizon_maps','hc_bake_wave','hc_bake_inter','hc_use_slabs','hc_horizon_mid','hc_wave_dop'):
     getattr(L,name).argtypes = getattr(ref,name).argtypes; getattr(L,name).restype = getattr(ref,name).restype
 from oracle import pyoracle as oracle
 from prt_b200 import meshes
