@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record of the session: the slab filter and its knob wave_filter were removed afterwards -- see DESIGN.md section 4)
 # Round-2 session M (1 GPU): oriented slabs in the horizon pass + slab filter in the traversal pass.  Parity tests of the touched paths,
 # A/B sweeps of the new knobs against the previous algorithm on both bench workloads, library variants, one default bench line.
 set -u

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record of the session: the slab filter and its knob wave_filter were removed afterwards -- see DESIGN.md section 4)
 # Round-2 session N (1 GPU): why is the slab filter of the traversal pass slow on the GPU?  One full ncu capture (with source) of the
 # filter variant and of the plain traversal on the same horizon settings, more A/B points without the filter, inline-filter variant.
 set -u

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record of the session: the slab filter and its knob wave_filter were removed afterwards -- see DESIGN.md section 4)
 # Round-2 session O (1 GPU): the slab filter with the stack capacities fixed (node stack 320, leaf stack 128, ready queue 64; ready items
 # count in the admission rule).  A/B against the plain traversal on both workloads, library variants, parity tests, ncu of the filter kernel.
 set -u
