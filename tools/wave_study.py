@@ -31,10 +31,11 @@ ap.add_argument("--slabs", type=int, default=1)
 ap.add_argument("--wave-dop", type=int, default=1, help="fourth slab axis in the node test of the traversal pass (product default: on)")
 ap.add_argument("--dop", type=int, default=0, help="study: fourth slab axis per node in the child test (1 quantised, 2 exact extents)")
 ap.add_argument("--budget", type=int, default=64)
+ap.add_argument("--folds", action="store_true", help="the heavily self-occluding twin of the bench mesh (amp 0.25, fscale 3)")
 a = ap.parse_args()
 
 hc = conftest.load_hostcheck()
-pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv)
+pos, nrm, tri = meshes.bumpy_torus(a.nu, a.nv, amp=0.25, fscale=3) if a.folds else meshes.bumpy_torus(a.nu, a.nv)
 order = meshes.morton_order(pos)
 sel = order[:: max(1, len(order) // a.n)][: a.n]
 h = hc.hc_build(pos.ctypes.data, 12, len(pos), tri.ctypes.data, len(tri))
